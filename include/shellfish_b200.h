@@ -1,0 +1,148 @@
+/* shellfish_b200.h -- C ABI of the B200 (sm_100a) line-of-sight shell finder.
+ *
+ * Drop-in boundary for the hot path of `shellfish shell`
+ * (phil-mansfield/shellfish v1.0.4).  The reference has no FFI layer; its seam
+ * is the set of los.Halo / analyze.* calls made from cmd/shell.go.  Each entry
+ * point below names the reference code it replaces; INTEGRATION.md shows the
+ * cgo stub that binds it from cmd/shell.go.
+ *
+ * Conventions: plain pointers and sizes, no CUDA or torch types.  Every call
+ * returns 0 on success or a negative SFK_E_* code; sfk_last_error() gives the
+ * message the host prints before "Shellfish terminating." (shellfish.go:441).
+ * Host input buffers are copied before the call returns (cgo may not retain
+ * Go pointers; io.VectorBuffer reuses its slices, io/io.go:57-67).  One
+ * context drives one GPU and is not re-entrant (cmd/shell.go's loop is a
+ * single goroutine).  There is no CPU fallback: sfk_create fails when no
+ * sm_100 device is present.
+ */
+#ifndef SHELLFISH_B200_H
+#define SHELLFISH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFK_OK 0
+#define SFK_E_INVALID (-1)   /* bad argument / call order */
+#define SFK_E_CUDA (-2)      /* CUDA runtime error */
+#define SFK_E_NODEVICE (-3)  /* no usable sm_100 GPU */
+#define SFK_E_NOMEM (-4)
+#define SFK_E_UNSUPPORTED (-5)
+
+/* per-halo status written by sfk_finish_snapshot */
+#define SFK_HALO_OK 0
+#define SFK_HALO_SKIPPED 1     /* r200m <= 0: cmd/shell.go:535-538 leaves a nil halo */
+#define SFK_HALO_NO_POINTS 2   /* a ring had no valid LoS: NewKDETree panic, kde.go:72-81 */
+#define SFK_HALO_NO_MAXIMUM 3  /* level-0 KDE without maximum: index panic, kde.go:212 */
+#define SFK_HALO_SPLINE 4      /* Spline table/bounds panic, spline.go:56-96 */
+#define SFK_HALO_SINGULAR 5    /* singular normal equations in the Penna fit */
+
+/* sfk_params.flags */
+#define SFK_FLAG_TAPS 1u /* keep parity taps: profiles, integer edge counts */
+
+typedef struct sfk_ctx sfk_ctx;
+
+/* ShellConfig, cmd/shell.go:24-35; defaults :105-119; validation :143-187.
+ * seed replaces cmd/cmd.go:658 randSeed (wall clock in the reference). */
+typedef struct {
+    int64_t radial_bins, spokes, rings;
+    double r_max_mult, r_min_mult, r_kernel_mult;
+    double eta;
+    int64_t order, smoothing_window, levels, subsample_factor;
+    double los_slope_cutoff, background_rho_mult;
+    int32_t percentile_profile; /* cmd/shell.go:28; must be 0 (not built yet) */
+    double percentile;
+    uint64_t seed;
+    int32_t device; /* CUDA ordinal */
+    uint32_t flags; /* SFK_FLAG_* */
+} sfk_params;
+
+/* io.CosmologyHeader, io/io.go:71-76 */
+typedef struct {
+    double z, omega_m, omega_l, h100;
+} sfk_cosmo;
+
+/* Work counters of the last finished snapshot. */
+typedef struct {
+    int64_t n_halos;
+    int64_t n_candidates;    /* particles passing Halo.Intersect, los/halo.go:147 */
+    int64_t n_ring_hits;     /* sphereIntersectRing successes, los/halo.go:218 */
+    int64_t n_intersections; /* ProfileRing.Insert calls past the early-out, profile_ring.go:92-95 */
+    int64_t n_points;        /* filtered points that reached the Penna fit */
+    double ms_cull, ms_hits, ms_bin, ms_los, ms_filter, ms_fit; /* CUDA-event time per stage */
+    int64_t bin_launches;    /* launches of the binning kernel */
+    int64_t launches;        /* kernel launches of this library since begin_snapshot */
+} sfk_stats;
+
+/* Fills *p with the defaults of cmd/shell.go:105-119. */
+void sfk_default_params(sfk_params *p);
+
+/* ShellConfig.ReadConfig + validate (cmd/shell.go:102-187) and the per-run
+ * set-up of loop() (cmd/shell.go:288-320): ring normals (normVecs :566),
+ * rotation matrices and LoS vectors (Halo.Init, los/halo.go:65-100). */
+int sfk_create(sfk_ctx **out, const sfk_params *params);
+void sfk_destroy(sfk_ctx *ctx);
+const char *sfk_last_error(const sfk_ctx *ctx);
+
+/* Start of one iteration of the snapshot loop, cmd/shell.go:322-344.  cosmo
+ * is the header of the first block of the first snapshot (hds[0], :305,:340)
+ * and min_mass is buf.MinMass() (:309). */
+int sfk_begin_snapshot(sfk_ctx *ctx, const sfk_cosmo *cosmo, float min_mass);
+
+/* createHalos, cmd/shell.go:530-564.  May be called once per snapshot. */
+int sfk_add_halos(sfk_ctx *ctx, int64_t n, const double *x, const double *y,
+                  const double *z, const double *r200m);
+
+/* binIntersections / Halo.SheetIntersect (cmd/shell.go:599-611,
+ * los/halo.go:442-467) for one block header.  hit may be NULL; *n_hit
+ * receives the number of halos touching the block. */
+int sfk_block_halo_mask(sfk_ctx *ctx, const float origin[3], const float width[3],
+                        double total_width, uint8_t *hit, int64_t *n_hit);
+
+/* Body of sphereLoop for one buf.Read (cmd/shell.go:399-410): for every halo
+ * touching the block, in halo order, Transform + Intersect
+ * (los/halo.go:168-197,147-164) and queueing of the surviving particles with
+ * the weight of chanLoadSphereVec (cmd/shell.go:479-500).  xyz is [n][3],
+ * mass is [n]; both are host pointers. */
+int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
+                   const sfk_cosmo *cosmo, double total_width,
+                   const float origin[3], const float width[3]);
+
+/* Same with xyz/mass already in device memory of ctx's GPU (used to time the
+ * kernels with inputs resident in HBM). */
+int sfk_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass,
+                          int64_t n, const sfk_cosmo *cosmo, double total_width,
+                          const float origin[3], const float width[3]);
+
+/* Halo.Insert for all queued particles (los/halo.go:201-277,
+ * profile_ring.go:92-120) followed by haloAnalysis (cmd/shell.go:502-528):
+ * RingBuffer.Splashback, FilterPoints, PennaVolumeFit.  coeffs is
+ * [n_halo][2*order*order] in catalog column order, status is [n_halo]
+ * SFK_HALO_*; either may be NULL. */
+int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status);
+
+int sfk_get_stats(const sfk_ctx *ctx, sfk_stats *out);
+
+/* ---- parity taps (valid after sfk_finish_snapshot) ---------------------- */
+
+/* Splashback radius per LoS, [rings][spokes], NaN where RingBuffer.Oks is
+ * false (ring_buffer.go:57-93).  Always available. */
+int sfk_get_rsp(sfk_ctx *ctx, int64_t halo, double *r);
+/* Number of particles queued for the halo (passing Halo.Intersect). */
+int sfk_get_candidate_count(sfk_ctx *ctx, int64_t halo, int64_t *n);
+/* Halo.GetRhos for every LoS: [rings][spokes][bins].  Needs SFK_FLAG_TAPS. */
+int sfk_get_profiles(sfk_ctx *ctx, int64_t halo, double *rho);
+/* Integer taps, need SFK_FLAG_TAPS: inserts per LoS [rings][spokes] and the
+ * number of start / end edges landing in each bin [rings][spokes][bins]. */
+int sfk_get_counts(sfk_ctx *ctx, int64_t halo, uint32_t *n_insert,
+                   uint32_t *start_edges, uint32_t *end_edges);
+/* Host-side tables the context was built with: normals [rings][3], rotation
+ * matrices rot / irot [rings][9]. */
+int sfk_get_ring_tables(const sfk_ctx *ctx, float *norms, float *rot, float *irot);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,245 @@
+"""ctypes binding of the C ABI in include/shellfish_b200.h.
+
+This is the Python stand-in for the cgo shim a Go maintainer would add to
+cmd/shell.go: the same calls in the same order as
+ShellConfig.Run / loop / sphereLoop / haloAnalysis.  There is no CPU path: if
+libsfk.so is missing or no sm_100 GPU is present the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsfk.so")
+
+SFK_FLAG_TAPS = 1
+HALO_STATUS = {0: "ok", 1: "skipped", 2: "no_points", 3: "no_maximum", 4: "spline", 5: "singular"}
+
+
+class Params(C.Structure):
+    """sfk_params == ShellConfig (cmd/shell.go:24-35) + seed/device/flags."""
+    _fields_ = [("radial_bins", C.c_int64), ("spokes", C.c_int64), ("rings", C.c_int64),
+                ("r_max_mult", C.c_double), ("r_min_mult", C.c_double), ("r_kernel_mult", C.c_double),
+                ("eta", C.c_double),
+                ("order", C.c_int64), ("smoothing_window", C.c_int64), ("levels", C.c_int64),
+                ("subsample_factor", C.c_int64),
+                ("los_slope_cutoff", C.c_double), ("background_rho_mult", C.c_double),
+                ("percentile_profile", C.c_int32), ("percentile", C.c_double),
+                ("seed", C.c_uint64), ("device", C.c_int32), ("flags", C.c_uint32)]
+
+
+class Cosmo(C.Structure):
+    _fields_ = [("z", C.c_double), ("omega_m", C.c_double), ("omega_l", C.c_double), ("h100", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_halos", C.c_int64), ("n_candidates", C.c_int64), ("n_ring_hits", C.c_int64),
+                ("n_intersections", C.c_int64), ("n_points", C.c_int64),
+                ("ms_cull", C.c_double), ("ms_hits", C.c_double), ("ms_bin", C.c_double),
+                ("ms_los", C.c_double), ("ms_filter", C.c_double), ("ms_fit", C.c_double),
+                ("bin_launches", C.c_int64), ("launches", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/shellfish_b200.h declares
+EXPORTS = ["sfk_default_params", "sfk_create", "sfk_destroy", "sfk_last_error", "sfk_begin_snapshot",
+           "sfk_add_halos", "sfk_block_halo_mask", "sfk_push_block", "sfk_push_block_device",
+           "sfk_finish_snapshot", "sfk_get_stats", "sfk_get_rsp", "sfk_get_candidate_count",
+           "sfk_get_profiles", "sfk_get_counts", "sfk_get_ring_tables"]
+
+_lib = None
+
+
+def lib():
+    """Loads libsfk.so (built by __graft_entry__.build()); never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: run __graft_entry__.build() (nvcc, sm_100a). "
+                               "There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, dp, fp = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)
+        L.sfk_default_params.argtypes = [C.POINTER(Params)]
+        L.sfk_default_params.restype = None
+        L.sfk_create.argtypes = [C.POINTER(vp), C.POINTER(Params)]
+        L.sfk_destroy.argtypes = [vp]
+        L.sfk_destroy.restype = None
+        L.sfk_last_error.argtypes = [vp]
+        L.sfk_last_error.restype = C.c_char_p
+        L.sfk_begin_snapshot.argtypes = [vp, C.POINTER(Cosmo), C.c_float]
+        L.sfk_add_halos.argtypes = [vp, C.c_int64, dp, dp, dp, dp]
+        L.sfk_block_halo_mask.argtypes = [vp, fp, fp, C.c_double, C.POINTER(C.c_uint8), C.POINTER(C.c_int64)]
+        L.sfk_push_block.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Cosmo), C.c_double, fp, fp]
+        L.sfk_push_block_device.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Cosmo), C.c_double, fp, fp]
+        L.sfk_finish_snapshot.argtypes = [vp, dp, C.POINTER(C.c_int32)]
+        L.sfk_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.sfk_get_rsp.argtypes = [vp, C.c_int64, dp]
+        L.sfk_get_candidate_count.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64)]
+        L.sfk_get_profiles.argtypes = [vp, C.c_int64, dp]
+        u32p = C.POINTER(C.c_uint32)
+        L.sfk_get_counts.argtypes = [vp, C.c_int64, u32p, u32p, u32p]
+        L.sfk_get_ring_tables.argtypes = [vp, fp, fp, fp]
+        for name in EXPORTS:
+            if getattr(L, name).restype is not None and name != "sfk_last_error":
+                getattr(L, name).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def default_params(**kw):
+    p = Params()
+    lib().sfk_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class ShellfishError(RuntimeError):
+    pass
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class ShellContext:
+    """One GPU's shell finder; mirrors the call sequence of cmd/shell.go."""
+
+    def __init__(self, params):
+        self.params = params
+        self._h = C.c_void_p()
+        rc = lib().sfk_create(C.byref(self._h), C.byref(params))
+        if rc:
+            msg = lib().sfk_last_error(self._h).decode() if self._h else "sfk_create failed"
+            if self._h:
+                lib().sfk_destroy(self._h)
+                self._h = C.c_void_p()
+            raise ShellfishError("sfk_create: %s (code %d)" % (msg, rc))
+        self.n_halos = 0
+
+    def close(self):
+        if self._h:
+            lib().sfk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, rc, what):
+        if rc:
+            raise ShellfishError("%s: %s (code %d)" % (what, lib().sfk_last_error(self._h).decode(), rc))
+
+    @property
+    def P2(self):
+        return int(2 * self.params.order * self.params.order)
+
+    def begin_snapshot(self, cosmo, min_mass):
+        c = Cosmo(cosmo["Z"], cosmo["OmegaM"], cosmo["OmegaL"], cosmo["H100"])
+        self._ck(lib().sfk_begin_snapshot(self._h, C.byref(c), C.c_float(min_mass)), "sfk_begin_snapshot")
+
+    def add_halos(self, halos):
+        halos = np.ascontiguousarray(halos, np.float64)
+        cols = [np.ascontiguousarray(halos[:, i]) for i in range(4)]
+        ptrs = [c.ctypes.data_as(C.POINTER(C.c_double)) for c in cols]
+        self._ck(lib().sfk_add_halos(self._h, len(halos), *ptrs), "sfk_add_halos")
+        self.n_halos = len(halos)
+
+    def block_halo_mask(self, origin, width, total_width):
+        hit = np.zeros(self.n_halos, np.uint8)
+        n = C.c_int64()
+        self._ck(lib().sfk_block_halo_mask(self._h, _f3(origin), _f3(width), float(total_width),
+                                           hit.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(n)),
+                 "sfk_block_halo_mask")
+        return hit.astype(bool)
+
+    def push_block(self, block):
+        """block: dict with Z, OmegaM, OmegaL, H100, TotalWidth, Origin, Width,
+        xs (N,3) float32 and ms (N,) float32 host arrays (numpy, or pinned
+        torch CPU tensors)."""
+        xs, ms = block["xs"], block["ms"]
+        c = Cosmo(block["Z"], block["OmegaM"], block["OmegaL"], block["H100"])
+        if hasattr(xs, "data_ptr"):
+            n, px, pm = xs.shape[0], xs.data_ptr(), ms.data_ptr()
+        else:
+            assert xs.dtype == np.float32 and ms.dtype == np.float32 and xs.flags.c_contiguous
+            n, px, pm = len(xs), xs.ctypes.data, ms.ctypes.data
+        self._ck(lib().sfk_push_block(self._h, px, pm, n, C.byref(c), float(block["TotalWidth"]),
+                                      _f3(block["Origin"]), _f3(block["Width"])), "sfk_push_block")
+
+    def push_block_device(self, block, d_xs, d_ms):
+        """Same with positions/masses already on this context's GPU (torch CUDA tensors)."""
+        c = Cosmo(block["Z"], block["OmegaM"], block["OmegaL"], block["H100"])
+        self._ck(lib().sfk_push_block_device(self._h, d_xs.data_ptr(), d_ms.data_ptr(), d_xs.shape[0],
+                                             C.byref(c), float(block["TotalWidth"]),
+                                             _f3(block["Origin"]), _f3(block["Width"])),
+                 "sfk_push_block_device")
+
+    def finish_snapshot(self):
+        coeffs = np.zeros((self.n_halos, self.P2))
+        status = np.zeros(self.n_halos, np.int32)
+        self._ck(lib().sfk_finish_snapshot(self._h, coeffs.ctypes.data_as(C.POINTER(C.c_double)),
+                                           status.ctypes.data_as(C.POINTER(C.c_int32))),
+                 "sfk_finish_snapshot")
+        return coeffs, status
+
+    def stats(self):
+        s = Stats()
+        self._ck(lib().sfk_get_stats(self._h, C.byref(s)), "sfk_get_stats")
+        return s.as_dict()
+
+    # ---- parity taps
+    def _shape(self):
+        p = self.params
+        return int(p.rings), int(p.spokes), int(p.radial_bins)
+
+    def rsp(self, halo):
+        R, n, _ = self._shape()
+        out = np.zeros((R, n))
+        self._ck(lib().sfk_get_rsp(self._h, halo, out.ctypes.data_as(C.POINTER(C.c_double))), "sfk_get_rsp")
+        return out
+
+    def candidate_count(self, halo):
+        n = C.c_int64()
+        self._ck(lib().sfk_get_candidate_count(self._h, halo, C.byref(n)), "sfk_get_candidate_count")
+        return n.value
+
+    def profiles(self, halo):
+        R, n, B = self._shape()
+        out = np.zeros((R, n, B))
+        self._ck(lib().sfk_get_profiles(self._h, halo, out.ctypes.data_as(C.POINTER(C.c_double))),
+                 "sfk_get_profiles")
+        return out
+
+    def counts(self, halo):
+        R, n, B = self._shape()
+        ins = np.zeros((R, n), np.uint32)
+        st = np.zeros((R, n, B), np.uint32)
+        en = np.zeros((R, n, B), np.uint32)
+        u32p = C.POINTER(C.c_uint32)
+        self._ck(lib().sfk_get_counts(self._h, halo, ins.ctypes.data_as(u32p), st.ctypes.data_as(u32p),
+                                      en.ctypes.data_as(u32p)), "sfk_get_counts")
+        return ins, st, en
+
+    def ring_tables(self):
+        R = int(self.params.rings)
+        norms, rot, irot = (np.zeros((R, 3), np.float32), np.zeros((R, 9), np.float32),
+                            np.zeros((R, 9), np.float32))
+        fp = C.POINTER(C.c_float)
+        self._ck(lib().sfk_get_ring_tables(self._h, norms.ctypes.data_as(fp), rot.ctypes.data_as(fp),
+                                           irot.ctypes.data_as(fp)), "sfk_get_ring_tables")
+        return norms, rot, irot
+
+
+def run_shell(params, min_mass, halos, blocks):
+    """loop() of cmd/shell.go:288-372 for one snapshot of in-memory blocks.
+    Returns (ctx, coeffs, status); the context keeps the parity taps."""
+    ctx = ShellContext(params)
+    ctx.begin_snapshot(blocks[0], min_mass)   # hds[0] of the first snapshot, cmd/shell.go:305
+    ctx.add_halos(halos)
+    for b in blocks:
+        ctx.push_block(b)
+    coeffs, status = ctx.finish_snapshot()
+    return ctx, coeffs, status

@@ -1,0 +1,720 @@
+// sfk_api.cu -- C ABI (include/shellfish_b200.h) and host orchestration of
+// the sm_100a shell-finder kernels.  Mirrors the control flow of
+// cmd/shell.go: createHalos -> sphereLoop (per block) -> haloAnalysis.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "sfk_kernels.cuh"
+
+using namespace sfk;
+
+namespace {
+
+// Go constant 4*math.Pi/3 folded exactly (cmd/shell.go:485,549).
+const double kFourPiOver3 = 4.18879020478639098461685784437267051226289253250014;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    // Grows without preserving contents.
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n; else p = nullptr;
+        return e;
+    }
+    cudaError_t upload(const std::vector<T> &v, cudaStream_t s) {
+        cudaError_t e = ensure(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};
+
+struct Seg { int64_t start; int32_t count; int32_t halo; };
+
+struct StageTimer {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[6];
+    void begin(int stage, cudaStream_t s) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, s);
+        ev[stage].push_back({a, b});
+    }
+    void end(int stage, cudaStream_t s) { cudaEventRecord(ev[stage].back().second, s); }
+    double collect(int stage) {
+        double ms = 0;
+        for (auto &pr : ev[stage]) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) ms += t;
+            cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        }
+        ev[stage].clear();
+        return ms;
+    }
+};
+enum { ST_CULL = 0, ST_HITS, ST_BIN, ST_LOS, ST_FILTER, ST_FIT };
+
+}  // namespace
+
+struct sfk_ctx {
+    sfk_params p{};
+    Tables tab;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    int rings = 0, spokes = 0, bins = 0, P2 = 0;
+    bool taps = false;
+
+    DevBuf<float> dNorms, dRots, dIrots;
+    DevBuf<double> dCos, dSin, dPhi, dTaps0, dTaps1;
+    bool tapsReady = false;  // Sav-Gol kernels cached for the process, smooth.go:84-96
+
+    // snapshot state
+    bool inSnapshot = false, finished = false;
+    sfk_cosmo cosmo0{};
+    float minMass = 0;
+    std::vector<HaloDev> halos;
+    std::vector<double> ox, oy, oz;   // float64 origins for SheetIntersect
+    DevBuf<HaloDev> dHalos;
+    DevBuf<Cand> dCands;
+    int64_t candCount = 0;
+    std::vector<Seg> segs;
+    std::vector<int64_t> candPerHalo;
+
+    // block staging
+    DevBuf<float> dXyz, dMass;
+    DevBuf<int32_t> dHaloList;
+    DevBuf<uint32_t> dCounts;
+    DevBuf<int64_t> dSegStart;
+
+    // results (per halo of the snapshot)
+    DevBuf<double> dRsp, dCoeffs;
+    DevBuf<int32_t> dStatus;
+    DevBuf<unsigned long long> dNInter, dRhoMax;
+    DevBuf<long long> dNPoints;
+    DevBuf<uint32_t> dHitCount;
+    DevBuf<double> dProfiles;
+    DevBuf<uint32_t> dTapInsert, dTapStart, dTapEnd;
+
+    // batch scratch
+    DevBuf<Piece> dPieces;
+    DevBuf<HitRec> dRecs;
+    DevBuf<int64_t> dHitOffset;
+    DevBuf<uint32_t> dHitCursor, dBatchHitCount;
+    DevBuf<int32_t> dBatchHalos, dHaloSlot;
+    DevBuf<unsigned long long> dGrid;
+    DevBuf<double> dFR, dM, dOut2, dRvec;
+    DevBuf<int32_t> dFIdx, dFCount;
+
+    sfk_stats stats{};
+    StageTimer timer;
+    std::vector<double> hCoeffs;
+    std::vector<int32_t> hStatus;
+};
+
+namespace {
+
+int fail(sfk_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CU(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess)                                                         \
+            return fail(ctx, SFK_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// ShellConfig.validate, cmd/shell.go:143-187
+int validate(sfk_ctx *ctx, const sfk_params &p) {
+    char buf[160];
+    auto bad_i = [&](const char *name, long long v) {
+        snprintf(buf, sizeof buf, "The variable '%s' was set to %lld.", name, v);
+        return fail(ctx, SFK_E_INVALID, buf);
+    };
+    auto bad_f = [&](const char *name, double v) {
+        snprintf(buf, sizeof buf, "The variable '%s' was set to %g.", name, v);
+        return fail(ctx, SFK_E_INVALID, buf);
+    };
+    if (p.subsample_factor <= 0) return bad_i("SubsampleFactor", p.subsample_factor);
+    if (p.radial_bins <= 0) return bad_i("RadialBins", p.radial_bins);
+    if (p.spokes <= 0) return bad_i("Spokes", p.spokes);
+    if (p.rings <= 0) return bad_i("Rings", p.rings);
+    if (p.r_max_mult <= 0) return bad_f("RMaxMult", p.r_max_mult);
+    if (p.r_min_mult <= 0) return bad_f("RMinMult", p.r_min_mult);
+    if (p.r_kernel_mult <= 0) return bad_f("RKernelMult", p.r_kernel_mult);
+    if (p.eta <= 0) return bad_f("Eta", p.eta);
+    if (p.order <= 0) return bad_i("Order", p.order);
+    if (p.levels <= 0) return bad_i("Levels", p.levels);
+    if (p.smoothing_window <= 0) return bad_i("SmoothingWindow", p.smoothing_window);
+    if (p.r_min_mult >= p.r_max_mult) {
+        snprintf(buf, sizeof buf,
+                 "The variable '%s' was set to %g, but the variable '%s' was set to %g.",
+                 "RMinMult", p.r_min_mult, "RMaxMult", p.r_max_mult);
+        return fail(ctx, SFK_E_INVALID, buf);
+    }
+    // limits of this implementation
+    if (p.percentile_profile) return fail(ctx, SFK_E_UNSUPPORTED, "PercentileProfile is not built yet.");
+    if (p.order > kMaxOrder) return fail(ctx, SFK_E_UNSUPPORTED, "Order above 4 is not supported.");
+    if (p.levels > kMaxLevels) return fail(ctx, SFK_E_UNSUPPORTED, "Levels above 6 is not supported.");
+    if (p.rings > kMaxRings) return fail(ctx, SFK_E_UNSUPPORTED, "Rings above 1024 is not supported.");
+    if (p.spokes > 16384) return fail(ctx, SFK_E_UNSUPPORTED, "Spokes above 16384 is not supported.");
+    if (p.smoothing_window % 2 != 1) return fail(ctx, SFK_E_INVALID, "Kernel width must be odd.");
+    if (p.smoothing_window <= 4) return fail(ctx, SFK_E_INVALID, "Kernel width cannot be smaller than pOrder.");
+    if (bin_smem_bytes(static_cast<int>(p.radial_bins)) > 227 * 1024)
+        return fail(ctx, SFK_E_UNSUPPORTED, "RadialBins too large for one shared-memory tile.");
+    return SFK_OK;
+}
+
+// los/halo.go:442-467
+double wrap_dist(double x1, double x2, double width) {
+    double dist = x1 - x2;
+    if (dist > width / 2) return dist - width;
+    if (dist < width / -2) return dist + width;
+    return dist;
+}
+bool in_range(double x, double r, double low, double width, double tw) {
+    return (x + r > low && x - r < low + width) ||
+           (wrap_dist(x, low, tw) > -r && wrap_dist(x, low + width, tw) < r);
+}
+bool sheet_intersect(const sfk_ctx *c, size_t i, const float origin[3], const float width[3], double tw) {
+    const double r = c->halos[i].rMax;
+    return in_range(c->ox[i], r, origin[0], width[0], tw) &&
+           in_range(c->oy[i], r, origin[1], width[1], tw) &&
+           in_range(c->oz[i], r, origin[2], width[2], tw);
+}
+
+int grow_cands(sfk_ctx *ctx, int64_t need) {
+    if (static_cast<size_t>(need) <= ctx->dCands.cap) return SFK_OK;
+    size_t cap = std::max<size_t>({static_cast<size_t>(need), ctx->dCands.cap * 3 / 2, size_t(1) << 20});
+    Cand *np = nullptr;
+    CU(cudaMalloc(&np, cap * sizeof(Cand)));
+    if (ctx->candCount > 0)
+        CU(cudaMemcpyAsync(np, ctx->dCands.p, ctx->candCount * sizeof(Cand), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->dCands.release();
+    ctx->dCands.p = np;
+    ctx->dCands.cap = cap;
+    return SFK_OK;
+}
+
+int push_block_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, int64_t n,
+                    const sfk_cosmo *cosmo, double tw, const float origin[3], const float width[3]) {
+    // binIntersections for this header, cmd/shell.go:599-611 (halo order kept)
+    std::vector<int32_t> list;
+    for (size_t i = 0; i < ctx->halos.size(); i++)
+        if (ctx->halos[i].valid && sheet_intersect(ctx, i, origin, width, tw)) list.push_back(static_cast<int32_t>(i));
+    if (list.empty() || n <= 0) return SFK_OK;
+    const int nList = static_cast<int>(list.size());
+    CU(ctx->dHaloList.upload(list, ctx->stream));
+    CU(ctx->dCounts.ensure(nList));
+    CU(ctx->dSegStart.ensure(nList));
+    CU(cudaMemsetAsync(ctx->dCounts.p, 0, nList * sizeof(uint32_t), ctx->stream));
+    const int64_t sf = ctx->p.subsample_factor;
+    CullArgs a{};
+    a.xyz = dxyz; a.mass = dmass; a.n = n; a.sf3 = sf * sf * sf;
+    a.haloList = ctx->dHaloList.p; a.nList = nList; a.halos = ctx->dHalos.p;
+    a.tw = static_cast<float>(tw);
+    // chanLoadSphereVec uses the block's own header, cmd/shell.go:487-488
+    a.rhoM = rho_average(cosmo->h100 * 100, cosmo->omega_m, cosmo->omega_l, cosmo->z);
+    a.counts = ctx->dCounts.p; a.segStart = ctx->dSegStart.p; a.cands = nullptr;
+    ctx->timer.begin(ST_CULL, ctx->stream);
+    CU(launch_cull(a, false, ctx->stream));
+    ctx->stats.launches++;
+    std::vector<uint32_t> counts(nList);
+    CU(cudaMemcpyAsync(counts.data(), ctx->dCounts.p, nList * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<int64_t> segStart(nList);
+    int64_t total = 0;
+    for (int k = 0; k < nList; k++) { segStart[k] = ctx->candCount + total; total += counts[k]; }
+    if (total > 0) {
+        int rc = grow_cands(ctx, ctx->candCount + total);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(ctx->dSegStart.p, segStart.data(), nList * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->dCounts.p, 0, nList * sizeof(uint32_t), ctx->stream));
+        a.cands = ctx->dCands.p;
+        CU(launch_cull(a, true, ctx->stream));
+        ctx->stats.launches++;
+        // segStart is a stack vector: the copy above must finish before return
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < nList; k++)
+            if (counts[k]) {
+                ctx->segs.push_back({segStart[k], static_cast<int32_t>(counts[k]), list[k]});
+                ctx->candPerHalo[list[k]] += counts[k];
+            }
+        ctx->candCount += total;
+    }
+    ctx->timer.end(ST_CULL, ctx->stream);
+    return SFK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void sfk_default_params(sfk_params *p) {
+    std::memset(p, 0, sizeof *p);
+    p->subsample_factor = 1; p->radial_bins = 256; p->spokes = 256; p->rings = 100;
+    p->r_max_mult = 3; p->r_min_mult = 0.3; p->r_kernel_mult = 0.2; p->eta = 10;
+    p->order = 3; p->levels = 3; p->smoothing_window = 121; p->los_slope_cutoff = 0.0;
+    p->background_rho_mult = 0.5; p->percentile_profile = 0; p->percentile = 50.0;
+    p->seed = 0; p->device = 0; p->flags = 0;
+}
+
+int sfk_create(sfk_ctx **out, const sfk_params *params) {
+    if (!out || !params) return SFK_E_INVALID;
+    *out = nullptr;
+    sfk_ctx *ctx = new sfk_ctx();
+    *out = ctx;  // returned even on failure so the caller can read the error
+    ctx->p = *params;
+    int rc = validate(ctx, *params);
+    if (rc) return rc;
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev <= 0)
+        return fail(ctx, SFK_E_NODEVICE, "no CUDA device: this library has no CPU path");
+    if (params->device < 0 || params->device >= nDev) return fail(ctx, SFK_E_INVALID, "bad device ordinal");
+    CU(cudaSetDevice(params->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, params->device));
+    if (prop.major != 10)
+        return fail(ctx, SFK_E_NODEVICE, "kernels are built for sm_100a only (found sm_" +
+                                             std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->rings = static_cast<int>(params->rings);
+    ctx->spokes = static_cast<int>(params->spokes);
+    ctx->bins = static_cast<int>(params->radial_bins);
+    ctx->P2 = static_cast<int>(2 * params->order * params->order);
+    ctx->taps = (params->flags & SFK_FLAG_TAPS) != 0;
+    build_tables(*params, ctx->tab);
+    CU(ctx->dNorms.upload(ctx->tab.norms, ctx->stream));
+    CU(ctx->dRots.upload(ctx->tab.rots, ctx->stream));
+    CU(ctx->dIrots.upload(ctx->tab.irots, ctx->stream));
+    CU(ctx->dCos.upload(ctx->tab.ringCos, ctx->stream));
+    CU(ctx->dSin.upload(ctx->tab.ringSin, ctx->stream));
+    CU(ctx->dPhi.upload(ctx->tab.ringPhi, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SFK_OK;
+}
+
+void sfk_destroy(sfk_ctx *ctx) {
+    if (!ctx) return;
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    delete ctx;
+}
+
+const char *sfk_last_error(const sfk_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int sfk_begin_snapshot(sfk_ctx *ctx, const sfk_cosmo *cosmo, float min_mass) {
+    if (!ctx || !cosmo) return SFK_E_INVALID;
+    CU(cudaSetDevice(ctx->p.device));
+    ctx->cosmo0 = *cosmo;
+    ctx->minMass = min_mass;
+    ctx->halos.clear(); ctx->ox.clear(); ctx->oy.clear(); ctx->oz.clear();
+    ctx->segs.clear(); ctx->candPerHalo.clear();
+    ctx->candCount = 0;
+    ctx->inSnapshot = true; ctx->finished = false;
+    ctx->stats = sfk_stats{};
+    return SFK_OK;
+}
+
+int sfk_add_halos(sfk_ctx *ctx, int64_t n, const double *x, const double *y, const double *z,
+                  const double *r200m) {
+    if (!ctx || !ctx->inSnapshot || n < 0) return fail(ctx, SFK_E_INVALID, "sfk_add_halos: no snapshot open");
+    if (!ctx->halos.empty()) return fail(ctx, SFK_E_INVALID, "sfk_add_halos: halos already set");
+    const sfk_params &p = ctx->p;
+    const int64_t sf = p.subsample_factor;
+    const double rhoM = rho_average(ctx->cosmo0.h100 * 100, ctx->cosmo0.omega_m, ctx->cosmo0.omega_l, ctx->cosmo0.z);
+    ctx->halos.resize(n);
+    ctx->ox.assign(x, x + n); ctx->oy.assign(y, y + n); ctx->oz.assign(z, z + n);
+    for (int64_t i = 0; i < n; i++) {
+        HaloDev h{};
+        const double r = r200m[i];
+        h.valid = r > 0 ? 1 : 0;   // cmd/shell.go:535-538
+        if (h.valid) {
+            // createHalos, cmd/shell.go:540-556
+            const double rMax = r * p.r_max_mult, rMin = r * p.r_min_mult;
+            const double rad0 = r * p.r_kernel_mult;
+            const double vol0 = kFourPiOver3 * rad0 * rad0 * rad0;
+            const double rho = ((static_cast<double>(ctx->minMass) * static_cast<double>(sf * sf * sf)) / vol0) / rhoM;
+            h.defaultRho = rho * p.background_rho_mult;
+            h.rMax = rMax;
+            h.x0 = static_cast<float>(x[i]); h.y0 = static_cast<float>(y[i]); h.z0 = static_cast<float>(z[i]);
+            // loadSphereVecs, cmd/shell.go:442 and Halo.Intersect, halo.go:148-152
+            h.rad = rMax * p.r_kernel_mult / p.r_max_mult;
+            h.rad2 = h.rad * h.rad;
+            h.sphVol = kFourPiOver3 * h.rad * h.rad * h.rad;
+            double lo = rMin - h.rad, hi = rMax + h.rad;
+            if (lo < 0) lo = 0;
+            h.lo2 = static_cast<float>(lo * lo); h.hi2 = static_cast<float>(hi * hi);
+            // ProfileRing.Init, profile_ring.go:75-82; GetRs, halo.go:365-366
+            h.lowR = std::log(rMin); h.highR = std::log(rMax);
+            h.dr = (h.highR - h.lowR) / static_cast<double>(ctx->bins);
+            h.lrMin = std::log(rMin);
+            h.dlr = (std::log(rMax) - std::log(rMin)) / static_cast<double>(ctx->bins);
+            h.scale = 1.0; h.quantum = 1.0;
+        }
+        ctx->halos[i] = h;
+    }
+    ctx->candPerHalo.assign(n, 0);
+    CU(ctx->dHalos.upload(ctx->halos, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.n_halos = n;
+    return SFK_OK;
+}
+
+int sfk_block_halo_mask(sfk_ctx *ctx, const float origin[3], const float width[3],
+                        double total_width, uint8_t *hit, int64_t *n_hit) {
+    if (!ctx || !ctx->inSnapshot) return fail(ctx, SFK_E_INVALID, "sfk_block_halo_mask: no snapshot open");
+    int64_t cnt = 0;
+    for (size_t i = 0; i < ctx->halos.size(); i++) {
+        const bool h = ctx->halos[i].valid && sheet_intersect(ctx, i, origin, width, total_width);
+        if (hit) hit[i] = h;
+        cnt += h;
+    }
+    if (n_hit) *n_hit = cnt;
+    return SFK_OK;
+}
+
+int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
+                   const sfk_cosmo *cosmo, double total_width, const float origin[3],
+                   const float width[3]) {
+    if (!ctx || !ctx->inSnapshot || ctx->finished || !cosmo || n < 0 || (n > 0 && (!xyz || !mass)))
+        return fail(ctx, SFK_E_INVALID, "sfk_push_block: bad arguments or no snapshot open");
+    CU(cudaSetDevice(ctx->p.device));
+    int64_t hits = 0;
+    sfk_block_halo_mask(ctx, origin, width, total_width, nullptr, &hits);
+    if (hits == 0 || n == 0) return SFK_OK;   // sphereLoop skips the read, cmd/shell.go:389-391
+    CU(ctx->dXyz.ensure(3 * n));
+    CU(ctx->dMass.ensure(n));
+    CU(cudaMemcpyAsync(ctx->dXyz.p, xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->dMass.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    return push_block_impl(ctx, ctx->dXyz.p, ctx->dMass.p, n, cosmo, total_width, origin, width);
+}
+
+int sfk_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass, int64_t n,
+                          const sfk_cosmo *cosmo, double total_width, const float origin[3],
+                          const float width[3]) {
+    if (!ctx || !ctx->inSnapshot || ctx->finished || !cosmo || n < 0 || (n > 0 && (!d_xyz || !d_mass)))
+        return fail(ctx, SFK_E_INVALID, "sfk_push_block_device: bad arguments or no snapshot open");
+    CU(cudaSetDevice(ctx->p.device));
+    // the caller's buffers live on other streams: order after everything queued so far
+    CU(cudaDeviceSynchronize());
+    return push_block_impl(ctx, d_xyz, d_mass, n, cosmo, total_width, origin, width);
+}
+
+int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) {
+    if (!ctx || !ctx->inSnapshot) return fail(ctx, SFK_E_INVALID, "sfk_finish_snapshot: no snapshot open");
+    CU(cudaSetDevice(ctx->p.device));
+    cudaStream_t st = ctx->stream;
+    const int64_t nHalo = static_cast<int64_t>(ctx->halos.size());
+    const int R = ctx->rings, n = ctx->spokes, B = ctx->bins, P2 = ctx->P2;
+    const size_t rn = static_cast<size_t>(R) * n, rnb = rn * B;
+    ctx->hCoeffs.assign(static_cast<size_t>(nHalo) * P2, 0.0);
+    ctx->hStatus.assign(nHalo, SFK_HALO_OK);
+    if (nHalo == 0) { ctx->finished = true; return SFK_OK; }
+
+    // per-halo result buffers
+    CU(ctx->dRsp.ensure(nHalo * rn));
+    CU(ctx->dCoeffs.ensure(static_cast<size_t>(nHalo) * P2));
+    CU(ctx->dStatus.ensure(nHalo));
+    CU(ctx->dNInter.ensure(nHalo));
+    CU(ctx->dRhoMax.ensure(nHalo));
+    CU(ctx->dNPoints.ensure(nHalo));
+    CU(ctx->dHitCount.ensure(static_cast<size_t>(nHalo) * R));
+    CU(cudaMemsetAsync(ctx->dRsp.p, 0xff, nHalo * rn * sizeof(double), st));  // NaN
+    CU(cudaMemsetAsync(ctx->dCoeffs.p, 0, static_cast<size_t>(nHalo) * P2 * sizeof(double), st));
+    CU(cudaMemsetAsync(ctx->dStatus.p, 0, nHalo * sizeof(int32_t), st));
+    CU(cudaMemsetAsync(ctx->dNInter.p, 0, nHalo * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(ctx->dRhoMax.p, 0, nHalo * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(ctx->dNPoints.p, 0, nHalo * sizeof(long long), st));
+    CU(cudaMemsetAsync(ctx->dHitCount.p, 0, static_cast<size_t>(nHalo) * R * sizeof(uint32_t), st));
+    if (ctx->taps) {
+        CU(ctx->dProfiles.ensure(nHalo * rnb));
+        CU(ctx->dTapInsert.ensure(nHalo * rn));
+        CU(ctx->dTapStart.ensure(nHalo * rnb));
+        CU(ctx->dTapEnd.ensure(nHalo * rnb));
+        CU(cudaMemsetAsync(ctx->dProfiles.p, 0, nHalo * rnb * sizeof(double), st));
+        CU(cudaMemsetAsync(ctx->dTapInsert.p, 0, nHalo * rn * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(ctx->dTapStart.p, 0, nHalo * rnb * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(ctx->dTapEnd.p, 0, nHalo * rnb * sizeof(uint32_t), st));
+    }
+
+    // Savitzky-Golay taps: built once per process from the first smoothed
+    // profile's dx = ln r1 - ln r0 (smooth.go:63,84-96)
+    if (!ctx->tapsReady && B > ctx->p.smoothing_window) {
+        for (const HaloDev &h : ctx->halos) {
+            if (!h.valid) continue;
+            const double r0 = std::exp(h.lrMin + h.dlr * (0.0 + 0.5));
+            const double r1 = std::exp(h.lrMin + h.dlr * (1.0 + 0.5));
+            const double dx = std::log(r1) - std::log(r0);
+            std::vector<double> k0, k1;
+            if (!savgol_taps(4, static_cast<int>(ctx->p.smoothing_window), 0, 0, k0) ||
+                !savgol_taps(4, static_cast<int>(ctx->p.smoothing_window), 1, dx, k1))
+                return fail(ctx, SFK_E_INVALID, "Savitzky-Golay kernel construction failed");
+            CU(ctx->dTaps0.upload(k0, st));
+            CU(ctx->dTaps1.upload(k1, st));
+            CU(cudaStreamSynchronize(st));
+            ctx->tapsReady = true;
+            break;
+        }
+    }
+    if (!ctx->tapsReady) {
+        std::vector<double> z(std::max<int64_t>(ctx->p.smoothing_window, 1), 0.0);
+        CU(ctx->dTaps0.upload(z, st));
+        CU(ctx->dTaps1.upload(z, st));
+        CU(cudaStreamSynchronize(st));
+    }
+
+    // pieces: <= 256 candidates of one halo each, grouped per halo
+    std::vector<std::vector<Piece>> perHalo(nHalo);
+    for (const Seg &s : ctx->segs)
+        for (int32_t off = 0; off < s.count; off += 256)
+            perHalo[s.halo].push_back({s.start + off, std::min<int32_t>(256, s.count - off), s.halo});
+    std::vector<Piece> all;
+    for (auto &v : perHalo) all.insert(all.end(), v.begin(), v.end());
+
+    // pass 1: hits per (halo, ring) and largest rho per halo
+    ctx->timer.begin(ST_HITS, st);
+    CU(ctx->dPieces.upload(all, st));
+    CU(launch_hits(ctx->dPieces.p, static_cast<int>(all.size()), ctx->dCands.p, ctx->dHalos.p,
+                   ctx->dNorms.p, ctx->dRots.p, R, n, ctx->tab.dPhi, ctx->dHitCount.p,
+                   ctx->dRhoMax.p, nullptr, nullptr, nullptr, nullptr, false, st));
+    ctx->stats.launches++;
+    ctx->timer.end(ST_HITS, st);
+    std::vector<uint32_t> hitCount(static_cast<size_t>(nHalo) * R);
+    std::vector<unsigned long long> rhoMaxBits(nHalo);
+    CU(cudaMemcpyAsync(hitCount.data(), ctx->dHitCount.p, hitCount.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(rhoMaxBits.data(), ctx->dRhoMax.p, nHalo * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+
+    // fixed-point scale per halo: |sum| <= 2 * hits_ring_max * rho_max < 2^62
+    std::vector<int64_t> hitsPerHalo(nHalo, 0);
+    for (int64_t i = 0; i < nHalo; i++) {
+        uint32_t hmax = 0;
+        for (int r = 0; r < R; r++) {
+            hmax = std::max(hmax, hitCount[i * R + r]);
+            hitsPerHalo[i] += hitCount[i * R + r];
+        }
+        double rhoMax;
+        std::memcpy(&rhoMax, &rhoMaxBits[i], sizeof rhoMax);
+        int e = 0;
+        if (hmax > 0 && rhoMax > 0 && std::isfinite(rhoMax)) {
+            const double bound = 2.0 * static_cast<double>(hmax) * rhoMax;
+            e = 61 - std::ilogb(bound);
+            e = std::max(-900, std::min(900, e));
+        }
+        ctx->halos[i].scale = std::ldexp(1.0, e);
+        ctx->halos[i].quantum = std::ldexp(1.0, -e);
+        ctx->stats.n_ring_hits += hitsPerHalo[i];
+    }
+    CU(ctx->dHalos.upload(ctx->halos, st));
+    CU(ctx->dHaloSlot.ensure(nHalo));
+
+    // batches of halos in input order, bounded by hit-record and grid memory
+    const int64_t maxBatch = 64;
+    const int64_t hitBudget = (int64_t(6) << 30) / static_cast<int64_t>(sizeof(HitRec));
+    std::vector<int32_t> order;
+    for (int64_t i = 0; i < nHalo; i++) {
+        if (ctx->halos[i].valid) order.push_back(static_cast<int32_t>(i));
+        else ctx->hStatus[i] = SFK_HALO_SKIPPED;
+    }
+    size_t pos = 0;
+    while (pos < order.size()) {
+        std::vector<int32_t> batch;
+        int64_t hits = 0;
+        while (pos < order.size() && static_cast<int64_t>(batch.size()) < maxBatch) {
+            const int64_t hh = hitsPerHalo[order[pos]];
+            if (!batch.empty() && hits + hh > hitBudget) break;
+            batch.push_back(order[pos++]);
+            hits += hh;
+        }
+        const int nb = static_cast<int>(batch.size());
+        std::vector<int32_t> haloSlot(nHalo, -1);
+        std::vector<int64_t> hitOffset(static_cast<size_t>(nb) * R);
+        std::vector<uint32_t> bHitCount(static_cast<size_t>(nb) * R);
+        std::vector<Piece> pieces;
+        int64_t run = 0;
+        for (int s = 0; s < nb; s++) {
+            const int32_t hIdx = batch[s];
+            haloSlot[hIdx] = s;
+            for (int r = 0; r < R; r++) {
+                hitOffset[static_cast<size_t>(s) * R + r] = run;
+                bHitCount[static_cast<size_t>(s) * R + r] = hitCount[static_cast<size_t>(hIdx) * R + r];
+                run += hitCount[static_cast<size_t>(hIdx) * R + r];
+            }
+            pieces.insert(pieces.end(), perHalo[hIdx].begin(), perHalo[hIdx].end());
+        }
+        CU(ctx->dRecs.ensure(std::max<int64_t>(run, 1)));
+        CU(ctx->dGrid.ensure(static_cast<size_t>(nb) * rnb));
+        CU(ctx->dHitCursor.ensure(static_cast<size_t>(nb) * R));
+        CU(ctx->dFR.ensure(static_cast<size_t>(nb) * rn));
+        CU(ctx->dFIdx.ensure(static_cast<size_t>(nb) * rn));
+        CU(ctx->dFCount.ensure(static_cast<size_t>(nb) * R));
+        CU(ctx->dM.ensure(static_cast<size_t>(nb) * rn * P2));
+        CU(ctx->dOut2.ensure(static_cast<size_t>(nb) * rn * P2));
+        CU(ctx->dRvec.ensure(static_cast<size_t>(nb) * rn));
+        CU(ctx->dPieces.upload(pieces, st));
+        CU(ctx->dBatchHalos.upload(batch, st));
+        CU(ctx->dHaloSlot.upload(haloSlot, st));
+        CU(ctx->dHitOffset.upload(hitOffset, st));
+        CU(ctx->dBatchHitCount.upload(bHitCount, st));
+        CU(cudaMemsetAsync(ctx->dHitCursor.p, 0, static_cast<size_t>(nb) * R * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(ctx->dGrid.p, 0, static_cast<size_t>(nb) * rnb * sizeof(unsigned long long), st));
+
+        // pass 2: ring-frame hit records
+        ctx->timer.begin(ST_HITS, st);
+        CU(launch_hits(ctx->dPieces.p, static_cast<int>(pieces.size()), ctx->dCands.p, ctx->dHalos.p,
+                       ctx->dNorms.p, ctx->dRots.p, R, n, ctx->tab.dPhi, ctx->dHitCount.p,
+                       ctx->dRhoMax.p, ctx->dHitOffset.p, ctx->dHitCursor.p, ctx->dHaloSlot.p,
+                       ctx->dRecs.p, true, st));
+        ctx->stats.launches++;
+        ctx->timer.end(ST_HITS, st);
+
+        // binning: Halo.Insert for every queued particle
+        BinArgs ba{};
+        ba.recs = ctx->dRecs.p; ba.hitOffset = ctx->dHitOffset.p; ba.hitCount = ctx->dBatchHitCount.p;
+        ba.halos = ctx->dHalos.p; ba.batchHalos = ctx->dBatchHalos.p;
+        ba.ringCos = ctx->dCos.p; ba.ringSin = ctx->dSin.p;
+        ba.grid = ctx->dGrid.p; ba.nIntersections = ctx->dNInter.p;
+        ba.tapInsert = ctx->dTapInsert.p; ba.tapStart = ctx->dTapStart.p; ba.tapEnd = ctx->dTapEnd.p;
+        ba.rings = R; ba.spokes = n; ba.bins = B;
+        // split long hit lists when there are too few CTAs to fill 148 SMs x 3
+        const int64_t ctas = static_cast<int64_t>((n + kTileLos - 1) / kTileLos) * R * nb;
+        ba.chunks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(64, (148 * 3 * 4 + ctas - 1) / ctas)));
+        ctx->timer.begin(ST_BIN, st);
+        CU(launch_bin(ba, nb, ctx->taps, st));
+        ctx->stats.launches++; ctx->stats.bin_launches++;
+        ctx->timer.end(ST_BIN, st);
+
+        // per-LoS analysis
+        LosArgs la{};
+        la.grid = ctx->dGrid.p; la.halos = ctx->dHalos.p; la.batchHalos = ctx->dBatchHalos.p;
+        la.valTaps = ctx->dTaps0.p; la.derivTaps = ctx->dTaps1.p;
+        la.rsp = ctx->dRsp.p; la.profiles = ctx->taps ? ctx->dProfiles.p : nullptr;
+        la.rings = R; la.spokes = n; la.bins = B; la.window = static_cast<int>(ctx->p.smoothing_window);
+        la.dLim = ctx->p.los_slope_cutoff;
+        ctx->timer.begin(ST_LOS, st);
+        CU(launch_los(la, nb, st));
+        ctx->stats.launches++;
+        ctx->timer.end(ST_LOS, st);
+
+        FilterArgs fa{};
+        fa.rsp = ctx->dRsp.p; fa.halos = ctx->dHalos.p; fa.batchHalos = ctx->dBatchHalos.p;
+        fa.fR = ctx->dFR.p; fa.fIdx = ctx->dFIdx.p; fa.fCount = ctx->dFCount.p; fa.status = ctx->dStatus.p;
+        fa.rings = R; fa.spokes = n; fa.levels = static_cast<int>(ctx->p.levels);
+        fa.eta = ctx->p.eta; fa.ringPhi = ctx->dPhi.p;
+        ctx->timer.begin(ST_FILTER, st);
+        CU(launch_filter(fa, nb, st));
+        ctx->stats.launches++;
+        ctx->timer.end(ST_FILTER, st);
+
+        FitArgs ft{};
+        ft.fR = ctx->dFR.p; ft.fIdx = ctx->dFIdx.p; ft.fCount = ctx->dFCount.p;
+        ft.batchHalos = ctx->dBatchHalos.p; ft.irots = ctx->dIrots.p;
+        ft.ringCos = ctx->dCos.p; ft.ringSin = ctx->dSin.p;
+        ft.M = ctx->dM.p; ft.out2 = ctx->dOut2.p; ft.rvec = ctx->dRvec.p;
+        ft.coeffs = ctx->dCoeffs.p; ft.status = ctx->dStatus.p; ft.nPoints = ctx->dNPoints.p;
+        ft.rings = R; ft.spokes = n; ft.order = static_cast<int>(ctx->p.order);
+        ctx->timer.begin(ST_FIT, st);
+        CU(launch_fit(ft, nb, st));
+        ctx->stats.launches++;
+        ctx->timer.end(ST_FIT, st);
+        // host vectors of this batch are read by async copies: drain before they die
+        CU(cudaStreamSynchronize(st));
+    }
+
+    // results
+    std::vector<int32_t> dstat(nHalo);
+    std::vector<unsigned long long> nInter(nHalo);
+    std::vector<long long> nPts(nHalo);
+    CU(cudaMemcpyAsync(ctx->hCoeffs.data(), ctx->dCoeffs.p, ctx->hCoeffs.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(dstat.data(), ctx->dStatus.p, nHalo * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(nInter.data(), ctx->dNInter.p, nHalo * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(nPts.data(), ctx->dNPoints.p, nHalo * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < nHalo; i++) {
+        if (ctx->hStatus[i] == SFK_HALO_OK) ctx->hStatus[i] = dstat[i];
+        if (ctx->hStatus[i] != SFK_HALO_OK)
+            for (int k = 0; k < P2; k++) ctx->hCoeffs[i * P2 + k] = 0.0;
+        ctx->stats.n_intersections += static_cast<int64_t>(nInter[i]);
+        ctx->stats.n_points += nPts[i];
+    }
+    ctx->stats.n_candidates = ctx->candCount;
+    ctx->stats.ms_cull = ctx->timer.collect(ST_CULL);
+    ctx->stats.ms_hits = ctx->timer.collect(ST_HITS);
+    ctx->stats.ms_bin = ctx->timer.collect(ST_BIN);
+    ctx->stats.ms_los = ctx->timer.collect(ST_LOS);
+    ctx->stats.ms_filter = ctx->timer.collect(ST_FILTER);
+    ctx->stats.ms_fit = ctx->timer.collect(ST_FIT);
+    if (coeffs) std::memcpy(coeffs, ctx->hCoeffs.data(), ctx->hCoeffs.size() * sizeof(double));
+    if (status) std::memcpy(status, ctx->hStatus.data(), nHalo * sizeof(int32_t));
+    ctx->finished = true;
+    return SFK_OK;
+}
+
+int sfk_get_stats(const sfk_ctx *ctx, sfk_stats *out) {
+    if (!ctx || !out) return SFK_E_INVALID;
+    *out = ctx->stats;
+    return SFK_OK;
+}
+
+static int check_halo(sfk_ctx *ctx, int64_t halo, bool needTaps) {
+    if (!ctx || !ctx->finished) return fail(ctx, SFK_E_INVALID, "taps are valid after sfk_finish_snapshot");
+    if (halo < 0 || halo >= static_cast<int64_t>(ctx->halos.size())) return fail(ctx, SFK_E_INVALID, "halo index out of range");
+    if (needTaps && !ctx->taps) return fail(ctx, SFK_E_INVALID, "context was created without SFK_FLAG_TAPS");
+    return SFK_OK;
+}
+
+int sfk_get_rsp(sfk_ctx *ctx, int64_t halo, double *r) {
+    int rc = check_halo(ctx, halo, false);
+    if (rc) return rc;
+    const size_t rn = static_cast<size_t>(ctx->rings) * ctx->spokes;
+    CU(cudaMemcpy(r, ctx->dRsp.p + halo * rn, rn * sizeof(double), cudaMemcpyDeviceToHost));
+    return SFK_OK;
+}
+
+int sfk_get_candidate_count(sfk_ctx *ctx, int64_t halo, int64_t *n) {
+    int rc = check_halo(ctx, halo, false);
+    if (rc) return rc;
+    *n = ctx->candPerHalo[halo];
+    return SFK_OK;
+}
+
+int sfk_get_profiles(sfk_ctx *ctx, int64_t halo, double *rho) {
+    int rc = check_halo(ctx, halo, true);
+    if (rc) return rc;
+    const size_t rnb = static_cast<size_t>(ctx->rings) * ctx->spokes * ctx->bins;
+    CU(cudaMemcpy(rho, ctx->dProfiles.p + halo * rnb, rnb * sizeof(double), cudaMemcpyDeviceToHost));
+    return SFK_OK;
+}
+
+int sfk_get_counts(sfk_ctx *ctx, int64_t halo, uint32_t *n_insert, uint32_t *start_edges,
+                   uint32_t *end_edges) {
+    int rc = check_halo(ctx, halo, true);
+    if (rc) return rc;
+    const size_t rn = static_cast<size_t>(ctx->rings) * ctx->spokes, rnb = rn * ctx->bins;
+    if (n_insert) CU(cudaMemcpy(n_insert, ctx->dTapInsert.p + halo * rn, rn * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (start_edges) CU(cudaMemcpy(start_edges, ctx->dTapStart.p + halo * rnb, rnb * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (end_edges) CU(cudaMemcpy(end_edges, ctx->dTapEnd.p + halo * rnb, rnb * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return SFK_OK;
+}
+
+int sfk_get_ring_tables(const sfk_ctx *ctx, float *norms, float *rot, float *irot) {
+    if (!ctx) return SFK_E_INVALID;
+    if (norms) std::memcpy(norms, ctx->tab.norms.data(), ctx->tab.norms.size() * sizeof(float));
+    if (rot) std::memcpy(rot, ctx->tab.rots.data(), ctx->tab.rots.size() * sizeof(float));
+    if (irot) std::memcpy(irot, ctx->tab.irots.data(), ctx->tab.irots.size() * sizeof(float));
+    return SFK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1064 @@
+// sfk_kernels.cu -- hand-written sm_100a kernels of the shell-finder hot path.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false.  FMA
+// contraction is off for the whole file so that every float32 / float64
+// expression rounds operation by operation, as the reference does on amd64;
+// the float32 decision chain (wrap, cull, ring test, rotation) must do so for
+// the integer taps to be bit-exact.
+//
+//   cull_kernel    Halo.Transform + Halo.Intersect     los/halo.go:147-197
+//   hits_kernel    sphereIntersectRing + ring geometry los/halo.go:218-258,284-320
+//   bin_kernel     per-LoS chords + ProfileRing.Insert los/halo.go:241-277, profile_ring.go:92-120
+//   los_kernel     GetRhos + Smooth + SplashbackRadius halo.go:350, smooth.go:46, splashback_radius.go:30
+//   filter_kernel  FilterPoints (KDE tree)             penna.go:115-165, kde.go
+//   fit_kernel     PennaVolumeFit                      penna.go:14-108,170-194
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "sfk_kernels.cuh"
+
+namespace sfk {
+
+namespace {
+
+constexpr double kTwoPi = 6.28318530717958647692528676655900576839433879875021;
+constexpr double kPi = 3.14159265358979323846264338327950288419716939937511;
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// Go's int(float64) on amd64 (CVTTSD2SQ): truncation toward zero.
+__device__ __forceinline__ long long go_int(double x) { return __double2ll_rz(x); }
+
+// ------------------------------------------------------------------ TMA --
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// 1-D bulk copy global -> shared through the TMA unit, completion on mbarrier.
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ----------------------------------------------------------------- cull --
+
+constexpr int kCullThreads = 256;
+constexpr int kCullHaloChunk = 64;
+
+struct CullHalo {
+    float x0, y0, z0, lo2, hi2;
+    double sphVol;
+};
+
+// One thread per (subsampled) particle.  The reference wraps the block's
+// positions in place, halo after halo (Halo.Transform mutates sphBuf.xs,
+// cmd/shell.go:441), so the position a halo sees depends on every earlier
+// halo of the block: the loop over the block's halo list is sequential per
+// particle and carries x, y, z in registers.
+template <bool FILL>
+__global__ void __launch_bounds__(kCullThreads) cull_kernel(CullArgs a) {
+    __shared__ CullHalo sh[kCullHaloChunk];
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * kCullThreads + threadIdx.x;
+    const int64_t i = j * a.sf3;
+    const bool live = i < a.n;
+    float x = 0.f, y = 0.f, z = 0.f;
+    double mScaled = 0.0;
+    if (live) {
+        x = a.xyz[3 * i];
+        y = a.xyz[3 * i + 1];
+        z = a.xyz[3 * i + 2];
+        // float64(ms[i]) * float64(sf^3), cmd/shell.go:494
+        mScaled = static_cast<double>(a.mass[i]) * static_cast<double>(a.sf3);
+    }
+    const float tw = a.tw;
+    const float tw2 = tw / 2;
+    for (int base = 0; base < a.nList; base += kCullHaloChunk) {
+        const int m = min(kCullHaloChunk, a.nList - base);
+        __syncthreads();
+        if (threadIdx.x < m) {
+            const HaloDev &h = a.halos[a.haloList[base + threadIdx.x]];
+            sh[threadIdx.x] = CullHalo{h.x0, h.y0, h.z0, h.lo2, h.hi2, h.sphVol};
+        }
+        __syncthreads();
+        for (int k = 0; k < m; k++) {
+            const CullHalo h = sh[k];
+            // Halo.Transform, los/halo.go:175-195
+            float dx = x - h.x0, dy = y - h.y0, dz = z - h.z0;
+            if (dx > tw2) x -= tw; else if (dx < -tw2) x += tw;
+            if (dy > tw2) y -= tw; else if (dy < -tw2) y += tw;
+            if (dz > tw2) z -= tw; else if (dz < -tw2) z += tw;
+            // Halo.Intersect, los/halo.go:158-163
+            dx = x - h.x0; dy = y - h.y0; dz = z - h.z0;
+            const float r2 = (dx * dx + dy * dy) + dz * dz;
+            const bool keep = live && r2 > h.lo2 && r2 < h.hi2;
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (mask == 0) continue;
+            const int leader = __ffs(mask) - 1;
+            uint32_t off = 0;
+            if (lane_id() == leader) off = atomicAdd(&a.counts[base + k], __popc(mask));
+            if (FILL) {
+                off = __shfl_sync(0xffffffffu, off, leader);
+                if (keep) {
+                    const int rank = __popc(mask & ((1u << lane_id()) - 1u));
+                    Cand c;
+                    c.vx = dx; c.vy = dy; c.vz = dz;   // Insert: vec - float32(origin)
+                    c.halo = a.haloList[base + k];
+                    c.rho = (mScaled / h.sphVol) / a.rhoM;
+                    a.cands[a.segStart[base + k] + off + rank] = c;
+                }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------- hits --
+
+constexpr int kHitThreads = 256;
+
+__device__ __forceinline__ void rotate_vec(const float *m, float vx, float vy, float vz,
+                                           float &ox, float &oy, float &oz) {
+    // los/geom/rotation.go:60-65, left-to-right float32
+    ox = (m[0] * vx + m[1] * vy) + m[2] * vz;
+    oy = (m[3] * vx + m[4] * vy) + m[5] * vz;
+    oz = (m[6] * vx + m[7] * vy) + m[8] * vz;
+}
+
+__device__ __forceinline__ uint16_t clamp_idx(long long v, int n) {
+    return static_cast<uint16_t>(v < 0 ? 0 : (v > n ? n : v));
+}
+
+// Ring-frame record of one (particle, ring) hit: insertToRing up to the LoS
+// loops, los/halo.go:231-258, and idxRange :284-310.
+__device__ __forceinline__ HitRec make_hit(const float *rot, const Cand &c, double rad2,
+                                           double dPhi, int n, double scale) {
+    HitRec r;
+    rotate_vec(rot, c.vx, c.vy, c.vz, r.cx, r.cy, r.cz);
+    const double cx = r.cx, cy = r.cy, cz = r.cz;
+    const double projDist2 = cx * cx + cy * cy;
+    double projRad2 = rad2 - cz * cz;
+    if (projRad2 < 0) projRad2 = 0;
+    r.rhoS = c.rho * scale;
+    if (projRad2 > projDist2) {
+        r.caseA = 1;
+        r.r[0] = 0; r.r[1] = static_cast<uint16_t>(n); r.r[2] = 0; r.r[3] = 0;
+        return r;
+    }
+    r.caseA = 0;
+    const double alpha = asin(sqrt(projRad2 / projDist2));
+    const double projPhi = atan2(cy, cx);
+    const double phiLo = projPhi - alpha, phiHi = projPhi + alpha;
+    long long i0, i1, i2, i3;
+    if (phiHi > kTwoPi) {
+        i0 = go_int(phiLo / dPhi); i1 = n; i2 = 0; i3 = go_int((phiHi - kTwoPi) / dPhi) + 1;
+    } else if (phiLo < 0) {
+        i0 = go_int((phiLo + kTwoPi) / dPhi); i1 = n; i2 = 0; i3 = go_int(phiHi / dPhi) + 1;
+    } else {
+        i0 = go_int(phiLo / dPhi); i1 = go_int(phiHi / dPhi) + 1; i2 = 0; i3 = 0;
+    }
+    r.r[0] = clamp_idx(i0, n); r.r[1] = clamp_idx(i1, n);
+    r.r[2] = clamp_idx(i2, n); r.r[3] = clamp_idx(i3, n);
+    return r;
+}
+
+// One CTA per Piece (<= 256 candidates of one halo).  COUNT pass: hits per
+// (halo, ring) and the halo's largest rho.  FILL pass: ring-frame records.
+template <bool FILL>
+__global__ void __launch_bounds__(kHitThreads)
+hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const float *norms,
+            const float *rots, int rings, int spokes, double dPhi, uint32_t *hitCount,
+            unsigned long long *rhoMaxBits, const int64_t *hitOffset, uint32_t *hitCursor,
+            const int32_t *haloSlot, HitRec *recs) {
+    extern __shared__ unsigned char smemRaw[];
+    float *sNorm = reinterpret_cast<float *>(smemRaw);                     // [rings][3]
+    uint32_t *sCnt = reinterpret_cast<uint32_t *>(sNorm + 3 * rings);      // [rings]
+    uint32_t *sBase = sCnt + rings;                                        // [rings]
+    const Piece pc = pieces[blockIdx.x];
+    const HaloDev &h = halos[pc.halo];
+    for (int k = threadIdx.x; k < 3 * rings; k += kHitThreads) sNorm[k] = norms[k];
+    for (int k = threadIdx.x; k < rings; k += kHitThreads) { sCnt[k] = 0; sBase[k] = 0; }
+    __syncthreads();
+    const bool live = threadIdx.x < pc.count;
+    Cand c;
+    c.vx = c.vy = c.vz = 0.f; c.halo = pc.halo; c.rho = 0.0;
+    if (live) c = cands[pc.start + threadIdx.x];
+    const double rad = h.rad;
+    // pass 1: count hits per ring
+    for (int ring = 0; ring < rings; ring++) {
+        // sphereIntersectRing, los/halo.go:218-224 (dot in float32)
+        const float d = (sNorm[3 * ring] * c.vx + sNorm[3 * ring + 1] * c.vy) + sNorm[3 * ring + 2] * c.vz;
+        const double dot = static_cast<double>(d);
+        const bool hit = live && dot < rad && dot > -rad;
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask && lane_id() == 0) atomicAdd(&sCnt[ring], __popc(mask));
+    }
+    __syncthreads();
+    if (!FILL) {
+        for (int k = threadIdx.x; k < rings; k += kHitThreads)
+            if (sCnt[k]) atomicAdd(&hitCount[static_cast<size_t>(pc.halo) * rings + k], sCnt[k]);
+        // rho > 0: IEEE doubles order like unsigned integers
+        unsigned long long bits = live ? static_cast<unsigned long long>(__double_as_longlong(c.rho)) : 0ull;
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+            bits = other > bits ? other : bits;
+        }
+        if (lane_id() == 0 && bits) atomicMax(&rhoMaxBits[pc.halo], bits);
+        return;
+    }
+    // reserve contiguous slots per ring for this piece
+    const int slot = haloSlot[pc.halo];
+    for (int k = threadIdx.x; k < rings; k += kHitThreads) {
+        const uint32_t cnt = sCnt[k];
+        sBase[k] = cnt ? atomicAdd(&hitCursor[static_cast<size_t>(slot) * rings + k], cnt) : 0u;
+        sCnt[k] = 0;
+    }
+    __syncthreads();
+    for (int ring = 0; ring < rings; ring++) {
+        const float d = (sNorm[3 * ring] * c.vx + sNorm[3 * ring + 1] * c.vy) + sNorm[3 * ring + 2] * c.vz;
+        const double dot = static_cast<double>(d);
+        const bool hit = live && dot < rad && dot > -rad;
+        if (!hit) continue;
+        const uint32_t pos = sBase[ring] + atomicAdd(&sCnt[ring], 1u);
+        const HitRec rec = make_hit(rots + 9 * ring, c, h.rad2, dPhi, spokes, h.scale);
+        recs[hitOffset[static_cast<size_t>(slot) * rings + ring] + pos] = rec;
+    }
+}
+
+// ------------------------------------------------------------------ bin --
+
+// 64-bit two's-complement add into split lo/hi words with native 32-bit
+// shared-memory atomics (64-bit shared atomics are CAS loops on sm_100).
+__device__ __forceinline__ void acc_add(uint32_t *lo, uint32_t *hi, int idx, long long v) {
+    const uint32_t vlo = static_cast<uint32_t>(v);
+    const uint32_t vhi = static_cast<uint32_t>(static_cast<unsigned long long>(v) >> 32);
+    const uint32_t old = atomicAdd(&lo[idx], vlo);
+    const uint32_t carry = (old + vlo) < old ? 1u : 0u;
+    const uint32_t add = vhi + carry;
+    if (add) atomicAdd(&hi[idx], add);
+}
+
+// One CTA per (LoS tile, ring, halo[, chunk]).  The tile's 32 x bins fixed-
+// point accumulators live in shared memory; the ring's hit records stream in
+// through TMA bulk copies (double buffered); each warp takes one record at a
+// time and its 32 lanes are the tile's 32 lines of sight.
+template <bool TAPS>
+__global__ void __launch_bounds__(kBinThreads, 3) bin_kernel(BinArgs a) {
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    const int bins = a.bins;
+    const int stride = bins + 1;  // +1: slot for modf index == bins (profile_ring.go:102-106)
+    HitRec *stage = reinterpret_cast<HitRec *>(smemRaw);                  // [2][kStageRecs]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + 2 * kStageRecs); // [2]
+    uint32_t *lo = reinterpret_cast<uint32_t *>(bars + 2);                // [32][stride]
+    uint32_t *hi = lo + kTileLos * stride;
+
+    const int nTiles = (a.spokes + kTileLos - 1) / kTileLos;
+    const int tile = blockIdx.x % nTiles;
+    const int chunk = blockIdx.x / nTiles;
+    const int ring = blockIdx.y;
+    const int slot = blockIdx.z;
+    const int haloIdx = a.batchHalos[slot];
+    const HaloDev &h = a.halos[haloIdx];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    constexpr int kWarps = kBinThreads / 32;
+
+    for (int k = threadIdx.x; k < 2 * kTileLos * stride; k += kBinThreads) lo[k] = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // this CTA's share of the ring's records
+    const size_t hr = static_cast<size_t>(slot) * a.rings + ring;
+    const int64_t total = a.hitCount[hr];
+    const int64_t nStages = (total + kStageRecs - 1) / kStageRecs;
+    const int64_t s0 = nStages * chunk / a.chunks, s1 = nStages * (chunk + 1) / a.chunks;
+    const HitRec *src = a.recs + a.hitOffset[hr];
+
+    auto issue = [&](int64_t s) {
+        const int64_t first = s * kStageRecs;
+        const uint32_t cnt = static_cast<uint32_t>(min(static_cast<int64_t>(kStageRecs), total - first));
+        const uint32_t bytes = cnt * sizeof(HitRec);
+        uint64_t *bar = &bars[(s - s0) & 1];
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(stage + ((s - s0) & 1) * kStageRecs, src + first, bytes, bar);
+    };
+    if (threadIdx.x == 0 && s0 < s1) issue(s0);
+
+    const int los = tile * kTileLos + lane;
+    const bool losOk = los < a.spokes;
+    const double rc = losOk ? a.ringCos[los] : 0.0, rs = losOk ? a.ringSin[los] : 0.0;
+    const double lowR = h.lowR, highR = h.highR, dr = h.dr, rad2 = h.rad2;
+    uint32_t *rowLo = lo + lane * stride, *rowHi = hi + lane * stride;
+    const size_t tapRow = (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes + los;
+    unsigned nIns = 0;
+
+    for (int64_t s = s0; s < s1; s++) {
+        const int buf = (s - s0) & 1;
+        if (threadIdx.x == 0 && s + 1 < s1) issue(s + 1);
+        mbar_wait(&bars[buf], ((s - s0) >> 1) & 1);
+        const int cnt = static_cast<int>(min(static_cast<int64_t>(kStageRecs), total - s * kStageRecs));
+        const HitRec *st = stage + buf * kStageRecs;
+        for (int r = warp; r < cnt; r += kWarps) {
+            const HitRec rec = st[r];
+            bool active;
+            if (rec.caseA) active = losOk;
+            else active = losOk && ((los >= rec.r[0] && los < rec.r[1]) || (los >= rec.r[2] && los < rec.r[3]));
+            if (!__any_sync(0xffffffffu, active)) continue;
+            if (!active) continue;
+            const double cx = rec.cx, cy = rec.cy, cz = rec.cz;
+            const double projDist2 = cx * cx + cy * cy;
+            double projRad2 = rad2 - cz * cz;
+            if (projRad2 < 0) projRad2 = 0;
+            const double b = cy * rc - cx * rs;   // impact parameter, halo.go:246,260
+            const double b2 = b * b;
+            double start, end;
+            if (rec.caseA) {
+                // oneValIntrDist, halo.go:337-346
+                const double dir = cx * rc + cy * rs;
+                const double radMid = sqrt(projRad2 - b2);
+                const double cMid = sqrt(projDist2 - b2);
+                const double rHi = dir > 0 ? radMid + cMid : radMid - cMid;
+                start = -INFINITY;
+                end = log(rHi);
+            } else {
+                // twoValIntrDist, halo.go:324-329
+                const double mid = sqrt(projDist2 - b2);
+                const double diff = sqrt(projRad2 - b2);
+                const double rLo = mid - diff, rHi = mid + diff;
+                if (isnan(rLo) || isnan(rHi)) continue;
+                start = log(rLo);
+                end = log(rHi);
+            }
+            // ProfileRing.Insert, profile_ring.go:92-120
+            if (end <= lowR || start >= highR) continue;
+            nIns++;
+            if (TAPS) atomicAdd(&a.tapInsert[tapRow], 1u);
+            const double rho = rec.rhoS;
+            if (start > lowR) {
+                const double xq = (start - lowR) / dr;
+                const double fidx = trunc(xq);
+                const double rem = xq - fidx;   // math.Modf
+                const int idx = static_cast<int>(fidx);
+                acc_add(rowLo, rowHi, idx, __double2ll_rn(rho * (1 - rem)));
+                if (idx < bins - 1) acc_add(rowLo, rowHi, idx + 1, __double2ll_rn(rho * rem));
+                if (TAPS && idx < bins) atomicAdd(&a.tapStart[tapRow * bins + idx], 1u);
+            } else {
+                acc_add(rowLo, rowHi, 0, __double2ll_rn(rho));
+                if (TAPS) atomicAdd(&a.tapStart[tapRow * bins], 1u);
+            }
+            if (end < highR) {
+                const double xq = (end - lowR) / dr;
+                const double fidx = trunc(xq);
+                const double rem = xq - fidx;
+                const int idx = static_cast<int>(fidx);
+                acc_add(rowLo, rowHi, idx, -__double2ll_rn(rho * (1 - rem)));
+                if (idx < bins - 1) acc_add(rowLo, rowHi, idx + 1, -__double2ll_rn(rho * rem));
+                if (TAPS && idx < bins) atomicAdd(&a.tapEnd[tapRow * bins + idx], 1u);
+            }
+        }
+        __syncthreads();  // everyone is done with stage `buf` before it is refilled
+    }
+
+    // intersections counter (the "particle-ray intersections" metric)
+    unsigned tot = nIns;
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0 && tot) atomicAdd(&a.nIntersections[haloIdx], static_cast<unsigned long long>(tot));
+
+    // flush the tile: [LoS][bin] rows, coalesced over bins
+    unsigned long long *g = a.grid + (static_cast<size_t>(slot) * a.rings + ring) * a.spokes * bins;
+    for (int k = threadIdx.x; k < kTileLos * stride; k += kBinThreads) {
+        const int l = k / stride, bin = k - l * stride;
+        const int gl = tile * kTileLos + l;
+        if (gl >= a.spokes) continue;
+        const unsigned long long v = (static_cast<unsigned long long>(hi[k]) << 32) | lo[k];
+        if (v == 0) continue;
+        if (bin < bins) {
+            atomicAdd(&g[static_cast<size_t>(gl) * bins + bin], v);
+        } else if (gl + 1 < a.spokes) {
+            // idx == bins lands in the next LoS's first bin (derivs is one slice)
+            atomicAdd(&g[static_cast<size_t>(gl + 1) * bins], v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ los --
+
+constexpr int kLosWarps = 8;
+
+// One warp per line of sight: prefix sum of the bin deltas (exact, in int64),
+// clamp to the background density, ln, two Savitzky-Golay FIRs with edge
+// extension, exp, steepest-slope search.
+__global__ void __launch_bounds__(kLosWarps * 32) los_kernel(LosArgs a, int nb) {
+    extern __shared__ double sm[];
+    const int bins = a.bins, window = a.window;
+    double *taps0 = sm;                 // [window]
+    double *taps1 = taps0 + window;     // [window]
+    double *wbuf = taps1 + window + (threadIdx.x >> 5) * 3 * bins;
+    double *ys = wbuf, *vals = wbuf + bins, *ders = wbuf + 2 * bins;
+    for (int k = threadIdx.x; k < window; k += blockDim.x) {
+        taps0[k] = a.valTaps[k];
+        taps1[k] = a.derivTaps[k];
+    }
+    __syncthreads();
+    const int lane = lane_id();
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kLosWarps + (threadIdx.x >> 5);
+    const int64_t perHalo = static_cast<int64_t>(a.rings) * a.spokes;
+    if (gw >= perHalo * nb) return;
+    const int slot = static_cast<int>(gw / perHalo);
+    const int64_t rl = gw - slot * perHalo;   // ring*spokes + los
+    const int haloIdx = a.batchHalos[slot];
+    const HaloDev &h = a.halos[haloIdx];
+    const unsigned long long *g = a.grid + (static_cast<size_t>(slot) * perHalo + rl) * bins;
+
+    // Retrieve + GetRhos (profile_ring.go:124-130, halo.go:350-357).  Each lane
+    // owns a contiguous run of bins; the carry between lanes is a warp scan.
+    const int per = (bins + 31) / 32;
+    const int b0 = lane * per, b1 = min(bins, b0 + per);
+    long long run = 0;
+    for (int k = b0; k < b1; k++) run += static_cast<long long>(g[k]);
+    long long incl = run;
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    long long acc = incl - run;
+    const double q = h.quantum, bg = h.defaultRho;
+    for (int k = b0; k < b1; k++) {
+        acc += static_cast<long long>(g[k]);
+        double rho = static_cast<double>(acc) * q;
+        if (rho < bg) rho = bg;
+        if (a.profiles) a.profiles[(static_cast<size_t>(haloIdx) * perHalo + rl) * bins + k] = rho;
+        ys[k] = log(rho);
+    }
+    __syncwarp();
+
+    double *out = a.rsp + static_cast<size_t>(haloIdx) * perHalo + rl;
+    if (bins <= window) {  // Smooth: ok = false, smooth.go:51-53
+        if (lane == 0) *out = __longlong_as_double(0x7ff8000000000000ll);
+        return;
+    }
+    // ConvolveAt with Extension, filter.go:104-161: taps ascending, mul then add
+    const int center = window / 2;
+    for (int i = lane; i < bins; i += 32) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int j = 0; j < window; j++) {
+            int idx = i + j - center;
+            idx = idx < 0 ? 0 : (idx >= bins ? bins - 1 : idx);
+            const double x = ys[idx];
+            s0 += x * taps0[j];
+            s1 += x * taps1[j];
+        }
+        vals[i] = exp(s0);
+        ders[i] = s1;
+    }
+    __syncwarp();
+    // SplashbackRadius, splashback_radius.go:30-58 (sequential semantics)
+    if (lane == 0) {
+        double rhoMin = vals[0];
+        double dMin = a.dLim;
+        int iMin = -1;
+        for (int i = 1; i < bins - 1; i++) {
+            const double v = vals[i];
+            if (v < rhoMin) {
+                rhoMin = v;
+                const double d = ders[i];
+                if (d < ders[i + 1] && d < ders[i - 1] && d < dMin) { dMin = d; iMin = i; }
+            }
+        }
+        // rs[iMin], halo.go:360-370
+        *out = iMin < 0 ? __longlong_as_double(0x7ff8000000000000ll)
+                        : exp(h.lrMin + h.dlr * (static_cast<double>(iMin) + 0.5));
+    }
+}
+
+// --------------------------------------------------------------- splines --
+
+// math/interpolate/spline.go:203-237,266-294: natural cubic spline second
+// derivatives.  Sequential (one thread).  tmp has n entries.
+__device__ bool spline_y2(const double *xs, const double *ys, int n, double *y2, double *tmp) {
+    y2[0] = 0; y2[n - 1] = 0;
+    const int m = n - 2;
+    if (m <= 0) return true;
+    // TriDiagAt with as/bs/cs/rs formed on the fly (same expressions, same order)
+    auto A = [&](int i) { return (xs[i + 1] - xs[i]) / 6; };
+    auto Bq = [&](int i) { return (xs[i + 2] - xs[i]) / 3; };
+    auto Cq = [&](int i) { return (xs[i + 2] - xs[i + 1]) / 6; };
+    auto Rq = [&](int i) {
+        return ((ys[i + 2] - ys[i + 1]) / (xs[i + 2] - xs[i + 1])) -
+               ((ys[i + 1] - ys[i]) / (xs[i + 1] - xs[i]));
+    };
+    double *out = y2 + 1;
+    double beta = Bq(0);
+    if (beta == 0) return false;
+    out[0] = Rq(0) / beta;
+    for (int i = 1; i < m; i++) {
+        tmp[i] = Cq(i - 1) / beta;
+        beta = Bq(i) - A(i) * tmp[i];
+        if (beta == 0) return false;
+        out[i] = (Rq(i) - A(i) * out[i - 1]) / beta;
+    }
+    for (int i = m - 2; i >= 0; i--) out[i] -= tmp[i + 1] * out[i + 1];
+    return true;
+}
+
+// Spline.Eval + bsearch, spline.go:80-97,176-200 (increasing tables only).
+__device__ bool spline_eval(const double *xs, const double *ys, const double *y2, int n,
+                            double x, double &y) {
+    if (x <= xs[0] || x >= xs[n - 1]) {
+        if (x == xs[0]) { y = ys[0]; return true; }
+        if (x == xs[n - 1]) { y = ys[n - 1]; return true; }
+        return false;
+    }
+    const double dxEst = (xs[n - 1] - xs[0]) / static_cast<double>(n - 1);
+    int i;
+    const long long guess = go_int((x - xs[0]) / dxEst);
+    if (guess >= 0 && guess < n - 1 && xs[guess] <= x && xs[guess + 1] >= x) {
+        i = static_cast<int>(guess);
+    } else {
+        int lo = 0, hi = n - 1;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) / 2;
+            if (x >= xs[mid]) lo = mid; else hi = mid;
+        }
+        if (lo == n - 1) return false;
+        i = lo;
+    }
+    // calcCoeffs, spline.go:228-237
+    const double h = xs[i + 1] - xs[i];
+    const double ca = (-y2[i] / 6 + y2[i + 1] / 6) / h;
+    const double cb = y2[i] / 2;
+    const double cc = (ys[i + 1] - ys[i]) / h + h * (-y2[i] / 3 - y2[i + 1] / 6);
+    const double cd = ys[i];
+    const double dx = x - xs[i];
+    y = ca * dx * dx * dx + cb * dx * dx + cc * dx + cd;
+    return true;
+}
+
+// --------------------------------------------------------------- filter --
+
+constexpr int kFilterThreads = 128;
+constexpr int kMaxKde = (1 << (kMaxLevels + 1)) - 1;
+constexpr int kMaxAnchor = (1 << kMaxLevels) + 10;
+constexpr int kMaxMax = kKdeKnots / 2;
+
+struct FilterSmem {
+    double X[kKdeKnots], spRs[kKdeKnots];
+    double th[kMaxAnchor], mx[kMaxAnchor], ay2[kMaxAnchor], atmp[kMaxAnchor];
+    double conn[kMaxLevels + 1][1 << kMaxLevels];
+    int nMax[kMaxKde];
+    int status, kept, nValid, anchorN;
+    double high, hCur;
+};
+
+// GetRFunc(level, Radial): kde.go:262-331.  Builds the (theta, r) spline of
+// the anchors of `level` into sm.th/mx/ay2.  One thread.
+__device__ bool build_rfunc(FilterSmem &sm, int level) {
+    const int n = 1 << level;
+    int buf = 5;
+    if (buf > n) buf = n;
+    auto finest = [&](int idx) {
+        for (int i = 0; i <= level; i++) {
+            const double r = sm.conn[level - i][idx >> i];
+            if (!isnan(r)) return r;
+        }
+        return __longlong_as_double(0x7ff8000000000000ll);
+    };
+    auto theta = [&](int j) { return kTwoPi * (static_cast<double>(j) + 0.5) / static_cast<double>(n); };
+    auto thAt = [&](int j) { return level == 0 ? kPi : theta(j); };
+    int k = 0;
+    for (int j = n - buf; j < n; j++, k++) { sm.th[k] = thAt(j) - kTwoPi; sm.mx[k] = finest(j); }
+    for (int j = 0; j < n; j++, k++) { sm.th[k] = thAt(j); sm.mx[k] = finest(j); }
+    for (int j = 0; j < buf; j++, k++) { sm.th[k] = thAt(j) + kTwoPi; sm.mx[k] = finest(j); }
+    sm.anchorN = k;
+    for (int i = 0; i < k - 1; i++) if (sm.th[i + 1] < sm.th[i]) return false;
+    return spline_y2(sm.th, sm.mx, k, sm.ay2, sm.atmp);
+}
+
+// One CTA per (halo, ring): FilterPoints for that ring, penna.go:115-165.
+__global__ void __launch_bounds__(kFilterThreads) filter_kernel(FilterArgs a) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    FilterSmem &sm = *reinterpret_cast<FilterSmem *>(raw);
+    const int nKde = (1 << (a.levels + 1)) - 1;
+    double *Y = reinterpret_cast<double *>(raw + sizeof(FilterSmem));   // [nKde][100]
+    double *Y2 = Y + nKde * kKdeKnots;                                 // [nKde][100]
+    double *V = Y2 + nKde * kKdeKnots;                                 // [nKde][100] (tmp, then values)
+    double *maxes = V + nKde * kKdeKnots;                              // [nKde][kMaxMax]
+    double *pR = maxes + nKde * kMaxMax;                               // [spokes]
+    int *pIdx = reinterpret_cast<int *>(pR + a.spokes);                // [spokes]
+    short *pLo = reinterpret_cast<short *>(pIdx + a.spokes);           // [spokes]
+    short *pHi = pLo + a.spokes;
+    unsigned char *keep = reinterpret_cast<unsigned char *>(pHi + a.spokes);
+
+    const int ring = blockIdx.x, slot = blockIdx.y;
+    const int haloIdx = a.batchHalos[slot];
+    const HaloDev &h = a.halos[haloIdx];
+    const int tid = threadIdx.x;
+    const size_t ringBase = (static_cast<size_t>(slot) * a.rings + ring) * a.spokes;
+    const double *rsp = a.rsp + (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes;
+
+    // valid points in LoS order (ring_buffer.go OkPolarCoords)
+    if (tid == 0) {
+        int n = 0;
+        double high = 0;
+        for (int i = 0; i < a.spokes; i++) {
+            const double r = rsp[i];
+            if (!isnan(r)) {
+                pR[n] = r; pIdx[n] = i;
+                if (n == 0 || r > high) high = r;
+                n++;
+            }
+        }
+        sm.nValid = n; sm.high = high; sm.status = 0; sm.kept = 0;
+        if (n == 0) sm.status = SFK_HALO_NO_POINTS;
+    }
+    __syncthreads();
+    const int nv = sm.nValid;
+    if (sm.status) {
+        if (tid == 0) { atomicMax(&a.status[haloIdx], sm.status); a.fCount[slot * a.rings + ring] = 0; }
+        return;
+    }
+    const double low = 0.0, high = sm.high;
+    const double h0 = h.rMax / a.eta;
+    double factor = 1.0;
+    for (int attempt = 0; attempt < 10; attempt++) {
+        const double hk = h0 * factor;
+        // NewKDETree: knots and evaluation radii, kde.go:83-99, 14-22
+        const double dxk = (high - low) / static_cast<double>(kKdeKnots - 1);
+        const double drk = (high - low) / static_cast<double>(kKdeKnots);
+        for (int i = tid; i < kKdeKnots; i += kFilterThreads) {
+            sm.X[i] = i < kKdeKnots - 1 ? low + dxk * static_cast<double>(i) : high;
+            sm.spRs[i] = i < kKdeKnots - 1 ? low + drk * static_cast<double>(i) : high;
+        }
+        const double maxDist = hk * 3;
+        for (int p = tid; p < nv; p += kFilterThreads) {
+            long long lo = go_int((pR[p] - maxDist - low) / dxk);
+            long long hi = go_int((pR[p] + maxDist - low) / dxk) + 1;
+            if (lo < 0) lo = 0;
+            if (hi >= kKdeKnots) hi = kKdeKnots - 1;
+            pLo[p] = static_cast<short>(lo);
+            pHi[p] = static_cast<short>(hi);
+        }
+        __syncthreads();
+        // GaussianKDE for every node of every level, kde.go:24-38; points in order
+        for (int t = tid; t < nKde * kKdeKnots; t += kFilterThreads) {
+            const int kde = t / kKdeKnots, i = t - kde * kKdeKnots;
+            int level = 0;
+            while ((1 << (level + 1)) - 1 <= kde) level++;
+            const int node = kde - ((1 << level) - 1);
+            const double dth = kTwoPi / static_cast<double>(1 << level);
+            double acc = 0.0;
+            for (int p = 0; p < nv; p++) {
+                if (i < pLo[p] || i > pHi[p]) continue;
+                if (level > 0 && go_int(a.ringPhi[pIdx[p]] / dth) != node) continue;
+                const double udx = (sm.X[i] - pR[p]) / hk;
+                acc += exp(-udx * udx);
+            }
+            Y[t] = acc;
+        }
+        __syncthreads();
+        for (int k = tid; k < nKde; k += kFilterThreads)
+            if (!spline_y2(sm.X, Y + k * kKdeKnots, kKdeKnots, Y2 + k * kKdeKnots, V + k * kKdeKnots))
+                sm.status = SFK_HALO_SPLINE;
+        __syncthreads();
+        // localSplineMaxes, kde.go:193-206
+        for (int t = tid; t < nKde * kKdeKnots; t += kFilterThreads) {
+            const int kde = t / kKdeKnots, i = t - kde * kKdeKnots;
+            double v = 0;
+            if (!spline_eval(sm.X, Y + kde * kKdeKnots, Y2 + kde * kKdeKnots, kKdeKnots, sm.spRs[i], v))
+                sm.status = SFK_HALO_SPLINE;
+            V[t] = v;
+        }
+        __syncthreads();
+        for (int k = tid; k < nKde; k += kFilterThreads) {
+            const double *v = V + k * kKdeKnots;
+            int m = 0;
+            for (int i = 1; i < kKdeKnots - 1; i++)
+                if (v[i] > v[i + 1] && v[i] > v[i - 1]) maxes[k * kMaxMax + m++] = sm.spRs[i];
+            sm.nMax[k] = m;
+        }
+        __syncthreads();
+        // connectMaxes, kde.go:211-258 (sequential tree walk)
+        if (tid == 0 && sm.status == 0) {
+            if (sm.nMax[0] == 0) {
+                sm.status = SFK_HALO_NO_MAXIMUM;
+            } else {
+                sm.conn[0][0] = maxes[0];
+                for (int split = 0; split < a.levels && sm.status == 0; split++) {
+                    const int l = split + 1, nodes = 1 << l;
+                    for (int node = 0; node < nodes; node++) {
+                        const int kde = (1 << l) - 1 + node;
+                        const double *nm = maxes + kde * kMaxMax;
+                        const int cnt = sm.nMax[kde];
+                        const double prev = sm.conn[split][node / 2];
+                        const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+                        double connMax = nanv, cur = nanv;
+                        if (!isnan(prev) && cnt > 0) {
+                            int ci = -1;
+                            double best = INFINITY;
+                            for (int i = 0; i < cnt; i++) {
+                                const double d = fabs(prev - nm[i]);
+                                if (d < best) { ci = i; best = d; }
+                            }
+                            connMax = nm[ci];
+                        }
+                        if (!isnan(connMax) && (split == 0 || fabs(connMax - prev) < hk)) {
+                            cur = connMax;
+                        } else if (cnt > 0) {
+                            if (!build_rfunc(sm, split)) { sm.status = SFK_HALO_SPLINE; break; }
+                            const double thc = kTwoPi * (static_cast<double>(node) + 0.5) / static_cast<double>(nodes);
+                            double spR;
+                            if (!spline_eval(sm.th, sm.mx, sm.ay2, sm.anchorN, thc, spR)) {
+                                sm.status = SFK_HALO_SPLINE;
+                                break;
+                            }
+                            for (int i = 0; i < cnt; i++)
+                                if (fabs(nm[i] - spR) < hk) cur = nm[i];
+                        }
+                        sm.conn[l][node] = cur;
+                    }
+                }
+                // FilterNearby's curve: GetRFunc(levels, Radial), kde.go:355-369
+                if (sm.status == 0 && !build_rfunc(sm, a.levels)) sm.status = SFK_HALO_SPLINE;
+            }
+        }
+        __syncthreads();
+        if (sm.status) break;
+        for (int p = tid; p < nv; p += kFilterThreads) {
+            double v;
+            if (!spline_eval(sm.th, sm.mx, sm.ay2, sm.anchorN, a.ringPhi[pIdx[p]], v)) {
+                sm.status = SFK_HALO_SPLINE;
+                keep[p] = 0;
+            } else {
+                keep[p] = fabs(v - pR[p]) < hk / 2 ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int m = 0;
+            for (int p = 0; p < nv; p++)
+                if (keep[p]) { a.fR[ringBase + m] = pR[p]; a.fIdx[ringBase + m] = pIdx[p]; m++; }
+            sm.kept = m;
+        }
+        __syncthreads();
+        if (sm.kept > 0 || sm.status) break;
+        factor *= 1.1;
+    }
+    if (tid == 0) {
+        if (sm.status) atomicMax(&a.status[haloIdx], sm.status);
+        a.fCount[slot * a.rings + ring] = sm.status ? 0 : sm.kept;
+    }
+}
+
+// ------------------------------------------------------------------ fit --
+
+// Go's math.Pow for small non-negative integer exponents (src/math/pow.go):
+// repeated squaring on frexp mantissas.
+__device__ double go_pow_int(double x, int yi) {
+    if (yi == 0 || x == 1) return 1;
+    if (yi == 1) return x;
+    if (isnan(x)) return x;
+    if (x == 0) return 0;   // y > 0
+    if (isinf(x)) return pow(x, static_cast<double>(yi));
+    double a1 = 1.0;
+    int ae = 0, xe;
+    double x1 = frexp(x, &xe);
+    for (int i = yi; i != 0; i >>= 1) {
+        if (i & 1) { a1 *= x1; ae += xe; }
+        x1 *= x1;
+        xe <<= 1;
+        if (x1 < .5) { x1 += x1; xe--; }
+    }
+    return ldexp(a1, ae);
+}
+
+// gonum Dgetf2 + Dtrti2 + Dgetri (unblocked, row-major) == LAPACK
+// DGETF2/DTRTI2/DGETRI: the inverse mat64.Dense.Inverse computes in pinv,
+// penna.go:170-186.  One thread; a is n x n in shared memory.
+__device__ bool invert_lu(double *a, int n, int *ipiv, double *work) {
+    for (int j = 0; j < n; j++) {
+        int jp = j;
+        double amax = fabs(a[j * n + j]);
+        for (int i = j + 1; i < n; i++) {
+            const double v = fabs(a[i * n + j]);
+            if (v > amax) { amax = v; jp = i; }
+        }
+        ipiv[j] = jp;
+        if (a[jp * n + j] != 0) {
+            if (jp != j)
+                for (int k = 0; k < n; k++) {
+                    const double t = a[j * n + k]; a[j * n + k] = a[jp * n + k]; a[jp * n + k] = t;
+                }
+            if (j < n - 1) {
+                const double inv = 1 / a[j * n + j];
+                for (int i = j + 1; i < n; i++) a[i * n + j] *= inv;
+            }
+        }
+        if (j < n - 1)
+            for (int i = j + 1; i < n; i++) {
+                const double tmp = -1 * a[i * n + j];
+                if (tmp == 0) continue;
+                for (int k = j + 1; k < n; k++) a[i * n + k] += tmp * a[j * n + k];
+            }
+    }
+    for (int i = 0; i < n; i++) if (a[i * n + i] == 0) return false;
+    for (int j = 0; j < n; j++) {
+        double ajj = 1 / a[j * n + j];
+        a[j * n + j] = ajj;
+        ajj *= -1;
+        for (int i = 0; i < j; i++) {
+            double tmp = 0;
+            for (int k = i; k < j; k++) tmp += a[i * n + k] * a[k * n + j];
+            a[i * n + j] = tmp;
+        }
+        for (int i = 0; i < j; i++) a[i * n + j] *= ajj;
+    }
+    for (int j = n - 1; j >= 0; j--) {
+        for (int i = j + 1; i < n; i++) { work[i] = a[i * n + j]; a[i * n + j] = 0; }
+        if (j < n - 1)
+            for (int i = 0; i < n; i++) {
+                double tmp = 0;
+                for (int k = j + 1; k < n; k++) tmp += a[i * n + k] * work[k];
+                a[i * n + j] += -1 * tmp;
+            }
+    }
+    for (int j = n - 2; j >= 0; j--) {
+        const int jp = ipiv[j];
+        if (jp != j)
+            for (int i = 0; i < n; i++) {
+                const double t = a[i * n + j]; a[i * n + j] = a[i * n + jp]; a[i * n + jp] = t;
+            }
+    }
+    return true;
+}
+
+constexpr int kFitThreads = 1024;
+constexpr int kMaxP2 = 2 * kMaxOrder * kMaxOrder;
+
+// One CTA per halo: PennaVolumeFit, penna.go:88-108 -> PennaCoeffs :14-58.
+__global__ void __launch_bounds__(kFitThreads) fit_kernel(FitArgs a) {
+    __shared__ double G[kMaxP2 * kMaxP2];
+    __shared__ double work[kMaxP2];
+    __shared__ int ipiv[kMaxP2];
+    __shared__ int ringOff[kMaxRings + 1];
+    __shared__ int okFlag;
+    const int slot = blockIdx.x, tid = threadIdx.x;
+    const int haloIdx = a.batchHalos[slot];
+    const int P = a.order, P2 = 2 * P * P;
+    const size_t cap = static_cast<size_t>(a.rings) * a.spokes;
+    double *M = a.M + static_cast<size_t>(slot) * cap * P2;
+    double *out2 = a.out2 + static_cast<size_t>(slot) * cap * P2;
+    double *rv = a.rvec + static_cast<size_t>(slot) * cap;
+    if (tid == 0) {
+        int s = 0;
+        for (int r = 0; r < a.rings; r++) { ringOff[r] = s; s += a.fCount[slot * a.rings + r]; }
+        ringOff[a.rings] = s;
+        okFlag = 1;
+    }
+    __syncthreads();
+    const int N = ringOff[a.rings];
+    if (tid == 0) a.nPoints[haloIdx] = N;
+    if (a.status[haloIdx] != 0) return;   // a ring already failed
+    if (N == 0) {
+        if (tid == 0) a.status[haloIdx] = SFK_HALO_NO_POINTS;
+        return;
+    }
+    // design rows: one thread per point
+    for (int ring = 0; ring < a.rings; ring++) {
+        const int cnt = ringOff[ring + 1] - ringOff[ring];
+        const float *irot = a.irots + 9 * ring;
+        for (int k = tid; k < cnt; k += kFitThreads) {
+            const size_t src = (static_cast<size_t>(slot) * a.rings + ring) * a.spokes + k;
+            const double R = a.fR[src];
+            const int li = a.fIdx[src];
+            // fXs, fYs (penna.go:157-160) then PlaneToVolume through float32 (halo.go:471-475)
+            const double px = R * a.ringCos[li], py = R * a.ringSin[li];
+            float fx, fy, fz;
+            rotate_vec(irot, static_cast<float>(px), static_cast<float>(py), 0.f, fx, fy, fz);
+            const double x = fx, y = fy, z = fz;
+            const double r = sqrt(x * x + y * y + z * z);
+            const double costh = z / r;
+            const double sinth = sqrt(1 - costh * costh);
+            const double cosphi = x / r / sinth;
+            const double sinphi = y / r / sinth;
+            const int n = ringOff[ring] + k;
+            rv[n] = r;
+            int m = 0;
+            for (int kk = 0; kk < 2; kk++) {
+                const double ck = go_pow_int(costh, kk);
+                for (int j = 0; j < P; j++) {
+                    const double sj = go_pow_int(sinphi, j);
+                    double cphi = 1.0;
+                    for (int i = 0; i < P; i++) {
+                        M[static_cast<size_t>(n) * P2 + m] = go_pow_int(sinth, i + j) * cphi * ck * sj;
+                        m++;
+                        cphi *= cosphi;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // out1 = M * M^T: one thread per entry, points in ascending order
+    if (tid < P2 * P2) {
+        const int i = tid / P2, j = tid - i * P2;
+        double acc = 0.0;
+        for (int n = 0; n < N; n++) {
+            const double t = M[static_cast<size_t>(n) * P2 + i];
+            if (t == 0) continue;
+            acc += t * M[static_cast<size_t>(n) * P2 + j];
+        }
+        G[tid] = acc;
+    }
+    __syncthreads();
+    if (tid == 0 && !invert_lu(G, P2, ipiv, work)) okFlag = 0;
+    __syncthreads();
+    if (!okFlag) {
+        if (tid == 0) a.status[haloIdx] = SFK_HALO_SINGULAR;
+        return;
+    }
+    // out2 = M^T * inv (row n), then cs = rs^T * out2 (mat.VecMult, mat.go:102)
+    for (int n = tid; n < N; n += kFitThreads) {
+        double row[kMaxP2];
+        for (int j = 0; j < P2; j++) row[j] = 0.0;
+        for (int l = 0; l < P2; l++) {
+            const double t = M[static_cast<size_t>(n) * P2 + l];
+            if (t == 0) continue;
+            for (int j = 0; j < P2; j++) row[j] += t * G[l * P2 + j];
+        }
+        for (int j = 0; j < P2; j++) out2[static_cast<size_t>(n) * P2 + j] = row[j];
+    }
+    __syncthreads();
+    if (tid < P2) {
+        double sum = 0.0;
+        for (int n = 0; n < N; n++) sum += rv[n] * out2[static_cast<size_t>(n) * P2 + tid];
+        a.coeffs[static_cast<size_t>(haloIdx) * P2 + tid] = sum;
+    }
+}
+
+}  // namespace
+
+// --------------------------------------------------------------- launch --
+
+cudaError_t launch_cull(const CullArgs &a, bool fill, cudaStream_t s) {
+    const int64_t live = (a.n + a.sf3 - 1) / a.sf3;
+    if (live <= 0 || a.nList <= 0) return cudaSuccess;
+    const unsigned grid = static_cast<unsigned>((live + kCullThreads - 1) / kCullThreads);
+    if (fill) cull_kernel<true><<<grid, kCullThreads, 0, s>>>(a);
+    else cull_kernel<false><<<grid, kCullThreads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hits(const Piece *pieces, int nPieces, const Cand *cands,
+                        const HaloDev *halos, const float *norms, const float *rots,
+                        int rings, int spokes, double dPhi, uint32_t *hitCount,
+                        unsigned long long *rhoMaxBits, const int64_t *hitOffset,
+                        uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs,
+                        bool fill, cudaStream_t s) {
+    if (nPieces <= 0) return cudaSuccess;
+    const size_t smem = sizeof(float) * 3 * rings + sizeof(uint32_t) * 2 * rings;
+    if (fill)
+        hits_kernel<true><<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rots, rings,
+                                                             spokes, dPhi, hitCount, rhoMaxBits,
+                                                             hitOffset, hitCursor, haloSlot, recs);
+    else
+        hits_kernel<false><<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rots, rings,
+                                                              spokes, dPhi, hitCount, rhoMaxBits,
+                                                              hitOffset, hitCursor, haloSlot, recs);
+    return cudaGetLastError();
+}
+
+size_t bin_smem_bytes(int bins) {
+    return sizeof(HitRec) * 2 * kStageRecs + 2 * sizeof(uint64_t) +
+           sizeof(uint32_t) * 2 * kTileLos * (bins + 1);
+}
+
+cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s) {
+    if (nb <= 0) return cudaSuccess;
+    const size_t smem = bin_smem_bytes(a.bins);
+    static bool attrSet[2] = {false, false};
+    if (!attrSet[taps]) {
+        cudaError_t e = taps ? cudaFuncSetAttribute(bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                             : cudaFuncSetAttribute(bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attrSet[taps] = true;
+    }
+    const int nTiles = (a.spokes + kTileLos - 1) / kTileLos;
+    dim3 grid(nTiles * a.chunks, a.rings, nb);
+    if (taps) bin_kernel<true><<<grid, kBinThreads, smem, s>>>(a);
+    else bin_kernel<false><<<grid, kBinThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s) {
+    if (nb <= 0) return cudaSuccess;
+    const size_t smem = sizeof(double) * (2 * a.window + kLosWarps * 3 * a.bins);
+    static bool attrSet = false;
+    if (!attrSet) {
+        cudaError_t e = cudaFuncSetAttribute(los_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attrSet = true;
+    }
+    const int64_t warps = static_cast<int64_t>(nb) * a.rings * a.spokes;
+    const unsigned grid = static_cast<unsigned>((warps + kLosWarps - 1) / kLosWarps);
+    los_kernel<<<grid, kLosWarps * 32, smem, s>>>(a, nb);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_filter(const FilterArgs &a, int nb, cudaStream_t s) {
+    if (nb <= 0) return cudaSuccess;
+    const int nKde = (1 << (a.levels + 1)) - 1;
+    const size_t smem = sizeof(FilterSmem) + sizeof(double) * (3 * nKde * kKdeKnots + nKde * kMaxMax + a.spokes) +
+                        sizeof(int) * a.spokes + 2 * sizeof(short) * a.spokes + a.spokes + 16;
+    static bool attrSet = false;
+    if (!attrSet) {
+        cudaError_t e = cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attrSet = true;
+    }
+    dim3 grid(a.rings, nb);
+    filter_kernel<<<grid, kFilterThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fit(const FitArgs &a, int nb, cudaStream_t s) {
+    if (nb <= 0) return cudaSuccess;
+    fit_kernel<<<nb, kFitThreads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace sfk

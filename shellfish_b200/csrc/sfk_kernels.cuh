@@ -1,0 +1,90 @@
+// sfk_kernels.cuh -- launch wrappers of the sm_100a kernels (sfk_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "sfk_internal.h"
+
+namespace sfk {
+
+struct CullArgs {
+    const float *xyz;        // [n][3] block positions (device)
+    const float *mass;       // [n]
+    int64_t n;
+    int64_t sf3;             // SubsampleFactor^3, cmd/shell.go:490-493
+    const int32_t *haloList; // halos touching the block, in halo order
+    int nList;
+    const HaloDev *halos;
+    float tw;                // float32(TotalWidth), los/halo.go:172
+    double rhoM;             // mean density of this block's cosmology
+    uint32_t *counts;        // [nList] candidates per listed halo
+    const int64_t *segStart; // [nList] first slot of each segment (fill pass)
+    Cand *cands;
+};
+
+struct BinArgs {
+    const HitRec *recs;
+    const int64_t *hitOffset;   // [nb][rings] first record of (halo, ring)
+    const uint32_t *hitCount;   // [nb][rings]
+    const HaloDev *halos;
+    const int32_t *batchHalos;  // [nb] halo index of each batch slot
+    const double *ringCos, *ringSin;
+    unsigned long long *grid;   // [nb][rings][spokes][bins] int64 fixed point
+    unsigned long long *nIntersections; // [nHalo]
+    uint32_t *tapInsert, *tapStart, *tapEnd; // TAPS only, indexed by halo
+    int rings, spokes, bins, chunks;
+};
+
+struct LosArgs {
+    const unsigned long long *grid;
+    const HaloDev *halos;
+    const int32_t *batchHalos;
+    const double *valTaps, *derivTaps;
+    double *rsp;        // [nHalo][rings][spokes]
+    double *profiles;   // TAPS: [nHalo][rings][spokes][bins], else null
+    int rings, spokes, bins, window;
+    double dLim;
+};
+
+struct FilterArgs {
+    const double *rsp;
+    const HaloDev *halos;
+    const int32_t *batchHalos;
+    double *fR;          // [nb][rings][spokes] kept radii
+    int32_t *fIdx;       // [nb][rings][spokes] LoS index of each kept point
+    int32_t *fCount;     // [nb][rings]
+    int32_t *status;     // [nHalo]
+    int rings, spokes, levels;
+    double eta, dPhiUnused;
+    const double *ringPhi;
+};
+
+struct FitArgs {
+    const double *fR;
+    const int32_t *fIdx, *fCount;
+    const int32_t *batchHalos;
+    const float *irots;
+    const double *ringCos, *ringSin;
+    double *M;       // [nb][rings*spokes][P2] design rows
+    double *out2;    // [nb][rings*spokes][P2]
+    double *rvec;    // [nb][rings*spokes]
+    double *coeffs;  // [nHalo][P2]
+    int32_t *status; // [nHalo]
+    long long *nPoints; // [nHalo]
+    int rings, spokes, order;
+};
+
+cudaError_t launch_cull(const CullArgs &a, bool fill, cudaStream_t s);
+cudaError_t launch_hits(const Piece *pieces, int nPieces, const Cand *cands,
+                        const HaloDev *halos, const float *norms, const float *rots,
+                        int rings, int spokes, double dPhi, uint32_t *hitCount,
+                        unsigned long long *rhoMaxBits, const int64_t *hitOffset,
+                        uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs,
+                        bool fill, cudaStream_t s);
+cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s);
+cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s);
+cudaError_t launch_filter(const FilterArgs &a, int nb, cudaStream_t s);
+cudaError_t launch_fit(const FitArgs &a, int nb, cudaStream_t s);
+size_t bin_smem_bytes(int bins);
+
+}  // namespace sfk

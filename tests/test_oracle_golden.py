@@ -146,19 +146,14 @@ def _insert_to_ring_cases():
 
 @pytest.mark.parametrize("case", _insert_to_ring_cases())
 def test_insert_to_ring(case):
-    """The reference table lists bins from large to small radius (edges run
-    10 -> 0.1) while GetRhos returns bins from rMin upward, and the table was
-    written against a Halo.Init that no longer compiles (geom.Vec); the
-    expected profiles are therefore compared after reversal, which is the
-    only orientation in which all six rows hold."""
+    """The reference file no longer compiles (geom.Vec is undefined) but its
+    six rows are valid known answers: rows 4-6 pass a negative radius
+    ((edges[4]-edges[3])/2 < 0), which insertToRing only ever squares."""
     los, n, vec, radius, want = case
     h = po.Halo([[0, 0, 1]], [1, 1, 1], 0.1, 10, 8, n)
     h.insert_to_ring(vec, radius, 1.0, 0)
     got = h.get_rhos(0, los)
-    want = np.array(want, float)
-    ok_fwd = np.all(np.abs(got - want) < 1e-4)
-    ok_rev = np.all(np.abs(got[::-1] - want) < 1e-4)
-    assert ok_fwd or ok_rev, (got, want)
+    assert np.all(np.abs(got - np.array(want, float)) < 1e-4), (got, want)
 
 
 # ---- math/interpolate/filter_test.go:39-60 TestSavGolKernel
