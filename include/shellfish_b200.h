@@ -38,6 +38,7 @@ extern "C" {
 #define SFK_HALO_NO_MAXIMUM 3  /* level-0 KDE without maximum: index panic, kde.go:212 */
 #define SFK_HALO_SPLINE 4      /* Spline table/bounds panic, spline.go:56-96 */
 #define SFK_HALO_SINGULAR 5    /* singular normal equations in the Penna fit */
+#define SFK_HALO_NOT_OWNED 6   /* left to another rank by sfk_set_owned */
 
 /* sfk_params.flags */
 #define SFK_FLAG_TAPS 1u /* keep parity taps: profiles, integer edge counts */
@@ -95,6 +96,14 @@ int sfk_begin_snapshot(sfk_ctx *ctx, const sfk_cosmo *cosmo, float min_mass);
 int sfk_add_halos(sfk_ctx *ctx, int64_t n, const double *x, const double *y,
                   const double *z, const double *r200m);
 
+/* Multi-GPU sharding: owned is [n_halo]; halos with owned[i] == 0 are left to
+ * another rank.  They still take part in Halo.Transform's cumulative in-place
+ * wrap of each block (los/halo.go:168-197, called per halo at
+ * cmd/shell.go:441), so the halos this rank does own see bit-identical
+ * positions to a single-process run.  Call after sfk_add_halos, before the
+ * first block. */
+int sfk_set_owned(sfk_ctx *ctx, int64_t n, const uint8_t *owned);
+
 /* binIntersections / Halo.SheetIntersect (cmd/shell.go:599-611,
  * los/halo.go:442-467) for one block header.  hit may be NULL; *n_hit
  * receives the number of halos touching the block. */
@@ -124,6 +133,10 @@ int sfk_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass,
 int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status);
 
 int sfk_get_stats(const sfk_ctx *ctx, sfk_stats *out);
+
+/* The cudaStream_t (as void*) every kernel of this context is launched on, so
+ * a caller can record its own CUDA events around the calls. */
+void *sfk_stream(const sfk_ctx *ctx);
 
 /* ---- parity taps (valid after sfk_finish_snapshot) ---------------------- */
 

@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsfk.so")
 
 SFK_FLAG_TAPS = 1
-HALO_STATUS = {0: "ok", 1: "skipped", 2: "no_points", 3: "no_maximum", 4: "spline", 5: "singular"}
+HALO_STATUS = {0: "ok", 1: "skipped", 2: "no_points", 3: "no_maximum", 4: "spline", 5: "singular",
+               6: "not_owned"}
 
 
 class Params(C.Structure):
@@ -46,8 +47,8 @@ class Stats(C.Structure):
 
 # every symbol include/shellfish_b200.h declares
 EXPORTS = ["sfk_default_params", "sfk_create", "sfk_destroy", "sfk_last_error", "sfk_begin_snapshot",
-           "sfk_add_halos", "sfk_block_halo_mask", "sfk_push_block", "sfk_push_block_device",
-           "sfk_finish_snapshot", "sfk_get_stats", "sfk_get_rsp", "sfk_get_candidate_count",
+           "sfk_add_halos", "sfk_set_owned", "sfk_block_halo_mask", "sfk_push_block", "sfk_push_block_device",
+           "sfk_finish_snapshot", "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count",
            "sfk_get_profiles", "sfk_get_counts", "sfk_get_ring_tables"]
 
 _lib = None
@@ -71,11 +72,14 @@ def lib():
         L.sfk_last_error.restype = C.c_char_p
         L.sfk_begin_snapshot.argtypes = [vp, C.POINTER(Cosmo), C.c_float]
         L.sfk_add_halos.argtypes = [vp, C.c_int64, dp, dp, dp, dp]
+        L.sfk_set_owned.argtypes = [vp, C.c_int64, C.POINTER(C.c_uint8)]
         L.sfk_block_halo_mask.argtypes = [vp, fp, fp, C.c_double, C.POINTER(C.c_uint8), C.POINTER(C.c_int64)]
         L.sfk_push_block.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Cosmo), C.c_double, fp, fp]
         L.sfk_push_block_device.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Cosmo), C.c_double, fp, fp]
         L.sfk_finish_snapshot.argtypes = [vp, dp, C.POINTER(C.c_int32)]
         L.sfk_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.sfk_stream.argtypes = [vp]
+        L.sfk_stream.restype = C.c_void_p
         L.sfk_get_rsp.argtypes = [vp, C.c_int64, dp]
         L.sfk_get_candidate_count.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64)]
         L.sfk_get_profiles.argtypes = [vp, C.c_int64, dp]
@@ -83,7 +87,7 @@ def lib():
         L.sfk_get_counts.argtypes = [vp, C.c_int64, u32p, u32p, u32p]
         L.sfk_get_ring_tables.argtypes = [vp, fp, fp, fp]
         for name in EXPORTS:
-            if getattr(L, name).restype is not None and name != "sfk_last_error":
+            if getattr(L, name).restype is not None and name not in ("sfk_last_error", "sfk_stream"):
                 getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -147,6 +151,12 @@ class ShellContext:
         self._ck(lib().sfk_add_halos(self._h, len(halos), *ptrs), "sfk_add_halos")
         self.n_halos = len(halos)
 
+    def set_owned(self, owned):
+        """owned: bool per halo; the rest is left to other ranks (shard.py)."""
+        o = np.ascontiguousarray(owned, np.uint8)
+        self._ck(lib().sfk_set_owned(self._h, len(o), o.ctypes.data_as(C.POINTER(C.c_uint8))),
+                 "sfk_set_owned")
+
     def block_halo_mask(self, origin, width, total_width):
         hit = np.zeros(self.n_halos, np.uint8)
         n = C.c_int64()
@@ -184,6 +194,10 @@ class ShellContext:
                                            status.ctypes.data_as(C.POINTER(C.c_int32))),
                  "sfk_finish_snapshot")
         return coeffs, status
+
+    def stream_ptr(self):
+        """cudaStream_t of this context as an integer (torch.cuda.ExternalStream)."""
+        return lib().sfk_stream(self._h)
 
     def stats(self):
         s = Stats()

@@ -340,6 +340,7 @@ int sfk_add_halos(sfk_ctx *ctx, int64_t n, const double *x, const double *y, con
         HaloDev h{};
         const double r = r200m[i];
         h.valid = r > 0 ? 1 : 0;   // cmd/shell.go:535-538
+        h.owned = 1;
         if (h.valid) {
             // createHalos, cmd/shell.go:540-556
             const double rMax = r * p.r_max_mult, rMin = r * p.r_min_mult;
@@ -369,6 +370,16 @@ int sfk_add_halos(sfk_ctx *ctx, int64_t n, const double *x, const double *y, con
     CU(ctx->dHalos.upload(ctx->halos, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stats.n_halos = n;
+    return SFK_OK;
+}
+
+int sfk_set_owned(sfk_ctx *ctx, int64_t n, const uint8_t *owned) {
+    if (!ctx || !ctx->inSnapshot || !owned || n != static_cast<int64_t>(ctx->halos.size()))
+        return fail(ctx, SFK_E_INVALID, "sfk_set_owned: call after sfk_add_halos with one flag per halo");
+    if (ctx->candCount != 0) return fail(ctx, SFK_E_INVALID, "sfk_set_owned: blocks were already pushed");
+    for (int64_t i = 0; i < n; i++) ctx->halos[i].owned = owned[i] ? 1 : 0;
+    CU(ctx->dHalos.upload(ctx->halos, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return SFK_OK;
 }
 
@@ -525,7 +536,8 @@ int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) {
     const int64_t hitBudget = (int64_t(6) << 30) / static_cast<int64_t>(sizeof(HitRec));
     std::vector<int32_t> order;
     for (int64_t i = 0; i < nHalo; i++) {
-        if (ctx->halos[i].valid) order.push_back(static_cast<int32_t>(i));
+        if (ctx->halos[i].valid && ctx->halos[i].owned) order.push_back(static_cast<int32_t>(i));
+        else if (ctx->halos[i].valid) ctx->hStatus[i] = SFK_HALO_NOT_OWNED;
         else ctx->hStatus[i] = SFK_HALO_SKIPPED;
     }
     size_t pos = 0;
@@ -667,6 +679,8 @@ int sfk_get_stats(const sfk_ctx *ctx, sfk_stats *out) {
     *out = ctx->stats;
     return SFK_OK;
 }
+
+void *sfk_stream(const sfk_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
 
 static int check_halo(sfk_ctx *ctx, int64_t halo, bool needTaps) {
     if (!ctx || !ctx->finished) return fail(ctx, SFK_E_INVALID, "taps are valid after sfk_finish_snapshot");

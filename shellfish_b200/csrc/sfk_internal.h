@@ -25,6 +25,7 @@ struct HaloDev {
     float x0, y0, z0;   // float32(origin), los/halo.go:156,169-171
     float lo2, hi2;     // Intersect bounds, los/halo.go:148-152
     int32_t valid;      // r200m > 0
+    int32_t owned;      // analysed by this context (else only replayed in Transform)
     double rad;         // kernel radius RMax*RKernelMult/RMaxMult, cmd/shell.go:442
     double rad2;        // radius*radius, los/halo.go:236
     double sphVol;      // 4*pi/3*rad^3, cmd/shell.go:485

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kCullThreads) cull_kernel(CullArgs a) {
         __syncthreads();
         if (threadIdx.x < m) {
             const HaloDev &h = a.halos[a.haloList[base + threadIdx.x]];
-            sh[threadIdx.x] = CullHalo{h.x0, h.y0, h.z0, h.lo2, h.hi2, h.sphVol};
+            sh[threadIdx.x] = CullHalo{h.x0, h.y0, h.z0, h.owned ? h.lo2 : INFINITY, h.hi2, h.sphVol};
         }
         __syncthreads();
         for (int k = 0; k < m; k++) {

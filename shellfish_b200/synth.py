@@ -3,7 +3,7 @@
 Shapes follow BASELINE.json's configs: particles of a
 periodic box cut into cubic blocks, each block carrying the io.Header fields
 (io/io.go:71-83) the `shell` loop reads, plus a halo table (x, y, z, R200m).
-Everything is seeded numpy; nothing here touches the GPU or the oracle.
+Everything is seeded numpy; nothing here touches the GPU.
 """
 import math
 
@@ -116,3 +116,29 @@ def single_halo(seed=1, n=100000, r200m=1.0, box=62.5, n_background=20000, cells
     """BASELINE config 1 analogue: one halo at the box centre."""
     return make_box(seed, box, 1, n, n_background, cells,
                     centers=[[box / 2] * 3], radii=[r200m])
+
+
+def r200m_from_count(n200, m_p, cosmo=COSMO):
+    """R200m (comoving Mpc/h) of a halo holding n200 particles of mass m_p."""
+    return (3.0 * n200 * m_p / (4.0 * math.pi * 200.0 * rho_m0(cosmo))) ** (1.0 / 3.0)
+
+
+def config2(seed=2, n_halos=1000, n_total=512 ** 3, box=250.0, cells=8,
+            n_per_halo_range=(5.0e4, 2.0e5), cosmo=COSMO):
+    """BASELINE config 2: `n_halos` halos with >= 5e4 particles each in a
+    periodic `n_total`-particle LGadget-2-like box cut into cells^3 blocks.
+    Per-halo particle counts are log-uniform in n_per_halo_range (scaled down
+    if they would exceed 80% of n_total); R200m follows from the count so that
+    densities in units of rho_m are self-consistent.  The rest of the budget is
+    a uniform background."""
+    rng = np.random.default_rng(seed)
+    lo, hi = n_per_halo_range
+    n_per = np.exp(rng.uniform(np.log(lo), np.log(hi), n_halos))
+    if n_per.sum() > 0.8 * n_total:
+        n_per *= 0.8 * n_total / n_per.sum()
+    n_per = np.maximum(n_per.astype(np.int64), 1)
+    m_p = float(uniform_mass(n_total, box, cosmo))
+    radii = np.array([r200m_from_count(0.567 * n, m_p, cosmo) for n in n_per])
+    centers = rng.random((n_halos, 3)) * box
+    n_bg = int(n_total - n_per.sum())
+    return make_box(seed + 1, box, n_halos, n_per, n_bg, cells, centers=centers, radii=radii, cosmo=cosmo)

@@ -1,0 +1,240 @@
+"""Parity of the CUDA path (through the C ABI, shellfish_b200/libsfk.so) with
+the CPU oracle on the same seeded inputs.  Runs on the B200 box only.
+
+Bars (BASELINE.json north_star):
+  * integer taps bit-exact: candidates per halo, inserts per LoS, start/end
+    edges per (LoS, bin);
+  * profiles (Halo.GetRhos), R_sp per LoS and Penna coefficients within 1e-5
+    relative.  Profiles are compared relative to max(|ref|, background rho),
+    coefficients relative to the halo's largest |coefficient| (the catalog
+    prints %.6g of each, cmd/catalog/catalog.go:125-140).
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from shellfish_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+ORC_STATUS = {0: 0, -2: 2, -3: 3, -4: 4, -1: 5}   # ORC_E_* -> SFK_HALO_*
+
+
+def run_both(halos, blocks, mass, taps=True, **kw):
+    names = {"rings": "rings", "spokes": "spokes", "radial_bins": "radialBins", "order": "order",
+             "levels": "levels", "smoothing_window": "smoothingWindow",
+             "subsample_factor": "subsampleFactor", "eta": "eta", "r_kernel_mult": "rKernelMult",
+             "background_rho_mult": "backgroundRhoMult", "los_slope_cutoff": "losSlopeCutoff"}
+    params = api.default_params(seed=1337, flags=api.SFK_FLAG_TAPS if taps else 0, **kw)
+    cfg = po.ShellConfig.default(seed=1337, threads=1, **{names[k]: v for k, v in kw.items()})
+    ctx, coeffs, status = api.run_shell(params, mass, halos, blocks)
+    want = ("rsp", "profiles", "nInsert", "startEdges", "endEdges", "nFiltered", "nCandidates",
+            "nIntersections") if taps else ("rsp", "nFiltered", "nCandidates")
+    ref = po.shell_run(cfg, mass, halos, blocks, taps=want)
+    return ctx, coeffs, status, ref
+
+
+def assert_parity(ctx, coeffs, status, ref, n_halos, taps=True):
+    for h in range(n_halos):
+        assert status[h] == ORC_STATUS[int(ref["status"][h])], (h, status[h], ref["status"][h])
+        assert ctx.candidate_count(h) == ref["nCandidates"][h]
+        if taps:
+            ins, st, en = ctx.counts(h)
+            assert np.array_equal(ins, ref["nInsert"][h]), "inserts per LoS differ (halo %d)" % h
+            assert np.array_equal(st, ref["startEdges"][h]), "start-edge counts differ (halo %d)" % h
+            assert np.array_equal(en, ref["endEdges"][h]), "end-edge counts differ (halo %d)" % h
+            prof, rp = ctx.profiles(h), ref["profiles"][h]
+            fin = np.isfinite(rp)
+            assert np.array_equal(np.isfinite(prof), fin)
+            bg = rp[fin].min() if fin.any() else 0.0
+            den = np.maximum(np.abs(rp[fin]), max(bg, 1e-300))
+            assert np.max(np.abs(prof[fin] - rp[fin]) / den, initial=0.0) <= RTOL
+        rsp, rr = ctx.rsp(h), ref["rsp"][h]
+        assert np.array_equal(np.isnan(rsp), np.isnan(rr)), "R_sp ok-mask differs (halo %d)" % h
+        m = ~np.isnan(rr)
+        assert np.all(np.abs(rsp[m] - rr[m]) <= RTOL * np.abs(rr[m]))
+        if status[h] == 0:
+            scale = np.max(np.abs(ref["coeffs"][h]))
+            assert np.all(np.abs(coeffs[h] - ref["coeffs"][h]) <= RTOL * scale), (coeffs[h], ref["coeffs"][h])
+        else:
+            assert np.all(coeffs[h] == 0)
+    if taps:
+        assert ctx.stats()["n_intersections"] == int(ref["nIntersections"].sum())
+
+
+def test_single_halo_rng_rings():
+    """BASELINE configs[0] shape at test size: one NFW halo, one block."""
+    halos, blocks, mass = synth.single_halo(seed=1, n=20000, n_background=5000)
+    ctx, c, s, ref = run_both(halos, blocks, mass, rings=10)
+    assert s[0] == 0
+    assert_parity(ctx, c, s, ref, 1)
+
+
+def test_three_rings_bypass_rng():
+    """Rings == 3 uses the axis triplet (cmd/shell.go:570-571)."""
+    halos, blocks, mass = synth.single_halo(seed=3, n=20000, n_background=5000)
+    ctx, c, s, ref = run_both(halos, blocks, mass, rings=3)
+    assert_parity(ctx, c, s, ref, 1)
+
+
+def test_default_config_full_halo():
+    """Default shell.config (100 x 256 x 256) on a 5e4-particle halo."""
+    halos, blocks, mass = synth.single_halo(seed=4, n=50000, n_background=10000)
+    ctx, c, s, ref = run_both(halos, blocks, mass)
+    assert s[0] == 0
+    assert_parity(ctx, c, s, ref, 1)
+
+
+def test_periodic_wrap_many_halos_many_blocks():
+    """Halos near the faces of a small periodic box cut into 64 blocks: the
+    cumulative in-place float32 wrap of Halo.Transform (los/halo.go:168-197)
+    and SheetIntersect's periodic branch (halo.go:442-467) are exercised
+    (blocks narrower than half the box, see test_sheet_intersect_periodic)."""
+    box = 8.0
+    centers = [[0.3, 4.0, 4.0], [7.8, 0.2, 4.1], [4.0, 4.0, 7.9], [0.1, 0.1, 0.1], [3.0, 5.0, 2.0]]
+    radii = [0.8, 0.7, 0.9, 0.6, 0.75]
+    halos, blocks, mass = synth.make_box(7, box, 5, 9000, 30000, 4, centers=centers, radii=radii)
+    ctx, c, s, ref = run_both(halos, blocks, mass, rings=6)
+    assert_parity(ctx, c, s, ref, 5)
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_penna_order(order):
+    halos, blocks, mass = synth.single_halo(seed=5, n=25000, n_background=5000)
+    ctx, c, s, ref = run_both(halos, blocks, mass, rings=12, order=order)
+    assert c.shape[1] == 2 * order * order
+    assert_parity(ctx, c, s, ref, 1)
+
+
+def test_subsample_factor():
+    """SubsampleFactor = 2 keeps every 8th particle with 8x weight (cmd/shell.go:490-495)."""
+    halos, blocks, mass = synth.single_halo(seed=6, n=80000, n_background=20000)
+    ctx, c, s, ref = run_both(halos, blocks, mass, rings=8, subsample_factor=2)
+    assert_parity(ctx, c, s, ref, 1)
+
+
+def test_ragged_shapes():
+    """Spokes not a multiple of the 32-LoS tile, bins/window of los/halo_bench_test.go."""
+    halos, blocks, mass = synth.single_halo(seed=8, n=20000, n_background=4000)
+    ctx, c, s, ref = run_both(halos, blocks, mass, rings=5, spokes=100, radial_bins=200,
+                              smoothing_window=61, levels=2)
+    assert_parity(ctx, c, s, ref, 1)
+
+
+def test_window_not_smaller_than_bins():
+    """Smooth returns ok=false for every LoS when bins <= window (smooth.go:51-53):
+    no valid point, NewKDETree panics in the reference -> status no_points."""
+    halos, blocks, mass = synth.single_halo(seed=9, n=5000, n_background=1000)
+    ctx, c, s, ref = run_both(halos, blocks, mass, rings=3, radial_bins=64, smoothing_window=121)
+    assert s[0] == 2
+    assert_parity(ctx, c, s, ref, 1)
+
+
+def test_zero_min_mass_like_gadget2():
+    """Gadget-2's reader never sets MinMass (io/gadget2.go:327,402): the
+    background density is 0, empty bins give ln 0 = -Inf and NaNs run through
+    the FIR; the ok-mask and every finite value must still agree."""
+    halos, blocks, mass = synth.single_halo(seed=10, n=20000, n_background=0)
+    ctx, c, s, ref = run_both(halos, blocks, 0.0, rings=6)
+    assert_parity(ctx, c, s, ref, 1)
+
+
+def test_skipped_and_empty_halos():
+    """r200m <= 0 is skipped (cmd/shell.go:535-538); a halo with no particle
+    in range has no valid LoS."""
+    halos, blocks, mass = synth.make_box(11, 40.0, 1, 20000, 0, 1, centers=[[20, 20, 20]], radii=[1.0])
+    halos = np.concatenate([halos, [[5.0, 5.0, 5.0, 0.5], [10.0, 10.0, 10.0, -1.0], [1.0, 2.0, 3.0, 0.0]]])
+    params = api.default_params(seed=1337, rings=4)
+    ctx, c, s = api.run_shell(params, mass, halos, blocks)
+    assert list(s) == [0, 2, 1, 1]
+    assert np.all(c[1:] == 0) and np.any(c[0] != 0)
+    cfg = po.ShellConfig.default(seed=1337, rings=4)
+    ref = po.shell_run(cfg, mass, halos, blocks)
+    assert list(ref["ok"]) == [1, 0, 0, 0]
+    assert np.all(np.abs(c[0] - ref["coeffs"][0]) <= RTOL * np.abs(ref["coeffs"][0]).max())
+
+
+def test_bitwise_reproducible_and_batch_invariant():
+    """int64 fixed-point bins make the result independent of atomic order, of
+    the batch a halo lands in and of how its hit list is chunked."""
+    halos, blocks, mass = synth.make_box(12, 30.0, 4, 15000, 20000, 2, r200m_range=(0.6, 0.9))
+    params = api.default_params(seed=1337, rings=16)
+    _, c1, s1 = api.run_shell(params, mass, halos, blocks)
+    _, c2, s2 = api.run_shell(params, mass, halos, blocks)
+    assert np.array_equal(c1, c2) and np.array_equal(s1, s2)
+    # one halo alone: different batch composition and chunking of its hit lists
+    for h in range(len(halos)):
+        ctx = api.ShellContext(params)
+        ctx.begin_snapshot(blocks[0], mass)
+        ctx.add_halos(halos)
+        owned = np.zeros(len(halos), bool)
+        owned[h] = True
+        ctx.set_owned(owned)
+        for b in blocks:
+            ctx.push_block(b)
+        c, s = ctx.finish_snapshot()
+        assert s[h] == s1[h] and all(s[k] == 6 for k in range(len(halos)) if k != h)
+        assert np.array_equal(c[h], c1[h])
+
+
+def test_device_and_host_push_agree():
+    import torch
+    halos, blocks, mass = synth.make_box(13, 20.0, 2, 12000, 8000, 2, r200m_range=(0.6, 0.9))
+    params = api.default_params(seed=1337, rings=8)
+    _, c_host, s_host = api.run_shell(params, mass, halos, blocks)
+    ctx = api.ShellContext(params)
+    ctx.begin_snapshot(blocks[0], mass)
+    ctx.add_halos(halos)
+    for b in blocks:
+        ctx.push_block_device(b, torch.from_numpy(b["xs"]).cuda(), torch.from_numpy(b["ms"]).cuda())
+    c_dev, s_dev = ctx.finish_snapshot()
+    assert np.array_equal(c_host, c_dev) and np.array_equal(s_host, s_dev)
+
+
+def test_ring_tables_match_oracle():
+    params = api.default_params(seed=987654321, rings=100)
+    ctx = api.ShellContext(params)
+    norms, rot, irot = ctx.ring_tables()
+    assert np.array_equal(norms, po.norm_vecs(987654321, 100))
+    h = po.Halo(norms, [0, 0, 0], 0.3, 3.0, 8, 8)
+    for r in range(100):
+        assert np.array_equal(rot[r], h.rot(r)) and np.array_equal(irot[r], h.irot(r))
+
+
+def test_validation_messages_follow_the_reference():
+    """ShellConfig.validate, cmd/shell.go:143-187."""
+    with pytest.raises(api.ShellfishError, match=r"The variable 'Rings' was set to 0\."):
+        api.ShellContext(api.default_params(rings=0))
+    with pytest.raises(api.ShellfishError, match=r"The variable 'RMinMult' was set to 3, but the variable 'RMaxMult' was set to 3\."):
+        api.ShellContext(api.default_params(r_min_mult=3.0))
+    with pytest.raises(api.ShellfishError, match="PercentileProfile"):
+        api.ShellContext(api.default_params(percentile_profile=1))
+
+
+def test_call_order_errors():
+    ctx = api.ShellContext(api.default_params(rings=3))
+    with pytest.raises(api.ShellfishError):
+        ctx.add_halos(np.array([[1.0, 1, 1, 1]]))
+    with pytest.raises(api.ShellfishError):
+        ctx.finish_snapshot()
+
+
+def test_full_size_properties():
+    """BASELINE-size halos (1e5 particles, default config) without the oracle:
+    counters are consistent and the recovered shell tracks the planted
+    truncation radius."""
+    halos, blocks, mass = synth.config2(seed=21, n_halos=12, n_total=12 * 140000, box=60.0, cells=3)
+    params = api.default_params(seed=1337)
+    ctx, c, s = api.run_shell(params, mass, halos, blocks)
+    st = ctx.stats()
+    assert np.all(s == 0)
+    assert st["n_candidates"] == sum(ctx.candidate_count(h) for h in range(len(halos)))
+    assert st["n_intersections"] > 500 * st["n_candidates"]
+    for h in range(len(halos)):
+        rsp = ctx.rsp(h)
+        assert np.isfinite(rsp).mean() > 0.9
+        # synth truncates the NFW body at 1.25 R200m (triaxial, so a band)
+        assert 0.8 < np.nanmedian(rsp) / halos[h, 3] < 1.7
+        # c_000 is the mean shell radius
+        assert 0.8 < c[h, 0] / halos[h, 3] < 1.7
