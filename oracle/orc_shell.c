@@ -96,26 +96,27 @@ static int calc_coeffs(orc_halo *h, const orc_shell_config *c, double *cs,
     double *profRs = (double *)malloc(sizeof(double) * (size_t)bins * 4);
     double *profRhos = profRs + bins, *smoothRhos = profRhos + bins,
            *smoothDerivs = smoothRhos + bins;
-    double *Rs = (double *)malloc(sizeof(double) * (size_t)n * 6);
-    double *Phis = Rs + n, *vRs = Phis + n, *vPhis = vRs + n, *fRs = vPhis + n,
-           *fPhis = fRs + n;
-    uint8_t *oks = (uint8_t *)malloc((size_t)n);
     size_t cap = (size_t)rings * (size_t)n;
+    /* the RingBuffers of loop(), cmd/shell.go:294-297: Rs/Phis/Oks per ring */
+    double *Rs = (double *)malloc(sizeof(double) * cap * 2);
+    double *Phis = Rs + cap;
+    uint8_t *oks = (uint8_t *)malloc(cap);
+    double *vRs = (double *)malloc(sizeof(double) * (size_t)n * 4);
+    double *vPhis = vRs + n, *fRs = vPhis + n, *fPhis = fRs + n;
     double *fX = (double *)malloc(sizeof(double) * cap * 3);
     double *fY = fX + cap, *fZ = fY + cap;
     int64_t nPts = 0;
     int rc = 0;
 
     orc_halo_get_rs(h, profRs);
+    /* calcCoeffs first runs Clear + Splashback on every ring (:614-617) ... */
     for (int ring = 0; ring < rings && rc == 0; ring++) {
-        /* RingBuffer.Clear + Splashback */
         for (int i = 0; i < n; i++) {
-            oks[i] = 0; Rs[i] = 0; Phis[i] = 0;
+            size_t at = (size_t)ring * n + i;
+            oks[at] = 0; Rs[at] = 0; Phis[at] = 0;
             orc_halo_get_rhos(h, ring, i, profRhos);
-            if (profOut)
-                memcpy(profOut + ((size_t)ring * n + i) * bins, profRhos,
-                       sizeof(double) * (size_t)bins);
-            if (rspOut) rspOut[(size_t)ring * n + i] = NAN;
+            if (profOut) memcpy(profOut + at * bins, profRhos, sizeof(double) * (size_t)bins);
+            if (rspOut) rspOut[at] = NAN;
             if (bins <= window) continue; /* Smooth returns ok=false */
             double dx = log(profRs[1]) - log(profRs[0]);
             const double *k, *kd;
@@ -125,17 +126,20 @@ static int calc_coeffs(orc_halo *h, const orc_shell_config *c, double *cs,
             if (!orc_splashback_radius(profRs, smoothRhos, smoothDerivs, bins,
                                        c->losSlopeCutoff, &r))
                 continue;
-            oks[i] = 1;
-            Rs[i] = r;
-            Phis[i] = orc_halo_phi(h, i);
-            if (Phis[i] < 0) Phis[i] += 3.14159265358979323846264338327950288;
-            if (rspOut) rspOut[(size_t)ring * n + i] = r;
+            oks[at] = 1;
+            Rs[at] = r;
+            Phis[at] = orc_halo_phi(h, i);
+            if (Phis[at] < 0) Phis[at] += 3.14159265358979323846264338327950288;
+            if (rspOut) rspOut[at] = r;
         }
-        if (rc) break;
-        /* FilterPoints for this ring */
+    }
+    /* ... then FilterPoints walks the rings in order (penna.go:119-162) */
+    for (int ring = 0; ring < rings && rc == 0; ring++) {
         int nv = 0;
-        for (int i = 0; i < n; i++)
-            if (oks[i]) { vRs[nv] = Rs[i]; vPhis[nv] = Phis[i]; nv++; }
+        for (int i = 0; i < n; i++) {
+            size_t at = (size_t)ring * n + i;
+            if (oks[at]) { vRs[nv] = Rs[at]; vPhis[nv] = Phis[at]; nv++; }
+        }
         int kept = orc_filter_ring(vRs, vPhis, nv, (int)c->levels,
                                    orc_halo_rmax(h) / c->eta, fRs, fPhis, NULL, NULL);
         if (kept < 0) { rc = kept; break; }
@@ -153,7 +157,7 @@ static int calc_coeffs(orc_halo *h, const orc_shell_config *c, double *cs,
         if (nPts == 0) rc = ORC_E_NO_POINTS;
         else if (orc_penna_coeffs(fX, fY, fZ, nPts, order, order, 2, cs)) rc = -1;
     }
-    free(fX); free(oks); free(Rs); free(profRs);
+    free(fX); free(vRs); free(oks); free(Rs); free(profRs);
     return rc;
 }
 
