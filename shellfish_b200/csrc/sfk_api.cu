@@ -75,7 +75,7 @@ struct sfk_ctx {
     bool taps = false;
 
     DevBuf<float> dNorms, dRots, dIrots;
-    DevBuf<double> dCos, dSin, dPhi, dTaps0, dTaps1;
+    DevBuf<double> dCos, dSin, dPhi, dTaps0, dTaps1, dBinInvG;
     bool tapsReady = false;  // Sav-Gol kernels cached for the process, smooth.go:84-96
 
     // snapshot state
@@ -302,6 +302,7 @@ int sfk_create(sfk_ctx **out, const sfk_params *params) {
     CU(ctx->dCos.upload(ctx->tab.ringCos, ctx->stream));
     CU(ctx->dSin.upload(ctx->tab.ringSin, ctx->stream));
     CU(ctx->dPhi.upload(ctx->tab.ringPhi, ctx->stream));
+    CU(ctx->dBinInvG.upload(ctx->tab.binInvG, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SFK_OK;
 }
@@ -348,8 +349,8 @@ int sfk_add_halos(sfk_ctx *ctx, int64_t n, const double *x, const double *y, con
             const double vol0 = kFourPiOver3 * rad0 * rad0 * rad0;
             const double rho = ((static_cast<double>(ctx->minMass) * static_cast<double>(sf * sf * sf)) / vol0) / rhoM;
             h.defaultRho = rho * p.background_rho_mult;
-            h.rMax = rMax;
-            h.x0 = static_cast<float>(x[i]); h.y0 = static_cast<float>(y[i]); h.z0 = static_cast<float>(z[i]);
+            h.rMax = rMax; h.rMin = rMin; h.invRMin = 1.0 / rMin;
+            h.x0 =static_cast<float>(x[i]); h.y0 = static_cast<float>(y[i]); h.z0 = static_cast<float>(z[i]);
             // loadSphereVecs, cmd/shell.go:442 and Halo.Intersect, halo.go:148-152
             h.rad = rMax * p.r_kernel_mult / p.r_max_mult;
             h.rad2 = h.rad * h.rad;
@@ -498,7 +499,7 @@ int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) {
     ctx->timer.begin(ST_HITS, st);
     CU(ctx->dPieces.upload(all, st));
     CU(launch_hits(ctx->dPieces.p, static_cast<int>(all.size()), ctx->dCands.p, ctx->dHalos.p,
-                   ctx->dNorms.p, ctx->dRots.p, R, n, ctx->tab.dPhi, ctx->dHitCount.p,
+                   ctx->dNorms.p, ctx->dRots.p, ctx->dCos.p, ctx->dSin.p, R, n, ctx->tab.dPhi, ctx->dHitCount.p,
                    ctx->dRhoMax.p, nullptr, nullptr, nullptr, nullptr, false, st));
     ctx->stats.launches++;
     ctx->timer.end(ST_HITS, st);
@@ -586,7 +587,7 @@ int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) {
         // pass 2: ring-frame hit records
         ctx->timer.begin(ST_HITS, st);
         CU(launch_hits(ctx->dPieces.p, static_cast<int>(pieces.size()), ctx->dCands.p, ctx->dHalos.p,
-                       ctx->dNorms.p, ctx->dRots.p, R, n, ctx->tab.dPhi, ctx->dHitCount.p,
+                       ctx->dNorms.p, ctx->dRots.p, ctx->dCos.p, ctx->dSin.p, R, n, ctx->tab.dPhi, ctx->dHitCount.p,
                        ctx->dRhoMax.p, ctx->dHitOffset.p, ctx->dHitCursor.p, ctx->dHaloSlot.p,
                        ctx->dRecs.p, true, st));
         ctx->stats.launches++;
@@ -600,9 +601,12 @@ int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) {
         ba.grid = ctx->dGrid.p; ba.nIntersections = ctx->dNInter.p;
         ba.tapInsert = ctx->dTapInsert.p; ba.tapStart = ctx->dTapStart.p; ba.tapEnd = ctx->dTapEnd.p;
         ba.rings = R; ba.spokes = n; ba.bins = B;
-        // split long hit lists when there are too few CTAs to fill 148 SMs x 3
+        ba.binInvG = ctx->dBinInvG.p;
+        ba.invDr = 1.0 / ctx->tab.dr0;
+        ba.cK = static_cast<float>(0.6931471805599453 / ctx->tab.dr0);
+        // split long hit lists when there are too few CTAs to fill 148 SMs x 2 for a few waves
         const int64_t ctas = static_cast<int64_t>((n + kTileLos - 1) / kTileLos) * R * nb;
-        ba.chunks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(64, (148 * 3 * 4 + ctas - 1) / ctas)));
+        ba.chunks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(64, (148 * 2 * 4 + ctas - 1) / ctas)));
         ctx->timer.begin(ST_BIN, st);
         CU(launch_bin(ba, nb, ctx->taps, st));
         ctx->stats.launches++; ctx->stats.bin_launches++;

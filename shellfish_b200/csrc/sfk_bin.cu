@@ -1,0 +1,329 @@
+// sfk_bin.cu -- the binning kernel: per-LoS chords of every (particle, ring)
+// hit and ProfileRing.Insert (los/halo.go:241-277, profile_ring.go:92-120).
+//
+// One CTA per (LoS tile of 32, ring, halo[, chunk of the hit list]).  The
+// tile's 32 x bins accumulators are 64-bit fixed point, split into lo/hi
+// 32-bit words in shared memory so that native 32-bit shared atomics can be
+// used (64-bit shared atomics are CAS loops on sm_100).  One producer warp
+// streams the ring's hit records through a 3-stage TMA (cp.async.bulk +
+// mbarrier) ring; 12 consumer warps each own one 32-record group per stage:
+// lanes first test the 32 records against the tile in parallel (ballot), then
+// the warp walks the overlapping records with lane == line of sight.
+//
+// Arithmetic.  Everything that DECIDES something is evaluated literally, in
+// the reference's operation order with no FMA contraction (-fmad=false): the
+// impact parameter b, b^2, the two radicands and their signs (NaN semantics of
+// twoValIntrDist / oneValIntrDist), and all comparisons.  ln() and the
+// division by dr of profile_ring.go:100 are replaced by a table of bin edges
+// g[k] = exp(k*dr): bin = k with g[k] <= r/rMin < g[k+1], rem = ln(r/(rMin
+// g[k]))/dr from a degree-7 log1p series (|t| < 0.0091, error < 1e-16).  This
+// differs from floor((ln r - lowR)/dr) only when r lies within a few ulp of a
+// bin edge, the same class of tie on which Go's and glibc's ln already differ.
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "sfk_kernels.cuh"
+
+namespace sfk {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep, do not spin
+            : "memory");
+    } while (!done);
+}
+// 1-D bulk copy global -> shared through the TMA unit, completion on mbarrier.
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// sqrt for x >= 0: MUFU.RSQ64H seed, two Newton steps on 1/sqrt, one residual
+// correction (<= 1 ulp, branch free).  Callers test the sign first.
+__device__ __forceinline__ double sqrt_pos(double x) {
+    x += 1e-300;   // 0 -> 1e-150 (still far below every rMin); exact no-op for x > 1e-284
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    double s = x * y;
+    const double r = fma(-s, s, x);
+    return fma(r, 0.5 * y, s);
+}
+
+// Bin index and fractional position of radius r, rMin < r < rMax
+// (profile_ring.go:100-101: Modf((ln r - lowR)/dr)).
+__device__ __forceinline__ void bin_of(double r, double invRMin, float cK, double invDr,
+                                       const double *sInvG, int bins, int &idx, double &rem) {
+    const double u = r * invRMin;
+    // float32 view of u (u in [1, rMax/rMin]): rebias the exponent, keep 20 mantissa bits
+    const float uf = __int_as_float((__double2hiint(u) - 0x38000000) << 3);
+    int k = static_cast<int>(__log2f(uf) * cK);
+    k = min(max(k, 0), bins - 1);
+    const double t = fma(u, sInvG[k], -1.0);   // r / (rMin g[k]) - 1
+    double L = fma(t, 1.0 / 7.0, -1.0 / 6.0);
+    L = fma(L, t, 0.2);
+    L = fma(L, t, -0.25);
+    L = fma(L, t, 1.0 / 3.0);
+    L = fma(L, t, -0.5);
+    L = fma(L, t, 1.0);
+    double x = (L * t) * invDr;
+    if (x < 0.0) { k -= 1; x += 1.0; }
+    else if (x >= 1.0) { k += 1; x -= 1.0; }
+    if (k < 0) { k = 0; x = 0.0; }
+    idx = k;
+    rem = x;
+}
+
+// 64-bit two's-complement add into split lo/hi words.
+__device__ __forceinline__ void acc_add(uint32_t *lo, uint32_t *hi, int idx, long long v) {
+    const uint32_t vlo = static_cast<uint32_t>(v);
+    const uint32_t vhi = static_cast<uint32_t>(static_cast<unsigned long long>(v) >> 32);
+    const uint32_t old = atomicAdd(&lo[idx], vlo);
+    const uint32_t add = vhi + ((old + vlo) < old ? 1u : 0u);
+    if (add) atomicAdd(&hi[idx], add);
+}
+
+template <bool TAPS>
+__global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    const int bins = a.bins;
+    const int stride = bins + 1;   // +1: slot for a start/end edge that lands exactly on rMax
+    HitRec *stage = reinterpret_cast<HitRec *>(smemRaw);                          // [kBinStages][kStageRecs]
+    uint64_t *full = reinterpret_cast<uint64_t *>(stage + kBinStages * kStageRecs);   // [kBinStages]
+    uint64_t *empty = full + kBinStages;                                          // [kBinStages]
+    unsigned int *nextGroup = reinterpret_cast<unsigned int *>(empty + kBinStages);   // 8-byte slot
+    double *sInvG = reinterpret_cast<double *>(empty + kBinStages + 1);           // [bins + 1]
+    uint32_t *lo = reinterpret_cast<uint32_t *>(sInvG + bins + 1);                // [32][stride]
+    uint32_t *hi = lo + kTileLos * stride;
+
+    const int nTiles = (a.spokes + kTileLos - 1) / kTileLos;
+    const int tile = blockIdx.x % nTiles;
+    const int chunk = blockIdx.x / nTiles;
+    const int ring = blockIdx.y;
+    const int slot = blockIdx.z;
+    const int haloIdx = a.batchHalos[slot];
+    const HaloDev &h = a.halos[haloIdx];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int k = threadIdx.x; k < 2 * kTileLos * stride; k += kBinThreads) lo[k] = 0;
+    for (int k = threadIdx.x; k <= bins; k += kBinThreads) sInvG[k] = a.binInvG[k];
+    if (threadIdx.x == 0) {
+        *nextGroup = 0;
+        for (int s = 0; s < kBinStages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kBinConsumers);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // this CTA's share of the ring's records, in whole stages
+    const size_t hr = static_cast<size_t>(slot) * a.rings + ring;
+    const int64_t total = a.hitCount[hr];
+    const int64_t nStages = (total + kStageRecs - 1) / kStageRecs;
+    const int64_t s0 = nStages * chunk / a.chunks, s1 = nStages * (chunk + 1) / a.chunks;
+    const HitRec *src = a.recs + a.hitOffset[hr];
+    unsigned nIns = 0;
+
+    if (warp == kBinConsumers) {
+        // ---- producer: keep the TMA ring full
+        if (lane == 0) {
+            for (int64_t s = s0; s < s1; s++) {
+                const int64_t t = s - s0;
+                const int buf = static_cast<int>(t % kBinStages);
+                if (t >= kBinStages) mbar_wait(&empty[buf], static_cast<uint32_t>((t / kBinStages - 1) & 1));
+                const int64_t first = s * kStageRecs;
+                const uint32_t cnt = static_cast<uint32_t>(min(static_cast<int64_t>(kStageRecs), total - first));
+                const uint32_t bytes = cnt * static_cast<uint32_t>(sizeof(HitRec));
+                mbar_expect_tx(&full[buf], bytes);
+                tma_load_1d(stage + buf * kStageRecs, src + first, bytes, &full[buf]);
+            }
+        }
+    } else {
+        // ---- consumers: lane == line of sight of the tile
+        const int t0 = tile * kTileLos, t1 = t0 + kTileLos;
+        const int los = t0 + lane;
+        const bool losOk = los < a.spokes;
+        const double rc = losOk ? a.ringCos[los] : 0.0, rs = losOk ? a.ringSin[los] : 0.0;
+        const double rMin = h.rMin, rMax = h.rMax, invRMin = h.invRMin, rad2 = h.rad2;
+        const double invDr = a.invDr;
+        const float cK = a.cK;
+        uint32_t *rowLo = lo + lane * stride, *rowHi = hi + lane * stride;
+        const size_t tapRow = (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes + los;
+
+        // 32-record groups are handed out in order from a shared counter, so a
+        // warp that drew light groups simply takes more of them
+        const unsigned nGroups = static_cast<unsigned>((s1 - s0) * kBinConsumers);
+        for (;;) {
+            unsigned g = 0;
+            if (lane == 0) g = atomicAdd(nextGroup, 1u);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g >= nGroups) break;
+            const unsigned t = g / kBinConsumers;          // stage sequence number
+            const int gi = static_cast<int>(g - t * kBinConsumers);
+            const int64_t s = s0 + t;
+            const int buf = static_cast<int>(t % kBinStages);
+            mbar_wait(&full[buf], (t / kBinStages) & 1u);
+            const int cnt = static_cast<int>(min(static_cast<int64_t>(kStageRecs), total - s * kStageRecs));
+            const HitRec *grp = stage + buf * kStageRecs + gi * 32;
+            // which of these 32 records touch this tile?
+            bool ov = false;
+            if (gi * 32 + lane < cnt) {
+                const HitRec *p = grp + lane;
+                const uint32_t r01 = p->r01, r23 = p->r23;
+                ov = (static_cast<int>(r01 & 0xffffu) < t1 && static_cast<int>(r01 >> 16) > t0) ||
+                     (static_cast<int>(r23 & 0xffffu) < t1 && static_cast<int>(r23 >> 16) > t0);
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, ov);
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const HitRec rec = grp[j];   // broadcast read
+                const bool isA = rec.caseA != 0;
+                const bool active =
+                    losOk && ((los >= static_cast<int>(rec.r01 & 0xffffu) && los < static_cast<int>(rec.r01 >> 16)) ||
+                              (los >= static_cast<int>(rec.r23 & 0xffffu) && los < static_cast<int>(rec.r23 >> 16)));
+                if (!active) continue;
+                // literal geometry of insertToRing, los/halo.go:233-262
+                const double cx = rec.cx, cy = rec.cy, cz = rec.cz;
+                const double projDist2 = cx * cx + cy * cy;
+                double projRad2 = rad2 - cz * cz;
+                if (projRad2 < 0) projRad2 = 0;
+                const double b = cy * rc - cx * rs;
+                const double b2 = b * b;
+                const double m2 = projDist2 - b2;   // radicand of midDist / cMidDist
+                const double d2 = projRad2 - b2;    // radicand of diff / radMidDist
+                double rLo, rHi;
+                bool hasStart, endNaN = false;
+                if (isA) {
+                    // oneValIntrDist, halo.go:337-346; Insert(-Inf, ln rHi)
+                    hasStart = false;
+                    rLo = 0.0;
+                    if (m2 < 0 || d2 < 0) {
+                        endNaN = true;   // sqrt of a negative: end = NaN, the plateau never ends
+                        rHi = 0.0;
+                    } else {
+                        const double dir = cx * rc + cy * rs;
+                        const double radMid = sqrt_pos(d2), cMid = sqrt_pos(m2);
+                        rHi = dir > 0 ? radMid + cMid : radMid - cMid;
+                    }
+                } else {
+                    // twoValIntrDist, halo.go:324-329; NaN -> skipped at :262
+                    if (!(m2 >= 0) || !(d2 >= 0)) continue;
+                    const double mid = sqrt_pos(m2), diff = sqrt_pos(d2);
+                    rLo = mid - diff;
+                    rHi = mid + diff;
+                    hasStart = true;
+                }
+                // ProfileRing.Insert, profile_ring.go:92-120, with ln monotone:
+                // end <= lowR <=> rHi <= rMin, start >= highR <=> rLo >= rMax, ...
+                if (!endNaN && rHi <= rMin) continue;
+                if (hasStart && rLo >= rMax) continue;
+                nIns++;
+                if (TAPS) atomicAdd(&a.tapInsert[tapRow], 1u);
+                const long long Q = __double2ll_rn(rec.rhoS);
+                if (hasStart && rLo > rMin) {
+                    int idx; double rem;
+                    bin_of(rLo, invRMin, cK, invDr, sInvG, bins, idx, rem);
+                    const long long q1 = __double2ll_rn(rec.rhoS * rem);
+                    acc_add(rowLo, rowHi, idx, Q - q1);
+                    if (idx < bins - 1) acc_add(rowLo, rowHi, idx + 1, q1);
+                    if (TAPS && idx < bins) atomicAdd(&a.tapStart[tapRow * bins + idx], 1u);
+                } else {
+                    acc_add(rowLo, rowHi, 0, Q);
+                    if (TAPS) atomicAdd(&a.tapStart[tapRow * bins], 1u);
+                }
+                if (!endNaN && rHi < rMax) {
+                    int idx; double rem;
+                    bin_of(rHi, invRMin, cK, invDr, sInvG, bins, idx, rem);
+                    const long long q1 = __double2ll_rn(rec.rhoS * rem);
+                    acc_add(rowLo, rowHi, idx, q1 - Q);
+                    if (idx < bins - 1) acc_add(rowLo, rowHi, idx + 1, -q1);
+                    if (TAPS && idx < bins) atomicAdd(&a.tapEnd[tapRow * bins + idx], 1u);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[buf]);
+        }
+        // the "particle-ray intersections" metric
+        unsigned tot = nIns;
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0 && tot) atomicAdd(&a.nIntersections[haloIdx], static_cast<unsigned long long>(tot));
+    }
+    __syncthreads();
+
+    // flush the tile: [LoS][bin] rows, coalesced over bins
+    unsigned long long *g = a.grid + (static_cast<size_t>(slot) * a.rings + ring) * a.spokes * bins;
+    for (int k = threadIdx.x; k < kTileLos * stride; k += kBinThreads) {
+        const int l = k / stride, bin = k - l * stride;
+        const int gl = tile * kTileLos + l;
+        if (gl >= a.spokes) continue;
+        const unsigned long long v = (static_cast<unsigned long long>(hi[k]) << 32) | lo[k];
+        if (v == 0) continue;
+        if (bin < bins) {
+            atomicAdd(&g[static_cast<size_t>(gl) * bins + bin], v);
+        } else if (gl + 1 < a.spokes) {
+            // index == bins lands in the next LoS's first bin (derivs is one slice)
+            atomicAdd(&g[static_cast<size_t>(gl + 1) * bins], v);
+        }
+    }
+}
+
+}  // namespace
+
+size_t bin_smem_bytes(int bins) {
+    return sizeof(HitRec) * kBinStages * kStageRecs + (2 * kBinStages + 1) * sizeof(uint64_t) +
+           sizeof(double) * (bins + 1) + sizeof(uint32_t) * 2 * kTileLos * (bins + 1);
+}
+
+cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s) {
+    if (nb <= 0) return cudaSuccess;
+    const size_t smem = bin_smem_bytes(a.bins);
+    static bool attrSet[2] = {false, false};
+    if (!attrSet[taps]) {
+        cudaError_t e = taps ? cudaFuncSetAttribute(bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                             : cudaFuncSetAttribute(bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attrSet[taps] = true;
+    }
+    const int nTiles = (a.spokes + kTileLos - 1) / kTileLos;
+    dim3 grid(nTiles * a.chunks, a.rings, nb);
+    if (taps) bin_kernel<true><<<grid, kBinThreads, smem, s>>>(a);
+    else bin_kernel<false><<<grid, kBinThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace sfk

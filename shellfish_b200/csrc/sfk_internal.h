@@ -11,9 +11,12 @@ namespace sfk {
 
 // LoS per binning tile: one lane per LoS, one warp pass per (particle, ring).
 constexpr int kTileLos = 32;
-// Hit records staged per TMA bulk copy (32 B each).
-constexpr int kStageRecs = 128;
-constexpr int kBinThreads = 256;
+// Binning CTA: consumer warps + one TMA producer warp; every consumer warp
+// owns one 32-record group of each stage.
+constexpr int kBinConsumers = 12;
+constexpr int kBinThreads = (kBinConsumers + 1) * 32;
+constexpr int kStageRecs = kBinConsumers * 32;   // hit records per TMA stage (32 B each)
+constexpr int kBinStages = 3;
 constexpr int kKdeKnots = 100;   // rn and the KDE knot count, kde.go:70,99
 constexpr int kMaxLevels = 6;    // KDE tree depth supported on the device
 constexpr int kMaxOrder = 4;     // Penna order (2*order^2 <= 32 coefficients)
@@ -31,7 +34,7 @@ struct HaloDev {
     double sphVol;      // 4*pi/3*rad^3, cmd/shell.go:485
     double lowR, highR, dr;  // ProfileRing.Init, profile_ring.go:75-82
     double lrMin, dlr;       // GetRs, los/halo.go:365-366
-    double rMax;
+    double rMax, rMin, invRMin;
     double defaultRho;
     double scale;       // fixed-point scale 2^e of the bin accumulators
     double quantum;     // 2^-e
@@ -49,7 +52,7 @@ static_assert(sizeof(Cand) == 24, "Cand layout");
 struct alignas(16) HitRec {
     float cx, cy, cz;   // RotateVec output (float32), los/halo.go:231
     uint32_t caseA;     // projected circle contains the centre, :241
-    uint16_t r[4];      // idxRange result iLo1,iHi1,iLo2,iHi2, :284-310
+    uint32_t r01, r23;  // idxRange result packed lo | hi << 16: [iLo1,iHi1), [iLo2,iHi2), :284-310
     double rhoS;        // rho * scale
 };
 static_assert(sizeof(HitRec) == 32, "HitRec layout");
@@ -66,6 +69,10 @@ struct Tables {
     std::vector<float> norms, rots, irots;     // [rings][3], [rings][9] x2
     std::vector<double> ringCos, ringSin, ringPhi;  // [spokes]
     double dPhi;
+    // log-radial bin edges in units of rMin: binInvG[k] = 1/exp(k*dr0),
+    // dr0 = ln(RMaxMult/RMinMult)/RadialBins (profile_ring.go:81 for every halo)
+    std::vector<double> binInvG;
+    double dr0;
 };
 
 void build_tables(const sfk_params &p, Tables &t);

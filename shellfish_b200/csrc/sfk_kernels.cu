@@ -161,23 +161,76 @@ __device__ __forceinline__ uint16_t clamp_idx(long long v, int n) {
     return static_cast<uint16_t>(v < 0 ? 0 : (v > n ? n : v));
 }
 
+// Does any line of sight of a centre-containing hit run into the reference's
+// NaN path?  oneValIntrDist takes sqrt(dist2 - b*b) (los/halo.go:337-346); for
+// a LoS perpendicular to the projected position the radicand is ~0 and can
+// round below zero, the distance becomes NaN and ProfileRing.Insert then adds
+// rho to bin 0 and never subtracts it (profile_ring.go:93-110).  Only the LoS
+// nearest to phiC +- pi/2 can qualify; they are evaluated literally.
+__device__ bool has_nan_los(double cx, double cy, double projDist2, double phiC, double dPhi,
+                            int n, const double *ringCos, const double *ringSin) {
+    bool any = false;
+    for (int sgn = -1; sgn <= 1; sgn += 2) {
+        double ph = phiC + sgn * (kPi / 2);
+        if (ph < 0) ph += kTwoPi;
+        const long long i0 = __double2ll_rd(ph / dPhi);
+        for (int d = -1; d <= 2; d++) {
+            const int i = static_cast<int>(((i0 + d) % n + n) % n);
+            const double b = cy * ringCos[i] - cx * ringSin[i];
+            const double b2 = b * b;
+            if (projDist2 - b2 < 0) any = true;
+        }
+    }
+    return any;
+}
+
 // Ring-frame record of one (particle, ring) hit: insertToRing up to the LoS
-// loops, los/halo.go:231-258, and idxRange :284-310.
-__device__ __forceinline__ HitRec make_hit(const float *rot, const Cand &c, double rad2,
-                                           double dPhi, int n, double scale) {
-    HitRec r;
+// loops (los/halo.go:231-258) and idxRange (:284-310).  Returns false for a
+// hit that provably reaches no bin of any LoS -- the whole chord range
+// [dist - prad, dist + prad] lies below rMin or above rMax, so every
+// ProfileRing.Insert would take the early-out of profile_ring.go:93-95 -- and
+// for centre-containing hits narrows the LoS range (all n in the reference) to
+// a superset of the LoS whose far intersection exceeds rMin.  Both prunings
+// only drop work the reference does to no effect; the per-LoS evaluation in
+// bin_kernel stays literal.
+__device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, double dPhi, int n,
+                         const double *ringCos, const double *ringSin, HitRec &r) {
     rotate_vec(rot, c.vx, c.vy, c.vz, r.cx, r.cy, r.cz);
     const double cx = r.cx, cy = r.cy, cz = r.cz;
     const double projDist2 = cx * cx + cy * cy;
-    double projRad2 = rad2 - cz * cz;
+    double projRad2 = h.rad2 - cz * cz;
     if (projRad2 < 0) projRad2 = 0;
-    r.rhoS = c.rho * scale;
+    r.rhoS = c.rho * h.scale;
+    const double D = sqrt(projDist2), P = sqrt(projRad2);
+    const double rMinSafe = h.rMin * (1.0 - 1e-9), rMaxSafe = h.rMax * (1.0 + 1e-9);
     if (projRad2 > projDist2) {
+        // circle contains the centre: Insert(-Inf, ln rHi) on every LoS, halo.go:241-250
         r.caseA = 1;
-        r.r[0] = 0; r.r[1] = static_cast<uint16_t>(n); r.r[2] = 0; r.r[3] = 0;
-        return r;
+        r.r01 = static_cast<uint32_t>(n) << 16; r.r23 = 0;
+        const double phiC = atan2(cy, cx);
+        const bool dead = D + P <= rMinSafe;
+        const double cosT = (h.rMin * h.rMin + projDist2 - projRad2) / (2.0 * h.rMin * D);
+        const bool full = !(D > 1e-9 * h.rMin) || !(cosT > -1.0);
+        if (!dead && full) return true;
+        if (has_nan_los(cx, cy, projDist2, phiC, dPhi, n, ringCos, ringSin)) return true;
+        if (dead) return false;
+        // rHi(theta) > rMin  <=>  cos(theta) > cosT, theta = angle(LoS, projected position)
+        const double theta = acos(fmin(cosT, 1.0)) + 2.0 * dPhi + 1e-9;
+        if (theta >= kPi) return true;
+        double a = phiC - theta;
+        a -= kTwoPi * floor(a / kTwoPi);
+        const long long iLo = min(static_cast<long long>(n - 1), __double2ll_rd(a / dPhi));
+        const long long iHi = __double2ll_rd((a + 2.0 * theta) / dPhi) + 1;
+        if (iHi <= n) {
+            r.r01 = static_cast<uint32_t>(iLo) | static_cast<uint32_t>(iHi) << 16;
+        } else if (iHi - n < iLo) {
+            r.r01 = static_cast<uint32_t>(iLo) | static_cast<uint32_t>(n) << 16;
+            r.r23 = static_cast<uint32_t>(iHi - n) << 16;
+        }
+        return true;
     }
     r.caseA = 0;
+    if (D + P <= rMinSafe || D - P >= rMaxSafe) return false;
     const double alpha = asin(sqrt(projRad2 / projDist2));
     const double projPhi = atan2(cy, cx);
     const double phiLo = projPhi - alpha, phiHi = projPhi + alpha;
@@ -189,19 +242,19 @@ __device__ __forceinline__ HitRec make_hit(const float *rot, const Cand &c, doub
     } else {
         i0 = go_int(phiLo / dPhi); i1 = go_int(phiHi / dPhi) + 1; i2 = 0; i3 = 0;
     }
-    r.r[0] = clamp_idx(i0, n); r.r[1] = clamp_idx(i1, n);
-    r.r[2] = clamp_idx(i2, n); r.r[3] = clamp_idx(i3, n);
-    return r;
+    r.r01 = clamp_idx(i0, n) | static_cast<uint32_t>(clamp_idx(i1, n)) << 16;
+    r.r23 = clamp_idx(i2, n) | static_cast<uint32_t>(clamp_idx(i3, n)) << 16;
+    return true;
 }
 
-// One CTA per Piece (<= 256 candidates of one halo).  COUNT pass: hits per
+// One CTA per Piece (<= 256 candidates of one halo).  COUNT pass: records per
 // (halo, ring) and the halo's largest rho.  FILL pass: ring-frame records.
 template <bool FILL>
 __global__ void __launch_bounds__(kHitThreads)
 hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const float *norms,
-            const float *rots, int rings, int spokes, double dPhi, uint32_t *hitCount,
-            unsigned long long *rhoMaxBits, const int64_t *hitOffset, uint32_t *hitCursor,
-            const int32_t *haloSlot, HitRec *recs) {
+            const float *rots, const double *ringCos, const double *ringSin, int rings, int spokes,
+            double dPhi, uint32_t *hitCount, unsigned long long *rhoMaxBits, const int64_t *hitOffset,
+            uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs) {
     extern __shared__ unsigned char smemRaw[];
     float *sNorm = reinterpret_cast<float *>(smemRaw);                     // [rings][3]
     uint32_t *sCnt = reinterpret_cast<uint32_t *>(sNorm + 3 * rings);      // [rings]
@@ -216,17 +269,19 @@ hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const 
     c.vx = c.vy = c.vz = 0.f; c.halo = pc.halo; c.rho = 0.0;
     if (live) c = cands[pc.start + threadIdx.x];
     const double rad = h.rad;
-    // pass 1: count hits per ring
-    for (int ring = 0; ring < rings; ring++) {
-        // sphereIntersectRing, los/halo.go:218-224 (dot in float32)
-        const float d = (sNorm[3 * ring] * c.vx + sNorm[3 * ring + 1] * c.vy) + sNorm[3 * ring + 2] * c.vz;
-        const double dot = static_cast<double>(d);
-        const bool hit = live && dot < rad && dot > -rad;
-        const unsigned mask = __ballot_sync(0xffffffffu, hit);
-        if (mask && lane_id() == 0) atomicAdd(&sCnt[ring], __popc(mask));
-    }
-    __syncthreads();
     if (!FILL) {
+        // pass 1: records per ring
+        for (int ring = 0; ring < rings; ring++) {
+            // sphereIntersectRing, los/halo.go:218-224 (dot in float32)
+            const float d = (sNorm[3 * ring] * c.vx + sNorm[3 * ring + 1] * c.vy) + sNorm[3 * ring + 2] * c.vz;
+            const double dot = static_cast<double>(d);
+            bool hit = live && dot < rad && dot > -rad;
+            HitRec rec;
+            if (hit) hit = make_hit(rots + 9 * ring, c, h, dPhi, spokes, ringCos, ringSin, rec);
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (mask && lane_id() == 0) atomicAdd(&sCnt[ring], __popc(mask));
+        }
+        __syncthreads();
         for (int k = threadIdx.x; k < rings; k += kHitThreads)
             if (sCnt[k]) atomicAdd(&hitCount[static_cast<size_t>(pc.halo) * rings + k], sCnt[k]);
         // rho > 0: IEEE doubles order like unsigned integers
@@ -238,180 +293,24 @@ hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const 
         if (lane_id() == 0 && bits) atomicMax(&rhoMaxBits[pc.halo], bits);
         return;
     }
-    // reserve contiguous slots per ring for this piece
+    // pass 2: write the records; slots are claimed per warp and ring
     const int slot = haloSlot[pc.halo];
-    for (int k = threadIdx.x; k < rings; k += kHitThreads) {
-        const uint32_t cnt = sCnt[k];
-        sBase[k] = cnt ? atomicAdd(&hitCursor[static_cast<size_t>(slot) * rings + k], cnt) : 0u;
-        sCnt[k] = 0;
-    }
-    __syncthreads();
     for (int ring = 0; ring < rings; ring++) {
         const float d = (sNorm[3 * ring] * c.vx + sNorm[3 * ring + 1] * c.vy) + sNorm[3 * ring + 2] * c.vz;
         const double dot = static_cast<double>(d);
-        const bool hit = live && dot < rad && dot > -rad;
-        if (!hit) continue;
-        const uint32_t pos = sBase[ring] + atomicAdd(&sCnt[ring], 1u);
-        const HitRec rec = make_hit(rots + 9 * ring, c, h.rad2, dPhi, spokes, h.scale);
-        recs[hitOffset[static_cast<size_t>(slot) * rings + ring] + pos] = rec;
-    }
-}
-
-// ------------------------------------------------------------------ bin --
-
-// 64-bit two's-complement add into split lo/hi words with native 32-bit
-// shared-memory atomics (64-bit shared atomics are CAS loops on sm_100).
-__device__ __forceinline__ void acc_add(uint32_t *lo, uint32_t *hi, int idx, long long v) {
-    const uint32_t vlo = static_cast<uint32_t>(v);
-    const uint32_t vhi = static_cast<uint32_t>(static_cast<unsigned long long>(v) >> 32);
-    const uint32_t old = atomicAdd(&lo[idx], vlo);
-    const uint32_t carry = (old + vlo) < old ? 1u : 0u;
-    const uint32_t add = vhi + carry;
-    if (add) atomicAdd(&hi[idx], add);
-}
-
-// One CTA per (LoS tile, ring, halo[, chunk]).  The tile's 32 x bins fixed-
-// point accumulators live in shared memory; the ring's hit records stream in
-// through TMA bulk copies (double buffered); each warp takes one record at a
-// time and its 32 lanes are the tile's 32 lines of sight.
-template <bool TAPS>
-__global__ void __launch_bounds__(kBinThreads, 3) bin_kernel(BinArgs a) {
-    extern __shared__ __align__(128) unsigned char smemRaw[];
-    const int bins = a.bins;
-    const int stride = bins + 1;  // +1: slot for modf index == bins (profile_ring.go:102-106)
-    HitRec *stage = reinterpret_cast<HitRec *>(smemRaw);                  // [2][kStageRecs]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + 2 * kStageRecs); // [2]
-    uint32_t *lo = reinterpret_cast<uint32_t *>(bars + 2);                // [32][stride]
-    uint32_t *hi = lo + kTileLos * stride;
-
-    const int nTiles = (a.spokes + kTileLos - 1) / kTileLos;
-    const int tile = blockIdx.x % nTiles;
-    const int chunk = blockIdx.x / nTiles;
-    const int ring = blockIdx.y;
-    const int slot = blockIdx.z;
-    const int haloIdx = a.batchHalos[slot];
-    const HaloDev &h = a.halos[haloIdx];
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    constexpr int kWarps = kBinThreads / 32;
-
-    for (int k = threadIdx.x; k < 2 * kTileLos * stride; k += kBinThreads) lo[k] = 0;
-    if (threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        fence_barrier_init();
-    }
-    __syncthreads();
-
-    // this CTA's share of the ring's records
-    const size_t hr = static_cast<size_t>(slot) * a.rings + ring;
-    const int64_t total = a.hitCount[hr];
-    const int64_t nStages = (total + kStageRecs - 1) / kStageRecs;
-    const int64_t s0 = nStages * chunk / a.chunks, s1 = nStages * (chunk + 1) / a.chunks;
-    const HitRec *src = a.recs + a.hitOffset[hr];
-
-    auto issue = [&](int64_t s) {
-        const int64_t first = s * kStageRecs;
-        const uint32_t cnt = static_cast<uint32_t>(min(static_cast<int64_t>(kStageRecs), total - first));
-        const uint32_t bytes = cnt * sizeof(HitRec);
-        uint64_t *bar = &bars[(s - s0) & 1];
-        mbar_expect_tx(bar, bytes);
-        tma_load_1d(stage + ((s - s0) & 1) * kStageRecs, src + first, bytes, bar);
-    };
-    if (threadIdx.x == 0 && s0 < s1) issue(s0);
-
-    const int los = tile * kTileLos + lane;
-    const bool losOk = los < a.spokes;
-    const double rc = losOk ? a.ringCos[los] : 0.0, rs = losOk ? a.ringSin[los] : 0.0;
-    const double lowR = h.lowR, highR = h.highR, dr = h.dr, rad2 = h.rad2;
-    uint32_t *rowLo = lo + lane * stride, *rowHi = hi + lane * stride;
-    const size_t tapRow = (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes + los;
-    unsigned nIns = 0;
-
-    for (int64_t s = s0; s < s1; s++) {
-        const int buf = (s - s0) & 1;
-        if (threadIdx.x == 0 && s + 1 < s1) issue(s + 1);
-        mbar_wait(&bars[buf], ((s - s0) >> 1) & 1);
-        const int cnt = static_cast<int>(min(static_cast<int64_t>(kStageRecs), total - s * kStageRecs));
-        const HitRec *st = stage + buf * kStageRecs;
-        for (int r = warp; r < cnt; r += kWarps) {
-            const HitRec rec = st[r];
-            bool active;
-            if (rec.caseA) active = losOk;
-            else active = losOk && ((los >= rec.r[0] && los < rec.r[1]) || (los >= rec.r[2] && los < rec.r[3]));
-            if (!__any_sync(0xffffffffu, active)) continue;
-            if (!active) continue;
-            const double cx = rec.cx, cy = rec.cy, cz = rec.cz;
-            const double projDist2 = cx * cx + cy * cy;
-            double projRad2 = rad2 - cz * cz;
-            if (projRad2 < 0) projRad2 = 0;
-            const double b = cy * rc - cx * rs;   // impact parameter, halo.go:246,260
-            const double b2 = b * b;
-            double start, end;
-            if (rec.caseA) {
-                // oneValIntrDist, halo.go:337-346
-                const double dir = cx * rc + cy * rs;
-                const double radMid = sqrt(projRad2 - b2);
-                const double cMid = sqrt(projDist2 - b2);
-                const double rHi = dir > 0 ? radMid + cMid : radMid - cMid;
-                start = -INFINITY;
-                end = log(rHi);
-            } else {
-                // twoValIntrDist, halo.go:324-329
-                const double mid = sqrt(projDist2 - b2);
-                const double diff = sqrt(projRad2 - b2);
-                const double rLo = mid - diff, rHi = mid + diff;
-                if (isnan(rLo) || isnan(rHi)) continue;
-                start = log(rLo);
-                end = log(rHi);
-            }
-            // ProfileRing.Insert, profile_ring.go:92-120
-            if (end <= lowR || start >= highR) continue;
-            nIns++;
-            if (TAPS) atomicAdd(&a.tapInsert[tapRow], 1u);
-            const double rho = rec.rhoS;
-            if (start > lowR) {
-                const double xq = (start - lowR) / dr;
-                const double fidx = trunc(xq);
-                const double rem = xq - fidx;   // math.Modf
-                const int idx = static_cast<int>(fidx);
-                acc_add(rowLo, rowHi, idx, __double2ll_rn(rho * (1 - rem)));
-                if (idx < bins - 1) acc_add(rowLo, rowHi, idx + 1, __double2ll_rn(rho * rem));
-                if (TAPS && idx < bins) atomicAdd(&a.tapStart[tapRow * bins + idx], 1u);
-            } else {
-                acc_add(rowLo, rowHi, 0, __double2ll_rn(rho));
-                if (TAPS) atomicAdd(&a.tapStart[tapRow * bins], 1u);
-            }
-            if (end < highR) {
-                const double xq = (end - lowR) / dr;
-                const double fidx = trunc(xq);
-                const double rem = xq - fidx;
-                const int idx = static_cast<int>(fidx);
-                acc_add(rowLo, rowHi, idx, -__double2ll_rn(rho * (1 - rem)));
-                if (idx < bins - 1) acc_add(rowLo, rowHi, idx + 1, -__double2ll_rn(rho * rem));
-                if (TAPS && idx < bins) atomicAdd(&a.tapEnd[tapRow * bins + idx], 1u);
-            }
-        }
-        __syncthreads();  // everyone is done with stage `buf` before it is refilled
-    }
-
-    // intersections counter (the "particle-ray intersections" metric)
-    unsigned tot = nIns;
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0 && tot) atomicAdd(&a.nIntersections[haloIdx], static_cast<unsigned long long>(tot));
-
-    // flush the tile: [LoS][bin] rows, coalesced over bins
-    unsigned long long *g = a.grid + (static_cast<size_t>(slot) * a.rings + ring) * a.spokes * bins;
-    for (int k = threadIdx.x; k < kTileLos * stride; k += kBinThreads) {
-        const int l = k / stride, bin = k - l * stride;
-        const int gl = tile * kTileLos + l;
-        if (gl >= a.spokes) continue;
-        const unsigned long long v = (static_cast<unsigned long long>(hi[k]) << 32) | lo[k];
-        if (v == 0) continue;
-        if (bin < bins) {
-            atomicAdd(&g[static_cast<size_t>(gl) * bins + bin], v);
-        } else if (gl + 1 < a.spokes) {
-            // idx == bins lands in the next LoS's first bin (derivs is one slice)
-            atomicAdd(&g[static_cast<size_t>(gl + 1) * bins], v);
+        bool hit = live && dot < rad && dot > -rad;
+        HitRec rec;
+        if (hit) hit = make_hit(rots + 9 * ring, c, h, dPhi, spokes, ringCos, ringSin, rec);
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask == 0) continue;
+        const int leader = __ffs(mask) - 1;
+        uint32_t base = 0;
+        if (lane_id() == leader)
+            base = atomicAdd(&hitCursor[static_cast<size_t>(slot) * rings + ring], __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (hit) {
+            const uint32_t pos = base + __popc(mask & ((1u << lane_id()) - 1u));
+            recs[hitOffset[static_cast<size_t>(slot) * rings + ring] + pos] = rec;
         }
     }
 }
@@ -985,6 +884,7 @@ cudaError_t launch_cull(const CullArgs &a, bool fill, cudaStream_t s) {
 
 cudaError_t launch_hits(const Piece *pieces, int nPieces, const Cand *cands,
                         const HaloDev *halos, const float *norms, const float *rots,
+                        const double *ringCos, const double *ringSin,
                         int rings, int spokes, double dPhi, uint32_t *hitCount,
                         unsigned long long *rhoMaxBits, const int64_t *hitOffset,
                         uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs,
@@ -992,35 +892,15 @@ cudaError_t launch_hits(const Piece *pieces, int nPieces, const Cand *cands,
     if (nPieces <= 0) return cudaSuccess;
     const size_t smem = sizeof(float) * 3 * rings + sizeof(uint32_t) * 2 * rings;
     if (fill)
-        hits_kernel<true><<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rots, rings,
-                                                             spokes, dPhi, hitCount, rhoMaxBits,
-                                                             hitOffset, hitCursor, haloSlot, recs);
+        hits_kernel<true><<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rots, ringCos,
+                                                             ringSin, rings, spokes, dPhi, hitCount,
+                                                             rhoMaxBits, hitOffset, hitCursor, haloSlot,
+                                                             recs);
     else
-        hits_kernel<false><<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rots, rings,
-                                                              spokes, dPhi, hitCount, rhoMaxBits,
-                                                              hitOffset, hitCursor, haloSlot, recs);
-    return cudaGetLastError();
-}
-
-size_t bin_smem_bytes(int bins) {
-    return sizeof(HitRec) * 2 * kStageRecs + 2 * sizeof(uint64_t) +
-           sizeof(uint32_t) * 2 * kTileLos * (bins + 1);
-}
-
-cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s) {
-    if (nb <= 0) return cudaSuccess;
-    const size_t smem = bin_smem_bytes(a.bins);
-    static bool attrSet[2] = {false, false};
-    if (!attrSet[taps]) {
-        cudaError_t e = taps ? cudaFuncSetAttribute(bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                             : cudaFuncSetAttribute(bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attrSet[taps] = true;
-    }
-    const int nTiles = (a.spokes + kTileLos - 1) / kTileLos;
-    dim3 grid(nTiles * a.chunks, a.rings, nb);
-    if (taps) bin_kernel<true><<<grid, kBinThreads, smem, s>>>(a);
-    else bin_kernel<false><<<grid, kBinThreads, smem, s>>>(a);
+        hits_kernel<false><<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rots, ringCos,
+                                                              ringSin, rings, spokes, dPhi, hitCount,
+                                                              rhoMaxBits, hitOffset, hitCursor, haloSlot,
+                                                              recs);
     return cudaGetLastError();
 }
 

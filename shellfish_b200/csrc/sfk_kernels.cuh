@@ -32,6 +32,9 @@ struct BinArgs {
     unsigned long long *grid;   // [nb][rings][spokes][bins] int64 fixed point
     unsigned long long *nIntersections; // [nHalo]
     uint32_t *tapInsert, *tapStart, *tapEnd; // TAPS only, indexed by halo
+    const double *binInvG;      // [bins+1] 1/exp(k*dr): reciprocal bin edges in units of rMin
+    double invDr;               // 1/dr
+    float cK;                   // bins per octave: ln 2 / dr
     int rings, spokes, bins, chunks;
 };
 
@@ -77,6 +80,7 @@ struct FitArgs {
 cudaError_t launch_cull(const CullArgs &a, bool fill, cudaStream_t s);
 cudaError_t launch_hits(const Piece *pieces, int nPieces, const Cand *cands,
                         const HaloDev *halos, const float *norms, const float *rots,
+                        const double *ringCos, const double *ringSin,
                         int rings, int spokes, double dPhi, uint32_t *hitCount,
                         unsigned long long *rhoMaxBits, const int64_t *hitOffset,
                         uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs,

@@ -126,6 +126,10 @@ void build_tables(const sfk_params &p, Tables &t) {
         t.ringCos[i] = std::cos(t.ringPhi[i]);
     }
     t.dPhi = 1 / static_cast<double>(n) * kTwoPi;
+    const int bins = static_cast<int>(p.radial_bins);
+    t.dr0 = std::log(p.r_max_mult / p.r_min_mult) / static_cast<double>(bins);
+    t.binInvG.resize(bins + 1);
+    for (int k = 0; k <= bins; k++) t.binInvG[k] = 1.0 / std::exp(static_cast<double>(k) * t.dr0);
 }
 
 // Go's math.Pow: repeated squaring on frexp mantissas (rounds more than once,
