@@ -498,9 +498,8 @@ int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) {
     // pass 1: hits per (halo, ring) and largest rho per halo
     ctx->timer.begin(ST_HITS, st);
     CU(ctx->dPieces.upload(all, st));
-    CU(launch_hits(ctx->dPieces.p, static_cast<int>(all.size()), ctx->dCands.p, ctx->dHalos.p,
-                   ctx->dNorms.p, ctx->dRots.p, ctx->dCos.p, ctx->dSin.p, R, n, ctx->tab.dPhi, ctx->dHitCount.p,
-                   ctx->dRhoMax.p, nullptr, nullptr, nullptr, nullptr, false, st));
+    CU(launch_hit_count(ctx->dPieces.p, static_cast<int>(all.size()), ctx->dCands.p, ctx->dHalos.p,
+                        ctx->dNorms.p, R, ctx->dHitCount.p, ctx->dRhoMax.p, st));
     ctx->stats.launches++;
     ctx->timer.end(ST_HITS, st);
     std::vector<uint32_t> hitCount(static_cast<size_t>(nHalo) * R);
@@ -587,15 +586,14 @@ int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) {
         // pass 2: ring-frame hit records
         ctx->timer.begin(ST_HITS, st);
         CU(launch_hits(ctx->dPieces.p, static_cast<int>(pieces.size()), ctx->dCands.p, ctx->dHalos.p,
-                       ctx->dNorms.p, ctx->dRots.p, ctx->dCos.p, ctx->dSin.p, R, n, ctx->tab.dPhi, ctx->dHitCount.p,
-                       ctx->dRhoMax.p, ctx->dHitOffset.p, ctx->dHitCursor.p, ctx->dHaloSlot.p,
-                       ctx->dRecs.p, true, st));
+                       ctx->dNorms.p, ctx->dRots.p, ctx->dCos.p, ctx->dSin.p, R, n, ctx->tab.dPhi,
+                       ctx->dHitOffset.p, ctx->dHitCursor.p, ctx->dHaloSlot.p, ctx->dRecs.p, st));
         ctx->stats.launches++;
         ctx->timer.end(ST_HITS, st);
 
         // binning: Halo.Insert for every queued particle
         BinArgs ba{};
-        ba.recs = ctx->dRecs.p; ba.hitOffset = ctx->dHitOffset.p; ba.hitCount = ctx->dBatchHitCount.p;
+        ba.recs = ctx->dRecs.p; ba.hitOffset = ctx->dHitOffset.p; ba.hitCount = ctx->dHitCursor.p;
         ba.halos = ctx->dHalos.p; ba.batchHalos = ctx->dBatchHalos.p;
         ba.ringCos = ctx->dCos.p; ba.ringSin = ctx->dSin.p;
         ba.grid = ctx->dGrid.p; ba.nIntersections = ctx->dNInter.p;

@@ -247,77 +247,250 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
     return true;
 }
 
-// One CTA per Piece (<= 256 candidates of one halo).  COUNT pass: records per
-// (halo, ring) and the halo's largest rho.  FILL pass: ring-frame records.
-template <bool FILL>
+// Raw hit counts: one CTA per Piece (<= 256 candidates of one halo).  Counts
+// sphereIntersectRing successes per (halo, ring) -- an upper bound of the
+// records hits_kernel will write -- and the halo's largest rho.
 __global__ void __launch_bounds__(kHitThreads)
-hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const float *norms,
-            const float *rots, const double *ringCos, const double *ringSin, int rings, int spokes,
-            double dPhi, uint32_t *hitCount, unsigned long long *rhoMaxBits, const int64_t *hitOffset,
-            uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs) {
+hit_count_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const float *norms,
+                 int rings, uint32_t *hitCount, unsigned long long *rhoMaxBits) {
     extern __shared__ unsigned char smemRaw[];
     float *sNorm = reinterpret_cast<float *>(smemRaw);                     // [rings][3]
     uint32_t *sCnt = reinterpret_cast<uint32_t *>(sNorm + 3 * rings);      // [rings]
-    uint32_t *sBase = sCnt + rings;                                        // [rings]
     const Piece pc = pieces[blockIdx.x];
-    const HaloDev &h = halos[pc.halo];
     for (int k = threadIdx.x; k < 3 * rings; k += kHitThreads) sNorm[k] = norms[k];
-    for (int k = threadIdx.x; k < rings; k += kHitThreads) { sCnt[k] = 0; sBase[k] = 0; }
+    for (int k = threadIdx.x; k < rings; k += kHitThreads) sCnt[k] = 0;
     __syncthreads();
     const bool live = threadIdx.x < pc.count;
     Cand c;
     c.vx = c.vy = c.vz = 0.f; c.halo = pc.halo; c.rho = 0.0;
     if (live) c = cands[pc.start + threadIdx.x];
-    const double rad = h.rad;
-    if (!FILL) {
-        // pass 1: records per ring
-        for (int ring = 0; ring < rings; ring++) {
-            // sphereIntersectRing, los/halo.go:218-224 (dot in float32)
-            const float d = (sNorm[3 * ring] * c.vx + sNorm[3 * ring + 1] * c.vy) + sNorm[3 * ring + 2] * c.vz;
-            const double dot = static_cast<double>(d);
-            bool hit = live && dot < rad && dot > -rad;
-            HitRec rec;
-            if (hit) hit = make_hit(rots + 9 * ring, c, h, dPhi, spokes, ringCos, ringSin, rec);
-            const unsigned mask = __ballot_sync(0xffffffffu, hit);
-            if (mask && lane_id() == 0) atomicAdd(&sCnt[ring], __popc(mask));
-        }
-        __syncthreads();
-        for (int k = threadIdx.x; k < rings; k += kHitThreads)
-            if (sCnt[k]) atomicAdd(&hitCount[static_cast<size_t>(pc.halo) * rings + k], sCnt[k]);
-        // rho > 0: IEEE doubles order like unsigned integers
-        unsigned long long bits = live ? static_cast<unsigned long long>(__double_as_longlong(c.rho)) : 0ull;
-        for (int o = 16; o > 0; o >>= 1) {
-            unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
-            bits = other > bits ? other : bits;
-        }
-        if (lane_id() == 0 && bits) atomicMax(&rhoMaxBits[pc.halo], bits);
-        return;
-    }
-    // pass 2: write the records; slots are claimed per warp and ring
-    const int slot = haloSlot[pc.halo];
+    const double rad = halos[pc.halo].rad;
     for (int ring = 0; ring < rings; ring++) {
+        // sphereIntersectRing, los/halo.go:218-224 (dot in float32)
         const float d = (sNorm[3 * ring] * c.vx + sNorm[3 * ring + 1] * c.vy) + sNorm[3 * ring + 2] * c.vz;
         const double dot = static_cast<double>(d);
-        bool hit = live && dot < rad && dot > -rad;
-        HitRec rec;
-        if (hit) hit = make_hit(rots + 9 * ring, c, h, dPhi, spokes, ringCos, ringSin, rec);
+        const bool hit = live && dot < rad && dot > -rad;
         const unsigned mask = __ballot_sync(0xffffffffu, hit);
-        if (mask == 0) continue;
-        const int leader = __ffs(mask) - 1;
-        uint32_t base = 0;
-        if (lane_id() == leader)
-            base = atomicAdd(&hitCursor[static_cast<size_t>(slot) * rings + ring], __popc(mask));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (hit) {
-            const uint32_t pos = base + __popc(mask & ((1u << lane_id()) - 1u));
-            recs[hitOffset[static_cast<size_t>(slot) * rings + ring] + pos] = rec;
+        if (mask && lane_id() == 0) atomicAdd(&sCnt[ring], __popc(mask));
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < rings; k += kHitThreads)
+        if (sCnt[k]) atomicAdd(&hitCount[static_cast<size_t>(pc.halo) * rings + k], sCnt[k]);
+    // rho > 0: IEEE doubles order like unsigned integers
+    unsigned long long bits = live ? static_cast<unsigned long long>(__double_as_longlong(c.rho)) : 0ull;
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+        bits = other > bits ? other : bits;
+    }
+    if (lane_id() == 0 && bits) atomicMax(&rhoMaxBits[pc.halo], bits);
+}
+
+constexpr int kHitRingChunk = 64;   // rings per queue pass: 256 x 64 entries of 4 B = 64 KB
+
+// Ring-frame records: one CTA per Piece.  Phase 1 tests every (candidate,
+// ring) pair of a ring chunk and queues the hits in shared memory; phase 2
+// walks the queue with all lanes busy (the hit rate is ~1/3, so computing the
+// geometry in place would idle two lanes out of three), builds the record and
+// claims a slot of the (halo, ring) list.
+__global__ void __launch_bounds__(kHitThreads)
+hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const float *norms,
+            const float *rots, const double *ringCos, const double *ringSin, int rings, int spokes,
+            double dPhi, const int64_t *hitOffset, uint32_t *hitCursor, const int32_t *haloSlot,
+            HitRec *recs) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    Cand *sCand = reinterpret_cast<Cand *>(smemRaw);                          // [256]
+    float *sNorm = reinterpret_cast<float *>(sCand + kHitThreads);            // [rings][3]
+    uint32_t *queue = reinterpret_cast<uint32_t *>(sNorm + 3 * rings);        // [256 * kHitRingChunk]
+    __shared__ uint32_t qCount;
+    const Piece pc = pieces[blockIdx.x];
+    const HaloDev &h = halos[pc.halo];
+    const int slot = haloSlot[pc.halo];
+    for (int k = threadIdx.x; k < 3 * rings; k += kHitThreads) sNorm[k] = norms[k];
+    const bool live = threadIdx.x < pc.count;
+    Cand c;
+    c.vx = c.vy = c.vz = 0.f; c.halo = pc.halo; c.rho = 0.0;
+    if (live) c = cands[pc.start + threadIdx.x];
+    sCand[threadIdx.x] = c;
+    const double rad = h.rad;
+    for (int r0 = 0; r0 < rings; r0 += kHitRingChunk) {
+        const int r1 = min(rings, r0 + kHitRingChunk);
+        if (threadIdx.x == 0) qCount = 0;
+        __syncthreads();
+        for (int ring = r0; ring < r1; ring++) {
+            const float d = (sNorm[3 * ring] * c.vx + sNorm[3 * ring + 1] * c.vy) + sNorm[3 * ring + 2] * c.vz;
+            const double dot = static_cast<double>(d);
+            const bool hit = live && dot < rad && dot > -rad;
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (mask == 0) continue;
+            const int leader = __ffs(mask) - 1;
+            uint32_t base = 0;
+            if (lane_id() == leader) base = atomicAdd(&qCount, __popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (hit) queue[base + __popc(mask & ((1u << lane_id()) - 1u))] = threadIdx.x | (ring << 8);
         }
+        __syncthreads();
+        const uint32_t nq = qCount;
+        for (uint32_t e0 = threadIdx.x & ~31u; e0 < nq; e0 += kHitThreads) {
+            const uint32_t e = e0 + lane_id();
+            const uint32_t q = e < nq ? queue[e] : 0u;
+            const int ring = static_cast<int>(q >> 8);
+            HitRec rec;
+            const bool alive = e < nq && make_hit(rots + 9 * ring, sCand[q & 0xffu], h, dPhi, spokes,
+                                                  ringCos, ringSin, rec);
+            // one slot claim per (warp, ring): queue order keeps a ring's hits together
+            const unsigned peers = __match_any_sync(0xffffffffu, alive ? ring : -1 - static_cast<int>(lane_id()));
+            if (alive) {
+                const size_t hr = static_cast<size_t>(slot) * rings + ring;
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (static_cast<int>(lane_id()) == leader) base = atomicAdd(&hitCursor[hr], __popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                recs[hitOffset[hr] + base + __popc(peers & ((1u << lane_id()) - 1u))] = rec;
+            }
+        }
+        __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------ los --
 
 constexpr int kLosWarps = 8;
+
+__device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8000000000000ll); }
+
+// Fast path of los_kernel for bins == 32 * PER: every lane keeps its PER
+// consecutive bins in registers.  The two Savitzky-Golay FIRs run as a sliding
+// window: per tap one shared-memory read of ln(rho) per lane (conflict-free
+// permuted layout) and one broadcast read of the tap pair feed 2*PER FMAs.
+// The steepest-slope search is the running-minimum scan of
+// splashback_radius.go:30-58 done as a warp prefix-min plus an arg-min.
+template <int PER>
+__global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int nb) {
+    extern __shared__ double sm[];
+    constexpr int B = 32 * PER;
+    constexpr int ROW = 33;
+    const int window = a.window;
+    double2 *taps = reinterpret_cast<double2 *>(sm);                       // [window] (value, deriv)
+    double *ys = sm + 2 * window + (threadIdx.x >> 5) * (PER * ROW);       // permuted: (i % PER) * 33 + i / PER
+    for (int k = threadIdx.x; k < window; k += blockDim.x) taps[k] = make_double2(a.valTaps[k], a.derivTaps[k]);
+    __syncthreads();
+    const int lane = lane_id();
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kLosWarps + (threadIdx.x >> 5);
+    const int64_t perHalo = static_cast<int64_t>(a.rings) * a.spokes;
+    if (gw >= perHalo * nb) return;
+    const int slot = static_cast<int>(gw / perHalo);
+    const int64_t rl = gw - slot * perHalo;
+    const int haloIdx = a.batchHalos[slot];
+    const HaloDev &h = a.halos[haloIdx];
+    const longlong2 *g = reinterpret_cast<const longlong2 *>(a.grid + (static_cast<size_t>(slot) * perHalo + rl) * B);
+
+    // Retrieve + GetRhos: exact int64 prefix sum, clamp, ln
+    long long d[PER];
+#pragma unroll
+    for (int c = 0; c < PER; c += 2) {
+        const longlong2 v = g[(lane * PER + c) / 2];
+        d[c] = v.x; d[c + 1] = v.y;
+    }
+    long long run = 0;
+#pragma unroll
+    for (int c = 0; c < PER; c++) run += d[c];
+    long long incl = run;
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    long long acc = incl - run;
+    const double q = h.quantum, bg = h.defaultRho;
+#pragma unroll
+    for (int c = 0; c < PER; c++) {
+        acc += d[c];
+        double rho = static_cast<double>(acc) * q;
+        if (rho < bg) rho = bg;
+        if (a.profiles) a.profiles[(static_cast<size_t>(haloIdx) * perHalo + rl) * B + lane * PER + c] = rho;
+        ys[c * ROW + lane] = log(rho);
+    }
+    __syncwarp();
+
+    double *out = a.rsp + static_cast<size_t>(haloIdx) * perHalo + rl;
+    if (B <= window) {   // Smooth: ok = false, smooth.go:51-53
+        if (lane == 0) *out = nan_f64();
+        return;
+    }
+    // ConvolveAt with Extension (filter.go:104-161), taps ascending.  w[m % PER]
+    // holds ln rho at clamp(i0 - center + m) for m = j .. j + PER - 1.
+    const int center = window / 2;
+    const int i0 = lane * PER;
+    auto ysAt = [&](int idx) {
+        idx = idx < 0 ? 0 : (idx >= B ? B - 1 : idx);
+        return ys[(idx % PER) * ROW + idx / PER];
+    };
+    double w[PER], s0[PER], s1[PER];
+#pragma unroll
+    for (int c = 0; c < PER; c++) { s0[c] = 0.0; s1[c] = 0.0; }
+#pragma unroll
+    for (int m = 0; m < PER - 1; m++) w[m] = ysAt(i0 - center + m);
+    for (int jb = 0; jb < window; jb += PER) {
+#pragma unroll
+        for (int jj = 0; jj < PER; jj++) {
+            const int j = jb + jj;
+            if (j < window) {
+                w[(jj + PER - 1) % PER] = ysAt(i0 - center + j + PER - 1);
+                const double2 tp = taps[j];
+#pragma unroll
+                for (int c = 0; c < PER; c++) {
+                    const double x = w[(c + jj) % PER];
+                    s0[c] = fma(x, tp.x, s0[c]);
+                    s1[c] = fma(x, tp.y, s1[c]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < PER; c++) s0[c] = exp(s0[c]);   // vals; s1 = d ln rho / d ln r
+
+    // SplashbackRadius: rhoMin starts at vals[0]; i = 1 .. B-2 is a candidate when
+    // vals[i] < min(vals[0..i-1]) and derivs[i] is a strict local minimum below dLim.
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const double v0 = __shfl_sync(0xffffffffu, s0[0], 0);
+    double lmin = inf;
+#pragma unroll
+    for (int c = 0; c < PER; c++) { const double v = s0[c]; if (v < lmin) lmin = v; }
+    double excl = lmin;   // inclusive prefix min over lanes, then shifted
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, excl, o);
+        if (lane >= o && up < excl) excl = up;
+    }
+    excl = __shfl_up_sync(0xffffffffu, excl, 1);
+    if (lane == 0) excl = inf;
+    const double dPrev = __shfl_up_sync(0xffffffffu, s1[PER - 1], 1);
+    const double dNext = __shfl_down_sync(0xffffffffu, s1[0], 1);
+    double runMin = excl, best = a.dLim;
+    int bestI = -1;
+#pragma unroll
+    for (int c = 0; c < PER; c++) {
+        const int i = i0 + c;
+        const double v = s0[c];
+        if (i == 0) { runMin = v; continue; }           // rhoMin := rhos[0]
+        if (v < runMin) {
+            runMin = v;
+            const double dm = c == 0 ? dPrev : s1[c == 0 ? 0 : c - 1];
+            const double dp = c == PER - 1 ? dNext : s1[c == PER - 1 ? c : c + 1];
+            const double dd = s1[c];
+            if (i < B - 1 && dd < dp && dd < dm && dd < best) { best = dd; bestI = i; }
+        }
+    }
+    // vals[0] NaN poisons the running minimum: no candidate anywhere
+    if (v0 != v0) bestI = -1;
+    // arg-min over lanes, earliest index on ties (sequential update semantics)
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bestI, o);
+        const bool take = oi >= 0 && (bestI < 0 || ob < best || (ob == best && oi < bestI));
+        if (take) { best = ob; bestI = oi; }
+    }
+    if (lane == 0)
+        *out = bestI < 0 ? nan_f64() : exp(h.lrMin + h.dlr * (static_cast<double>(bestI) + 0.5));
+}
 
 // One warp per line of sight: prefix sum of the bin deltas (exact, in int64),
 // clamp to the background density, ln, two Savitzky-Golay FIRs with edge
@@ -882,27 +1055,34 @@ cudaError_t launch_cull(const CullArgs &a, bool fill, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+cudaError_t launch_hit_count(const Piece *pieces, int nPieces, const Cand *cands, const HaloDev *halos,
+                             const float *norms, int rings, uint32_t *hitCount,
+                             unsigned long long *rhoMaxBits, cudaStream_t s) {
+    if (nPieces <= 0) return cudaSuccess;
+    const size_t smem = sizeof(float) * 3 * rings + sizeof(uint32_t) * rings;
+    hit_count_kernel<<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rings, hitCount, rhoMaxBits);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_hits(const Piece *pieces, int nPieces, const Cand *cands,
                         const HaloDev *halos, const float *norms, const float *rots,
                         const double *ringCos, const double *ringSin,
-                        int rings, int spokes, double dPhi, uint32_t *hitCount,
-                        unsigned long long *rhoMaxBits, const int64_t *hitOffset,
-                        uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs,
-                        bool fill, cudaStream_t s) {
+                        int rings, int spokes, double dPhi, const int64_t *hitOffset,
+                        uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs, cudaStream_t s) {
     if (nPieces <= 0) return cudaSuccess;
-    const size_t smem = sizeof(float) * 3 * rings + sizeof(uint32_t) * 2 * rings;
-    if (fill)
-        hits_kernel<true><<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rots, ringCos,
-                                                             ringSin, rings, spokes, dPhi, hitCount,
-                                                             rhoMaxBits, hitOffset, hitCursor, haloSlot,
-                                                             recs);
-    else
-        hits_kernel<false><<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rots, ringCos,
-                                                              ringSin, rings, spokes, dPhi, hitCount,
-                                                              rhoMaxBits, hitOffset, hitCursor, haloSlot,
-                                                              recs);
+    const size_t smem = sizeof(Cand) * kHitThreads + sizeof(float) * 3 * rings +
+                        sizeof(uint32_t) * kHitThreads * kHitRingChunk;
+    static bool attrSet = false;
+    if (!attrSet) {
+        cudaError_t e = cudaFuncSetAttribute(hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attrSet = true;
+    }
+    hits_kernel<<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rots, ringCos, ringSin, rings,
+                                                   spokes, dPhi, hitOffset, hitCursor, haloSlot, recs);
     return cudaGetLastError();
 }
+
 
 cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s) {
     if (nb <= 0) return cudaSuccess;
@@ -915,7 +1095,12 @@ cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s) {
     }
     const int64_t warps = static_cast<int64_t>(nb) * a.rings * a.spokes;
     const unsigned grid = static_cast<unsigned>((warps + kLosWarps - 1) / kLosWarps);
-    los_kernel<<<grid, kLosWarps * 32, smem, s>>>(a, nb);
+    if (a.bins == 256) {
+        const size_t fsmem = sizeof(double) * (2 * a.window + kLosWarps * 8 * 33);
+        los_kernel_fast<8><<<grid, kLosWarps * 32, fsmem, s>>>(a, nb);
+    } else {
+        los_kernel<<<grid, kLosWarps * 32, smem, s>>>(a, nb);
+    }
     return cudaGetLastError();
 }
 

@@ -78,13 +78,14 @@ struct FitArgs {
 };
 
 cudaError_t launch_cull(const CullArgs &a, bool fill, cudaStream_t s);
+cudaError_t launch_hit_count(const Piece *pieces, int nPieces, const Cand *cands, const HaloDev *halos,
+                             const float *norms, int rings, uint32_t *hitCount,
+                             unsigned long long *rhoMaxBits, cudaStream_t s);
 cudaError_t launch_hits(const Piece *pieces, int nPieces, const Cand *cands,
                         const HaloDev *halos, const float *norms, const float *rots,
                         const double *ringCos, const double *ringSin,
-                        int rings, int spokes, double dPhi, uint32_t *hitCount,
-                        unsigned long long *rhoMaxBits, const int64_t *hitOffset,
-                        uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs,
-                        bool fill, cudaStream_t s);
+                        int rings, int spokes, double dPhi, const int64_t *hitOffset,
+                        uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs, cudaStream_t s);
 cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s);
 cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s);
 cudaError_t launch_filter(const FilterArgs &a, int nb, cudaStream_t s);
