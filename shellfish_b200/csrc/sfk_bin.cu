@@ -6,9 +6,11 @@
 // 32-bit words in shared memory so that native 32-bit shared atomics can be
 // used (64-bit shared atomics are CAS loops on sm_100).  One producer warp
 // streams the ring's hit records through a 3-stage TMA (cp.async.bulk +
-// mbarrier) ring; 12 consumer warps each own one 32-record group per stage:
-// lanes first test the 32 records against the tile in parallel (ballot), then
-// the warp walks the overlapping records with lane == line of sight.
+// mbarrier) ring; 12 consumer warps draw 32-record groups from a shared
+// counter.  For a group, lanes first clip the 32 records' LoS ranges against
+// the tile in parallel, a warp scan turns the clipped lengths into a list of
+// (record, LoS) pairs, and the pairs are then processed 32 at a time with one
+// pair per lane, so every lane does useful work whatever the range widths.
 //
 // Arithmetic.  Everything that DECIDES something is evaluated literally, in
 // the reference's operation order with no FMA contraction (-fmad=false): the
@@ -16,7 +18,7 @@
 // twoValIntrDist / oneValIntrDist), and all comparisons.  ln() and the
 // division by dr of profile_ring.go:100 are replaced by a table of bin edges
 // g[k] = exp(k*dr): bin = k with g[k] <= r/rMin < g[k+1], rem = ln(r/(rMin
-// g[k]))/dr from a degree-7 log1p series (|t| < 0.0091, error < 1e-16).  This
+// g[k]))/dr from a degree-6 log1p series (|t| < 0.0092, error < 1e-14).  This
 // differs from floor((ln r - lowR)/dr) only when r lies within a few ulp of a
 // bin edge, the same class of tie on which Go's and glibc's ln already differ.
 #include <cstdint>
@@ -67,18 +69,17 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
         : "memory");
 }
 
-// sqrt for x >= 0: MUFU.RSQ64H seed, two Newton steps on 1/sqrt, one residual
-// correction (<= 1 ulp, branch free).  Callers test the sign first.
+// sqrt for x >= 0: MUFU.RSQ64H seed (~2^-22), one Newton step on 1/sqrt
+// (~2^-44), one residual correction of the root (<= 1 ulp), branch free.
+// Callers test the sign first.
 __device__ __forceinline__ double sqrt_pos(double x) {
     x += 1e-300;   // 0 -> 1e-150 (still far below every rMin); exact no-op for x > 1e-284
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double hx = 0.5 * x;
-    double e = fma(-hx * y, y, 0.5);
+    const double e = fma(-hx * y, y, 0.5);
     y = fma(y, e, y);
-    e = fma(-hx * y, y, 0.5);
-    y = fma(y, e, y);
-    double s = x * y;
+    const double s = x * y;
     const double r = fma(-s, s, x);
     return fma(r, 0.5 * y, s);
 }
@@ -88,21 +89,20 @@ __device__ __forceinline__ double sqrt_pos(double x) {
 __device__ __forceinline__ void bin_of(double r, double invRMin, float cK, double invDr,
                                        const double *sInvG, int bins, int &idx, double &rem) {
     const double u = r * invRMin;
-    // float32 view of u (u in [1, rMax/rMin]): rebias the exponent, keep 20 mantissa bits
+    // float32 view of u (u in [1, rMax/rMin]): rebias the exponent, keep 20 mantissa bits.
+    // The estimate is biased low by 1e-3 bins (its error is < 3e-4), so the true
+    // bin is k or k + 1 and the series argument t is never negative.
     const float uf = __int_as_float((__double2hiint(u) - 0x38000000) << 3);
-    int k = static_cast<int>(__log2f(uf) * cK);
-    k = min(max(k, 0), bins - 1);
+    int k = static_cast<int>(fmaf(__log2f(uf), cK, -1.0e-3f));
+    k = min(k, bins - 1);
     const double t = fma(u, sInvG[k], -1.0);   // r / (rMin g[k]) - 1
-    double L = fma(t, 1.0 / 7.0, -1.0 / 6.0);
-    L = fma(L, t, 0.2);
+    double L = fma(t, -1.0 / 6.0, 0.2);
     L = fma(L, t, -0.25);
     L = fma(L, t, 1.0 / 3.0);
     L = fma(L, t, -0.5);
     L = fma(L, t, 1.0);
     double x = (L * t) * invDr;
-    if (x < 0.0) { k -= 1; x += 1.0; }
-    else if (x >= 1.0) { k += 1; x -= 1.0; }
-    if (k < 0) { k = 0; x = 0.0; }
+    if (x >= 1.0) { k += 1; x -= 1.0; }
     idx = k;
     rem = x;
 }
@@ -125,8 +125,10 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     uint64_t *full = reinterpret_cast<uint64_t *>(stage + kBinStages * kStageRecs);   // [kBinStages]
     uint64_t *empty = full + kBinStages;                                          // [kBinStages]
     unsigned int *nextGroup = reinterpret_cast<unsigned int *>(empty + kBinStages);   // 8-byte slot
-    double *sInvG = reinterpret_cast<double *>(empty + kBinStages + 1);           // [bins + 1]
-    uint32_t *lo = reinterpret_cast<uint32_t *>(sInvG + bins + 1);                // [32][stride]
+    double2 *sTrig = reinterpret_cast<double2 *>(empty + kBinStages + 2);         // [32] (cos, sin), 16-byte aligned
+    double *sInvG = reinterpret_cast<double *>(sTrig + kTileLos);                 // [bins + 1]
+    uint32_t *sPair = reinterpret_cast<uint32_t *>(sInvG + bins + 1);             // [consumers][64]: prefix, meta
+    uint32_t *lo = sPair + kBinConsumers * 64;                                    // [32][stride]
     uint32_t *hi = lo + kTileLos * stride;
 
     const int nTiles = (a.spokes + kTileLos - 1) / kTileLos;
@@ -137,9 +139,15 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     const int haloIdx = a.batchHalos[slot];
     const HaloDev &h = a.halos[haloIdx];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = tile * kTileLos;
+    const int t1 = min(t0 + kTileLos, a.spokes);
 
     for (int k = threadIdx.x; k < 2 * kTileLos * stride; k += kBinThreads) lo[k] = 0;
     for (int k = threadIdx.x; k <= bins; k += kBinThreads) sInvG[k] = a.binInvG[k];
+    if (threadIdx.x < kTileLos) {
+        const int l = min(t0 + static_cast<int>(threadIdx.x), a.spokes - 1);
+        sTrig[threadIdx.x] = make_double2(a.ringCos[l], a.ringSin[l]);
+    }
     if (threadIdx.x == 0) {
         *nextGroup = 0;
         for (int s = 0; s < kBinStages; s++) {
@@ -173,16 +181,12 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
             }
         }
     } else {
-        // ---- consumers: lane == line of sight of the tile
-        const int t0 = tile * kTileLos, t1 = t0 + kTileLos;
-        const int los = t0 + lane;
-        const bool losOk = los < a.spokes;
-        const double rc = losOk ? a.ringCos[los] : 0.0, rs = losOk ? a.ringSin[los] : 0.0;
+        // ---- consumers
         const double rMin = h.rMin, rMax = h.rMax, invRMin = h.invRMin, rad2 = h.rad2;
         const double invDr = a.invDr;
         const float cK = a.cK;
-        uint32_t *rowLo = lo + lane * stride, *rowHi = hi + lane * stride;
-        const size_t tapRow = (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes + los;
+        uint32_t *sPrefix = sPair + warp * 64, *sMeta = sPrefix + 32;
+        const size_t tapRing = (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes;
 
         // 32-record groups are handed out in order from a shared counter, so a
         // warp that drew light groups simply takes more of them
@@ -199,63 +203,74 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
             mbar_wait(&full[buf], (t / kBinStages) & 1u);
             const int cnt = static_cast<int>(min(static_cast<int64_t>(kStageRecs), total - s * kStageRecs));
             const HitRec *grp = stage + buf * kStageRecs + gi * 32;
-            // which of these 32 records touch this tile?
-            bool ov = false;
+
+            // clip my record's two LoS ranges to the tile
+            int len1 = 0, len2 = 0, st1 = 0, st2 = 0;
             if (gi * 32 + lane < cnt) {
-                const HitRec *p = grp + lane;
-                const uint32_t r01 = p->r01, r23 = p->r23;
-                ov = (static_cast<int>(r01 & 0xffffu) < t1 && static_cast<int>(r01 >> 16) > t0) ||
-                     (static_cast<int>(r23 & 0xffffu) < t1 && static_cast<int>(r23 >> 16) > t0);
+                const uint32_t r01 = grp[lane].r01, r23 = grp[lane].r23;
+                st1 = max(static_cast<int>(r01 & 0xffffu), t0);
+                len1 = max(min(static_cast<int>(r01 >> 16), t1) - st1, 0);
+                st2 = max(static_cast<int>(r23 & 0xffffu), t0);
+                len2 = max(min(static_cast<int>(r23 >> 16), t1) - st2, 0);
+                if (len1 == 0) st1 = t0;   // keep the packed start offsets within 0..31
+                if (len2 == 0) st2 = t0;
             }
-            unsigned todo = __ballot_sync(0xffffffffu, ov);
-            while (todo) {
-                const int j = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const HitRec rec = grp[j];   // broadcast read
+            unsigned incl = static_cast<unsigned>(len1 + len2);
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const unsigned nPairs = __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            sPrefix[lane] = incl;
+            sMeta[lane] = static_cast<unsigned>(st1 - t0) | static_cast<unsigned>(len1) << 8 |
+                          static_cast<unsigned>(st2 - t0) << 16;
+            __syncwarp();
+
+            for (unsigned p0 = 0; p0 < nPairs; p0 += 32) {
+                const unsigned p = p0 + lane;
+                if (p >= nPairs) continue;
+                // record of pair p: first r with prefix[r] > p
+                int r = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1)
+                    if (sPrefix[r + step - 1] <= p) r += step;
+                const unsigned before = r ? sPrefix[r - 1] : 0u;
+                const unsigned meta = sMeta[r];
+                const int off = static_cast<int>(p - before);
+                const int l1 = static_cast<int>((meta >> 8) & 0xffu);
+                const int ll = off < l1 ? static_cast<int>(meta & 0xffu) + off
+                                        : static_cast<int>(meta >> 16) + (off - l1);   // LoS within the tile
+                const HitRec rec = grp[r];
+                const double2 cs = sTrig[ll];
                 const bool isA = rec.caseA != 0;
-                const bool active =
-                    losOk && ((los >= static_cast<int>(rec.r01 & 0xffffu) && los < static_cast<int>(rec.r01 >> 16)) ||
-                              (los >= static_cast<int>(rec.r23 & 0xffffu) && los < static_cast<int>(rec.r23 >> 16)));
-                if (!active) continue;
                 // literal geometry of insertToRing, los/halo.go:233-262
                 const double cx = rec.cx, cy = rec.cy, cz = rec.cz;
                 const double projDist2 = cx * cx + cy * cy;
                 double projRad2 = rad2 - cz * cz;
                 if (projRad2 < 0) projRad2 = 0;
-                const double b = cy * rc - cx * rs;
+                const double b = cy * cs.x - cx * cs.y;
                 const double b2 = b * b;
                 const double m2 = projDist2 - b2;   // radicand of midDist / cMidDist
                 const double d2 = projRad2 - b2;    // radicand of diff / radMidDist
-                double rLo, rHi;
-                bool hasStart, endNaN = false;
-                if (isA) {
-                    // oneValIntrDist, halo.go:337-346; Insert(-Inf, ln rHi)
-                    hasStart = false;
-                    rLo = 0.0;
-                    if (m2 < 0 || d2 < 0) {
-                        endNaN = true;   // sqrt of a negative: end = NaN, the plateau never ends
-                        rHi = 0.0;
-                    } else {
-                        const double dir = cx * rc + cy * rs;
-                        const double radMid = sqrt_pos(d2), cMid = sqrt_pos(m2);
-                        rHi = dir > 0 ? radMid + cMid : radMid - cMid;
-                    }
-                } else {
-                    // twoValIntrDist, halo.go:324-329; NaN -> skipped at :262
-                    if (!(m2 >= 0) || !(d2 >= 0)) continue;
-                    const double mid = sqrt_pos(m2), diff = sqrt_pos(d2);
-                    rLo = mid - diff;
-                    rHi = mid + diff;
-                    hasStart = true;
-                }
+                const bool bad = !(m2 >= 0) || !(d2 >= 0);   // a sqrt of the reference returns NaN
+                // twoValIntrDist skips NaN (halo.go:262); oneValIntrDist's NaN goes into Insert
+                if (bad && !isA) continue;
+                const double dir = cx * cs.x + cy * cs.y;
+                const double mid = sqrt_pos(m2), diff = sqrt_pos(d2);
+                const double rLo = mid - diff;
+                const double rHi = (isA && !(dir > 0)) ? diff - mid : mid + diff;
+                const bool endNaN = bad;            // only reachable with isA
                 // ProfileRing.Insert, profile_ring.go:92-120, with ln monotone:
                 // end <= lowR <=> rHi <= rMin, start >= highR <=> rLo >= rMax, ...
                 if (!endNaN && rHi <= rMin) continue;
-                if (hasStart && rLo >= rMax) continue;
+                if (!isA && rLo >= rMax) continue;
                 nIns++;
+                uint32_t *rowLo = lo + ll * stride, *rowHi = hi + ll * stride;
+                const size_t tapRow = tapRing + t0 + ll;
                 if (TAPS) atomicAdd(&a.tapInsert[tapRow], 1u);
                 const long long Q = __double2ll_rn(rec.rhoS);
-                if (hasStart && rLo > rMin) {
+                if (!isA && rLo > rMin) {
                     int idx; double rem;
                     bin_of(rLo, invRMin, cK, invDr, sInvG, bins, idx, rem);
                     const long long q1 = __double2ll_rn(rec.rhoS * rem);
@@ -305,8 +320,9 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
 }  // namespace
 
 size_t bin_smem_bytes(int bins) {
-    return sizeof(HitRec) * kBinStages * kStageRecs + (2 * kBinStages + 1) * sizeof(uint64_t) +
-           sizeof(double) * (bins + 1) + sizeof(uint32_t) * 2 * kTileLos * (bins + 1);
+    return sizeof(HitRec) * kBinStages * kStageRecs + (2 * kBinStages + 2) * sizeof(uint64_t) +
+           sizeof(double2) * kTileLos + sizeof(double) * (bins + 1) + sizeof(uint32_t) * kBinConsumers * 64 +
+           sizeof(uint32_t) * 2 * kTileLos * (bins + 1);
 }
 
 cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s) {
