@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     unsigned int *nextGroup = reinterpret_cast<unsigned int *>(empty + kBinStages);   // 8-byte slot
     double2 *sTrig = reinterpret_cast<double2 *>(empty + kBinStages + 2);         // [32] (cos, sin), 16-byte aligned
     double *sInvG = reinterpret_cast<double *>(sTrig + kTileLos);                 // [bins + 1]
-    uint32_t *sPair = reinterpret_cast<uint32_t *>(sInvG + bins + 1);             // [consumers][64]: prefix, meta
-    uint32_t *lo = sPair + kBinConsumers * 64;                                    // [32][stride]
+    uint32_t *sPair = reinterpret_cast<uint32_t *>(sInvG + bins + 1);             // [consumers][32]: record heads
+    uint32_t *lo = sPair + kBinConsumers * 32;                                    // [32][stride]
     uint32_t *hi = lo + kTileLos * stride;
 
     const int nTiles = (a.spokes + kTileLos - 1) / kTileLos;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
         const double rMin = h.rMin, rMax = h.rMax, invRMin = h.invRMin, rad2 = h.rad2;
         const double invDr = a.invDr;
         const float cK = a.cK;
-        uint32_t *sPrefix = sPair + warp * 64, *sMeta = sPrefix + 32;
+        uint32_t *sHead = sPair + warp * 32;
         const size_t tapRing = (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes;
 
         // 32-record groups are handed out in order from a shared counter, so a
@@ -215,32 +215,39 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
                 if (len1 == 0) st1 = t0;   // keep the packed start offsets within 0..31
                 if (len2 == 0) st2 = t0;
             }
-            unsigned incl = static_cast<unsigned>(len1 + len2);
+            const unsigned nMine = static_cast<unsigned>(len1 + len2);
+            unsigned incl = nMine;
             for (int o = 1; o < 32; o <<= 1) {
                 const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += up;
             }
             const unsigned nPairs = __shfl_sync(0xffffffffu, incl, 31);
-            __syncwarp();
-            sPrefix[lane] = incl;
-            sMeta[lane] = static_cast<unsigned>(st1 - t0) | static_cast<unsigned>(len1) << 8 |
-                          static_cast<unsigned>(st2 - t0) << 16;
-            __syncwarp();
+            const unsigned first = incl - nMine;   // index of my record's first pair
+            const unsigned meta = static_cast<unsigned>(st1 - t0) | static_cast<unsigned>(len1) << 8 |
+                                  static_cast<unsigned>(st2 - t0) << 16;
 
             for (unsigned p0 = 0; p0 < nPairs; p0 += 32) {
+                // pair p0 + lane -> record: lanes whose record starts inside this chunk
+                // plant their lane number at the start position; every pair lane then
+                // takes the nearest planted record at or below its position
+                const unsigned rAtP0 = __popc(__ballot_sync(0xffffffffu, incl <= p0));
+                __syncwarp();
+                sHead[lane] = lane == 0 ? rAtP0 : 0xffu;
+                __syncwarp();
+                if (nMine > 0 && first > p0 && first < p0 + 32) sHead[first - p0] = lane;
+                __syncwarp();
+                const unsigned hv = sHead[lane];
+                const unsigned heads = __ballot_sync(0xffffffffu, hv != 0xffu);
+                const int hpos = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+                const int r = static_cast<int>(__shfl_sync(0xffffffffu, hv, hpos));
+                const unsigned before = __shfl_sync(0xffffffffu, first, r);
+                const unsigned rmeta = __shfl_sync(0xffffffffu, meta, r);
                 const unsigned p = p0 + lane;
                 if (p >= nPairs) continue;
-                // record of pair p: first r with prefix[r] > p
-                int r = 0;
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1)
-                    if (sPrefix[r + step - 1] <= p) r += step;
-                const unsigned before = r ? sPrefix[r - 1] : 0u;
-                const unsigned meta = sMeta[r];
                 const int off = static_cast<int>(p - before);
-                const int l1 = static_cast<int>((meta >> 8) & 0xffu);
-                const int ll = off < l1 ? static_cast<int>(meta & 0xffu) + off
-                                        : static_cast<int>(meta >> 16) + (off - l1);   // LoS within the tile
+                const int l1 = static_cast<int>((rmeta >> 8) & 0xffu);
+                const int ll = off < l1 ? static_cast<int>(rmeta & 0xffu) + off
+                                        : static_cast<int>(rmeta >> 16) + (off - l1);   // LoS within the tile
                 const HitRec rec = grp[r];
                 const double2 cs = sTrig[ll];
                 const bool isA = rec.caseA != 0;
@@ -259,7 +266,8 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
                 const double dir = cx * cs.x + cy * cs.y;
                 const double mid = sqrt_pos(m2), diff = sqrt_pos(d2);
                 const double rLo = mid - diff;
-                const double rHi = (isA && !(dir > 0)) ? diff - mid : mid + diff;
+                // mid + diff, or diff - mid on the far side of a centre-containing circle
+                const double rHi = fma((isA && !(dir > 0)) ? -1.0 : 1.0, mid, diff);
                 const bool endNaN = bad;            // only reachable with isA
                 // ProfileRing.Insert, profile_ring.go:92-120, with ln monotone:
                 // end <= lowR <=> rHi <= rMin, start >= highR <=> rLo >= rMax, ...
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
 
 size_t bin_smem_bytes(int bins) {
     return sizeof(HitRec) * kBinStages * kStageRecs + (2 * kBinStages + 2) * sizeof(uint64_t) +
-           sizeof(double2) * kTileLos + sizeof(double) * (bins + 1) + sizeof(uint32_t) * kBinConsumers * 64 +
+           sizeof(double2) * kTileLos + sizeof(double) * (bins + 1) + sizeof(uint32_t) * kBinConsumers * 32 +
            sizeof(uint32_t) * 2 * kTileLos * (bins + 1);
 }
 
