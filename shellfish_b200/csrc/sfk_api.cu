@@ -112,7 +112,7 @@ struct sfk_ctx {
     DevBuf<uint32_t> dHitCursor, dBatchHitCount;
     DevBuf<int32_t> dBatchHalos, dHaloSlot;
     DevBuf<unsigned long long> dGrid;
-    DevBuf<double> dFR, dM, dOut2, dRvec;
+    DevBuf<double> dFR;
     DevBuf<int32_t> dFIdx, dFCount;
 
     sfk_stats stats{};
@@ -572,9 +572,6 @@ int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) {
         CU(ctx->dFR.ensure(static_cast<size_t>(nb) * rn));
         CU(ctx->dFIdx.ensure(static_cast<size_t>(nb) * rn));
         CU(ctx->dFCount.ensure(static_cast<size_t>(nb) * R));
-        CU(ctx->dM.ensure(static_cast<size_t>(nb) * rn * P2));
-        CU(ctx->dOut2.ensure(static_cast<size_t>(nb) * rn * P2));
-        CU(ctx->dRvec.ensure(static_cast<size_t>(nb) * rn));
         CU(ctx->dPieces.upload(pieces, st));
         CU(ctx->dBatchHalos.upload(batch, st));
         CU(ctx->dHaloSlot.upload(haloSlot, st));
@@ -636,7 +633,7 @@ int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) {
         ft.fR = ctx->dFR.p; ft.fIdx = ctx->dFIdx.p; ft.fCount = ctx->dFCount.p;
         ft.batchHalos = ctx->dBatchHalos.p; ft.irots = ctx->dIrots.p;
         ft.ringCos = ctx->dCos.p; ft.ringSin = ctx->dSin.p;
-        ft.M = ctx->dM.p; ft.out2 = ctx->dOut2.p; ft.rvec = ctx->dRvec.p;
+
         ft.coeffs = ctx->dCoeffs.p; ft.status = ctx->dStatus.p; ft.nPoints = ctx->dNPoints.p;
         ft.rings = R; ft.spokes = n; ft.order = static_cast<int>(ctx->p.order);
         ctx->timer.begin(ST_FIT, st);

@@ -939,10 +939,48 @@ __device__ bool invert_lu(double *a, int n, int *ipiv, double *work) {
 }
 
 constexpr int kFitThreads = 1024;
+constexpr int kFitTile = 256;   // points per shared-memory tile
 constexpr int kMaxP2 = 2 * kMaxOrder * kMaxOrder;
 
+// Design-matrix row of one filtered point, penna.go:25-52: the point is lifted
+// to the box frame through irot in float32 (PlaneToVolume, halo.go:471-475).
+__device__ __forceinline__ double penna_row(const FitArgs &a, int slot, int ring, int k, int P, double *row) {
+    const size_t src = (static_cast<size_t>(slot) * a.rings + ring) * a.spokes + k;
+    const double R = a.fR[src];
+    const int li = a.fIdx[src];
+    // fXs, fYs (penna.go:157-160)
+    const double px = R * a.ringCos[li], py = R * a.ringSin[li];
+    float fx, fy, fz;
+    rotate_vec(a.irots + 9 * ring, static_cast<float>(px), static_cast<float>(py), 0.f, fx, fy, fz);
+    const double x = fx, y = fy, z = fz;
+    const double r = sqrt(x * x + y * y + z * z);
+    const double costh = z / r;
+    const double sinth = sqrt(1 - costh * costh);
+    const double cosphi = x / r / sinth;
+    const double sinphi = y / r / sinth;
+    int m = 0;
+    for (int kk = 0; kk < 2; kk++) {
+        const double ck = go_pow_int(costh, kk);
+        for (int j = 0; j < P; j++) {
+            const double sj = go_pow_int(sinphi, j);
+            double cphi = 1.0;
+            for (int i = 0; i < P; i++) {
+                row[m] = go_pow_int(sinth, i + j) * cphi * ck * sj;
+                m++;
+                cphi *= cosphi;
+            }
+        }
+    }
+    return r;
+}
+
 // One CTA per halo: PennaVolumeFit, penna.go:88-108 -> PennaCoeffs :14-58.
+// The N x P2 design matrix is never stored: rows are rebuilt tile by tile in
+// shared memory, once for the Gram matrix M M^T and once for rs^T (M^T inv).
+// Every accumulator adds its terms in ascending point order, like the
+// reference's loops (and gonum's Dgemm) do.
 __global__ void __launch_bounds__(kFitThreads) fit_kernel(FitArgs a) {
+    extern __shared__ double fsm[];
     __shared__ double G[kMaxP2 * kMaxP2];
     __shared__ double work[kMaxP2];
     __shared__ int ipiv[kMaxP2];
@@ -951,10 +989,8 @@ __global__ void __launch_bounds__(kFitThreads) fit_kernel(FitArgs a) {
     const int slot = blockIdx.x, tid = threadIdx.x;
     const int haloIdx = a.batchHalos[slot];
     const int P = a.order, P2 = 2 * P * P;
-    const size_t cap = static_cast<size_t>(a.rings) * a.spokes;
-    double *M = a.M + static_cast<size_t>(slot) * cap * P2;
-    double *out2 = a.out2 + static_cast<size_t>(slot) * cap * P2;
-    double *rv = a.rvec + static_cast<size_t>(slot) * cap;
+    double *tileM = fsm;                        // [kFitTile][P2]
+    double *tileR = tileM + kFitTile * P2;      // [kFitTile]
     if (tid == 0) {
         int s = 0;
         for (int r = 0; r < a.rings; r++) { ringOff[r] = s; s += a.fCount[slot * a.rings + r]; }
@@ -969,53 +1005,46 @@ __global__ void __launch_bounds__(kFitThreads) fit_kernel(FitArgs a) {
         if (tid == 0) a.status[haloIdx] = SFK_HALO_NO_POINTS;
         return;
     }
-    // design rows: one thread per point
-    for (int ring = 0; ring < a.rings; ring++) {
-        const int cnt = ringOff[ring + 1] - ringOff[ring];
-        const float *irot = a.irots + 9 * ring;
-        for (int k = tid; k < cnt; k += kFitThreads) {
-            const size_t src = (static_cast<size_t>(slot) * a.rings + ring) * a.spokes + k;
-            const double R = a.fR[src];
-            const int li = a.fIdx[src];
-            // fXs, fYs (penna.go:157-160) then PlaneToVolume through float32 (halo.go:471-475)
-            const double px = R * a.ringCos[li], py = R * a.ringSin[li];
-            float fx, fy, fz;
-            rotate_vec(irot, static_cast<float>(px), static_cast<float>(py), 0.f, fx, fy, fz);
-            const double x = fx, y = fy, z = fz;
-            const double r = sqrt(x * x + y * y + z * z);
-            const double costh = z / r;
-            const double sinth = sqrt(1 - costh * costh);
-            const double cosphi = x / r / sinth;
-            const double sinphi = y / r / sinth;
-            const int n = ringOff[ring] + k;
-            rv[n] = r;
-            int m = 0;
-            for (int kk = 0; kk < 2; kk++) {
-                const double ck = go_pow_int(costh, kk);
-                for (int j = 0; j < P; j++) {
-                    const double sj = go_pow_int(sinphi, j);
-                    double cphi = 1.0;
-                    for (int i = 0; i < P; i++) {
-                        M[static_cast<size_t>(n) * P2 + m] = go_pow_int(sinth, i + j) * cphi * ck * sj;
-                        m++;
-                        cphi *= cosphi;
-                    }
-                }
+    auto load_tile = [&](int n0, bool timesInv) {
+        // thread t < kFitTile builds the row of point n0 + t
+        const int n = n0 + tid;
+        if (tid < kFitTile && n < N) {
+            int lo = 0, hi = a.rings;   // ring with ringOff[ring] <= n < ringOff[ring + 1]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) / 2;
+                if (ringOff[mid] <= n) lo = mid; else hi = mid;
             }
+            double row[kMaxP2];
+            tileR[tid] = penna_row(a, slot, lo, n - ringOff[lo], P, row);
+            if (!timesInv) {
+                for (int j = 0; j < P2; j++) tileM[tid * P2 + j] = row[j];
+            } else {
+                // row of out2 = M^T inv (gonum Dense.Mul: axpy over l ascending)
+                double o2[kMaxP2];
+                for (int j = 0; j < P2; j++) o2[j] = 0.0;
+                for (int l = 0; l < P2; l++) {
+                    const double t = row[l];
+                    if (t == 0) continue;
+                    for (int j = 0; j < P2; j++) o2[j] += t * G[l * P2 + j];
+                }
+                for (int j = 0; j < P2; j++) tileM[tid * P2 + j] = o2[j];
+            }
+        }
+    };
+    // out1 = M M^T: thread (i, j) adds the tile's points in ascending order
+    double acc = 0.0;
+    const int gi = tid / P2, gj = tid - gi * P2;
+    for (int n0 = 0; n0 < N; n0 += kFitTile) {
+        __syncthreads();
+        load_tile(n0, false);
+        __syncthreads();
+        if (tid < P2 * P2) {
+            const int cnt = min(kFitTile, N - n0);
+            for (int k = 0; k < cnt; k++) acc += tileM[k * P2 + gi] * tileM[k * P2 + gj];
         }
     }
     __syncthreads();
-    // out1 = M * M^T: one thread per entry, points in ascending order
-    if (tid < P2 * P2) {
-        const int i = tid / P2, j = tid - i * P2;
-        double acc = 0.0;
-        for (int n = 0; n < N; n++) {
-            const double t = M[static_cast<size_t>(n) * P2 + i];
-            if (t == 0) continue;
-            acc += t * M[static_cast<size_t>(n) * P2 + j];
-        }
-        G[tid] = acc;
-    }
+    if (tid < P2 * P2) G[tid] = acc;
     __syncthreads();
     if (tid == 0 && !invert_lu(G, P2, ipiv, work)) okFlag = 0;
     __syncthreads();
@@ -1023,23 +1052,18 @@ __global__ void __launch_bounds__(kFitThreads) fit_kernel(FitArgs a) {
         if (tid == 0) a.status[haloIdx] = SFK_HALO_SINGULAR;
         return;
     }
-    // out2 = M^T * inv (row n), then cs = rs^T * out2 (mat.VecMult, mat.go:102)
-    for (int n = tid; n < N; n += kFitThreads) {
-        double row[kMaxP2];
-        for (int j = 0; j < P2; j++) row[j] = 0.0;
-        for (int l = 0; l < P2; l++) {
-            const double t = M[static_cast<size_t>(n) * P2 + l];
-            if (t == 0) continue;
-            for (int j = 0; j < P2; j++) row[j] += t * G[l * P2 + j];
+    // cs = rs^T (M^T inv) (mat.VecMult, mat.go:102): thread i sums over points in order
+    double sum = 0.0;
+    for (int n0 = 0; n0 < N; n0 += kFitTile) {
+        __syncthreads();
+        load_tile(n0, true);
+        __syncthreads();
+        if (tid < P2) {
+            const int cnt = min(kFitTile, N - n0);
+            for (int k = 0; k < cnt; k++) sum += tileR[k] * tileM[k * P2 + tid];
         }
-        for (int j = 0; j < P2; j++) out2[static_cast<size_t>(n) * P2 + j] = row[j];
     }
-    __syncthreads();
-    if (tid < P2) {
-        double sum = 0.0;
-        for (int n = 0; n < N; n++) sum += rv[n] * out2[static_cast<size_t>(n) * P2 + tid];
-        a.coeffs[static_cast<size_t>(haloIdx) * P2 + tid] = sum;
-    }
+    if (tid < P2) a.coeffs[static_cast<size_t>(haloIdx) * P2 + tid] = sum;
 }
 
 }  // namespace
@@ -1122,7 +1146,15 @@ cudaError_t launch_filter(const FilterArgs &a, int nb, cudaStream_t s) {
 
 cudaError_t launch_fit(const FitArgs &a, int nb, cudaStream_t s) {
     if (nb <= 0) return cudaSuccess;
-    fit_kernel<<<nb, kFitThreads, 0, s>>>(a);
+    const int P2 = 2 * a.order * a.order;
+    const size_t smem = sizeof(double) * (kFitTile * P2 + kFitTile);
+    static bool attrSet = false;
+    if (!attrSet) {
+        cudaError_t e = cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return e;
+        attrSet = true;
+    }
+    fit_kernel<<<nb, kFitThreads, smem, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -68,9 +68,6 @@ struct FitArgs {
     const int32_t *batchHalos;
     const float *irots;
     const double *ringCos, *ringSin;
-    double *M;       // [nb][rings*spokes][P2] design rows
-    double *out2;    // [nb][rings*spokes][P2]
-    double *rvec;    // [nb][rings*spokes]
     double *coeffs;  // [nHalo][P2]
     int32_t *status; // [nHalo]
     long long *nPoints; // [nHalo]
