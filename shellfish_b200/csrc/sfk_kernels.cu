@@ -695,6 +695,7 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(FilterArgs a) {
     short *pLo = reinterpret_cast<short *>(pIdx + a.spokes);           // [spokes]
     short *pHi = pLo + a.spokes;
     unsigned char *keep = reinterpret_cast<unsigned char *>(pHi + a.spokes);
+    unsigned char *pNode = keep + a.spokes;                            // [levels][spokes]
 
     const int ring = blockIdx.x, slot = blockIdx.y;
     const int haloIdx = a.batchHalos[slot];
@@ -720,6 +721,10 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(FilterArgs a) {
     }
     __syncthreads();
     const int nv = sm.nValid;
+    for (int p = tid; p < nv; p += kFilterThreads)
+        for (int l = 1; l <= a.levels; l++)
+            pNode[(l - 1) * a.spokes + p] =
+                static_cast<unsigned char>(go_int(a.ringPhi[pIdx[p]] / (kTwoPi / static_cast<double>(1 << l))));
     if (sm.status) {
         if (tid == 0) { atomicMax(&a.status[haloIdx], sm.status); a.fCount[slot * a.rings + ring] = 0; }
         return;
@@ -746,21 +751,24 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(FilterArgs a) {
             pHi[p] = static_cast<short>(hi);
         }
         __syncthreads();
-        // GaussianKDE for every node of every level, kde.go:24-38; points in order
-        for (int t = tid; t < nKde * kKdeKnots; t += kFilterThreads) {
-            const int kde = t / kKdeKnots, i = t - kde * kKdeKnots;
-            int level = 0;
-            while ((1 << (level + 1)) - 1 <= kde) level++;
-            const int node = kde - ((1 << level) - 1);
-            const double dth = kTwoPi / static_cast<double>(1 << level);
-            double acc = 0.0;
+        // GaussianKDE for every node of every level, kde.go:24-38.  One thread per
+        // knot walks the points in order; exp() is evaluated once per (point, knot)
+        // and added to the point's node at every level (binByTheta, kde.go:156-174),
+        // so each KDE still sums its own points in the reference's order.
+        for (int t = tid; t < nKde * kKdeKnots; t += kFilterThreads) Y[t] = 0.0;
+        __syncthreads();
+        for (int i = tid; i < kKdeKnots; i += kFilterThreads) {
+            const double xi = sm.X[i];
+            double acc0 = 0.0;
             for (int p = 0; p < nv; p++) {
                 if (i < pLo[p] || i > pHi[p]) continue;
-                if (level > 0 && go_int(a.ringPhi[pIdx[p]] / dth) != node) continue;
-                const double udx = (sm.X[i] - pR[p]) / hk;
-                acc += exp(-udx * udx);
+                const double udx = (xi - pR[p]) / hk;
+                const double e = exp(-udx * udx);
+                acc0 += e;
+                for (int l = 1; l <= a.levels; l++)
+                    Y[((1 << l) - 1 + pNode[(l - 1) * a.spokes + p]) * kKdeKnots + i] += e;
             }
-            Y[t] = acc;
+            Y[i] = acc0;
         }
         __syncthreads();
         for (int k = tid; k < nKde; k += kFilterThreads)
@@ -1132,7 +1140,7 @@ cudaError_t launch_filter(const FilterArgs &a, int nb, cudaStream_t s) {
     if (nb <= 0) return cudaSuccess;
     const int nKde = (1 << (a.levels + 1)) - 1;
     const size_t smem = sizeof(FilterSmem) + sizeof(double) * (3 * nKde * kKdeKnots + nKde * kMaxMax + a.spokes) +
-                        sizeof(int) * a.spokes + 2 * sizeof(short) * a.spokes + a.spokes + 16;
+                        sizeof(int) * a.spokes + 2 * sizeof(short) * a.spokes + a.spokes * (1 + a.levels) + 16;
     static bool attrSet = false;
     if (!attrSet) {
         cudaError_t e = cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
