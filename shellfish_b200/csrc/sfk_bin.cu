@@ -111,9 +111,9 @@ __device__ __forceinline__ void bin_of(double r, double invRMin, float cK, doubl
 __device__ __forceinline__ void acc_add(uint32_t *lo, uint32_t *hi, int idx, long long v) {
     const uint32_t vlo = static_cast<uint32_t>(v);
     const uint32_t vhi = static_cast<uint32_t>(static_cast<unsigned long long>(v) >> 32);
-    const uint32_t old = atomicAdd(&lo[idx], vlo);
+    const uint32_t old = atomicAdd(&lo[idx * kTileLos], vlo);
     const uint32_t add = vhi + ((old + vlo) < old ? 1u : 0u);
-    if (add) atomicAdd(&hi[idx], add);
+    if (add) atomicAdd(&hi[idx * kTileLos], add);
 }
 
 template <bool TAPS>
@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     double2 *sTrig = reinterpret_cast<double2 *>(empty + kBinStages + 2);         // [32] (cos, sin), 16-byte aligned
     double *sInvG = reinterpret_cast<double *>(sTrig + kTileLos);                 // [bins + 1]
     uint32_t *sPair = reinterpret_cast<uint32_t *>(sInvG + bins + 1);             // [consumers][32]: record heads
-    uint32_t *lo = sPair + kBinConsumers * 32;                                    // [32][stride]
+    // accumulators are bin-major, [stride][32]: a warp's lanes are different LoS of (mostly) one
+    // record, so the bank is the LoS and the atomics are conflict-free whatever the bins are
+    uint32_t *lo = sPair + kBinConsumers * 32;
     uint32_t *hi = lo + kTileLos * stride;
 
     const int nTiles = (a.spokes + kTileLos - 1) / kTileLos;
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
                 if (!endNaN && rHi <= rMin) continue;
                 if (!isA && rLo >= rMax) continue;
                 nIns++;
-                uint32_t *rowLo = lo + ll * stride, *rowHi = hi + ll * stride;
+                uint32_t *rowLo = lo + ll, *rowHi = hi + ll;
                 const size_t tapRow = tapRing + t0 + ll;
                 if (TAPS) atomicAdd(&a.tapInsert[tapRow], 1u);
                 const long long Q = __double2ll_rn(rec.rhoS);
@@ -314,7 +316,8 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
         const int l = k / stride, bin = k - l * stride;
         const int gl = tile * kTileLos + l;
         if (gl >= a.spokes) continue;
-        const unsigned long long v = (static_cast<unsigned long long>(hi[k]) << 32) | lo[k];
+        const int at = bin * kTileLos + l;   // bank-conflicting read, once per CTA
+        const unsigned long long v = (static_cast<unsigned long long>(hi[at]) << 32) | lo[at];
         if (v == 0) continue;
         if (bin < bins) {
             atomicAdd(&g[static_cast<size_t>(gl) * bins + bin], v);
