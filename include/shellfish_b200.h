@@ -132,6 +132,26 @@ int sfk_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass,
  * SFK_HALO_*; either may be NULL. */
 int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status);
 
+/* ---- split-halo mode ------------------------------------------------------
+ * One giant halo whose particles are spread over several GPUs (each rank
+ * pushes its own part of the blocks).  The private grids of Halo.Split/Join
+ * (los/halo.go:107-140) become one exchange step: the caller all-reduces three
+ * device buffers with its own collective library (NCCL through
+ * torch.distributed in this repo) between the calls:
+ *   sfk_split_count  -> all-reduce SFK_SPLIT_HIT_COUNTS (int32, SUM) and
+ *                       SFK_SPLIT_RHO_MAX (int64 bit patterns, MAX)
+ *   sfk_split_bin    -> all-reduce SFK_SPLIT_GRID (int64, SUM)
+ *   sfk_split_finish -> haloAnalysis on the summed grid (same result on every rank)
+ * The grid is int64 fixed point, so the sum is exact and independent of the
+ * number of GPUs. */
+#define SFK_SPLIT_HIT_COUNTS 0
+#define SFK_SPLIT_RHO_MAX 1
+#define SFK_SPLIT_GRID 2
+int sfk_split_count(sfk_ctx *ctx);
+int sfk_split_bin(sfk_ctx *ctx);
+int sfk_split_buffer(sfk_ctx *ctx, int32_t which, void **d_ptr, int64_t *count);
+int sfk_split_finish(sfk_ctx *ctx, double *coeffs, int32_t *status);
+
 int sfk_get_stats(const sfk_ctx *ctx, sfk_stats *out);
 
 /* The cudaStream_t (as void*) every kernel of this context is launched on, so

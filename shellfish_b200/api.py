@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsfk.so")
 
 SFK_FLAG_TAPS = 1
+SPLIT_HIT_COUNTS, SPLIT_RHO_MAX, SPLIT_GRID = 0, 1, 2
 HALO_STATUS = {0: "ok", 1: "skipped", 2: "no_points", 3: "no_maximum", 4: "spline", 5: "singular",
                6: "not_owned"}
 
@@ -48,7 +49,8 @@ class Stats(C.Structure):
 # every symbol include/shellfish_b200.h declares
 EXPORTS = ["sfk_default_params", "sfk_create", "sfk_destroy", "sfk_last_error", "sfk_begin_snapshot",
            "sfk_add_halos", "sfk_set_owned", "sfk_block_halo_mask", "sfk_push_block", "sfk_push_block_device",
-           "sfk_finish_snapshot", "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count",
+           "sfk_finish_snapshot", "sfk_split_count", "sfk_split_bin", "sfk_split_buffer", "sfk_split_finish",
+           "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count",
            "sfk_get_profiles", "sfk_get_counts", "sfk_get_ring_tables"]
 
 _lib = None
@@ -77,6 +79,10 @@ def lib():
         L.sfk_push_block.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Cosmo), C.c_double, fp, fp]
         L.sfk_push_block_device.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Cosmo), C.c_double, fp, fp]
         L.sfk_finish_snapshot.argtypes = [vp, dp, C.POINTER(C.c_int32)]
+        L.sfk_split_count.argtypes = [vp]
+        L.sfk_split_bin.argtypes = [vp]
+        L.sfk_split_buffer.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_int64)]
+        L.sfk_split_finish.argtypes = [vp, dp, C.POINTER(C.c_int32)]
         L.sfk_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.sfk_stream.argtypes = [vp]
         L.sfk_stream.restype = C.c_void_p
@@ -193,6 +199,36 @@ class ShellContext:
         self._ck(lib().sfk_finish_snapshot(self._h, coeffs.ctypes.data_as(C.POINTER(C.c_double)),
                                            status.ctypes.data_as(C.POINTER(C.c_int32))),
                  "sfk_finish_snapshot")
+        return coeffs, status
+
+    # ---- split-halo mode (one halo's particles spread over several GPUs)
+    def split_count(self):
+        self._ck(lib().sfk_split_count(self._h), "sfk_split_count")
+
+    def split_bin(self):
+        self._ck(lib().sfk_split_bin(self._h), "sfk_split_bin")
+
+    def split_buffer(self, which):
+        """Device view (torch tensor sharing memory) of one exchange buffer:
+        SPLIT_HIT_COUNTS (int32), SPLIT_RHO_MAX (int64), SPLIT_GRID (int64)."""
+        import torch
+        ptr, n = C.c_void_p(), C.c_int64()
+        self._ck(lib().sfk_split_buffer(self._h, which, C.byref(ptr), C.byref(n)), "sfk_split_buffer")
+        typestr = "<i4" if which == SPLIT_HIT_COUNTS else "<i8"
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": typestr,
+                                        "data": (int(ptr.value or 0), False), "version": 2}
+        if n.value == 0:
+            return torch.zeros(0, dtype=torch.int32 if which == SPLIT_HIT_COUNTS else torch.int64,
+                               device="cuda:%d" % self.params.device)
+        return torch.as_tensor(_View(), device="cuda:%d" % self.params.device)
+
+    def split_finish(self):
+        coeffs = np.zeros((self.n_halos, self.P2))
+        status = np.zeros(self.n_halos, np.int32)
+        self._ck(lib().sfk_split_finish(self._h, coeffs.ctypes.data_as(C.POINTER(C.c_double)),
+                                        status.ctypes.data_as(C.POINTER(C.c_int32))), "sfk_split_finish")
         return coeffs, status
 
     def stream_ptr(self):

@@ -115,6 +115,14 @@ struct sfk_ctx {
     DevBuf<double> dFR;
     DevBuf<int32_t> dFIdx, dFCount;
 
+    // state shared by the stages of sfk_finish_snapshot / the split-halo calls
+    std::vector<std::vector<Piece>> perHalo;
+    std::vector<uint32_t> hHitCount;
+    std::vector<int64_t> hitsPerHalo;
+    std::vector<int32_t> order;
+    DevBuf<uint32_t> dHitCountGlobal;
+    int splitPhase = 0;
+
     sfk_stats stats{};
     StageTimer timer;
     std::vector<double> hCoeffs;
@@ -258,9 +266,274 @@ int push_block_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, int64_t
     return SFK_OK;
 }
 
+// ---- stages of haloAnalysis' GPU replacement ---------------------------------
+
+// Result buffers, Savitzky-Golay taps, work pieces and the raw hit-count pass.
+int stage_prepare(sfk_ctx *ctx) {
+    cudaStream_t st = ctx->stream;
+    const int64_t nHalo = static_cast<int64_t>(ctx->halos.size());
+    const int R = ctx->rings, n = ctx->spokes, B = ctx->bins, P2 = ctx->P2;
+    const size_t rn = static_cast<size_t>(R) * n, rnb = rn * B;
+    ctx->hCoeffs.assign(static_cast<size_t>(nHalo) * P2, 0.0);
+    ctx->hStatus.assign(nHalo, SFK_HALO_OK);
+    ctx->perHalo.assign(nHalo, {});
+    ctx->order.clear();
+    if (nHalo == 0) return SFK_OK;
+
+    CU(ctx->dRsp.ensure(nHalo * rn));
+    CU(ctx->dCoeffs.ensure(static_cast<size_t>(nHalo) * P2));
+    CU(ctx->dStatus.ensure(nHalo));
+    CU(ctx->dNInter.ensure(nHalo));
+    CU(ctx->dRhoMax.ensure(nHalo));
+    CU(ctx->dNPoints.ensure(nHalo));
+    CU(ctx->dHitCount.ensure(static_cast<size_t>(nHalo) * R));
+    CU(cudaMemsetAsync(ctx->dRsp.p, 0xff, nHalo * rn * sizeof(double), st));  // NaN
+    CU(cudaMemsetAsync(ctx->dCoeffs.p, 0, static_cast<size_t>(nHalo) * P2 * sizeof(double), st));
+    CU(cudaMemsetAsync(ctx->dStatus.p, 0, nHalo * sizeof(int32_t), st));
+    CU(cudaMemsetAsync(ctx->dNInter.p, 0, nHalo * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(ctx->dRhoMax.p, 0, nHalo * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(ctx->dNPoints.p, 0, nHalo * sizeof(long long), st));
+    CU(cudaMemsetAsync(ctx->dHitCount.p, 0, static_cast<size_t>(nHalo) * R * sizeof(uint32_t), st));
+    if (ctx->taps) {
+        CU(ctx->dProfiles.ensure(nHalo * rnb));
+        CU(ctx->dTapInsert.ensure(nHalo * rn));
+        CU(ctx->dTapStart.ensure(nHalo * rnb));
+        CU(ctx->dTapEnd.ensure(nHalo * rnb));
+        CU(cudaMemsetAsync(ctx->dProfiles.p, 0, nHalo * rnb * sizeof(double), st));
+        CU(cudaMemsetAsync(ctx->dTapInsert.p, 0, nHalo * rn * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(ctx->dTapStart.p, 0, nHalo * rnb * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(ctx->dTapEnd.p, 0, nHalo * rnb * sizeof(uint32_t), st));
+    }
+
+    // Savitzky-Golay taps: built once per process from the first smoothed
+    // profile's dx = ln r1 - ln r0 (smooth.go:63,84-96)
+    if (!ctx->tapsReady && B > ctx->p.smoothing_window) {
+        for (const HaloDev &h : ctx->halos) {
+            if (!h.valid) continue;
+            const double r0 = std::exp(h.lrMin + h.dlr * (0.0 + 0.5));
+            const double r1 = std::exp(h.lrMin + h.dlr * (1.0 + 0.5));
+            const double dx = std::log(r1) - std::log(r0);
+            std::vector<double> k0, k1;
+            if (!savgol_taps(4, static_cast<int>(ctx->p.smoothing_window), 0, 0, k0) ||
+                !savgol_taps(4, static_cast<int>(ctx->p.smoothing_window), 1, dx, k1))
+                return fail(ctx, SFK_E_INVALID, "Savitzky-Golay kernel construction failed");
+            CU(ctx->dTaps0.upload(k0, st));
+            CU(ctx->dTaps1.upload(k1, st));
+            CU(cudaStreamSynchronize(st));
+            ctx->tapsReady = true;
+            break;
+        }
+    }
+    if (!ctx->tapsReady) {
+        std::vector<double> z(std::max<int64_t>(ctx->p.smoothing_window, 1), 0.0);
+        CU(ctx->dTaps0.upload(z, st));
+        CU(ctx->dTaps1.upload(z, st));
+        CU(cudaStreamSynchronize(st));
+    }
+
+    // pieces: <= 256 candidates of one halo each, grouped per halo
+    for (const Seg &s : ctx->segs)
+        for (int32_t off = 0; off < s.count; off += 256)
+            ctx->perHalo[s.halo].push_back({s.start + off, std::min<int32_t>(256, s.count - off), s.halo});
+    std::vector<Piece> all;
+    for (auto &v : ctx->perHalo) all.insert(all.end(), v.begin(), v.end());
+
+    // raw hits per (halo, ring) and largest rho per halo
+    ctx->timer.begin(ST_HITS, st);
+    CU(ctx->dPieces.upload(all, st));
+    CU(launch_hit_count(ctx->dPieces.p, static_cast<int>(all.size()), ctx->dCands.p, ctx->dHalos.p,
+                        ctx->dNorms.p, R, ctx->dHitCount.p, ctx->dRhoMax.p, st));
+    ctx->stats.launches++;
+    ctx->timer.end(ST_HITS, st);
+    CU(cudaStreamSynchronize(st));   // `all` is a local vector
+    return SFK_OK;
+}
+
+// Fixed-point scale per halo and the processing order.  Record offsets use this
+// GPU's own raw counts; the scale uses the counts of the whole halo (all GPUs
+// in split mode) so that every rank quantises identically:
+// |sum| <= 2 * hits_ring_max * rho_max < 2^62.
+int stage_scale(sfk_ctx *ctx, bool split) {
+    cudaStream_t st = ctx->stream;
+    const int64_t nHalo = static_cast<int64_t>(ctx->halos.size());
+    const int R = ctx->rings;
+    ctx->hHitCount.assign(static_cast<size_t>(nHalo) * R, 0);
+    std::vector<uint32_t> global(static_cast<size_t>(nHalo) * R);
+    std::vector<unsigned long long> rhoMaxBits(nHalo);
+    CU(cudaMemcpyAsync(ctx->hHitCount.data(), ctx->dHitCount.p, ctx->hHitCount.size() * sizeof(uint32_t),
+                       cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(global.data(), split ? ctx->dHitCountGlobal.p : ctx->dHitCount.p,
+                       global.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(rhoMaxBits.data(), ctx->dRhoMax.p, nHalo * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->hitsPerHalo.assign(nHalo, 0);
+    for (int64_t i = 0; i < nHalo; i++) {
+        uint32_t hmax = 0;
+        for (int r = 0; r < R; r++) {
+            hmax = std::max(hmax, global[i * R + r]);
+            ctx->hitsPerHalo[i] += ctx->hHitCount[i * R + r];
+        }
+        double rhoMax;
+        std::memcpy(&rhoMax, &rhoMaxBits[i], sizeof rhoMax);
+        int e = 0;
+        if (hmax > 0 && rhoMax > 0 && std::isfinite(rhoMax)) {
+            const double bound = 2.0 * static_cast<double>(hmax) * rhoMax;
+            e = 61 - std::ilogb(bound);
+            e = std::max(-900, std::min(900, e));
+        }
+        ctx->halos[i].scale = std::ldexp(1.0, e);
+        ctx->halos[i].quantum = std::ldexp(1.0, -e);
+        ctx->stats.n_ring_hits += ctx->hitsPerHalo[i];
+    }
+    CU(ctx->dHalos.upload(ctx->halos, st));
+    CU(ctx->dHaloSlot.ensure(nHalo));
+    for (int64_t i = 0; i < nHalo; i++) {
+        if (ctx->halos[i].valid && ctx->halos[i].owned) ctx->order.push_back(static_cast<int32_t>(i));
+        else if (ctx->halos[i].valid) ctx->hStatus[i] = SFK_HALO_NOT_OWNED;
+        else ctx->hStatus[i] = SFK_HALO_SKIPPED;
+    }
+    return SFK_OK;
+}
+
+// Halo.Insert for one batch of halos: ring-frame records, then the binning kernel.
+int stage_bin(sfk_ctx *ctx, const std::vector<int32_t> &batch) {
+    cudaStream_t st = ctx->stream;
+    const int64_t nHalo = static_cast<int64_t>(ctx->halos.size());
+    const int R = ctx->rings, n = ctx->spokes, B = ctx->bins;
+    const size_t rn = static_cast<size_t>(R) * n, rnb = rn * B;
+    const int nb = static_cast<int>(batch.size());
+    std::vector<int32_t> haloSlot(nHalo, -1);
+    std::vector<int64_t> hitOffset(static_cast<size_t>(nb) * R);
+    std::vector<Piece> pieces;
+    int64_t run = 0;
+    for (int s = 0; s < nb; s++) {
+        const int32_t hIdx = batch[s];
+        haloSlot[hIdx] = s;
+        for (int r = 0; r < R; r++) {
+            hitOffset[static_cast<size_t>(s) * R + r] = run;
+            run += ctx->hHitCount[static_cast<size_t>(hIdx) * R + r];
+        }
+        pieces.insert(pieces.end(), ctx->perHalo[hIdx].begin(), ctx->perHalo[hIdx].end());
+    }
+    CU(ctx->dRecs.ensure(std::max<int64_t>(run, 1)));
+    CU(ctx->dGrid.ensure(static_cast<size_t>(nb) * rnb));
+    CU(ctx->dHitCursor.ensure(static_cast<size_t>(nb) * R));
+    CU(ctx->dFR.ensure(static_cast<size_t>(nb) * rn));
+    CU(ctx->dFIdx.ensure(static_cast<size_t>(nb) * rn));
+    CU(ctx->dFCount.ensure(static_cast<size_t>(nb) * R));
+    CU(ctx->dPieces.upload(pieces, st));
+    CU(ctx->dBatchHalos.upload(batch, st));
+    CU(ctx->dHaloSlot.upload(haloSlot, st));
+    CU(ctx->dHitOffset.upload(hitOffset, st));
+    CU(cudaMemsetAsync(ctx->dHitCursor.p, 0, static_cast<size_t>(nb) * R * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(ctx->dGrid.p, 0, static_cast<size_t>(nb) * rnb * sizeof(unsigned long long), st));
+
+    ctx->timer.begin(ST_HITS, st);
+    CU(launch_hits(ctx->dPieces.p, static_cast<int>(pieces.size()), ctx->dCands.p, ctx->dHalos.p,
+                   ctx->dNorms.p, ctx->dRots.p, ctx->dCos.p, ctx->dSin.p, R, n, ctx->tab.dPhi,
+                   ctx->dHitOffset.p, ctx->dHitCursor.p, ctx->dHaloSlot.p, ctx->dRecs.p, st));
+    ctx->stats.launches++;
+    ctx->timer.end(ST_HITS, st);
+
+    BinArgs ba{};
+    ba.recs = ctx->dRecs.p; ba.hitOffset = ctx->dHitOffset.p; ba.hitCount = ctx->dHitCursor.p;
+    ba.halos = ctx->dHalos.p; ba.batchHalos = ctx->dBatchHalos.p;
+    ba.ringCos = ctx->dCos.p; ba.ringSin = ctx->dSin.p;
+    ba.grid = ctx->dGrid.p; ba.nIntersections = ctx->dNInter.p;
+    ba.tapInsert = ctx->dTapInsert.p; ba.tapStart = ctx->dTapStart.p; ba.tapEnd = ctx->dTapEnd.p;
+    ba.rings = R; ba.spokes = n; ba.bins = B;
+    ba.binInvG = ctx->dBinInvG.p;
+    ba.invDr = 1.0 / ctx->tab.dr0;
+    ba.cK = static_cast<float>(0.6931471805599453 / ctx->tab.dr0);
+    // split long hit lists when there are too few CTAs to fill 148 SMs x 2 for a few waves
+    const int64_t ctas = static_cast<int64_t>((n + kTileLos - 1) / kTileLos) * R * nb;
+    ba.chunks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(64, (148 * 2 * 4 + ctas - 1) / ctas)));
+    ctx->timer.begin(ST_BIN, st);
+    CU(launch_bin(ba, nb, ctx->taps, st));
+    ctx->stats.launches++; ctx->stats.bin_launches++;
+    ctx->timer.end(ST_BIN, st);
+    // host vectors of this batch are read by async copies: drain before they die
+    CU(cudaStreamSynchronize(st));
+    return SFK_OK;
+}
+
+// haloAnalysis for the batch whose grid is resident: RingBuffer.Splashback,
+// FilterPoints, PennaVolumeFit (cmd/shell.go:613-627).
+int stage_analyze(sfk_ctx *ctx, int nb) {
+    cudaStream_t st = ctx->stream;
+    const int R = ctx->rings, n = ctx->spokes, B = ctx->bins;
+    LosArgs la{};
+    la.grid = ctx->dGrid.p; la.halos = ctx->dHalos.p; la.batchHalos = ctx->dBatchHalos.p;
+    la.valTaps = ctx->dTaps0.p; la.derivTaps = ctx->dTaps1.p;
+    la.rsp = ctx->dRsp.p; la.profiles = ctx->taps ? ctx->dProfiles.p : nullptr;
+    la.rings = R; la.spokes = n; la.bins = B; la.window = static_cast<int>(ctx->p.smoothing_window);
+    la.dLim = ctx->p.los_slope_cutoff;
+    ctx->timer.begin(ST_LOS, st);
+    CU(launch_los(la, nb, st));
+    ctx->stats.launches++;
+    ctx->timer.end(ST_LOS, st);
+
+    FilterArgs fa{};
+    fa.rsp = ctx->dRsp.p; fa.halos = ctx->dHalos.p; fa.batchHalos = ctx->dBatchHalos.p;
+    fa.fR = ctx->dFR.p; fa.fIdx = ctx->dFIdx.p; fa.fCount = ctx->dFCount.p; fa.status = ctx->dStatus.p;
+    fa.rings = R; fa.spokes = n; fa.levels = static_cast<int>(ctx->p.levels);
+    fa.eta = ctx->p.eta; fa.ringPhi = ctx->dPhi.p;
+    ctx->timer.begin(ST_FILTER, st);
+    CU(launch_filter(fa, nb, st));
+    ctx->stats.launches++;
+    ctx->timer.end(ST_FILTER, st);
+
+    FitArgs ft{};
+    ft.fR = ctx->dFR.p; ft.fIdx = ctx->dFIdx.p; ft.fCount = ctx->dFCount.p;
+    ft.batchHalos = ctx->dBatchHalos.p; ft.irots = ctx->dIrots.p;
+    ft.ringCos = ctx->dCos.p; ft.ringSin = ctx->dSin.p;
+    ft.coeffs = ctx->dCoeffs.p; ft.status = ctx->dStatus.p; ft.nPoints = ctx->dNPoints.p;
+    ft.rings = R; ft.spokes = n; ft.order = static_cast<int>(ctx->p.order);
+    ctx->timer.begin(ST_FIT, st);
+    CU(launch_fit(ft, nb, st));
+    ctx->stats.launches++;
+    ctx->timer.end(ST_FIT, st);
+    return SFK_OK;
+}
+
+int stage_collect(sfk_ctx *ctx, double *coeffs, int32_t *status) {
+    cudaStream_t st = ctx->stream;
+    const int64_t nHalo = static_cast<int64_t>(ctx->halos.size());
+    const int P2 = ctx->P2;
+    std::vector<int32_t> dstat(nHalo);
+    std::vector<unsigned long long> nInter(nHalo);
+    std::vector<long long> nPts(nHalo);
+    CU(cudaMemcpyAsync(ctx->hCoeffs.data(), ctx->dCoeffs.p, ctx->hCoeffs.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(dstat.data(), ctx->dStatus.p, nHalo * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(nInter.data(), ctx->dNInter.p, nHalo * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(nPts.data(), ctx->dNPoints.p, nHalo * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < nHalo; i++) {
+        if (ctx->hStatus[i] == SFK_HALO_OK) ctx->hStatus[i] = dstat[i];
+        if (ctx->hStatus[i] != SFK_HALO_OK)
+            for (int k = 0; k < P2; k++) ctx->hCoeffs[i * P2 + k] = 0.0;
+        ctx->stats.n_intersections += static_cast<int64_t>(nInter[i]);
+        ctx->stats.n_points += nPts[i];
+    }
+    ctx->stats.n_candidates = ctx->candCount;
+    ctx->stats.ms_cull = ctx->timer.collect(ST_CULL);
+    ctx->stats.ms_hits = ctx->timer.collect(ST_HITS);
+    ctx->stats.ms_bin = ctx->timer.collect(ST_BIN);
+    ctx->stats.ms_los = ctx->timer.collect(ST_LOS);
+    ctx->stats.ms_filter = ctx->timer.collect(ST_FILTER);
+    ctx->stats.ms_fit = ctx->timer.collect(ST_FIT);
+    if (coeffs) std::memcpy(coeffs, ctx->hCoeffs.data(), ctx->hCoeffs.size() * sizeof(double));
+    if (status) std::memcpy(status, ctx->hStatus.data(), nHalo * sizeof(int32_t));
+    ctx->finished = true;
+    ctx->splitPhase = 0;
+    return SFK_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
 
 void sfk_default_params(sfk_params *p) {
     std::memset(p, 0, sizeof *p);
@@ -323,7 +596,7 @@ int sfk_begin_snapshot(sfk_ctx *ctx, const sfk_cosmo *cosmo, float min_mass) {
     ctx->halos.clear(); ctx->ox.clear(); ctx->oy.clear(); ctx->oz.clear();
     ctx->segs.clear(); ctx->candPerHalo.clear();
     ctx->candCount = 0;
-    ctx->inSnapshot = true; ctx->finished = false;
+    ctx->inSnapshot = true; ctx->finished = false; ctx->splitPhase = 0;
     ctx->stats = sfk_stats{};
     return SFK_OK;
 }
@@ -426,251 +699,92 @@ int sfk_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass,
 
 int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) {
     if (!ctx || !ctx->inSnapshot) return fail(ctx, SFK_E_INVALID, "sfk_finish_snapshot: no snapshot open");
+    if (ctx->splitPhase != 0) return fail(ctx, SFK_E_INVALID, "sfk_finish_snapshot: a split-halo pass is open");
     CU(cudaSetDevice(ctx->p.device));
-    cudaStream_t st = ctx->stream;
-    const int64_t nHalo = static_cast<int64_t>(ctx->halos.size());
-    const int R = ctx->rings, n = ctx->spokes, B = ctx->bins, P2 = ctx->P2;
-    const size_t rn = static_cast<size_t>(R) * n, rnb = rn * B;
-    ctx->hCoeffs.assign(static_cast<size_t>(nHalo) * P2, 0.0);
-    ctx->hStatus.assign(nHalo, SFK_HALO_OK);
-    if (nHalo == 0) { ctx->finished = true; return SFK_OK; }
-
-    // per-halo result buffers
-    CU(ctx->dRsp.ensure(nHalo * rn));
-    CU(ctx->dCoeffs.ensure(static_cast<size_t>(nHalo) * P2));
-    CU(ctx->dStatus.ensure(nHalo));
-    CU(ctx->dNInter.ensure(nHalo));
-    CU(ctx->dRhoMax.ensure(nHalo));
-    CU(ctx->dNPoints.ensure(nHalo));
-    CU(ctx->dHitCount.ensure(static_cast<size_t>(nHalo) * R));
-    CU(cudaMemsetAsync(ctx->dRsp.p, 0xff, nHalo * rn * sizeof(double), st));  // NaN
-    CU(cudaMemsetAsync(ctx->dCoeffs.p, 0, static_cast<size_t>(nHalo) * P2 * sizeof(double), st));
-    CU(cudaMemsetAsync(ctx->dStatus.p, 0, nHalo * sizeof(int32_t), st));
-    CU(cudaMemsetAsync(ctx->dNInter.p, 0, nHalo * sizeof(unsigned long long), st));
-    CU(cudaMemsetAsync(ctx->dRhoMax.p, 0, nHalo * sizeof(unsigned long long), st));
-    CU(cudaMemsetAsync(ctx->dNPoints.p, 0, nHalo * sizeof(long long), st));
-    CU(cudaMemsetAsync(ctx->dHitCount.p, 0, static_cast<size_t>(nHalo) * R * sizeof(uint32_t), st));
-    if (ctx->taps) {
-        CU(ctx->dProfiles.ensure(nHalo * rnb));
-        CU(ctx->dTapInsert.ensure(nHalo * rn));
-        CU(ctx->dTapStart.ensure(nHalo * rnb));
-        CU(ctx->dTapEnd.ensure(nHalo * rnb));
-        CU(cudaMemsetAsync(ctx->dProfiles.p, 0, nHalo * rnb * sizeof(double), st));
-        CU(cudaMemsetAsync(ctx->dTapInsert.p, 0, nHalo * rn * sizeof(uint32_t), st));
-        CU(cudaMemsetAsync(ctx->dTapStart.p, 0, nHalo * rnb * sizeof(uint32_t), st));
-        CU(cudaMemsetAsync(ctx->dTapEnd.p, 0, nHalo * rnb * sizeof(uint32_t), st));
-    }
-
-    // Savitzky-Golay taps: built once per process from the first smoothed
-    // profile's dx = ln r1 - ln r0 (smooth.go:63,84-96)
-    if (!ctx->tapsReady && B > ctx->p.smoothing_window) {
-        for (const HaloDev &h : ctx->halos) {
-            if (!h.valid) continue;
-            const double r0 = std::exp(h.lrMin + h.dlr * (0.0 + 0.5));
-            const double r1 = std::exp(h.lrMin + h.dlr * (1.0 + 0.5));
-            const double dx = std::log(r1) - std::log(r0);
-            std::vector<double> k0, k1;
-            if (!savgol_taps(4, static_cast<int>(ctx->p.smoothing_window), 0, 0, k0) ||
-                !savgol_taps(4, static_cast<int>(ctx->p.smoothing_window), 1, dx, k1))
-                return fail(ctx, SFK_E_INVALID, "Savitzky-Golay kernel construction failed");
-            CU(ctx->dTaps0.upload(k0, st));
-            CU(ctx->dTaps1.upload(k1, st));
-            CU(cudaStreamSynchronize(st));
-            ctx->tapsReady = true;
-            break;
-        }
-    }
-    if (!ctx->tapsReady) {
-        std::vector<double> z(std::max<int64_t>(ctx->p.smoothing_window, 1), 0.0);
-        CU(ctx->dTaps0.upload(z, st));
-        CU(ctx->dTaps1.upload(z, st));
-        CU(cudaStreamSynchronize(st));
-    }
-
-    // pieces: <= 256 candidates of one halo each, grouped per halo
-    std::vector<std::vector<Piece>> perHalo(nHalo);
-    for (const Seg &s : ctx->segs)
-        for (int32_t off = 0; off < s.count; off += 256)
-            perHalo[s.halo].push_back({s.start + off, std::min<int32_t>(256, s.count - off), s.halo});
-    std::vector<Piece> all;
-    for (auto &v : perHalo) all.insert(all.end(), v.begin(), v.end());
-
-    // pass 1: hits per (halo, ring) and largest rho per halo
-    ctx->timer.begin(ST_HITS, st);
-    CU(ctx->dPieces.upload(all, st));
-    CU(launch_hit_count(ctx->dPieces.p, static_cast<int>(all.size()), ctx->dCands.p, ctx->dHalos.p,
-                        ctx->dNorms.p, R, ctx->dHitCount.p, ctx->dRhoMax.p, st));
-    ctx->stats.launches++;
-    ctx->timer.end(ST_HITS, st);
-    std::vector<uint32_t> hitCount(static_cast<size_t>(nHalo) * R);
-    std::vector<unsigned long long> rhoMaxBits(nHalo);
-    CU(cudaMemcpyAsync(hitCount.data(), ctx->dHitCount.p, hitCount.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(rhoMaxBits.data(), ctx->dRhoMax.p, nHalo * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-
-    // fixed-point scale per halo: |sum| <= 2 * hits_ring_max * rho_max < 2^62
-    std::vector<int64_t> hitsPerHalo(nHalo, 0);
-    for (int64_t i = 0; i < nHalo; i++) {
-        uint32_t hmax = 0;
-        for (int r = 0; r < R; r++) {
-            hmax = std::max(hmax, hitCount[i * R + r]);
-            hitsPerHalo[i] += hitCount[i * R + r];
-        }
-        double rhoMax;
-        std::memcpy(&rhoMax, &rhoMaxBits[i], sizeof rhoMax);
-        int e = 0;
-        if (hmax > 0 && rhoMax > 0 && std::isfinite(rhoMax)) {
-            const double bound = 2.0 * static_cast<double>(hmax) * rhoMax;
-            e = 61 - std::ilogb(bound);
-            e = std::max(-900, std::min(900, e));
-        }
-        ctx->halos[i].scale = std::ldexp(1.0, e);
-        ctx->halos[i].quantum = std::ldexp(1.0, -e);
-        ctx->stats.n_ring_hits += hitsPerHalo[i];
-    }
-    CU(ctx->dHalos.upload(ctx->halos, st));
-    CU(ctx->dHaloSlot.ensure(nHalo));
-
+    int rc = stage_prepare(ctx);
+    if (rc) return rc;
+    if (ctx->halos.empty()) { ctx->finished = true; return SFK_OK; }
+    rc = stage_scale(ctx, false);
+    if (rc) return rc;
     // batches of halos in input order, bounded by hit-record and grid memory
     const int64_t maxBatch = 64;
     const int64_t hitBudget = (int64_t(6) << 30) / static_cast<int64_t>(sizeof(HitRec));
-    std::vector<int32_t> order;
-    for (int64_t i = 0; i < nHalo; i++) {
-        if (ctx->halos[i].valid && ctx->halos[i].owned) order.push_back(static_cast<int32_t>(i));
-        else if (ctx->halos[i].valid) ctx->hStatus[i] = SFK_HALO_NOT_OWNED;
-        else ctx->hStatus[i] = SFK_HALO_SKIPPED;
-    }
     size_t pos = 0;
-    while (pos < order.size()) {
+    while (pos < ctx->order.size()) {
         std::vector<int32_t> batch;
         int64_t hits = 0;
-        while (pos < order.size() && static_cast<int64_t>(batch.size()) < maxBatch) {
-            const int64_t hh = hitsPerHalo[order[pos]];
+        while (pos < ctx->order.size() && static_cast<int64_t>(batch.size()) < maxBatch) {
+            const int64_t hh = ctx->hitsPerHalo[ctx->order[pos]];
             if (!batch.empty() && hits + hh > hitBudget) break;
-            batch.push_back(order[pos++]);
+            batch.push_back(ctx->order[pos++]);
             hits += hh;
         }
-        const int nb = static_cast<int>(batch.size());
-        std::vector<int32_t> haloSlot(nHalo, -1);
-        std::vector<int64_t> hitOffset(static_cast<size_t>(nb) * R);
-        std::vector<uint32_t> bHitCount(static_cast<size_t>(nb) * R);
-        std::vector<Piece> pieces;
-        int64_t run = 0;
-        for (int s = 0; s < nb; s++) {
-            const int32_t hIdx = batch[s];
-            haloSlot[hIdx] = s;
-            for (int r = 0; r < R; r++) {
-                hitOffset[static_cast<size_t>(s) * R + r] = run;
-                bHitCount[static_cast<size_t>(s) * R + r] = hitCount[static_cast<size_t>(hIdx) * R + r];
-                run += hitCount[static_cast<size_t>(hIdx) * R + r];
-            }
-            pieces.insert(pieces.end(), perHalo[hIdx].begin(), perHalo[hIdx].end());
-        }
-        CU(ctx->dRecs.ensure(std::max<int64_t>(run, 1)));
-        CU(ctx->dGrid.ensure(static_cast<size_t>(nb) * rnb));
-        CU(ctx->dHitCursor.ensure(static_cast<size_t>(nb) * R));
-        CU(ctx->dFR.ensure(static_cast<size_t>(nb) * rn));
-        CU(ctx->dFIdx.ensure(static_cast<size_t>(nb) * rn));
-        CU(ctx->dFCount.ensure(static_cast<size_t>(nb) * R));
-        CU(ctx->dPieces.upload(pieces, st));
-        CU(ctx->dBatchHalos.upload(batch, st));
-        CU(ctx->dHaloSlot.upload(haloSlot, st));
-        CU(ctx->dHitOffset.upload(hitOffset, st));
-        CU(ctx->dBatchHitCount.upload(bHitCount, st));
-        CU(cudaMemsetAsync(ctx->dHitCursor.p, 0, static_cast<size_t>(nb) * R * sizeof(uint32_t), st));
-        CU(cudaMemsetAsync(ctx->dGrid.p, 0, static_cast<size_t>(nb) * rnb * sizeof(unsigned long long), st));
-
-        // pass 2: ring-frame hit records
-        ctx->timer.begin(ST_HITS, st);
-        CU(launch_hits(ctx->dPieces.p, static_cast<int>(pieces.size()), ctx->dCands.p, ctx->dHalos.p,
-                       ctx->dNorms.p, ctx->dRots.p, ctx->dCos.p, ctx->dSin.p, R, n, ctx->tab.dPhi,
-                       ctx->dHitOffset.p, ctx->dHitCursor.p, ctx->dHaloSlot.p, ctx->dRecs.p, st));
-        ctx->stats.launches++;
-        ctx->timer.end(ST_HITS, st);
-
-        // binning: Halo.Insert for every queued particle
-        BinArgs ba{};
-        ba.recs = ctx->dRecs.p; ba.hitOffset = ctx->dHitOffset.p; ba.hitCount = ctx->dHitCursor.p;
-        ba.halos = ctx->dHalos.p; ba.batchHalos = ctx->dBatchHalos.p;
-        ba.ringCos = ctx->dCos.p; ba.ringSin = ctx->dSin.p;
-        ba.grid = ctx->dGrid.p; ba.nIntersections = ctx->dNInter.p;
-        ba.tapInsert = ctx->dTapInsert.p; ba.tapStart = ctx->dTapStart.p; ba.tapEnd = ctx->dTapEnd.p;
-        ba.rings = R; ba.spokes = n; ba.bins = B;
-        ba.binInvG = ctx->dBinInvG.p;
-        ba.invDr = 1.0 / ctx->tab.dr0;
-        ba.cK = static_cast<float>(0.6931471805599453 / ctx->tab.dr0);
-        // split long hit lists when there are too few CTAs to fill 148 SMs x 2 for a few waves
-        const int64_t ctas = static_cast<int64_t>((n + kTileLos - 1) / kTileLos) * R * nb;
-        ba.chunks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(64, (148 * 2 * 4 + ctas - 1) / ctas)));
-        ctx->timer.begin(ST_BIN, st);
-        CU(launch_bin(ba, nb, ctx->taps, st));
-        ctx->stats.launches++; ctx->stats.bin_launches++;
-        ctx->timer.end(ST_BIN, st);
-
-        // per-LoS analysis
-        LosArgs la{};
-        la.grid = ctx->dGrid.p; la.halos = ctx->dHalos.p; la.batchHalos = ctx->dBatchHalos.p;
-        la.valTaps = ctx->dTaps0.p; la.derivTaps = ctx->dTaps1.p;
-        la.rsp = ctx->dRsp.p; la.profiles = ctx->taps ? ctx->dProfiles.p : nullptr;
-        la.rings = R; la.spokes = n; la.bins = B; la.window = static_cast<int>(ctx->p.smoothing_window);
-        la.dLim = ctx->p.los_slope_cutoff;
-        ctx->timer.begin(ST_LOS, st);
-        CU(launch_los(la, nb, st));
-        ctx->stats.launches++;
-        ctx->timer.end(ST_LOS, st);
-
-        FilterArgs fa{};
-        fa.rsp = ctx->dRsp.p; fa.halos = ctx->dHalos.p; fa.batchHalos = ctx->dBatchHalos.p;
-        fa.fR = ctx->dFR.p; fa.fIdx = ctx->dFIdx.p; fa.fCount = ctx->dFCount.p; fa.status = ctx->dStatus.p;
-        fa.rings = R; fa.spokes = n; fa.levels = static_cast<int>(ctx->p.levels);
-        fa.eta = ctx->p.eta; fa.ringPhi = ctx->dPhi.p;
-        ctx->timer.begin(ST_FILTER, st);
-        CU(launch_filter(fa, nb, st));
-        ctx->stats.launches++;
-        ctx->timer.end(ST_FILTER, st);
-
-        FitArgs ft{};
-        ft.fR = ctx->dFR.p; ft.fIdx = ctx->dFIdx.p; ft.fCount = ctx->dFCount.p;
-        ft.batchHalos = ctx->dBatchHalos.p; ft.irots = ctx->dIrots.p;
-        ft.ringCos = ctx->dCos.p; ft.ringSin = ctx->dSin.p;
-
-        ft.coeffs = ctx->dCoeffs.p; ft.status = ctx->dStatus.p; ft.nPoints = ctx->dNPoints.p;
-        ft.rings = R; ft.spokes = n; ft.order = static_cast<int>(ctx->p.order);
-        ctx->timer.begin(ST_FIT, st);
-        CU(launch_fit(ft, nb, st));
-        ctx->stats.launches++;
-        ctx->timer.end(ST_FIT, st);
-        // host vectors of this batch are read by async copies: drain before they die
-        CU(cudaStreamSynchronize(st));
+        rc = stage_bin(ctx, batch);
+        if (rc) return rc;
+        rc = stage_analyze(ctx, static_cast<int>(batch.size()));
+        if (rc) return rc;
     }
+    return stage_collect(ctx, coeffs, status);
+}
 
-    // results
-    std::vector<int32_t> dstat(nHalo);
-    std::vector<unsigned long long> nInter(nHalo);
-    std::vector<long long> nPts(nHalo);
-    CU(cudaMemcpyAsync(ctx->hCoeffs.data(), ctx->dCoeffs.p, ctx->hCoeffs.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(dstat.data(), ctx->dStatus.p, nHalo * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(nInter.data(), ctx->dNInter.p, nHalo * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(nPts.data(), ctx->dNPoints.p, nHalo * sizeof(long long), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    for (int64_t i = 0; i < nHalo; i++) {
-        if (ctx->hStatus[i] == SFK_HALO_OK) ctx->hStatus[i] = dstat[i];
-        if (ctx->hStatus[i] != SFK_HALO_OK)
-            for (int k = 0; k < P2; k++) ctx->hCoeffs[i * P2 + k] = 0.0;
-        ctx->stats.n_intersections += static_cast<int64_t>(nInter[i]);
-        ctx->stats.n_points += nPts[i];
-    }
-    ctx->stats.n_candidates = ctx->candCount;
-    ctx->stats.ms_cull = ctx->timer.collect(ST_CULL);
-    ctx->stats.ms_hits = ctx->timer.collect(ST_HITS);
-    ctx->stats.ms_bin = ctx->timer.collect(ST_BIN);
-    ctx->stats.ms_los = ctx->timer.collect(ST_LOS);
-    ctx->stats.ms_filter = ctx->timer.collect(ST_FILTER);
-    ctx->stats.ms_fit = ctx->timer.collect(ST_FIT);
-    if (coeffs) std::memcpy(coeffs, ctx->hCoeffs.data(), ctx->hCoeffs.size() * sizeof(double));
-    if (status) std::memcpy(status, ctx->hStatus.data(), nHalo * sizeof(int32_t));
-    ctx->finished = true;
+// ---- split-halo mode: one halo's particles spread over several GPUs -----------
+
+int sfk_split_count(sfk_ctx *ctx) {
+    if (!ctx || !ctx->inSnapshot || ctx->splitPhase != 0)
+        return fail(ctx, SFK_E_INVALID, "sfk_split_count: no snapshot open or split pass already started");
+    CU(cudaSetDevice(ctx->p.device));
+    int rc = stage_prepare(ctx);
+    if (rc) return rc;
+    const size_t nc = ctx->halos.size() * static_cast<size_t>(ctx->rings);
+    CU(ctx->dHitCountGlobal.ensure(nc));
+    if (nc) CU(cudaMemcpyAsync(ctx->dHitCountGlobal.p, ctx->dHitCount.p, nc * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->splitPhase = 1;
     return SFK_OK;
+}
+
+int sfk_split_bin(sfk_ctx *ctx) {
+    if (!ctx || ctx->splitPhase != 1) return fail(ctx, SFK_E_INVALID, "sfk_split_bin: call sfk_split_count first");
+    CU(cudaSetDevice(ctx->p.device));
+    CU(cudaDeviceSynchronize());   // the caller's collectives ran on other streams
+    int rc = stage_scale(ctx, true);
+    if (rc) return rc;
+    const size_t rnb = static_cast<size_t>(ctx->rings) * ctx->spokes * ctx->bins;
+    if (ctx->order.size() * rnb * sizeof(unsigned long long) > (size_t(96) << 30))
+        return fail(ctx, SFK_E_NOMEM, "sfk_split_bin: the bin grids of all halos must fit in HBM at once");
+    rc = stage_bin(ctx, ctx->order);
+    if (rc) return rc;
+    ctx->splitPhase = 2;
+    return SFK_OK;
+}
+
+int sfk_split_buffer(sfk_ctx *ctx, int32_t which, void **d_ptr, int64_t *count) {
+    if (!ctx || !d_ptr || !count) return SFK_E_INVALID;
+    const int64_t nHalo = static_cast<int64_t>(ctx->halos.size());
+    switch (which) {
+    case SFK_SPLIT_HIT_COUNTS:
+        if (ctx->splitPhase < 1) break;
+        *d_ptr = ctx->dHitCountGlobal.p; *count = nHalo * ctx->rings; return SFK_OK;
+    case SFK_SPLIT_RHO_MAX:
+        if (ctx->splitPhase < 1) break;
+        *d_ptr = ctx->dRhoMax.p; *count = nHalo; return SFK_OK;
+    case SFK_SPLIT_GRID:
+        if (ctx->splitPhase < 2) break;
+        *d_ptr = ctx->dGrid.p;
+        *count = static_cast<int64_t>(ctx->order.size()) * ctx->rings * ctx->spokes * ctx->bins;
+        return SFK_OK;
+    default: break;
+    }
+    return fail(ctx, SFK_E_INVALID, "sfk_split_buffer: buffer not available in this phase");
+}
+
+int sfk_split_finish(sfk_ctx *ctx, double *coeffs, int32_t *status) {
+    if (!ctx || ctx->splitPhase != 2) return fail(ctx, SFK_E_INVALID, "sfk_split_finish: call sfk_split_bin first");
+    CU(cudaSetDevice(ctx->p.device));
+    CU(cudaDeviceSynchronize());   // the caller's all-reduce of the grid
+    int rc = stage_analyze(ctx, static_cast<int>(ctx->order.size()));
+    if (rc) return rc;
+    return stage_collect(ctx, coeffs, status);
 }
 
 int sfk_get_stats(const sfk_ctx *ctx, sfk_stats *out) {

@@ -70,3 +70,19 @@ def gather_rows(local_idx, local_rows, n_total, dist=None, device="cpu"):
         m = i_np >= 0
         full[i_np[m]] = r_np[m]
     return full
+
+
+def split_halo_finish(ctx, dist):
+    """Split-halo exchange (BASELINE config 3): every rank has pushed its share
+    of the particle blocks into `ctx`; the three all-reduces below replace
+    Halo.Split/Join (los/halo.go:107-140).  Returns (coeffs, status), identical
+    on every rank."""
+    from . import api
+    ctx.split_count()
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(ctx.split_buffer(api.SPLIT_HIT_COUNTS), op=dist.ReduceOp.SUM)
+        dist.all_reduce(ctx.split_buffer(api.SPLIT_RHO_MAX), op=dist.ReduceOp.MAX)
+    ctx.split_bin()
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(ctx.split_buffer(api.SPLIT_GRID), op=dist.ReduceOp.SUM)
+    return ctx.split_finish()

@@ -254,3 +254,42 @@ def test_full_size_properties():
         assert 0.8 < np.nanmedian(rsp) / halos[h, 3] < 1.7
         # c_000 is the mean shell radius
         assert 0.8 < c[h, 0] / halos[h, 3] < 1.7
+
+
+def test_split_halo_emulated_ranks_match_single_gpu():
+    """BASELINE config 3 at test size: the blocks of one halo are dealt to
+    'ranks' (contexts on this GPU); the NCCL all-reduces of shard.split_halo_finish
+    are emulated with tensor adds on the exchange buffers.  int64 bins make the
+    result bitwise equal to the single-context run for any number of ranks."""
+    import torch
+    halos, blocks, mass = synth.make_box(31, 12.0, 1, 60000, 6000, 3, centers=[[6.0, 6.0, 6.0]], radii=[1.2])
+    params = api.default_params(seed=1337, rings=24)
+    _, c_ref, s_ref = api.run_shell(params, mass, halos, blocks)
+    assert s_ref[0] == 0
+    for world in (2, 3):
+        ctxs = []
+        for r in range(world):
+            ctx = api.ShellContext(params)
+            ctx.begin_snapshot(blocks[0], mass)
+            ctx.add_halos(halos)
+            for b in blocks[r::world]:
+                ctx.push_block(b)
+            ctx.split_count()
+            ctxs.append(ctx)
+        for which, op in ((api.SPLIT_HIT_COUNTS, torch.sum), (api.SPLIT_RHO_MAX, torch.amax)):
+            bufs = [c.split_buffer(which) for c in ctxs]
+            red = op(torch.stack(bufs), dim=0)
+            for b in bufs:
+                b.copy_(red)
+        torch.cuda.synchronize()
+        for c in ctxs:
+            c.split_bin()
+        grids = [c.split_buffer(api.SPLIT_GRID) for c in ctxs]
+        total = torch.stack(grids).sum(dim=0)
+        for g in grids:
+            g.copy_(total)
+        torch.cuda.synchronize()
+        for c in ctxs:
+            coeffs, status = c.split_finish()
+            assert status[0] == 0
+            assert np.array_equal(coeffs, c_ref)
