@@ -1,0 +1,163 @@
+// sf_capi.cpp -- C entry points over the host modules for the CPU test tier
+// (ctypes).  No CUDA here: libsfhost.so loads without a GPU.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sf_catalog.hpp"
+#include "sf_config.hpp"
+#include "sf_shell.hpp"
+#include "sf_snapshot.hpp"
+
+using namespace sfhost;
+
+namespace { std::string g_text; const char *keep(const std::string &s) { g_text = s; return g_text.c_str(); } }
+
+extern "C" {
+
+const char *sfh_go_g6(double v) { return keep(go_g6(v)); }
+
+// names: '\n'-separated; order/sizes: int arrays
+const char *sfh_comment_string(const char *intNames, const char *floatNames, const int *order, int nOrder,
+                               const int *sizes, int nSizes) {
+    auto split = [](const char *s) {
+        std::vector<std::string> out;
+        std::string cur;
+        for (const char *p = s; *p; p++) { if (*p == '\n') { out.push_back(cur); cur.clear(); } else cur += *p; }
+        if (!cur.empty()) out.push_back(cur);
+        return out;
+    };
+    return keep(CommentString(split(intNames), split(floatNames), std::vector<int>(order, order + nOrder),
+                              std::vector<int>(sizes, sizes + nSizes)));
+}
+
+// ints: [nInt][rows], floats: [nFloat][rows]; returns '\n'-joined lines
+const char *sfh_format_cols(const int64_t *ints, int nInt, const double *floats, int nFloat, int rows,
+                            const int *order, int nOrder) {
+    std::vector<std::vector<int64_t>> ic(nInt);
+    std::vector<std::vector<double>> fc(nFloat);
+    for (int i = 0; i < nInt; i++) ic[i].assign(ints + static_cast<size_t>(i) * rows, ints + static_cast<size_t>(i + 1) * rows);
+    for (int i = 0; i < nFloat; i++) fc[i].assign(floats + static_cast<size_t>(i) * rows, floats + static_cast<size_t>(i + 1) * rows);
+    std::string out;
+    for (const std::string &l : FormatCols(ic, fc, std::vector<int>(order, order + nOrder))) { out += l; out += '\n'; }
+    return keep(out);
+}
+
+// Parses `data`; writes up to cap rows of each requested column; returns rows or -1 (error text via sfh_last_text)
+int sfh_parse_catalog(const char *data, const int *icols, int nI, const int *fcols, int nF, int64_t *iout, double *fout, int cap) {
+    std::vector<std::vector<int64_t>> ic;
+    std::vector<std::vector<double>> fc;
+    std::string err = Parse(data, std::vector<int>(icols, icols + nI), std::vector<int>(fcols, fcols + nF), ic, fc);
+    if (!err.empty()) { keep(err); return -1; }
+    const int rows = static_cast<int>(nI ? ic[0].size() : (nF ? fc[0].size() : 0));
+    for (int j = 0; j < nI; j++) for (int i = 0; i < rows && i < cap; i++) iout[static_cast<size_t>(j) * cap + i] = ic[j][i];
+    for (int j = 0; j < nF; j++) for (int i = 0; i < rows && i < cap; i++) fout[static_cast<size_t>(j) * cap + i] = fc[j][i];
+    return rows;
+}
+const char *sfh_last_text() { return g_text.c_str(); }
+
+// makeTestConfig of parse/config_test.go:300-321: one variable of every kind
+// under the header [config].  text == NULL skips the file step; flags is
+// '\n'-separated.  Lists come back joined by ','.
+const char *sfh_read_test_config(const char *text, const char *fname, const char *flags, int64_t *num, double *flt,
+                                 int *okay, char *word, char *nums, char *floats, char *okays, char *words, int cap) {
+    ConfigVars vars("config");
+    int64_t vi; double vf; std::string vs; bool vb;
+    std::vector<int64_t> vis; std::vector<double> vfs; std::vector<std::string> vss; std::vector<bool> vbs;
+    vars.Int(&vi, "num", 0); vars.Ints(&vis, "nums", {}); vars.Float(&vf, "float", 0); vars.Floats(&vfs, "floats", {});
+    vars.Bool(&vb, "okay", false); vars.Bools(&vbs, "okays", {}); vars.String(&vs, "word", "");
+    vars.Strings(&vss, "words", {});
+    std::string err = text ? vars.ReadConfigText(text, fname) : "";
+    if (err.empty() && flags && *flags) {
+        std::vector<std::string> args;
+        std::string cur;
+        for (const char *p = flags; ; p++) {
+            if (*p == '\n' || !*p) { args.push_back(cur); cur.clear(); if (!*p) break; } else cur += *p;
+        }
+        err = vars.ReadFlags(args);
+    }
+    auto put = [cap](char *dst, const std::string &v) { std::strncpy(dst, v.c_str(), cap - 1); dst[cap - 1] = 0; };
+    *num = vi; *flt = vf; *okay = vb;
+    put(word, vs);
+    std::string t;
+    for (size_t k = 0; k < vis.size(); k++) t += (k ? "," : "") + std::to_string(vis[k]);
+    put(nums, t); t.clear();
+    for (size_t k = 0; k < vfs.size(); k++) t += (k ? "," : "") + go_g6(vfs[k]);
+    put(floats, t); t.clear();
+    for (size_t k = 0; k < vbs.size(); k++) t += std::string(k ? "," : "") + (vbs[k] ? "true" : "false");
+    put(okays, t); t.clear();
+    for (size_t k = 0; k < vss.size(); k++) t += (k ? "," : "") + vss[k];
+    put(words, t);
+    return keep(err);
+}
+
+const char *sfh_read_shell_config(const char *fname, const char *flags, int64_t *ints7, double *floats7, int *pp) {
+    ShellConfig c;
+    std::vector<std::string> args;
+    if (flags && *flags) {
+        std::string cur;
+        for (const char *p = flags; ; p++) {
+            if (*p == '\n' || !*p) { args.push_back(cur); cur.clear(); if (!*p) break; } else cur += *p;
+        }
+    }
+    std::string err = c.ReadConfig(fname ? fname : "", args);
+    ints7[0] = c.subsampleFactor; ints7[1] = c.radialBins; ints7[2] = c.spokes; ints7[3] = c.rings;
+    ints7[4] = c.order; ints7[5] = c.levels; ints7[6] = c.smoothingWindow;
+    floats7[0] = c.rMaxMult; floats7[1] = c.rMinMult; floats7[2] = c.rKernelMult; floats7[3] = c.eta;
+    floats7[4] = c.losSlopeCutoff; floats7[5] = c.backgroundRhoMult; floats7[6] = c.percentile;
+    *pp = c.percentileProfile;
+    return keep(err);
+}
+
+const char *sfh_read_global_config(const char *fname, char *snapType, int cap, int64_t *blocks) {
+    GlobalConfig g;
+    std::string err = g.ReadConfig(fname);
+    std::strncpy(snapType, g.SnapshotType.c_str(), cap - 1); snapType[cap - 1] = 0;
+    if (err.empty()) {
+        Catalogs cat;
+        err = cat.Init(g.particle, g.SnapshotType == "gotetra");
+        *blocks = cat.Blocks();
+    }
+    return keep(err);
+}
+
+// expands SnapshotFormat for (snap, block) -> file name
+const char *sfh_catalog_name(const char *format, const char *meanings, const int64_t *mins, const int64_t *maxes,
+                             int nBlockDims, int64_t snapMin, int64_t snapMax, int snap, int block, int *nBlocks) {
+    ParticleInfo info;
+    info.SnapshotFormat = format;
+    std::string cur;
+    for (const char *p = meanings; ; p++) { if (*p == ',' || !*p) { info.SnapshotFormatMeanings.push_back(trim_spaces(cur)); cur.clear(); if (!*p) break; } else cur += *p; }
+    info.BlockMins.assign(mins, mins + nBlockDims); info.BlockMaxes.assign(maxes, maxes + nBlockDims);
+    info.SnapMin = snapMin; info.SnapMax = snapMax;
+    Catalogs cat;
+    std::string err = cat.Init(info, false);
+    if (!err.empty()) { *nBlocks = -1; return keep(err); }
+    *nBlocks = cat.Blocks();
+    return keep(cat.ParticleCatalog(snap, block));
+}
+
+// Reads one block with the named reader.  Returns N or -1; data copied to xs/ms (cap entries).
+int64_t sfh_read_block(const char *type, const char *fname, const char *endianness, int64_t npartNum, double posUnits,
+                       double massUnits, float *xs, float *ms, int64_t cap, void *header72, float *minMass,
+                       int64_t *total) {
+    Context ctx;
+    ctx.LGadgetNPartNum = npartNum; ctx.GadgetPositionUnits = posUnits; ctx.GadgetMassUnits = massUnits;
+    std::unique_ptr<VectorBuffer> buf;
+    std::string err = NewVectorBuffer(type, fname, endianness, ctx, buf);
+    if (!err.empty()) { keep(err); return -1; }
+    const float *px, *pm;
+    int64_t n;
+    if (!(err = buf->Read(fname, &px, &pm, &n)).empty()) { keep(err); return -1; }
+    for (int64_t i = 0; i < n && i < cap; i++) { std::memcpy(xs + 3 * i, px + 3 * i, 12); ms[i] = pm[i]; }
+    Header hd;
+    if (!(err = buf->ReadHeader(fname, hd)).empty()) { keep(err); return -1; }
+    std::memcpy(header72, &hd, sizeof hd);
+    *minMass = buf->MinMass();
+    if (!(err = buf->TotalParticles(fname, *total)).empty()) { keep(err); return -1; }
+    return n;
+}
+
+void sfh_bounding_box(const float *xs, int64_t n, double tw, float *origin, float *width) { boundingBox(xs, n, tw, origin, width); }
+
+}  // extern "C"

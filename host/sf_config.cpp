@@ -2,6 +2,9 @@
 #include "sf_config.hpp"
 
 #include <cerrno>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>

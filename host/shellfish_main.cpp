@@ -1,0 +1,129 @@
+// shellfish_main.cpp -- `shellfish shell [shell.config] [--Flag value ...]`:
+// the reference's CLI protocol (shellfish.go:305-450) for the one mode this
+// repository rebuilds.  stdin: halo table `ID Snap X Y Z R200m`; stdout: the
+// Penna coefficient catalog; errors go to stderr and "Shellfish terminating."
+// to stdout so that the next pipe stage aborts.
+//
+// New knobs are environment variables (config files stay valid for the Go
+// binary): SHELLFISH_SEED pins cmd/cmd.go:658's wall-clock seed,
+// SHELLFISH_GPU picks the CUDA device.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <iterator>
+#include <sstream>
+
+#include "sf_config.hpp"
+#include "sf_shell.hpp"
+
+using namespace sfhost;
+
+namespace {
+
+[[noreturn]] void die(const std::string &mode, const std::string &msg) {
+    std::fprintf(stderr, "Error running mode %s:\n%s\n", mode.c_str(), msg.c_str());
+    std::printf("Shellfish terminating.\n");
+    std::exit(1);
+}
+
+bool file_equal_config(const GlobalConfig &a, const GlobalConfig &b) {   // configEqual, shellfish.go:566-600
+    return a.Version == b.Version && a.particle.SnapshotFormat == b.particle.SnapshotFormat &&
+           a.SnapshotType == b.SnapshotType && a.HaloDir == b.HaloDir && a.HaloType == b.HaloType &&
+           a.TreeDir == b.TreeDir && a.particle.BlockMins == b.particle.BlockMins &&
+           a.particle.BlockMaxes == b.particle.BlockMaxes && a.particle.SnapMin == b.particle.SnapMin &&
+           a.particle.SnapMax == b.particle.SnapMax &&
+           a.particle.SnapshotFormatMeanings == b.particle.SnapshotFormatMeanings &&
+           a.HaloValueNames == b.HaloValueNames && a.HaloValueColumns == b.HaloValueColumns &&
+           a.HaloPositionUnits == b.HaloPositionUnits && a.HaloRadiusUnits == b.HaloRadiusUnits &&
+           a.HaloMassUnits == b.HaloMassUnits && a.Endianness == b.Endianness;
+}
+
+std::string check_memo_dir(const std::string &memoDir, const std::string &configFile) {   // shellfish.go:491-521
+    const std::string memoConfig = memoDir + "/memo.config";
+    std::ifstream probe(memoConfig);
+    if (!probe) {
+        std::ifstream src(configFile, std::ios::binary);
+        std::ofstream dst(memoConfig, std::ios::binary);
+        if (!src || !dst) return "could not copy " + configFile + " to " + memoConfig;
+        dst << src.rdbuf();
+        return "";
+    }
+    GlobalConfig a, b;
+    std::string err;
+    if (!(err = a.ReadConfig(configFile)).empty()) return err;
+    if (!(err = b.ReadConfig(memoConfig)).empty()) return err;
+    if (!file_equal_config(a, b))
+        return "You've changed the variables in the config file " + configFile +
+               " in a way that would invlalidate the files Shellfish cached in " + memoDir +
+               " (i.e. MemoDir) to speed up performance. Remove the contents of MemoDir (a copy of the old config "
+               "is in " + memoConfig + ") or fix the MemoDir variable.";
+    return "";
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc <= 1) {
+        std::fprintf(stderr, "I was not supplied with a mode.\nFor help, type './shellfish help'.\n");
+        return 1;
+    }
+    const std::string mode = argv[1];
+    if (mode == "help") {
+        if (argc == 3 && std::string(argv[2]) == "shell.config") std::printf("%s\n", ShellConfig::ExampleConfig());
+        else std::printf("shellfish shell [shell.config] [--Flag value ...]   (B200 build: only the shell mode is built)\n");
+        return 0;
+    }
+    if (mode == "version") { std::printf("Shellfish version %s\n", kSourceVersion); return 0; }
+    if (mode == "hello") { std::printf("Hello back at you! Installation was successful.\n"); return 0; }
+    if (mode != "shell") {
+        std::fprintf(stderr, "You passed me the mode '%s', which this B200 build does not provide.\n"
+                             "For help, type './shellfish help'\n", mode.c_str());
+        std::printf("Shellfish terminating.\n");
+        return 1;
+    }
+    // all of stdin (shellfish.go:351-373)
+    std::string stdinData((std::istreambuf_iterator<char>(std::cin)), std::istreambuf_iterator<char>());
+    if (stdinData.empty()) return 0;
+    size_t lineEnd = stdinData.find('\n');
+    if (lineEnd == std::string::npos) lineEnd = stdinData.size();
+    if (lineEnd >= 9 && stdinData.compare(0, 9, "Shellfish") == 0) {
+        std::printf("%s\n", stdinData.substr(0, lineEnd).c_str());
+        return 1;
+    }
+    std::vector<std::string> rest(argv + 2, argv + argc), flags;
+    std::string configName;
+    if (!rest.empty() && !rest[0].empty() && rest[0][0] != '-') { configName = rest[0]; flags.assign(rest.begin() + 1, rest.end()); }
+    else flags = rest;
+
+    const char *gName = std::getenv("SHELLFISH_GLOBAL_CONFIG");
+    if (!gName || !*gName) die(mode, "$SHELLFISH_GLOBAL_CONFIG has not been set.");
+    GlobalConfig g;
+    std::string err = g.ReadConfig(gName);
+    if (!err.empty()) die(mode, err);
+    ShellConfig c;
+    if (!(err = c.ReadConfig(configName, flags)).empty()) die(mode, err);
+    if (!(err = check_memo_dir(g.MemoDir, gName)).empty()) die(mode, err);
+    if (g.SnapshotType == "nil") {
+        std::fprintf(stderr, "Cannot run mode %s with SnapshotType = nil\n", mode.c_str());
+        std::printf("Shellfish terminating\n");
+        return 1;
+    }
+    if (g.Logging != "nil" && g.Logging != "performance" && g.Logging != "debug") {
+        std::fprintf(stderr, "Unrecognized logging mode, %s\n", g.Logging.c_str());
+        return 1;
+    }
+    uint64_t seed = static_cast<uint64_t>(std::chrono::system_clock::now().time_since_epoch().count());
+    if (const char *s = std::getenv("SHELLFISH_SEED")) seed = std::strtoull(s, nullptr, 10);
+    const int device = std::getenv("SHELLFISH_GPU") ? std::atoi(std::getenv("SHELLFISH_GPU")) : 0;
+    if (g.Logging != "nil") {
+        std::fprintf(stderr, "\n#####################\n## shellfish shell ##\n#####################\n");
+        std::fprintf(stderr, "RNG Seed is %llu\n", static_cast<unsigned long long>(seed));
+    }
+    std::vector<std::string> lines;
+    if (!(err = RunShell(g, c, stdinData, seed, device, lines)).empty()) die(mode, err);
+    for (const std::string &l : lines) std::printf("%s\n", l.c_str());
+    return 0;
+}

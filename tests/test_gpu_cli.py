@@ -1,0 +1,106 @@
+"""End to end through the `shellfish shell` binary (host/shellfish_main.cpp):
+LGadget-2 files on disk -> stdin halo table -> catalog text on stdout, compared
+with (a) the same run driven through the Python C-ABI binding and (b) the CPU
+oracle, at the precision the catalog prints (%.6g, cmd/catalog/catalog.go:118).
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from shellfish_b200 import api, hostlib as H, snapio, synth
+
+pytestmark = pytest.mark.gpu
+
+GLOBAL = """[config]
+Version = 1.0.4
+SnapshotFormat = %s/snap_%%03d.%%d
+SnapshotFormatMeanings = Snapshot, Block
+SnapshotType = LGadget-2
+BlockMins = 0
+BlockMaxes = %d
+SnapMin = 100
+SnapMax = 100
+MemoDir = %s/memo
+"""
+
+
+def _setup(tmp_path, seed, n_halos, n_per, n_bg, cells, box=62.5):
+    halos, blocks, mass = synth.make_box(seed, box, n_halos, n_per, n_bg, cells, margin=8.0)
+    names = snapio.write_box_lgadget2(str(tmp_path), "snap_%03d.%d", blocks)
+    cfg = tmp_path / "g.config"
+    cfg.write_text(GLOBAL % (tmp_path, len(blocks) - 1, tmp_path))
+    # what the reader hands to the loop: tight bounding boxes, uniform mass from NPartTotal
+    rb = []
+    for f in names:
+        xs, ms, hd, min_mass, _ = H.read_block("LGadget-2", f)
+        rb.append(dict(Z=hd["z"], OmegaM=hd["omega_m"], OmegaL=hd["omega_l"], H100=hd["h100"],
+                       TotalWidth=hd["total_width"], Origin=tuple(hd["origin"]), Width=tuple(hd["width"]),
+                       xs=xs.copy(), ms=ms.copy()))
+    return halos, rb, min_mass, str(cfg)
+
+
+def _run_cli(cfg, halos, flags, seed=1337, snap=100):
+    stdin = "# ID Snap X Y Z R200m\n" + "".join(
+        "%d %d %.17g %.17g %.17g %.17g\n" % (i, snap, *h[:4]) for i, h in enumerate(halos))
+    env = dict(os.environ, SHELLFISH_GLOBAL_CONFIG=cfg, SHELLFISH_SEED=str(seed))
+    r = subprocess.run([H.cli_path(), "shell"] + flags, input=stdin, capture_output=True, text=True, env=env,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr
+    return r.stdout.split("\n")[:-1]
+
+
+def test_cli_matches_binding_and_oracle(tmp_path):
+    halos, blocks, min_mass, cfg = _setup(tmp_path, 11, 3, 30000, 20000, 2)
+    lines = _run_cli(cfg, halos, ["--Rings", "12"])
+    assert lines[0] == ("# Column contents: ID(0) Snapshot(1) X [cMpc/h](2) Y [cMpc/h](3) Z [cMpc/h](4) "
+                        "R200m [cMpc/h](5) P_ijk(6-23)")
+    assert len(lines) == 1 + len(halos)
+
+    # (a) same run through the ctypes binding, printed by the same formatter: text-identical
+    params = api.default_params(seed=1337, rings=12)
+    _, coeffs, status = api.run_shell(params, min_mass, halos, blocks)
+    assert np.all(status == 0)
+    ids = np.arange(len(halos))
+    fcols = [halos[:, k] for k in range(4)] + [coeffs[:, k] for k in range(coeffs.shape[1])]
+    want = H.format_cols([ids, np.full(len(halos), 100)], fcols, list(range(2 + len(fcols))))
+    assert lines[1:] == want
+
+    # (b) the oracle on the same blocks: every printed coefficient within 1e-5 of the halo's scale
+    ref = po.shell_run(po.ShellConfig.default(seed=1337, threads=1, rings=12), min_mass, halos, blocks)
+    ic, fc = H.parse_catalog("\n".join(lines) + "\n", [0, 1], list(range(2, 24)))
+    assert ic[0].tolist() == ids.tolist() and np.all(ic[1] == 100)
+    got = fc[4:].T
+    for h in range(len(halos)):
+        scale = np.max(np.abs(ref["coeffs"][h]))
+        assert np.all(np.abs(got[h] - ref["coeffs"][h]) <= (1e-5 + 5e-6) * scale)   # + the %.6g rounding
+
+
+def test_cli_memo_and_skipped_halo(tmp_path):
+    """Second run reuses MemoDir/hd_snap100.dat; a halo with R200m <= 0 and a
+    Snap == -1 row keep all-zero coefficient rows (cmd/shell.go:325,535-538)."""
+    halos, blocks, min_mass, cfg = _setup(tmp_path, 12, 2, 20000, 10000, 2)
+    first = _run_cli(cfg, halos, ["--Rings", "6"])
+    memo = os.path.join(os.path.dirname(cfg), "memo", "hd_snap100.dat")
+    assert os.path.getsize(memo) == 72 * len(blocks)
+    assert _run_cli(cfg, halos, ["--Rings", "6"]) == first
+    bad = halos.copy()
+    bad[1, 3] = -1.0
+    lines = _run_cli(cfg, bad, ["--Rings", "6"])
+    assert lines[1].split() == first[1].split()
+    assert all(float(v) == 0.0 for v in lines[2].split()[6:])
+    stdin_extra = _run_cli(cfg, halos, ["--Rings", "6"], snap=100)
+    assert stdin_extra == first
+
+
+def test_cli_changed_config_is_refused(tmp_path):   # checkMemoDir, shellfish.go:491-521
+    halos, blocks, min_mass, cfg = _setup(tmp_path, 13, 1, 5000, 2000, 1)
+    _run_cli(cfg, halos, ["--Rings", "4"])
+    text = open(cfg).read().replace("Endianness", "Endianness")
+    open(cfg, "w").write(text + "Endianness = LittleEndian\n")
+    env = dict(os.environ, SHELLFISH_GLOBAL_CONFIG=cfg)
+    r = subprocess.run([H.cli_path(), "shell"], input="0 100 1 1 1 1\n", capture_output=True, text=True, env=env)
+    assert r.returncode == 1 and "invlalidate the files Shellfish cached" in r.stderr
+    assert r.stdout == "Shellfish terminating.\n"
