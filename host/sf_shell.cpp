@@ -245,7 +245,9 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
     if (!err.empty()) return err;
     const std::vector<int64_t> &ids = intCols[0], &snaps = intCols[1];
     if (ids.empty()) return "No input IDs.";
-    const size_t rowLen = c.percentileProfile ? static_cast<size_t>(c.radialBins) : static_cast<size_t>(c.order * c.order * 2);
+    // cmd/shell.go:223-231 sizes percentile rows as RadialBins, but haloAnalysis replaces each
+    // processed row by calcPercentile's 2*RadialBins slice (:516,:632): radii then densities
+    const size_t rowLen = c.percentileProfile ? static_cast<size_t>(2 * c.radialBins) : static_cast<size_t>(c.order * c.order * 2);
     std::vector<std::vector<double>> out(ids.size(), std::vector<double>(rowLen, 0.0));
 
     Catalogs cat;

@@ -53,8 +53,8 @@ typedef struct {
     double eta;
     int64_t order, smoothing_window, levels, subsample_factor;
     double los_slope_cutoff, background_rho_mult;
-    int32_t percentile_profile; /* cmd/shell.go:28; must be 0 (not built yet) */
-    double percentile;
+    int32_t percentile_profile; /* cmd/shell.go:28: output calcPercentile rows instead of coefficients */
+    double percentile;          /* in [0, 100], cmd/shell.go:119,656 */
     uint64_t seed;
     int32_t device; /* CUDA ordinal */
     uint32_t flags; /* SFK_FLAG_* */
@@ -128,9 +128,16 @@ int sfk_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass,
 /* Halo.Insert for all queued particles (los/halo.go:201-277,
  * profile_ring.go:92-120) followed by haloAnalysis (cmd/shell.go:502-528):
  * RingBuffer.Splashback, FilterPoints, PennaVolumeFit.  coeffs is
- * [n_halo][2*order*order] in catalog column order, status is [n_halo]
- * SFK_HALO_*; either may be NULL. */
+ * [n_halo][sfk_row_length()] in catalog column order, status is [n_halo]
+ * SFK_HALO_*; either may be NULL.  With percentile_profile set, a row is
+ * calcPercentile's output instead (cmd/shell.go:629-660): radial_bins bin
+ * radii (Halo.GetRs) followed by radial_bins densities, each the
+ * percentile-th value over all rings*spokes profiles (msort.Percentile). */
 int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status);
+
+/* Values per halo in the result table: 2*order*order (cmd/shell.go:223), or
+ * 2*radial_bins in percentile mode (cmd/shell.go:632). */
+int64_t sfk_row_length(const sfk_ctx *ctx);
 
 /* ---- split-halo mode ------------------------------------------------------
  * One giant halo whose particles are spread over several GPUs (each rank

@@ -95,6 +95,13 @@ def lib():
         L.orc_penna_func.restype = C.c_double
         L.orc_penna_func.argtypes = [c_double_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
         L.orc_shell_run.restype = C.c_int
+        L.orc_nth_largest.restype = C.c_double
+        L.orc_nth_largest.argtypes = [c_double_p, C.c_int64, C.c_int64, c_double_p]
+        L.orc_percentile.restype = C.c_double
+        L.orc_percentile.argtypes = [c_double_p, C.c_int64, C.c_double, c_double_p]
+        L.orc_calc_percentile.restype = None
+        L.orc_calc_percentile.argtypes = [C.c_double, C.c_double, C.c_int, c_double_p, C.c_int64, C.c_double,
+                                          c_double_p]
         _LIB = L
     return _LIB
 
@@ -271,4 +278,29 @@ def shell_run(cfg, minMass, halos, blocks, taps=(), reset_cache=True):
                          out["status"].ctypes.data_as(C.POINTER(C.c_int32)), C.byref(t))
     if rc:
         raise RuntimeError("orc_shell_run failed: %d" % rc)
+    return out
+
+
+def nth_largest(xs, n):
+    """math/sort/median.go:40-65 (1-indexed)."""
+    xs = np.ascontiguousarray(xs, np.float64)
+    buf = np.empty_like(xs)
+    return lib().orc_nth_largest(dp(xs), len(xs), n, dp(buf))
+
+
+def percentile(xs, p):
+    """math/sort/median.go:8-22, p in [0, 1]."""
+    xs = np.ascontiguousarray(xs, np.float64)
+    buf = np.empty_like(xs)
+    return lib().orc_percentile(dp(xs), len(xs), p, dp(buf))
+
+
+def calc_percentile(r200m, profiles, percentile_value, rMinMult=0.3, rMaxMult=3.0):
+    """calcPercentile (cmd/shell.go:629-660) of one halo from its GetRhos tap
+    [rings][spokes][bins]: returns [2*bins] = radii, percentile densities."""
+    prof = np.ascontiguousarray(profiles, np.float64)
+    bins = prof.shape[-1]
+    prof = prof.reshape(-1, bins)
+    out = np.zeros(2 * bins)
+    lib().orc_calc_percentile(r200m * rMinMult, r200m * rMaxMult, bins, dp(prof), len(prof), percentile_value, dp(out))
     return out

@@ -188,6 +188,12 @@ int orc_shell_run(const orc_shell_config *cfg, float minMass, int64_t nHalo,
                   double *coeffs, uint8_t *ok, int32_t *status,
                   const orc_taps *taps);
 
+/* ---- PercentileProfile mode, cmd/shell.go:629-660 + math/sort/median.go */
+double orc_nth_largest(const double *xs, int64_t len, int64_t n, double *buf);
+double orc_percentile(const double *xs, int64_t len, double p, double *buf);
+void orc_calc_percentile(double rMin, double rMax, int bins, const double *profiles,
+                         int64_t nLos, double percentile, double *out);
+
 /* Resets the process-wide Savitzky-Golay kernel cache (smooth.go:9-12). */
 void orc_reset_kernel_cache(void);
 

@@ -49,7 +49,7 @@ class Stats(C.Structure):
 # every symbol include/shellfish_b200.h declares
 EXPORTS = ["sfk_default_params", "sfk_create", "sfk_destroy", "sfk_last_error", "sfk_begin_snapshot",
            "sfk_add_halos", "sfk_set_owned", "sfk_block_halo_mask", "sfk_push_block", "sfk_push_block_device",
-           "sfk_finish_snapshot", "sfk_split_count", "sfk_split_bin", "sfk_split_buffer", "sfk_split_finish",
+           "sfk_finish_snapshot", "sfk_row_length", "sfk_split_count", "sfk_split_bin", "sfk_split_buffer", "sfk_split_finish",
            "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count",
            "sfk_get_profiles", "sfk_get_counts", "sfk_get_ring_tables"]
 
@@ -95,6 +95,7 @@ def lib():
         for name in EXPORTS:
             if getattr(L, name).restype is not None and name not in ("sfk_last_error", "sfk_stream"):
                 getattr(L, name).restype = C.c_int
+        L.sfk_row_length.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -144,7 +145,8 @@ class ShellContext:
 
     @property
     def P2(self):
-        return int(2 * self.params.order * self.params.order)
+        """Row length of the result table (sfk_row_length)."""
+        return int(lib().sfk_row_length(self._h))
 
     def begin_snapshot(self, cosmo, min_mass):
         c = Cosmo(cosmo["Z"], cosmo["OmegaM"], cosmo["OmegaL"], cosmo["H100"])

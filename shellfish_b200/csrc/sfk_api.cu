@@ -172,7 +172,8 @@ int validate(sfk_ctx *ctx, const sfk_params &p) {
         return fail(ctx, SFK_E_INVALID, buf);
     }
     // limits of this implementation
-    if (p.percentile_profile) return fail(ctx, SFK_E_UNSUPPORTED, "PercentileProfile is not built yet.");
+    if (p.percentile_profile && !(p.percentile >= 0 && p.percentile <= 100))   // msort.Percentile panics, median.go:11-13
+        return fail(ctx, SFK_E_INVALID, "percentile must be in the range [0, 1]");
     if (p.order > kMaxOrder) return fail(ctx, SFK_E_UNSUPPORTED, "Order above 4 is not supported.");
     if (p.levels > kMaxLevels) return fail(ctx, SFK_E_UNSUPPORTED, "Levels above 6 is not supported.");
     if (p.rings > kMaxRings) return fail(ctx, SFK_E_UNSUPPORTED, "Rings above 1024 is not supported.");
@@ -463,6 +464,21 @@ int stage_bin(sfk_ctx *ctx, const std::vector<int32_t> &batch) {
 int stage_analyze(sfk_ctx *ctx, int nb) {
     cudaStream_t st = ctx->stream;
     const int R = ctx->rings, n = ctx->spokes, B = ctx->bins;
+    if (ctx->p.percentile_profile) {
+        // calcPercentile replaces calcCoeffs, cmd/shell.go:515-517
+        PercentileArgs pa{};
+        pa.grid = ctx->dGrid.p; pa.halos = ctx->dHalos.p; pa.batchHalos = ctx->dBatchHalos.p;
+        pa.rows = ctx->dCoeffs.p; pa.nLos = static_cast<int64_t>(R) * n; pa.bins = B;
+        // msort.Percentile, median.go:15-21
+        long long nth = static_cast<long long>(ctx->p.percentile / 100 * static_cast<double>(pa.nLos));
+        if (nth == 0) nth++;
+        pa.nth = nth;
+        ctx->timer.begin(ST_LOS, st);
+        CU(launch_percentile(pa, nb, st));
+        ctx->stats.launches += 2;
+        ctx->timer.end(ST_LOS, st);
+        return SFK_OK;
+    }
     LosArgs la{};
     la.grid = ctx->dGrid.p; la.halos = ctx->dHalos.p; la.batchHalos = ctx->dBatchHalos.p;
     la.valTaps = ctx->dTaps0.p; la.derivTaps = ctx->dTaps1.p;
@@ -513,6 +529,9 @@ int stage_collect(sfk_ctx *ctx, double *coeffs, int32_t *status) {
         if (ctx->hStatus[i] == SFK_HALO_OK) ctx->hStatus[i] = dstat[i];
         if (ctx->hStatus[i] != SFK_HALO_OK)
             for (int k = 0; k < P2; k++) ctx->hCoeffs[i * P2 + k] = 0.0;
+        else if (ctx->p.percentile_profile)   // Halo.GetRs, halo.go:360-370
+            for (int k = 0; k < ctx->bins; k++)
+                ctx->hCoeffs[i * P2 + k] = std::exp(ctx->halos[i].lrMin + ctx->halos[i].dlr * (static_cast<double>(k) + 0.5));
         ctx->stats.n_intersections += static_cast<int64_t>(nInter[i]);
         ctx->stats.n_points += nPts[i];
     }
@@ -566,7 +585,10 @@ int sfk_create(sfk_ctx **out, const sfk_params *params) {
     ctx->rings = static_cast<int>(params->rings);
     ctx->spokes = static_cast<int>(params->spokes);
     ctx->bins = static_cast<int>(params->radial_bins);
-    ctx->P2 = static_cast<int>(2 * params->order * params->order);
+    // row length of the result table: Penna coefficients, or radii + densities
+    // (calcPercentile returns 2*RadialBins values, cmd/shell.go:632)
+    ctx->P2 = params->percentile_profile ? static_cast<int>(2 * params->radial_bins)
+                                         : static_cast<int>(2 * params->order * params->order);
     ctx->taps = (params->flags & SFK_FLAG_TAPS) != 0;
     build_tables(*params, ctx->tab);
     CU(ctx->dNorms.upload(ctx->tab.norms, ctx->stream));
@@ -696,6 +718,8 @@ int sfk_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass,
     CU(cudaDeviceSynchronize());
     return push_block_impl(ctx, d_xyz, d_mass, n, cosmo, total_width, origin, width);
 }
+
+int64_t sfk_row_length(const sfk_ctx *ctx) { return ctx ? ctx->P2 : 0; }
 
 int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) {
     if (!ctx || !ctx->inSnapshot) return fail(ctx, SFK_E_INVALID, "sfk_finish_snapshot: no snapshot open");

@@ -29,51 +29,6 @@ __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 // Go's int(float64) on amd64 (CVTTSD2SQ): truncation toward zero.
 __device__ __forceinline__ long long go_int(double x) { return __double2ll_rz(x); }
 
-// ------------------------------------------------------------------ TMA --
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-
-// 1-D bulk copy global -> shared through the TMA unit, completion on mbarrier.
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes,
-                                            uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-            "r"(smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
 // ----------------------------------------------------------------- cull --
 
 constexpr int kCullThreads = 256;
@@ -1115,6 +1070,87 @@ cudaError_t launch_hits(const Piece *pieces, int nPieces, const Cand *cands,
     return cudaGetLastError();
 }
 
+
+// ---- PercentileProfile mode ---------------------------------------------------
+// calcPercentile (cmd/shell.go:629-660): for every radial bin, the n-th largest
+// GetRhos value over all rings*spokes lines of sight.  GetRhos is
+// max(prefix * quantum, defaultRho) (halo.go:350-357), monotone in the int64
+// prefix sum, so the selection runs on the exact integers and the clamp is
+// applied to the selected one: same value as msort.NthLargest on the float64s.
+
+// ProfileRing.Retrieve (profile_ring.go:124-130) in place: one warp per LoS.
+__global__ void __launch_bounds__(256) prefix_kernel(unsigned long long *grid, int64_t nRows, int bins) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= nRows) return;
+    long long *g = reinterpret_cast<long long *>(grid) + row * bins;
+    long long carry = 0;
+    for (int base = 0; base < bins; base += 32) {
+        const int k = base + lane;
+        long long v = k < bins ? g[k] : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long up = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += up;
+        }
+        v += carry;
+        if (k < bins) g[k] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+}
+
+// One CTA per (radial bin, halo): most-significant-byte-first radix select of
+// the nth largest key, 8 passes over the bin's column of the prefix grid.
+__global__ void __launch_bounds__(256) percentile_kernel(PercentileArgs a) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long sPrefix;
+    __shared__ long long sNth;
+    const int bin = blockIdx.x, slot = blockIdx.y;
+    const int haloIdx = a.batchHalos[slot];
+    const HaloDev &h = a.halos[haloIdx];
+    const long long *col = reinterpret_cast<const long long *>(a.grid) +
+                           static_cast<size_t>(slot) * a.nLos * a.bins + bin;
+    if (threadIdx.x == 0) { sPrefix = 0; sNth = a.nth; }
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        const unsigned long long prefix = sPrefix;
+        const unsigned long long mask = pass == 0 ? 0ull : ~0ull << (shift + 8);
+        for (int64_t i = threadIdx.x; i < a.nLos; i += blockDim.x) {
+            // order-preserving map int64 -> uint64
+            const unsigned long long key = static_cast<unsigned long long>(col[i * a.bins]) ^ 0x8000000000000000ull;
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long n = sNth;
+            int b = 255;
+            for (; b > 0; b--) {
+                if (static_cast<long long>(hist[b]) >= n) break;
+                n -= hist[b];
+            }
+            sNth = n;
+            sPrefix = prefix | (static_cast<unsigned long long>(b) << shift);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const long long acc = static_cast<long long>(sPrefix ^ 0x8000000000000000ull);
+        double rho = static_cast<double>(acc) * h.quantum;
+        if (rho < h.defaultRho) rho = h.defaultRho;   // GetRhos clamp, halo.go:353-355
+        a.rows[static_cast<size_t>(haloIdx) * 2 * a.bins + a.bins + bin] = rho;
+    }
+}
+
+cudaError_t launch_percentile(const PercentileArgs &a, int nb, cudaStream_t s) {
+    if (nb <= 0) return cudaSuccess;
+    const int64_t rows = static_cast<int64_t>(nb) * a.nLos;
+    prefix_kernel<<<static_cast<unsigned>((rows * 32 + 255) / 256), 256, 0, s>>>(a.grid, rows, a.bins);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    percentile_kernel<<<dim3(a.bins, nb), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s) {
     if (nb <= 0) return cudaSuccess;

@@ -74,6 +74,18 @@ struct FitArgs {
     int rings, spokes, order;
 };
 
+// PercentileProfile mode, cmd/shell.go:629-660
+struct PercentileArgs {
+    unsigned long long *grid;   // [nb][rings*spokes][bins] int64 derivative bins, prefix-summed in place
+    const HaloDev *halos;
+    const int32_t *batchHalos;
+    double *rows;               // [nHalo][2*bins]; this stage fills [bins, 2*bins)
+    int64_t nLos;               // rings*spokes
+    int bins;
+    long long nth;              // 1-indexed n of msort.NthLargest, math/sort/median.go:15-21
+};
+
+cudaError_t launch_percentile(const PercentileArgs &a, int nb, cudaStream_t s);
 cudaError_t launch_cull(const CullArgs &a, bool fill, cudaStream_t s);
 cudaError_t launch_hit_count(const Piece *pieces, int nPieces, const Cand *cands, const HaloDev *halos,
                              const float *norms, int rings, uint32_t *hitCount,

@@ -104,3 +104,21 @@ def test_cli_changed_config_is_refused(tmp_path):   # checkMemoDir, shellfish.go
     r = subprocess.run([H.cli_path(), "shell"], input="0 100 1 1 1 1\n", capture_output=True, text=True, env=env)
     assert r.returncode == 1 and "invlalidate the files Shellfish cached" in r.stderr
     assert r.stdout == "Shellfish terminating.\n"
+
+
+def test_cli_percentile_profile(tmp_path):   # cmd/shell.go:629-660 through shell.config
+    halos, blocks, min_mass, cfg = _setup(tmp_path, 14, 2, 15000, 5000, 1)
+    sc = tmp_path / "shell.config"
+    sc.write_text("[shell.config]\nRings = 6\nPercentileProfile = true\nPercentile = 75\n")
+    stdin = "".join("%d 100 %.17g %.17g %.17g %.17g\n" % (i, *h[:4]) for i, h in enumerate(halos))
+    env = dict(os.environ, SHELLFISH_GLOBAL_CONFIG=cfg, SHELLFISH_SEED="1337")
+    r = subprocess.run([H.cli_path(), "shell", str(sc)], input=stdin, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.split("\n")[:-1]
+    assert lines[0].endswith("R200m [cMpc/h](5) P_ijk(6-517)")
+    ref = po.shell_run(po.ShellConfig.default(seed=1337, threads=1, rings=6), min_mass, halos, blocks,
+                       taps=("profiles",))
+    _, fc = H.parse_catalog("\n".join(lines) + "\n", [0, 1], list(range(6, 518)))
+    for h in range(len(halos)):
+        want = po.calc_percentile(halos[h, 3], ref["profiles"][h], 75.0)
+        np.testing.assert_allclose(fc[:, h], want, rtol=2e-5)

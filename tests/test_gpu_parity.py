@@ -224,8 +224,8 @@ def test_validation_messages_follow_the_reference():
         api.ShellContext(api.default_params(rings=0))
     with pytest.raises(api.ShellfishError, match=r"The variable 'RMinMult' was set to 3, but the variable 'RMaxMult' was set to 3\."):
         api.ShellContext(api.default_params(r_min_mult=3.0))
-    with pytest.raises(api.ShellfishError, match="PercentileProfile"):
-        api.ShellContext(api.default_params(percentile_profile=1))
+    with pytest.raises(api.ShellfishError, match="Order above 4"):
+        api.ShellContext(api.default_params(order=5))
 
 
 def test_call_order_errors():
@@ -293,3 +293,22 @@ def test_split_halo_emulated_ranks_match_single_gpu():
             coeffs, status = c.split_finish()
             assert status[0] == 0
             assert np.array_equal(coeffs, c_ref)
+
+
+def test_percentile_profile_mode():
+    """PercentileProfile output (cmd/shell.go:629-660): bin radii + the
+    percentile-th density over all rings*spokes profiles, against the oracle's
+    restated msort.Percentile on its own GetRhos tap."""
+    halos, blocks, mass = synth.make_box(31, 62.5, 2, 20000, 8000, 2, margin=8.0)
+    cfg = po.ShellConfig.default(seed=1337, threads=1, rings=10)
+    ref = po.shell_run(cfg, mass, halos, blocks, taps=("profiles",))
+    for pct in (50.0, 90.0, 0.0, 100.0, 12.5):
+        params = api.default_params(seed=1337, rings=10, percentile_profile=1, percentile=pct)
+        ctx, rows, status = api.run_shell(params, mass, halos, blocks)
+        assert rows.shape == (2, 512) and np.all(status == 0)
+        for h in range(2):
+            want = po.calc_percentile(halos[h, 3], ref["profiles"][h], pct)
+            assert np.array_equal(rows[h, :256], want[:256]), "GetRs radii differ"
+            assert np.all(np.abs(rows[h, 256:] - want[256:]) <= RTOL * np.abs(want[256:])), (pct, h)
+    with pytest.raises(RuntimeError, match="percentile must be in the range"):
+        api.ShellContext(api.default_params(percentile_profile=1, percentile=120.0))

@@ -277,3 +277,27 @@ def test_go_constant_folding():
     assert po.lib().orc_go_pow(0.0, 0.0) == 1.0
     assert po.lib().orc_go_pow(7.5, 1.0) == 7.5
     assert abs(po.lib().orc_rho_average(70.0, 0.27, 0.73, 0.0) - 7.4935e10) / 7.4935e10 < 1e-3
+
+
+# ---- math/sort (PercentileProfile mode) ------------------------------------------
+
+def test_nth_largest_property():
+    """sort_test.go:274-293 TestMedian: NthLargest(mixed, j) == sorted[len-j] for all j."""
+    rng = np.random.default_rng(7)
+    for n in (1, 2, 3, 4, 5, 24, 25, 26, 1000):
+        xs = rng.random(n)
+        s = np.sort(xs)
+        for j in range(1, n + 1):
+            assert po.nth_largest(xs, j) == s[n - j]
+    xs = np.round(rng.random(3000) * 20)   # heavy duplication, like profiles clamped to the background
+    s = np.sort(xs)
+    assert all(po.nth_largest(xs, j) == s[len(xs) - j] for j in range(1, 3001, 11))
+
+
+def test_percentile_index():
+    """median.go:8-22: n = int(p*len), n == 0 -> 1 (p = 0 returns the maximum)."""
+    xs = np.arange(100.0)
+    assert po.percentile(xs, 0.5) == 50.0
+    assert po.percentile(xs, 0.0) == 99.0
+    assert po.percentile(xs, 1.0) == 0.0
+    assert po.percentile(xs, 0.999) == 1.0
