@@ -128,9 +128,12 @@ __device__ bool has_nan_los(double cx, double cy, double projDist2, double phiC,
     for (int sgn = -1; sgn <= 1; sgn += 2) {
         double ph = phiC + sgn * (kPi / 2);
         if (ph < 0) ph += kTwoPi;
-        const long long i0 = __double2ll_rd(ph / dPhi);
+        const int i0 = static_cast<int>(__double2ll_rd(ph / dPhi));   // ph in [0, 2.5 pi): 0 <= i0 < 2n
         for (int d = -1; d <= 2; d++) {
-            const int i = static_cast<int>(((i0 + d) % n + n) % n);
+            int i = i0 + d;   // in [-1, 2n + 2)
+            if (i < 0) i += n;
+            if (i >= n) i -= n;
+            if (i >= n) i -= n;
             const double b = cy * ringCos[i] - cx * ringSin[i];
             const double b2 = b * b;
             if (projDist2 - b2 < 0) any = true;
@@ -310,6 +313,8 @@ hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const 
 // ------------------------------------------------------------------ los --
 
 constexpr int kLosWarps = 8;
+// columns of the padded ln(rho) rows of los_kernel_fast<8> (256 bins): positions 0 .. B + window + 8
+__host__ __device__ constexpr int los_fast_row(int window) { return (256 + window + 16) / 8 + 1; }
 
 __device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8000000000000ll); }
 
@@ -321,12 +326,19 @@ __device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8
 // splashback_radius.go:30-58 done as a warp prefix-min plus an arg-min.
 template <int PER>
 __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int nb) {
+    const int i0 = (threadIdx.x & 31) * PER;
     extern __shared__ double sm[];
     constexpr int B = 32 * PER;
-    constexpr int ROW = 33;
     const int window = a.window;
+    const int center = window / 2;
+    // ln(rho) with the Extension boundary (filter.go:104-161) materialised: sample i sits at
+    // position p = i + padL, padL = center + 1, the positions below / above hold sample 0 / B-1.
+    // Position p is stored at row p % PER, column p / PER, so the FIR below reads row jj at
+    // column (lane + const): conflict-free and with no index arithmetic.
+    const int padL = center + 1;
+    const int rowLen = los_fast_row(window);
     double2 *taps = reinterpret_cast<double2 *>(sm);                       // [window] (value, deriv)
-    double *ys = sm + 2 * window + (threadIdx.x >> 5) * (PER * ROW);       // permuted: (i % PER) * 33 + i / PER
+    double *ys = sm + 2 * window + (threadIdx.x >> 5) * (PER * rowLen);
     for (int k = threadIdx.x; k < window; k += blockDim.x) taps[k] = make_double2(a.valTaps[k], a.derivTaps[k]);
     __syncthreads();
     const int lane = lane_id();
@@ -356,14 +368,24 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
     }
     long long acc = incl - run;
     const double q = h.quantum, bg = h.defaultRho;
+    double yFirst = 0.0, yLast = 0.0;
 #pragma unroll
     for (int c = 0; c < PER; c++) {
         acc += d[c];
         double rho = static_cast<double>(acc) * q;
         if (rho < bg) rho = bg;
         if (a.profiles) a.profiles[(static_cast<size_t>(haloIdx) * perHalo + rl) * B + lane * PER + c] = rho;
-        ys[c * ROW + lane] = log(rho);
+        const double y = log(rho);
+        const int p = lane * PER + c + padL;
+        ys[(p % PER) * rowLen + p / PER] = y;
+        if (c == 0) yFirst = y;
+        if (c == PER - 1) yLast = y;
     }
+    // Extension: repeat the end samples
+    yFirst = __shfl_sync(0xffffffffu, yFirst, 0);
+    yLast = __shfl_sync(0xffffffffu, yLast, 31);
+    for (int e = lane; e < padL; e += 32) ys[(e % PER) * rowLen + e / PER] = yFirst;
+    for (int e = B + padL + lane; e < PER * rowLen; e += 32) ys[(e % PER) * rowLen + e / PER] = yLast;
     __syncwarp();
 
     double *out = a.rsp + static_cast<size_t>(haloIdx) * perHalo + rl;
@@ -371,25 +393,22 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
         if (lane == 0) *out = nan_f64();
         return;
     }
-    // ConvolveAt with Extension (filter.go:104-161), taps ascending.  w[m % PER]
-    // holds ln rho at clamp(i0 - center + m) for m = j .. j + PER - 1.
-    const int center = window / 2;
-    const int i0 = lane * PER;
-    auto ysAt = [&](int idx) {
-        idx = idx < 0 ? 0 : (idx >= B ? B - 1 : idx);
-        return ys[(idx % PER) * ROW + idx / PER];
-    };
+    // ConvolveAt with Extension (filter.go:104-161), taps ascending.  Output i0 + c needs
+    // sample i0 + c - center + j for tap j, i.e. position lane*PER + (c + j + 1): w[m % PER]
+    // holds position lane*PER + 1 + m for m = j .. j + PER - 1.
+    const double *yl = ys + lane;
     double w[PER], s0[PER], s1[PER];
 #pragma unroll
     for (int c = 0; c < PER; c++) { s0[c] = 0.0; s1[c] = 0.0; }
 #pragma unroll
-    for (int m = 0; m < PER - 1; m++) w[m] = ysAt(i0 - center + m);
+    for (int m = 0; m < PER - 1; m++) w[m] = yl[(1 + m) * rowLen];
     for (int jb = 0; jb < window; jb += PER) {
+        const double *yj = yl + jb / PER + 1;   // position lane*PER + jb + PER + jj: row jj, column lane + jb/PER + 1
 #pragma unroll
         for (int jj = 0; jj < PER; jj++) {
             const int j = jb + jj;
             if (j < window) {
-                w[(jj + PER - 1) % PER] = ysAt(i0 - center + j + PER - 1);
+                w[(jj + PER - 1) % PER] = yj[jj * rowLen];
                 const double2 tp = taps[j];
 #pragma unroll
                 for (int c = 0; c < PER; c++) {
@@ -1164,7 +1183,7 @@ cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s) {
     const int64_t warps = static_cast<int64_t>(nb) * a.rings * a.spokes;
     const unsigned grid = static_cast<unsigned>((warps + kLosWarps - 1) / kLosWarps);
     if (a.bins == 256) {
-        const size_t fsmem = sizeof(double) * (2 * a.window + kLosWarps * 8 * 33);
+        const size_t fsmem = sizeof(double) * (2 * a.window + kLosWarps * 8 * los_fast_row(a.window));
         los_kernel_fast<8><<<grid, kLosWarps * 32, fsmem, s>>>(a, nb);
     } else {
         los_kernel<<<grid, kLosWarps * 32, smem, s>>>(a, nb);
