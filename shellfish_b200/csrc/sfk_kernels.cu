@@ -202,6 +202,27 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
     }
     r.r01 = clamp_idx(i0, n) | static_cast<uint32_t>(clamp_idx(i1, n)) << 16;
     r.r23 = clamp_idx(i2, n) | static_cast<uint32_t>(clamp_idx(i3, n)) << 16;
+    if (phiLo < 0 && i3 <= 0) {
+        // atan2 put the whole wedge below zero, so idxRange scans from its start all
+        // the way to LoS n-1 (halo.go:297-303) and the reference drops the LoS past
+        // the wedge one by one through the NaN test of :262.  A LoS at angle
+        // delta from the projected position has b^2 = dist2 sin^2(delta), so it is
+        // NaN whenever alpha < delta < pi - alpha; with a guard of two LoS spacings
+        // on both sides the margin on sin(delta) is >= 2 sin^2(dPhi), nine orders of
+        // magnitude above the rounding of the literal test.  Those LoS are cut out;
+        // the ones near the anti-direction (delta > pi - alpha), where the reference
+        // does insert, stay in the second range.
+        const double phiC = projPhi + kTwoPi;
+        const double a1 = phiC + alpha + 2.0 * dPhi, a2 = phiC + kPi - alpha - 2.0 * dPhi;
+        if (a1 < a2) {
+            const long long deadLo = __double2ll_rd(a1 / dPhi) + 1;   // first dead LoS
+            const long long deadHi = __double2ll_rd(a2 / dPhi);       // last dead LoS
+            if (deadLo < n && deadLo > i0 && deadHi >= deadLo) {
+                r.r01 = clamp_idx(i0, n) | static_cast<uint32_t>(clamp_idx(deadLo, n)) << 16;
+                r.r23 = deadHi + 1 < n ? (clamp_idx(deadHi + 1, n) | static_cast<uint32_t>(n) << 16) : 0u;
+            }
+        }
+    }
     return true;
 }
 
