@@ -191,7 +191,28 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
     if (D + P <= rMinSafe || D - P >= rMaxSafe) return false;
     const double alpha = asin(sqrt(projRad2 / projDist2));
     const double projPhi = atan2(cy, cx);
-    const double phiLo = projPhi - alpha, phiHi = projPhi + alpha;
+    // Radial trimming.  Along a LoS at angle delta from the projected position the chord is
+    // [rLo, rHi](delta), rLo increasing and rHi decreasing in |delta| up to the tangent length
+    // T = sqrt(D^2 - P^2) at delta = alpha.  Where the projected circle crosses the sphere r = R
+    // the crossing is at cos(delta*) = (D^2 + R^2 - P^2)/(2 D R); it is the NEAR end of the chord
+    // when T > R and the far end when T < R.  So for T > rMax every LoS beyond delta*(rMax) has
+    // rLo >= rMax, for T < rMin every LoS beyond delta*(rMin) has rHi <= rMin, and
+    // ProfileRing.Insert takes its early-out (profile_ring.go:93-95).  With a guard of two LoS
+    // spacings the relative margin on the compared radius is >= 2 dPhi^2.
+    double half = alpha;        // half-width handed to idxRange
+    double edge = alpha + 2.0 * dPhi;   // first angle past which a LoS is provably dead
+    {
+        const double T2 = projDist2 - projRad2;
+        double dStar = alpha;
+        if (T2 > rMaxSafe * rMaxSafe && D - P < h.rMax)
+            dStar = acos(fmin(fmax((projDist2 + h.rMax * h.rMax - projRad2) / (2.0 * D * h.rMax), -1.0), 1.0));
+        else if (T2 < rMinSafe * rMinSafe && D + P > h.rMin)
+            dStar = acos(fmin(fmax((projDist2 + h.rMin * h.rMin - projRad2) / (2.0 * D * h.rMin), -1.0), 1.0));
+        if (dStar + 2.0 * dPhi < alpha) { half = dStar + 2.0 * dPhi; edge = half; }
+    }
+    const double phiLo = projPhi - half, phiHi = projPhi + half;
+    // idxRange, halo.go:284-310 (literal when half == alpha; otherwise a subset of the literal
+    // ranges that still holds every LoS within `half` of the projected position)
     long long i0, i1, i2, i3;
     if (phiHi > kTwoPi) {
         i0 = go_int(phiLo / dPhi); i1 = n; i2 = 0; i3 = go_int((phiHi - kTwoPi) / dPhi) + 1;
@@ -211,9 +232,10 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
         // on both sides the margin on sin(delta) is >= 2 sin^2(dPhi), nine orders of
         // magnitude above the rounding of the literal test.  Those LoS are cut out;
         // the ones near the anti-direction (delta > pi - alpha), where the reference
-        // does insert, stay in the second range.
+        // does insert (twoValIntrDist only sees b^2, so the chord is that of the
+        // mirrored LoS pi - delta), stay in the second range.
         const double phiC = projPhi + kTwoPi;
-        const double a1 = phiC + alpha + 2.0 * dPhi, a2 = phiC + kPi - alpha - 2.0 * dPhi;
+        const double a1 = phiC + edge, a2 = phiC + kPi - edge;
         if (a1 < a2) {
             const long long deadLo = __double2ll_rd(a1 / dPhi) + 1;   // first dead LoS
             const long long deadHi = __double2ll_rd(a2 / dPhi);       // last dead LoS
