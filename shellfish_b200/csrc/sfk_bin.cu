@@ -5,8 +5,8 @@
 // tile's 32 x bins accumulators are 64-bit fixed point, split into lo/hi
 // 32-bit words in shared memory so that native 32-bit shared atomics can be
 // used (64-bit shared atomics are CAS loops on sm_100).  One producer warp
-// streams the ring's hit records through a 3-stage TMA (cp.async.bulk +
-// mbarrier) ring; 12 consumer warps draw 32-record groups from a shared
+// streams the ring's hit records through a 2-stage TMA (cp.async.bulk +
+// mbarrier) ring; 16 consumer warps draw 32-record groups from a shared
 // counter.  For a group, lanes first clip the 32 records' LoS ranges against
 // the tile in parallel, a warp scan turns the clipped lengths into a list of
 // (record, LoS) pairs, and the pairs are then processed 32 at a time with one
@@ -93,7 +93,9 @@ __device__ __forceinline__ void bin_of(double r, double invRMin, float cK, doubl
     // The estimate is biased low by 1e-3 bins (its error is < 3e-4), so the true
     // bin is k or k + 1 and the series argument t is never negative.
     const float uf = __int_as_float((__double2hiint(u) - 0x38000000) << 3);
-    int k = static_cast<int>(fmaf(__log2f(uf), cK, -1.0e-3f));
+    float lg;   // uf is a normal number >= 1: the flush-to-zero form skips __log2f's denormal path
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(uf));
+    int k = static_cast<int>(fmaf(lg, cK, -1.0e-3f));
     k = min(k, bins - 1);
     const double t = fma(u, sInvG[k], -1.0);   // r / (rMin g[k]) - 1
     double L = fma(t, -1.0 / 6.0, 0.2);
