@@ -144,6 +144,10 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one bin_kernel launch over its algorithmic bytes
+NCU_TRAFFIC_RATIO = (2.202771 + 0.803971) / 1.704478
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -257,11 +261,18 @@ def main():
                                   ("ms_cull", "ms_hits", "ms_bin", "ms_los", "ms_filter", "ms_fit")},
             "gpu_launches": int(agg["launches"]),
             "roofline": {"bound": "hbm", "kernel": "bin_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         # DRAM bytes of one launch = NCU_TRAFFIC_RATIO x its algorithmic bytes (ncu --set
+                         # full capture of a 16-halo launch: dram read 2.203 GB + write 0.804 GB against
+                         # 1.704 GB algorithmic, profiles/r01e_bin_kernel_v5_by_line.txt)
+                         "traffic": NCU_TRAFFIC_RATIO * alg_bytes / launches / 1e9,
+                         "traffic_unit": "GB per launch (ncu ratio x algorithmic bytes)",
                          "peak_source": peak_src,
                          "alg_bytes_per_launch": alg_bytes / launches,
                          "ms_per_launch": agg["ms_bin"] / launches,
-                         "note": "bin_kernel is FP64-pipe bound, not HBM bound: see profiles/ and DESIGN.md"},
+                         "note": "bin_kernel is instruction-issue bound (FP64 chord geometry + shared-memory "
+                                 "atomics), not HBM bound: ncu issue-active 78%, FP64 pipe 35%, DRAM 2.5% "
+                                 "(profiles/r01e_bin_kernel_v5_by_line.txt, DESIGN.md)"},
             "clocks": clocks, "e2e": e2e,
         }
         if world == 1 and not args.no_cpu:
