@@ -53,7 +53,7 @@ def main():
         if m:
             cur = int(m.group(2)) if m.group(1).endswith(unit + ".cu") else -1
             continue
-        m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);", l)
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
         if m:
             seq.append((cur, m.group(2)))
     assert len(seq) == len(data), (len(seq), len(data))

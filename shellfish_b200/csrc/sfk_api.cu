@@ -103,6 +103,7 @@ struct sfk_ctx {
     DevBuf<long long> dNPoints;
     DevBuf<uint32_t> dHitCount;
     DevBuf<double> dProfiles;
+    DevBuf<double> dFitScratch;
     DevBuf<uint32_t> dTapInsert, dTapStart, dTapEnd;
 
     // batch scratch
@@ -506,9 +507,13 @@ int stage_analyze(sfk_ctx *ctx, int nb) {
     ft.ringCos = ctx->dCos.p; ft.ringSin = ctx->dSin.p;
     ft.coeffs = ctx->dCoeffs.p; ft.status = ctx->dStatus.p; ft.nPoints = ctx->dNPoints.p;
     ft.rings = R; ft.spokes = n; ft.order = static_cast<int>(ctx->p.order);
+    size_t nRows, nGram, nInv, nCs;
+    CU(ctx->dFitScratch.ensure(fit_scratch_doubles(nb, R, n, ft.order, &nRows, &nGram, &nInv, &nCs)));
+    ft.rows = ctx->dFitScratch.p; ft.gramPart = ft.rows + nRows; ft.gramInv = ft.gramPart + nGram;
+    ft.csPart = ft.gramInv + nInv;
     ctx->timer.begin(ST_FIT, st);
     CU(launch_fit(ft, nb, st));
-    ctx->stats.launches++;
+    ctx->stats.launches += 4;
     ctx->timer.end(ST_FIT, st);
     return SFK_OK;
 }

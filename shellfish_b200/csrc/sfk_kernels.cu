@@ -11,7 +11,7 @@
 //   bin_kernel     per-LoS chords + ProfileRing.Insert los/halo.go:241-277, profile_ring.go:92-120
 //   los_kernel     GetRhos + Smooth + SplashbackRadius halo.go:350, smooth.go:46, splashback_radius.go:30
 //   filter_kernel  FilterPoints (KDE tree)             penna.go:115-165, kde.go
-//   fit_kernel     PennaVolumeFit                      penna.go:14-108,170-194
+//   fit_*_kernel   PennaVolumeFit                      penna.go:14-108,170-194
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -963,13 +963,17 @@ __device__ bool invert_lu(double *a, int n, int *ipiv, double *work) {
     return true;
 }
 
-constexpr int kFitThreads = 1024;
+constexpr int kFitThreads = 256;
 constexpr int kFitTile = 256;   // points per shared-memory tile
+constexpr int kFitChunks = 8;   // CTAs per halo
 constexpr int kMaxP2 = 2 * kMaxOrder * kMaxOrder;
 
 // Design-matrix row of one filtered point, penna.go:25-52: the point is lifted
 // to the box frame through irot in float32 (PlaneToVolume, halo.go:471-475).
-__device__ __forceinline__ double penna_row(const FitArgs &a, int slot, int ring, int k, int P, double *row) {
+// math.Pow is called per entry in the reference; the distinct (base, exponent)
+// pairs are evaluated once here, same values.
+template <int P>
+__device__ __forceinline__ double penna_row(const FitArgs &a, int slot, int ring, int k, double *row) {
     const size_t src = (static_cast<size_t>(slot) * a.rings + ring) * a.spokes + k;
     const double R = a.fR[src];
     const int li = a.fIdx[src];
@@ -983,14 +987,21 @@ __device__ __forceinline__ double penna_row(const FitArgs &a, int slot, int ring
     const double sinth = sqrt(1 - costh * costh);
     const double cosphi = x / r / sinth;
     const double sinphi = y / r / sinth;
+    double sinPow[2 * P - 1], sphiPow[P];
+#pragma unroll
+    for (int e = 0; e < 2 * P - 1; e++) sinPow[e] = go_pow_int(sinth, e);
+#pragma unroll
+    for (int j = 0; j < P; j++) sphiPow[j] = go_pow_int(sinphi, j);
     int m = 0;
+#pragma unroll
     for (int kk = 0; kk < 2; kk++) {
         const double ck = go_pow_int(costh, kk);
+#pragma unroll
         for (int j = 0; j < P; j++) {
-            const double sj = go_pow_int(sinphi, j);
             double cphi = 1.0;
+#pragma unroll
             for (int i = 0; i < P; i++) {
-                row[m] = go_pow_int(sinth, i + j) * cphi * ck * sj;
+                row[m] = sinPow[i + j] * cphi * ck * sphiPow[j];
                 m++;
                 cphi *= cosphi;
             }
@@ -999,96 +1010,178 @@ __device__ __forceinline__ double penna_row(const FitArgs &a, int slot, int ring
     return r;
 }
 
-// One CTA per halo: PennaVolumeFit, penna.go:88-108 -> PennaCoeffs :14-58.
-// The N x P2 design matrix is never stored: rows are rebuilt tile by tile in
-// shared memory, once for the Gram matrix M M^T and once for rs^T (M^T inv).
-// Every accumulator adds its terms in ascending point order, like the
-// reference's loops (and gonum's Dgemm) do.
-__global__ void __launch_bounds__(kFitThreads) fit_kernel(FitArgs a) {
-    extern __shared__ double fsm[];
-    __shared__ double G[kMaxP2 * kMaxP2];
-    __shared__ double work[kMaxP2];
-    __shared__ int ipiv[kMaxP2];
-    __shared__ int ringOff[kMaxRings + 1];
-    __shared__ int okFlag;
-    const int slot = blockIdx.x, tid = threadIdx.x;
-    const int haloIdx = a.batchHalos[slot];
-    const int P = a.order, P2 = 2 * P * P;
-    double *tileM = fsm;                        // [kFitTile][P2]
-    double *tileR = tileM + kFitTile * P2;      // [kFitTile]
-    if (tid == 0) {
+// PennaVolumeFit, penna.go:88-108 -> PennaCoeffs :14-58, in four small kernels so that a
+// halo's <= rings*spokes points are spread over kFitChunks CTAs instead of one:
+//   fit_rows_kernel    design rows -> scratch; partial Gram matrices M M^T per chunk
+//   fit_solve_kernel   sum of the partials (chunk order), gonum's LU inverse
+//   fit_apply_kernel   partial rs^T (M^T inv) per chunk
+//   fit_finish_kernel  sum of the partials (chunk order) -> coefficients
+// Inside a chunk every accumulator adds its terms in ascending point order, like the
+// reference's loops (and gonum's Dgemm); chunk partials are added in chunk order, which
+// regroups the sum but keeps it deterministic.
+__device__ __forceinline__ int fit_point_count(const FitArgs &a, int slot, int *ringOff) {
+    // ringOff[r] = number of points in rings < r (shared memory, rings + 1 entries)
+    if (threadIdx.x == 0) {
         int s = 0;
         for (int r = 0; r < a.rings; r++) { ringOff[r] = s; s += a.fCount[slot * a.rings + r]; }
         ringOff[a.rings] = s;
-        okFlag = 1;
     }
     __syncthreads();
-    const int N = ringOff[a.rings];
-    if (tid == 0) a.nPoints[haloIdx] = N;
-    if (a.status[haloIdx] != 0) return;   // a ring already failed
-    if (N == 0) {
-        if (tid == 0) a.status[haloIdx] = SFK_HALO_NO_POINTS;
-        return;
+    return ringOff[a.rings];
+}
+
+__device__ __forceinline__ void fit_chunk_range(int N, int chunk, int &n0, int &n1) {
+    const int tiles = (N + kFitTile - 1) / kFitTile;
+    const int per = (tiles + kFitChunks - 1) / kFitChunks * kFitTile;
+    n0 = min(N, chunk * per);
+    n1 = min(N, n0 + per);
+}
+
+template <int P>
+__global__ void __launch_bounds__(kFitThreads) fit_rows_kernel(FitArgs a) {
+    constexpr int P2 = 2 * P * P;
+    constexpr int NE = P2 * (P2 + 1) / 2;                       // upper triangle incl. diagonal
+    constexpr int EPT = (NE + kFitThreads - 1) / kFitThreads;   // entries per thread
+    extern __shared__ double fsm[];
+    __shared__ int ringOff[kMaxRings + 1];
+    double *tileM = fsm;   // [kFitTile][P2 + 1]: padded rows, conflict-free column walks
+    const int chunk = blockIdx.x, slot = blockIdx.y, tid = threadIdx.x;
+    const int haloIdx = a.batchHalos[slot];
+    const int N = fit_point_count(a, slot, ringOff);
+    if (chunk == 0 && tid == 0) a.nPoints[haloIdx] = N;
+    int c0, c1;
+    fit_chunk_range(N, chunk, c0, c1);
+    // entry e of the upper triangle -> (gi, gj), gi <= gj
+    int gi[EPT], gj[EPT];
+    double acc[EPT];
+#pragma unroll
+    for (int q = 0; q < EPT; q++) {
+        int e = tid + q * kFitThreads, i = 0;
+        if (e >= NE) e = 0;
+        while (e >= P2 - i) { e -= P2 - i; i++; }
+        gi[q] = i; gj[q] = i + e; acc[q] = 0.0;
     }
-    auto load_tile = [&](int n0, bool timesInv) {
-        // thread t < kFitTile builds the row of point n0 + t
+    const size_t rowBase = static_cast<size_t>(slot) * a.rings * a.spokes;
+    for (int n0 = c0; n0 < c1; n0 += kFitTile) {
+        __syncthreads();
         const int n = n0 + tid;
-        if (tid < kFitTile && n < N) {
+        if (n < c1) {
             int lo = 0, hi = a.rings;   // ring with ringOff[ring] <= n < ringOff[ring + 1]
             while (hi - lo > 1) {
                 const int mid = (lo + hi) / 2;
                 if (ringOff[mid] <= n) lo = mid; else hi = mid;
             }
-            double row[kMaxP2];
-            tileR[tid] = penna_row(a, slot, lo, n - ringOff[lo], P, row);
-            if (!timesInv) {
-                for (int j = 0; j < P2; j++) tileM[tid * P2 + j] = row[j];
-            } else {
-                // row of out2 = M^T inv (gonum Dense.Mul: axpy over l ascending)
-                double o2[kMaxP2];
-                for (int j = 0; j < P2; j++) o2[j] = 0.0;
-                for (int l = 0; l < P2; l++) {
-                    const double t = row[l];
-                    if (t == 0) continue;
-                    for (int j = 0; j < P2; j++) o2[j] += t * G[l * P2 + j];
-                }
-                for (int j = 0; j < P2; j++) tileM[tid * P2 + j] = o2[j];
+            double row[P2];
+            const double r = penna_row<P>(a, slot, lo, n - ringOff[lo], row);
+            double *dst = a.rows + (rowBase + n) * (P2 + 1);
+#pragma unroll
+            for (int j = 0; j < P2; j++) { tileM[tid * (P2 + 1) + j] = row[j]; dst[j] = row[j]; }
+            dst[P2] = r;
+        }
+        __syncthreads();
+        const int cnt = min(kFitTile, c1 - n0);
+#pragma unroll
+        for (int q = 0; q < EPT; q++) {
+            if (tid + q * kFitThreads < NE) {
+                const double *pi = tileM + gi[q], *pj = tileM + gj[q];
+                double s = acc[q];
+#pragma unroll 8
+                for (int k = 0; k < cnt; k++) s += pi[k * (P2 + 1)] * pj[k * (P2 + 1)];
+                acc[q] = s;
             }
         }
-    };
-    // out1 = M M^T: thread (i, j) adds the tile's points in ascending order
-    double acc = 0.0;
-    const int gi = tid / P2, gj = tid - gi * P2;
-    for (int n0 = 0; n0 < N; n0 += kFitTile) {
-        __syncthreads();
-        load_tile(n0, false);
-        __syncthreads();
-        if (tid < P2 * P2) {
-            const int cnt = min(kFitTile, N - n0);
-            for (int k = 0; k < cnt; k++) acc += tileM[k * P2 + gi] * tileM[k * P2 + gj];
-        }
     }
-    __syncthreads();
-    if (tid < P2 * P2) G[tid] = acc;
-    __syncthreads();
-    if (tid == 0 && !invert_lu(G, P2, ipiv, work)) okFlag = 0;
-    __syncthreads();
-    if (!okFlag) {
-        if (tid == 0) a.status[haloIdx] = SFK_HALO_SINGULAR;
+    double *out = a.gramPart + (static_cast<size_t>(slot) * kFitChunks + chunk) * (P2 * P2);
+#pragma unroll
+    for (int q = 0; q < EPT; q++)
+        if (tid + q * kFitThreads < NE) {
+            out[gi[q] * P2 + gj[q]] = acc[q];
+            out[gj[q] * P2 + gi[q]] = acc[q];   // a*b == b*a: Dense.Mul's result is bitwise symmetric
+        }
+}
+
+__global__ void __launch_bounds__(kMaxP2 * kMaxP2) fit_solve_kernel(FitArgs a) {
+    __shared__ double G[kMaxP2 * kMaxP2];
+    __shared__ double work[kMaxP2];
+    __shared__ int ipiv[kMaxP2];
+    __shared__ int ringOff[kMaxRings + 1];
+    const int slot = blockIdx.x, tid = threadIdx.x;
+    const int haloIdx = a.batchHalos[slot];
+    const int P2 = 2 * a.order * a.order;
+    const int N = fit_point_count(a, slot, ringOff);
+    if (a.status[haloIdx] != 0) return;   // a ring already failed
+    if (N == 0) {
+        if (tid == 0) a.status[haloIdx] = SFK_HALO_NO_POINTS;
         return;
     }
-    // cs = rs^T (M^T inv) (mat.VecMult, mat.go:102): thread i sums over points in order
+    if (tid < P2 * P2) {
+        double s = 0.0;
+        for (int c = 0; c < kFitChunks; c++)
+            s += a.gramPart[(static_cast<size_t>(slot) * kFitChunks + c) * (P2 * P2) + tid];
+        G[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0 && !invert_lu(G, P2, ipiv, work)) a.status[haloIdx] = SFK_HALO_SINGULAR;
+    __syncthreads();
+    if (tid < P2 * P2) a.gramInv[static_cast<size_t>(slot) * (P2 * P2) + tid] = G[tid];
+}
+
+template <int P>
+__global__ void __launch_bounds__(kFitThreads) fit_apply_kernel(FitArgs a) {
+    constexpr int P2 = 2 * P * P;
+    extern __shared__ double fsm[];
+    __shared__ int ringOff[kMaxRings + 1];
+    double *tileM = fsm;                              // [kFitTile][P2 + 1], last column = r
+    double *inv = tileM + kFitTile * (P2 + 1);        // [P2][P2]
+    const int chunk = blockIdx.x, slot = blockIdx.y, tid = threadIdx.x;
+    const int haloIdx = a.batchHalos[slot];
+    const int N = fit_point_count(a, slot, ringOff);
+    double *out = a.csPart + (static_cast<size_t>(slot) * kFitChunks + chunk) * P2;
+    if (a.status[haloIdx] != 0 || N == 0) return;
+    for (int k = tid; k < P2 * P2; k += kFitThreads) inv[k] = a.gramInv[static_cast<size_t>(slot) * (P2 * P2) + k];
+    int c0, c1;
+    fit_chunk_range(N, chunk, c0, c1);
+    const size_t rowBase = static_cast<size_t>(slot) * a.rings * a.spokes;
+    // cs = rs^T (M^T inv) (mat.VecMult, mat.go:102): thread j sums over points in order
     double sum = 0.0;
-    for (int n0 = 0; n0 < N; n0 += kFitTile) {
+    for (int n0 = c0; n0 < c1; n0 += kFitTile) {
         __syncthreads();
-        load_tile(n0, true);
+        const int n = n0 + tid;
+        if (n < c1) {
+            const double *src = a.rows + (rowBase + n) * (P2 + 1);
+            // row of out2 = M^T inv (gonum Dense.Mul: axpy over l ascending)
+            double o2[P2];
+#pragma unroll
+            for (int j = 0; j < P2; j++) o2[j] = 0.0;
+#pragma unroll 1
+            for (int l = 0; l < P2; l++) {
+                const double t = src[l];
+                if (t == 0) continue;
+#pragma unroll
+                for (int j = 0; j < P2; j++) o2[j] += t * inv[l * P2 + j];
+            }
+#pragma unroll
+            for (int j = 0; j < P2; j++) tileM[tid * (P2 + 1) + j] = o2[j];
+            tileM[tid * (P2 + 1) + P2] = src[P2];
+        }
         __syncthreads();
         if (tid < P2) {
-            const int cnt = min(kFitTile, N - n0);
-            for (int k = 0; k < cnt; k++) sum += tileR[k] * tileM[k * P2 + tid];
+            const int cnt = min(kFitTile, c1 - n0);
+#pragma unroll 8
+            for (int k = 0; k < cnt; k++) sum += tileM[k * (P2 + 1) + P2] * tileM[k * (P2 + 1) + tid];
         }
     }
-    if (tid < P2) a.coeffs[static_cast<size_t>(haloIdx) * P2 + tid] = sum;
+    if (tid < P2) out[tid] = sum;
+}
+
+__global__ void fit_finish_kernel(FitArgs a) {
+    const int slot = blockIdx.x, tid = threadIdx.x;
+    const int haloIdx = a.batchHalos[slot];
+    const int P2 = 2 * a.order * a.order;
+    if (tid >= P2 || a.status[haloIdx] != 0) return;
+    double s = 0.0;
+    for (int c = 0; c < kFitChunks; c++) s += a.csPart[(static_cast<size_t>(slot) * kFitChunks + c) * P2 + tid];
+    a.coeffs[static_cast<size_t>(haloIdx) * P2 + tid] = s;
 }
 
 }  // namespace
@@ -1250,18 +1343,45 @@ cudaError_t launch_filter(const FilterArgs &a, int nb, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_fit(const FitArgs &a, int nb, cudaStream_t s) {
-    if (nb <= 0) return cudaSuccess;
-    const int P2 = 2 * a.order * a.order;
-    const size_t smem = sizeof(double) * (kFitTile * P2 + kFitTile);
+template <int P>
+cudaError_t launch_fit_p(const FitArgs &a, int nb, cudaStream_t s) {
+    constexpr int P2 = 2 * P * P;
+    const size_t smemA = sizeof(double) * kFitTile * (P2 + 1);
+    const size_t smemC = smemA + sizeof(double) * P2 * P2;
     static bool attrSet = false;
     if (!attrSet) {
-        cudaError_t e = cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(fit_rows_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fit_apply_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return e;
         attrSet = true;
     }
-    fit_kernel<<<nb, kFitThreads, smem, s>>>(a);
+    fit_rows_kernel<P><<<dim3(kFitChunks, nb), kFitThreads, smemA, s>>>(a);
+    fit_solve_kernel<<<nb, kMaxP2 * kMaxP2, 0, s>>>(a);
+    fit_apply_kernel<P><<<dim3(kFitChunks, nb), kFitThreads, smemC, s>>>(a);
+    fit_finish_kernel<<<nb, 32, 0, s>>>(a);
     return cudaGetLastError();
+}
+
+cudaError_t launch_fit(const FitArgs &a, int nb, cudaStream_t s) {
+    if (nb <= 0) return cudaSuccess;
+    switch (a.order) {
+    case 1: return launch_fit_p<1>(a, nb, s);
+    case 2: return launch_fit_p<2>(a, nb, s);
+    case 3: return launch_fit_p<3>(a, nb, s);
+    case 4: return launch_fit_p<4>(a, nb, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+size_t fit_scratch_doubles(int nb, int rings, int spokes, int order, size_t *rows, size_t *gramPart, size_t *gramInv,
+                           size_t *csPart) {
+    const size_t P2 = 2 * static_cast<size_t>(order) * order;
+    *rows = static_cast<size_t>(nb) * rings * spokes * (P2 + 1);
+    *gramPart = static_cast<size_t>(nb) * kFitChunks * P2 * P2;
+    *gramInv = static_cast<size_t>(nb) * P2 * P2;
+    *csPart = static_cast<size_t>(nb) * kFitChunks * P2;
+    return *rows + *gramPart + *gramInv + *csPart;
 }
 
 }  // namespace sfk

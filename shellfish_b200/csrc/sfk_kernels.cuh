@@ -71,6 +71,9 @@ struct FitArgs {
     double *coeffs;  // [nHalo][P2]
     int32_t *status; // [nHalo]
     long long *nPoints; // [nHalo]
+    // scratch (fit_scratch_doubles): design rows + r [nb][rings*spokes][P2+1], partial Gram
+    // matrices [nb][chunks][P2*P2], inverse [nb][P2*P2], partial coefficients [nb][chunks][P2]
+    double *rows, *gramPart, *gramInv, *csPart;
     int rings, spokes, order;
 };
 
@@ -100,5 +103,7 @@ cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s);
 cudaError_t launch_filter(const FilterArgs &a, int nb, cudaStream_t s);
 cudaError_t launch_fit(const FitArgs &a, int nb, cudaStream_t s);
 size_t bin_smem_bytes(int bins);
+size_t fit_scratch_doubles(int nb, int rings, int spokes, int order, size_t *rows, size_t *gramPart, size_t *gramInv,
+                           size_t *csPart);
 
 }  // namespace sfk
