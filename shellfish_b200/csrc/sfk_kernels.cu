@@ -356,8 +356,10 @@ hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const 
 // ------------------------------------------------------------------ los --
 
 constexpr int kLosWarps = 8;
-// columns of the padded ln(rho) rows of los_kernel_fast<8> (256 bins): positions 0 .. B + window + 8
-__host__ __device__ constexpr int los_fast_row(int window) { return (256 + window + 16) / 8 + 1; }
+// columns of the padded ln(rho) rows of los_kernel_fast<8> (256 bins): positions
+// 0 .. B + window + 8 must fit in 8 rows, so the fast path serves windows up to 231
+constexpr int kLosFastRow = 64;
+constexpr int kLosFastMaxWindow = 8 * kLosFastRow - 256 - 24;
 
 __device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8000000000000ll); }
 
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
     // Position p is stored at row p % PER, column p / PER, so the FIR below reads row jj at
     // column (lane + const): conflict-free and with no index arithmetic.
     const int padL = center + 1;
-    const int rowLen = los_fast_row(window);
+    constexpr int rowLen = kLosFastRow;
     double2 *taps = reinterpret_cast<double2 *>(sm);                       // [window] (value, deriv)
     double *ys = sm + 2 * window + (threadIdx.x >> 5) * (PER * rowLen);
     for (int k = threadIdx.x; k < window; k += blockDim.x) taps[k] = make_double2(a.valTaps[k], a.derivTaps[k]);
@@ -445,14 +447,28 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
     for (int c = 0; c < PER; c++) { s0[c] = 0.0; s1[c] = 0.0; }
 #pragma unroll
     for (int m = 0; m < PER - 1; m++) w[m] = yl[(1 + m) * rowLen];
-    for (int jb = 0; jb < window; jb += PER) {
+    int jb = 0;
+    for (; jb + PER <= window; jb += PER) {
         const double *yj = yl + jb / PER + 1;   // position lane*PER + jb + PER + jj: row jj, column lane + jb/PER + 1
 #pragma unroll
         for (int jj = 0; jj < PER; jj++) {
-            const int j = jb + jj;
-            if (j < window) {
+            w[(jj + PER - 1) % PER] = yj[jj * rowLen];
+            const double2 tp = taps[jb + jj];
+#pragma unroll
+            for (int c = 0; c < PER; c++) {
+                const double x = w[(c + jj) % PER];
+                s0[c] = fma(x, tp.x, s0[c]);
+                s1[c] = fma(x, tp.y, s1[c]);
+            }
+        }
+    }
+    {   // the last window % PER taps
+        const double *yj = yl + jb / PER + 1;
+#pragma unroll
+        for (int jj = 0; jj < PER; jj++) {
+            if (jb + jj < window) {
                 w[(jj + PER - 1) % PER] = yj[jj * rowLen];
-                const double2 tp = taps[j];
+                const double2 tp = taps[jb + jj];
 #pragma unroll
                 for (int c = 0; c < PER; c++) {
                     const double x = w[(c + jj) % PER];
@@ -1318,8 +1334,8 @@ cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s) {
     }
     const int64_t warps = static_cast<int64_t>(nb) * a.rings * a.spokes;
     const unsigned grid = static_cast<unsigned>((warps + kLosWarps - 1) / kLosWarps);
-    if (a.bins == 256) {
-        const size_t fsmem = sizeof(double) * (2 * a.window + kLosWarps * 8 * los_fast_row(a.window));
+    if (a.bins == 256 && a.window <= kLosFastMaxWindow) {
+        const size_t fsmem = sizeof(double) * (2 * a.window + kLosWarps * 8 * kLosFastRow);
         los_kernel_fast<8><<<grid, kLosWarps * 32, fsmem, s>>>(a, nb);
     } else {
         los_kernel<<<grid, kLosWarps * 32, smem, s>>>(a, nb);
