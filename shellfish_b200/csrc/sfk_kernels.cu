@@ -23,6 +23,7 @@ namespace {
 
 constexpr double kTwoPi = 6.28318530717958647692528676655900576839433879875021;
 constexpr double kPi = 3.14159265358979323846264338327950288419716939937511;
+constexpr double kTrigEps = 2e-5;   // see make_hit
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
@@ -165,7 +166,7 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
         // circle contains the centre: Insert(-Inf, ln rHi) on every LoS, halo.go:241-250
         r.caseA = 1;
         r.r01 = static_cast<uint32_t>(n) << 16; r.r23 = 0;
-        const double phiC = atan2(cy, cx);
+        const double phiC = static_cast<double>(atan2f(r.cy, r.cx));   // only used with >= 1-LoS guards
         const bool dead = D + P <= rMinSafe;
         const double cosT = (h.rMin * h.rMin + projDist2 - projRad2) / (2.0 * h.rMin * D);
         const bool full = !(D > 1e-9 * h.rMin) || !(cosT > -1.0);
@@ -173,7 +174,7 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
         if (has_nan_los(cx, cy, projDist2, phiC, dPhi, n, ringCos, ringSin)) return true;
         if (dead) return false;
         // rHi(theta) > rMin  <=>  cos(theta) > cosT, theta = angle(LoS, projected position)
-        const double theta = acos(fmin(cosT, 1.0)) + 2.0 * dPhi + 1e-9;
+        const double theta = static_cast<double>(acosf(static_cast<float>(fmin(cosT, 1.0)))) + 2.0 * dPhi + 1e-5;
         if (theta >= kPi) return true;
         double a = phiC - theta;
         a -= kTwoPi * floor(a / kTwoPi);
@@ -189,8 +190,27 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
     }
     r.caseA = 0;
     if (D + P <= rMinSafe || D - P >= rMaxSafe) return false;
-    const double alpha = asin(sqrt(projRad2 / projDist2));
-    const double projPhi = atan2(cy, cx);
+    // halfAngularWidth and Atan2 (halo.go:252-253, 315-318) only feed idxRange's int()
+    // truncations and the guarded trims below, so float32 libm (error < 3e-6 rad for a width
+    // below asin(sqrt(0.98))) decides them unless a truncated value lies within kTrigEps of a
+    // LoS boundary or the branch point phiLo = 0; those few hits take the float64 functions.
+    double alpha, projPhi;
+    {
+        const float qf = static_cast<float>(projRad2) / static_cast<float>(projDist2);
+        bool fast = qf < 0.98f;
+        if (fast) {
+            alpha = static_cast<double>(asinf(sqrtf(qf)));
+            projPhi = static_cast<double>(atan2f(r.cy, r.cx));
+            const double lo = projPhi - alpha, hi = projPhi + alpha;
+            const double tlo = (lo < 0 ? lo + kTwoPi : lo) / dPhi, thi = hi / dPhi;
+            const double tol = kTrigEps / dPhi;
+            if (fabs(lo) < kTrigEps || fabs(tlo - rint(tlo)) < tol || fabs(thi - rint(thi)) < tol) fast = false;
+        }
+        if (!fast) {
+            alpha = asin(sqrt(projRad2 / projDist2));
+            projPhi = atan2(cy, cx);
+        }
+    }
     // Radial trimming.  Along a LoS at angle delta from the projected position the chord is
     // [rLo, rHi](delta), rLo increasing and rHi decreasing in |delta| up to the tangent length
     // T = sqrt(D^2 - P^2) at delta = alpha.  Where the projected circle crosses the sphere r = R
