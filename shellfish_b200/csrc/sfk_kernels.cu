@@ -129,7 +129,11 @@ __device__ bool has_nan_los(double cx, double cy, double projDist2, double phiC,
     for (int sgn = -1; sgn <= 1; sgn += 2) {
         double ph = phiC + sgn * (kPi / 2);
         if (ph < 0) ph += kTwoPi;
-        const int i0 = static_cast<int>(__double2ll_rd(ph / dPhi));   // ph in [0, 2.5 pi): 0 <= i0 < 2n
+        const double t = ph / dPhi, ft = floor(t);
+        // b^2 can round above dist2 only for a LoS within ~3e-8 rad of the perpendicular; phiC
+        // is good to 1e-6, so unless a LoS lies within 1e-5 rad there is nothing to test
+        if (fmin(t - ft, ft + 1.0 - t) * dPhi > 1e-5) continue;
+        const int i0 = static_cast<int>(ft);   // ph in [0, 2.5 pi): 0 <= i0 < 2n
         for (int d = -1; d <= 2; d++) {
             int i = i0 + d;   // in [-1, 2n + 2)
             if (i < 0) i += n;
@@ -224,11 +228,12 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
     {
         const double T2 = projDist2 - projRad2;
         double dStar = alpha;
+        // float32 acos: its error (< 4e-4 rad even where cos -> 1) is inside the 2 dPhi guard
         if (T2 > rMaxSafe * rMaxSafe && D - P < h.rMax)
-            dStar = acos(fmin(fmax((projDist2 + h.rMax * h.rMax - projRad2) / (2.0 * D * h.rMax), -1.0), 1.0));
+            dStar = acosf(fminf(fmaxf(static_cast<float>((projDist2 + h.rMax * h.rMax - projRad2) / (2.0 * D * h.rMax)), -1.f), 1.f));
         else if (T2 < rMinSafe * rMinSafe && D + P > h.rMin)
-            dStar = acos(fmin(fmax((projDist2 + h.rMin * h.rMin - projRad2) / (2.0 * D * h.rMin), -1.0), 1.0));
-        if (dStar + 2.0 * dPhi < alpha) { half = dStar + 2.0 * dPhi; edge = half; }
+            dStar = acosf(fminf(fmaxf(static_cast<float>((projDist2 + h.rMin * h.rMin - projRad2) / (2.0 * D * h.rMin)), -1.f), 1.f));
+        if (dStar + 2.0 * dPhi + 1e-3 < alpha) { half = dStar + 2.0 * dPhi + 1e-3; edge = half; }
     }
     const double phiLo = projPhi - half, phiHi = projPhi + half;
     // idxRange, halo.go:284-310 (literal when half == alpha; otherwise a subset of the literal
