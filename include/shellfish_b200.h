@@ -159,6 +159,30 @@ int sfk_split_bin(sfk_ctx *ctx);
 int sfk_split_buffer(sfk_ctx *ctx, int32_t which, void **d_ptr, int64_t *count);
 int sfk_split_finish(sfk_ctx *ctx, double *coeffs, int32_t *status);
 
+/* ---- `shellfish stats`, splashback mass M_sp ---------------------------------
+ * massContained (cmd/stats.go:451-543) for every halo of a snapshot: the mass of
+ * the particles inside the Penna-Dines surface R(phi, theta) given by a halo's
+ * coefficient row (Shell.Contains, los/analyze/shell.go:349-354), with the
+ * reference's float32 distance chain and its periodic `wrap` (cmd/stats.go:
+ * 429-436, which shifts by half the box).  Call order, mirroring Run()
+ * (cmd/stats.go:268-341): begin -> push every block for which
+ * sfk_sphere_block_hit is true for at least one halo (binSphereIntersections,
+ * :694) -> finish.  Every pushed block is tested against every halo, as
+ * cmd/stats.go:322-327 does.
+ *   centers  [n_halo][3]  float32(X, Y, Z) of the halo table (boundingSpheres, :407-421)
+ *   coeffs   [n_halo][2*order*order]  the P_ijk columns of the `shell` catalog
+ *   r_low, r_high  [n_halo]  Shell.RadialRange of each halo (rangeSp, :445-449) */
+int sfk_mass_begin(sfk_ctx *ctx, int64_t n_halo, int32_t order, const float *centers,
+                   const double *coeffs, const double *r_low, const double *r_high);
+int sfk_mass_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
+                        double total_width);
+int sfk_mass_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass,
+                               int64_t n, double total_width);
+int sfk_mass_finish(sfk_ctx *ctx, double *masses);
+/* sphereSheetIntersect, cmd/stats.go:685-692 (radius = float32(R200m)); returns 0 or 1. */
+int sfk_sphere_block_hit(const float center[3], float radius, const float origin[3],
+                         const float width[3], double total_width);
+
 int sfk_get_stats(const sfk_ctx *ctx, sfk_stats *out);
 
 /* The cudaStream_t (as void*) every kernel of this context is launched on, so

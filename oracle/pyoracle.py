@@ -95,6 +95,13 @@ def lib():
         L.orc_penna_func.restype = C.c_double
         L.orc_penna_func.argtypes = [c_double_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
         L.orc_shell_run.restype = C.c_int
+        L.orc_shell_contains.restype = C.c_int
+        L.orc_shell_contains.argtypes = [c_double_p, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.orc_mass_contained.restype = C.c_double
+        L.orc_mass_contained.argtypes = [C.c_double, c_float_p, c_float_p, C.c_int64, c_double_p, C.c_int,
+                                         c_float_p, C.c_double, C.c_double, C.c_int]
+        L.orc_sphere_sheet_intersect.restype = C.c_int
+        L.orc_sphere_sheet_intersect.argtypes = [c_float_p, C.c_float, c_float_p, c_float_p, C.c_double]
         L.orc_nth_largest.restype = C.c_double
         L.orc_nth_largest.argtypes = [c_double_p, C.c_int64, C.c_int64, c_double_p]
         L.orc_percentile.restype = C.c_double
@@ -304,3 +311,28 @@ def calc_percentile(r200m, profiles, percentile_value, rMinMult=0.3, rMaxMult=3.
     out = np.zeros(2 * bins)
     lib().orc_calc_percentile(r200m * rMinMult, r200m * rMaxMult, bins, dp(prof), len(prof), percentile_value, dp(out))
     return out
+
+
+def shell_contains(cs, x, y, z):
+    """Shell.Contains, los/analyze/shell.go:349-354 (order from the coefficient count)."""
+    cs = np.ascontiguousarray(cs, np.float64)
+    order = int(round((len(cs) / 2) ** 0.5))
+    return bool(lib().orc_shell_contains(dp(cs), order, x, y, z))
+
+
+def mass_contained(total_width, xs, ms, cs, center, r_low, r_high, workers=1):
+    """massContained, cmd/stats.go:451-543, for one halo over one block."""
+    xs = np.ascontiguousarray(xs, np.float32)
+    ms = np.ascontiguousarray(ms, np.float32)
+    cs = np.ascontiguousarray(cs, np.float64)
+    c = np.ascontiguousarray(center, np.float32)
+    order = int(round((len(cs) / 2) ** 0.5))
+    return lib().orc_mass_contained(total_width, fp(xs), fp(ms), len(ms), dp(cs), order, fp(c), r_low, r_high,
+                                    workers)
+
+
+def sphere_sheet_intersect(center, r, origin, width, total_width):
+    c = np.ascontiguousarray(center, np.float32)
+    o = np.ascontiguousarray(origin, np.float32)
+    w = np.ascontiguousarray(width, np.float32)
+    return bool(lib().orc_sphere_sheet_intersect(fp(c), float(r), fp(o), fp(w), total_width))

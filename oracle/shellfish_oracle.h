@@ -194,6 +194,14 @@ double orc_percentile(const double *xs, int64_t len, double p, double *buf);
 void orc_calc_percentile(double rMin, double rMax, int bins, const double *profiles,
                          int64_t nLos, double percentile, double *out);
 
+/* ---- `stats` M_sp pass, cmd/stats.go:429-543,685-692; los/analyze/shell.go:349 */
+int orc_shell_contains(const double *cs, int order, double x, double y, double z);
+double orc_mass_contained(double totalWidth, const float *xs, const float *ms, int64_t n,
+                          const double *cs, int order, const float c[3],
+                          double rLow, double rHigh, int workers);
+int orc_sphere_sheet_intersect(const float c[3], float r, const float origin[3],
+                               const float width[3], double tw);
+
 /* Resets the process-wide Savitzky-Golay kernel cache (smooth.go:9-12). */
 void orc_reset_kernel_cache(void);
 

@@ -50,7 +50,8 @@ class Stats(C.Structure):
 EXPORTS = ["sfk_default_params", "sfk_create", "sfk_destroy", "sfk_last_error", "sfk_begin_snapshot",
            "sfk_add_halos", "sfk_set_owned", "sfk_block_halo_mask", "sfk_push_block", "sfk_push_block_device",
            "sfk_finish_snapshot", "sfk_row_length", "sfk_split_count", "sfk_split_bin", "sfk_split_buffer", "sfk_split_finish",
-           "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count",
+           "sfk_mass_begin", "sfk_mass_push_block", "sfk_mass_push_block_device", "sfk_mass_finish",
+           "sfk_sphere_block_hit", "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count",
            "sfk_get_profiles", "sfk_get_counts", "sfk_get_ring_tables"]
 
 _lib = None
@@ -232,6 +233,43 @@ class ShellContext:
         self._ck(lib().sfk_split_finish(self._h, coeffs.ctypes.data_as(C.POINTER(C.c_double)),
                                         status.ctypes.data_as(C.POINTER(C.c_int32))), "sfk_split_finish")
         return coeffs, status
+
+    # ---- stats mode: M_sp ----------------------------------------------------------
+    def mass_contained(self, centers, coeffs, r_low, r_high, blocks, radii=None, device_blocks=None):
+        """massContained (cmd/stats.go:451-543) for every halo over `blocks`
+        (dicts with xs, ms, TotalWidth, Origin, Width).  With `radii` given, blocks
+        no bounding sphere touches are skipped like cmd/stats.go:319-320 does."""
+        centers = np.ascontiguousarray(centers, np.float32)
+        coeffs = np.ascontiguousarray(coeffs, np.float64)
+        r_low = np.ascontiguousarray(r_low, np.float64)
+        r_high = np.ascontiguousarray(r_high, np.float64)
+        n = len(centers)
+        order = int(round((coeffs.shape[1] / 2) ** 0.5))
+        dp_, fp_ = C.POINTER(C.c_double), C.POINTER(C.c_float)
+        self._ck(lib().sfk_mass_begin(self._h, C.c_int64(n), C.c_int32(order), centers.ctypes.data_as(fp_),
+                                      coeffs.ctypes.data_as(dp_), r_low.ctypes.data_as(dp_),
+                                      r_high.ctypes.data_as(dp_)), "sfk_mass_begin")
+        for bi, b in enumerate(blocks):
+            if radii is not None:
+                o = np.ascontiguousarray(b["Origin"], np.float32)
+                w = np.ascontiguousarray(b["Width"], np.float32)
+                if not any(lib().sfk_sphere_block_hit(centers[i].ctypes.data_as(fp_), C.c_float(radii[i]),
+                                                      o.ctypes.data_as(fp_), w.ctypes.data_as(fp_),
+                                                      C.c_double(b["TotalWidth"])) for i in range(n)):
+                    continue
+            if device_blocks is not None:
+                dx, dm = device_blocks[bi]
+                self._ck(lib().sfk_mass_push_block_device(self._h, C.c_void_p(dx.data_ptr()), C.c_void_p(dm.data_ptr()),
+                                                          C.c_int64(dm.numel()), C.c_double(b["TotalWidth"])),
+                         "sfk_mass_push_block_device")
+                continue
+            xs = np.ascontiguousarray(b["xs"], np.float32)
+            ms = np.ascontiguousarray(b["ms"], np.float32)
+            self._ck(lib().sfk_mass_push_block(self._h, xs.ctypes.data_as(fp_), ms.ctypes.data_as(fp_),
+                                               C.c_int64(len(ms)), C.c_double(b["TotalWidth"])), "sfk_mass_push_block")
+        out = np.zeros(n)
+        self._ck(lib().sfk_mass_finish(self._h, out.ctypes.data_as(dp_)), "sfk_mass_finish")
+        return out
 
     def stream_ptr(self):
         """cudaStream_t of this context as an integer (torch.cuda.ExternalStream)."""

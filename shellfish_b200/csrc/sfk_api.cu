@@ -104,6 +104,12 @@ struct sfk_ctx {
     DevBuf<uint32_t> dHitCount;
     DevBuf<double> dProfiles;
     DevBuf<double> dFitScratch;
+    // `stats` M_sp pass
+    DevBuf<float> dMassCenters, dMassLow2, dMassHigh2;
+    DevBuf<double> dMassCoeffs, dMassSums;
+    int64_t massHalos = 0;
+    int massOrder = 0;
+    bool massOpen = false;
     DevBuf<uint32_t> dTapInsert, dTapStart, dTapEnd;
 
     // batch scratch
@@ -814,6 +820,89 @@ int sfk_split_finish(sfk_ctx *ctx, double *coeffs, int32_t *status) {
     int rc = stage_analyze(ctx, static_cast<int>(ctx->order.size()));
     if (rc) return rc;
     return stage_collect(ctx, coeffs, status);
+}
+
+// ---- `stats` mode: splashback mass --------------------------------------------------
+
+int sfk_sphere_block_hit(const float center[3], float radius, const float origin[3], const float width[3],
+                         double total_width) {
+    // sphereSheetIntersect, cmd/stats.go:685-692
+    return in_range(center[0], radius, origin[0], width[0], total_width) &&
+           in_range(center[1], radius, origin[1], width[1], total_width) &&
+           in_range(center[2], radius, origin[2], width[2], total_width);
+}
+
+int sfk_mass_begin(sfk_ctx *ctx, int64_t n_halo, int32_t order, const float *centers, const double *coeffs,
+                   const double *r_low, const double *r_high) {
+    if (!ctx || n_halo < 0 || order <= 0 || (n_halo > 0 && (!centers || !coeffs || !r_low || !r_high)))
+        return fail(ctx, SFK_E_INVALID, "sfk_mass_begin: bad arguments");
+    if (order > kMaxOrder) return fail(ctx, SFK_E_UNSUPPORTED, "Order above 4 is not supported.");
+    CU(cudaSetDevice(ctx->p.device));
+    const size_t P2 = 2 * static_cast<size_t>(order) * order;
+    std::vector<float> c(centers, centers + 3 * n_halo), lo(n_halo), hi(n_halo);
+    for (int64_t i = 0; i < n_halo; i++) {
+        // low2, high2 := float32(rLow*rLow), float32(rHigh*rHigh), cmd/stats.go:522
+        lo[i] = static_cast<float>(r_low[i] * r_low[i]);
+        hi[i] = static_cast<float>(r_high[i] * r_high[i]);
+    }
+    std::vector<double> cs(coeffs, coeffs + P2 * n_halo);
+    CU(ctx->dMassCenters.upload(c, ctx->stream));
+    CU(ctx->dMassLow2.upload(lo, ctx->stream));
+    CU(ctx->dMassHigh2.upload(hi, ctx->stream));
+    CU(ctx->dMassCoeffs.upload(cs, ctx->stream));
+    CU(ctx->dMassSums.ensure(n_halo));
+    if (n_halo) CU(cudaMemsetAsync(ctx->dMassSums.p, 0, n_halo * sizeof(double), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // the host vectors die here
+    ctx->massHalos = n_halo; ctx->massOrder = order; ctx->massOpen = true;
+    return SFK_OK;
+}
+
+static int mass_push_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, int64_t n, double total_width) {
+    MassArgs a{};
+    a.xyz = dxyz; a.mass = dmass; a.n = n;
+    a.tw2 = static_cast<float>(total_width) / 2;
+    a.centers = ctx->dMassCenters.p; a.low2 = ctx->dMassLow2.p; a.high2 = ctx->dMassHigh2.p;
+    a.coeffs = ctx->dMassCoeffs.p; a.masses = ctx->dMassSums.p;
+    a.nHalo = static_cast<int>(ctx->massHalos); a.order = ctx->massOrder; a.P2 = 2 * ctx->massOrder * ctx->massOrder;
+    CU(launch_mass(a, ctx->stream));
+    ctx->stats.launches++;
+    return SFK_OK;
+}
+
+int sfk_mass_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n, double total_width) {
+    if (!ctx || !ctx->massOpen || n < 0 || (n > 0 && (!xyz || !mass)))
+        return fail(ctx, SFK_E_INVALID, "sfk_mass_push_block: call sfk_mass_begin first");
+    if (n == 0 || ctx->massHalos == 0) return SFK_OK;
+    CU(cudaSetDevice(ctx->p.device));
+    CU(ctx->dXyz.ensure(3 * n));
+    CU(ctx->dMass.ensure(n));
+    CU(cudaMemcpyAsync(ctx->dXyz.p, xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->dMass.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = mass_push_impl(ctx, ctx->dXyz.p, ctx->dMass.p, n, total_width);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));   // the caller may reuse its buffers (io.VectorBuffer does)
+    return SFK_OK;
+}
+
+int sfk_mass_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass, int64_t n,
+                               double total_width) {
+    if (!ctx || !ctx->massOpen || n < 0 || (n > 0 && (!d_xyz || !d_mass)))
+        return fail(ctx, SFK_E_INVALID, "sfk_mass_push_block_device: call sfk_mass_begin first");
+    if (n == 0 || ctx->massHalos == 0) return SFK_OK;
+    CU(cudaSetDevice(ctx->p.device));
+    CU(cudaDeviceSynchronize());   // the caller's buffers live on other streams
+    return mass_push_impl(ctx, d_xyz, d_mass, n, total_width);
+}
+
+int sfk_mass_finish(sfk_ctx *ctx, double *masses) {
+    if (!ctx || !ctx->massOpen || (ctx->massHalos > 0 && !masses))
+        return fail(ctx, SFK_E_INVALID, "sfk_mass_finish: call sfk_mass_begin first");
+    CU(cudaSetDevice(ctx->p.device));
+    if (ctx->massHalos)
+        CU(cudaMemcpyAsync(masses, ctx->dMassSums.p, ctx->massHalos * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->massOpen = false;
+    return SFK_OK;
 }
 
 int sfk_get_stats(const sfk_ctx *ctx, sfk_stats *out) {

@@ -89,6 +89,19 @@ struct PercentileArgs {
 };
 
 cudaError_t launch_percentile(const PercentileArgs &a, int nb, cudaStream_t s);
+
+// `stats` M_sp pass, cmd/stats.go:451-543
+struct MassArgs {
+    const float *xyz, *mass;     // one particle block
+    int64_t n;
+    float tw2;                   // float32(TotalWidth) / 2, cmd/stats.go:518
+    const float *centers;        // [nHalo][3] float32 sphere centres, cmd/stats.go:411-415
+    const float *low2, *high2;   // float32(rLow*rLow), float32(rHigh*rHigh), :522
+    const double *coeffs;        // [nHalo][P2]
+    double *masses;              // [nHalo], accumulated across blocks
+    int nHalo, order, P2;
+};
+cudaError_t launch_mass(const MassArgs &a, cudaStream_t s);
 cudaError_t launch_cull(const CullArgs &a, bool fill, cudaStream_t s);
 cudaError_t launch_hit_count(const Piece *pieces, int nPieces, const Cand *cands, const HaloDev *halos,
                              const float *norms, int rings, uint32_t *hitCount,
