@@ -107,6 +107,7 @@ struct sfk_ctx {
     // `stats` M_sp pass
     DevBuf<float> dMassCenters, dMassLow2, dMassHigh2;
     DevBuf<double> dMassCoeffs, dMassSums;
+    DevBuf<int> dMassList;       // [nHalo + 1 + 6]: halo list, its length, bounding-box keys
     int64_t massHalos = 0;
     int massOrder = 0;
     bool massOpen = false;
@@ -851,6 +852,7 @@ int sfk_mass_begin(sfk_ctx *ctx, int64_t n_halo, int32_t order, const float *cen
     CU(ctx->dMassHigh2.upload(hi, ctx->stream));
     CU(ctx->dMassCoeffs.upload(cs, ctx->stream));
     CU(ctx->dMassSums.ensure(n_halo));
+    CU(ctx->dMassList.ensure(n_halo + 7));
     if (n_halo) CU(cudaMemsetAsync(ctx->dMassSums.p, 0, n_halo * sizeof(double), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));   // the host vectors die here
     ctx->massHalos = n_halo; ctx->massOrder = order; ctx->massOpen = true;
@@ -863,9 +865,11 @@ static int mass_push_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, i
     a.tw2 = static_cast<float>(total_width) / 2;
     a.centers = ctx->dMassCenters.p; a.low2 = ctx->dMassLow2.p; a.high2 = ctx->dMassHigh2.p;
     a.coeffs = ctx->dMassCoeffs.p; a.masses = ctx->dMassSums.p;
+    a.list = ctx->dMassList.p; a.listCount = ctx->dMassList.p + ctx->massHalos;
+    a.bboxKeys = reinterpret_cast<unsigned *>(ctx->dMassList.p + ctx->massHalos + 1);
     a.nHalo = static_cast<int>(ctx->massHalos); a.order = ctx->massOrder; a.P2 = 2 * ctx->massOrder * ctx->massOrder;
     CU(launch_mass(a, ctx->stream));
-    ctx->stats.launches++;
+    ctx->stats.launches += 3;
     return SFK_OK;
 }
 

@@ -99,6 +99,8 @@ struct MassArgs {
     const float *low2, *high2;   // float32(rLow*rLow), float32(rHigh*rHigh), :522
     const double *coeffs;        // [nHalo][P2]
     double *masses;              // [nHalo], accumulated across blocks
+    unsigned *bboxKeys;          // [6] scratch: the block's coordinate range
+    int *list, *listCount;       // [nHalo] + [1] scratch: halos this block can reach
     int nHalo, order, P2;
 };
 cudaError_t launch_mass(const MassArgs &a, cudaStream_t s);
