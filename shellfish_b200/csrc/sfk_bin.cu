@@ -341,12 +341,10 @@ size_t bin_smem_bytes(int bins) {
 cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s) {
     if (nb <= 0) return cudaSuccess;
     const size_t smem = bin_smem_bytes(a.bins);
-    static bool attrSet[2] = {false, false};
-    if (!attrSet[taps]) {
+    {   // per device, so set it on every launch
         cudaError_t e = taps ? cudaFuncSetAttribute(bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
                              : cudaFuncSetAttribute(bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attrSet[taps] = true;
     }
     const int nTiles = (a.spokes + kTileLos - 1) / kTileLos;
     dim3 grid(nTiles * a.chunks, a.rings, nb);

@@ -1255,11 +1255,9 @@ cudaError_t launch_hits(const Piece *pieces, int nPieces, const Cand *cands,
     if (nPieces <= 0) return cudaSuccess;
     const size_t smem = sizeof(Cand) * kHitThreads + sizeof(float) * 3 * rings +
                         sizeof(uint32_t) * kHitThreads * kHitRingChunk;
-    static bool attrSet = false;
-    if (!attrSet) {
+    {   // per device, so set it on every launch (a second GPU in the same process must get it too)
         cudaError_t e = cudaFuncSetAttribute(hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attrSet = true;
     }
     hits_kernel<<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rots, ringCos, ringSin, rings,
                                                    spokes, dPhi, hitOffset, hitCursor, haloSlot, recs);
@@ -1351,11 +1349,9 @@ cudaError_t launch_percentile(const PercentileArgs &a, int nb, cudaStream_t s) {
 cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s) {
     if (nb <= 0) return cudaSuccess;
     const size_t smem = sizeof(double) * (2 * a.window + kLosWarps * 3 * a.bins);
-    static bool attrSet = false;
-    if (!attrSet) {
+    {   // per device, so set it on every launch (a second GPU in the same process must get it too)
         cudaError_t e = cudaFuncSetAttribute(los_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attrSet = true;
     }
     const int64_t warps = static_cast<int64_t>(nb) * a.rings * a.spokes;
     const unsigned grid = static_cast<unsigned>((warps + kLosWarps - 1) / kLosWarps);
@@ -1373,11 +1369,9 @@ cudaError_t launch_filter(const FilterArgs &a, int nb, cudaStream_t s) {
     const int nKde = (1 << (a.levels + 1)) - 1;
     const size_t smem = sizeof(FilterSmem) + sizeof(double) * (3 * nKde * kKdeKnots + nKde * kMaxMax + a.spokes) +
                         sizeof(int) * a.spokes + 2 * sizeof(short) * a.spokes + a.spokes * (1 + a.levels) + 16;
-    static bool attrSet = false;
-    if (!attrSet) {
+    {   // per device, so set it on every launch (a second GPU in the same process must get it too)
         cudaError_t e = cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attrSet = true;
     }
     dim3 grid(a.rings, nb);
     filter_kernel<<<grid, kFilterThreads, smem, s>>>(a);
@@ -1389,13 +1383,11 @@ cudaError_t launch_fit_p(const FitArgs &a, int nb, cudaStream_t s) {
     constexpr int P2 = 2 * P * P;
     const size_t smemA = sizeof(double) * kFitTile * (P2 + 1);
     const size_t smemC = smemA + sizeof(double) * P2 * P2;
-    static bool attrSet = false;
-    if (!attrSet) {
+    {   // per device, so set it on every launch (a second GPU in the same process must get it too)
         cudaError_t e = cudaFuncSetAttribute(fit_rows_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(fit_apply_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return e;
-        attrSet = true;
     }
     fit_rows_kernel<P><<<dim3(kFitChunks, nb), kFitThreads, smemA, s>>>(a);
     fit_solve_kernel<<<nb, kMaxP2 * kMaxP2, 0, s>>>(a);
