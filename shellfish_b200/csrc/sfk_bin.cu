@@ -95,8 +95,9 @@ __device__ __forceinline__ void bin_of(double r, double invRMin, float cK, doubl
     const float uf = __int_as_float((__double2hiint(u) - 0x38000000) << 3);
     float lg;   // uf is a normal number >= 1: the flush-to-zero form skips __log2f's denormal path
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(uf));
+    // callers guarantee rMin < r < rMax, and the estimate never exceeds the true position:
+    // 0 <= k <= bins - 1 without clamping
     int k = static_cast<int>(fmaf(lg, cK, -1.0e-3f));
-    k = min(k, bins - 1);
     const double t = fma(u, sInvG[k], -1.0);   // r / (rMin g[k]) - 1
     double L = fma(t, -1.0 / 6.0, 0.2);
     L = fma(L, t, -0.25);
@@ -104,7 +105,9 @@ __device__ __forceinline__ void bin_of(double r, double invRMin, float cK, doubl
     L = fma(L, t, -0.5);
     L = fma(L, t, 1.0);
     double x = (L * t) * invDr;
-    if (x >= 1.0) { k += 1; x -= 1.0; }
+    // if (x >= 1.0) { k += 1; x -= 1.0; } as two predicated instructions
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.f64 p, %0, 0d3FF0000000000000;\n\t@p add.f64 %0, %0, 0dBFF0000000000000;\n\t"
+        "@p add.s32 %1, %1, 1;\n\t}" : "+d"(x), "+r"(k));
     idx = k;
     rem = x;
 }
@@ -114,8 +117,11 @@ __device__ __forceinline__ void acc_add(uint32_t *lo, uint32_t *hi, int idx, lon
     const uint32_t vlo = static_cast<uint32_t>(v);
     const uint32_t vhi = static_cast<uint32_t>(static_cast<unsigned long long>(v) >> 32);
     const uint32_t old = atomicAdd(&lo[idx * kTileLos], vlo);
-    const uint32_t add = vhi + ((old + vlo) < old ? 1u : 0u);
-    if (add) atomicAdd(&hi[idx * kTileLos], add);
+    // hi += vhi + carry(old + vlo): add.cc / addc keep it at two integer instructions, and the
+    // second atomic is issued unconditionally (vhi is almost never zero: values are ~2^45)
+    uint32_t add;
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(add) : "r"(old), "r"(vlo), "r"(vhi));
+    atomicAdd(&hi[idx * kTileLos], add);
 }
 
 template <bool TAPS>
