@@ -312,3 +312,66 @@ def test_percentile_profile_mode():
             assert np.all(np.abs(rows[h, 256:] - want[256:]) <= RTOL * np.abs(want[256:])), (pct, h)
     with pytest.raises(RuntimeError, match="percentile must be in the range"):
         api.ShellContext(api.default_params(percentile_profile=1, percentile=120.0))
+
+
+def test_dense_core_centre_containing_hits():
+    """A cloud inside 0.35 R200m: almost every ring hit is centre-containing
+    (insertToRing's first branch, halo.go:241-250), the case whose LoS ranges are
+    trimmed.  Integer taps must stay bit-exact."""
+    rng = np.random.default_rng(77)
+    n = 120000
+    v = rng.normal(size=(n, 3))
+    v *= (0.35 * rng.random(n) ** (1 / 3) / np.linalg.norm(v, axis=1))[:, None]
+    box = 62.5
+    c = np.array([30.0, 31.0, 32.0])
+    xs = (c + v).astype(np.float32)
+    halos = np.array([[c[0], c[1], c[2], 1.0]])
+    mass = float(synth.uniform_mass(n, box))
+    blocks = [dict(synth.COSMO, TotalWidth=box, Origin=(np.float32(0),) * 3, Width=(np.float32(box),) * 3,
+                   xs=xs, ms=np.full(n, mass, np.float32))]
+    params = api.default_params(seed=1337, rings=16, flags=api.SFK_FLAG_TAPS)
+    ctx, coeffs, status = api.run_shell(params, mass, halos, blocks)
+    ref = po.shell_run(po.ShellConfig.default(seed=1337, threads=4, rings=16), mass, halos, blocks,
+                       taps=("nInsert", "startEdges", "endEdges", "profiles", "nIntersections"))
+    ins, st, en = ctx.counts(0)
+    assert np.array_equal(ins, ref["nInsert"][0])
+    assert np.array_equal(st, ref["startEdges"][0])
+    assert np.array_equal(en, ref["endEdges"][0])
+    assert ctx.stats()["n_intersections"] == ref["nIntersections"][0]
+    prof, rp = ctx.profiles(0), ref["profiles"][0]
+    den = np.maximum(np.abs(rp), rp.min())
+    assert np.max(np.abs(prof - rp) / den) <= RTOL
+
+
+def test_nan_line_of_sight_is_reproduced():
+    """oneValIntrDist takes sqrt(dist2 - b*b) (halo.go:337-346).  For a particle at
+    (-a, a) in the plane of the z ring and the LoS at phi = pi/4, b = a (cos + sin) and
+    (cos(pi/4) + sin(pi/4))^2 rounds to 2.0000000000000004 > 2: the radicand is negative,
+    rHi is NaN, and ProfileRing.Insert adds rho to bin 0 without ever taking it out
+    (profile_ring.go:93-110).  The pruning in make_hit must keep exactly these LoS."""
+    halos, blocks, mass = synth.single_halo(seed=5, n=30000, n_background=5000)
+    c = halos[0, :3]
+    assert np.all(c == c.astype(np.float32))          # box centre 31.25: exact in float32
+    extra = []
+    for a in (2.0 ** -4, 2.0 ** -5, 3 * 2.0 ** -6, 2.0 ** -3):
+        for cz in (2.0 ** -5, -2.0 ** -6):
+            extra += [[-a, a, cz], [a, -a, cz], [a, a, cz], [-a, -a, cz]]
+    extra = (c + np.array(extra)).astype(np.float32)
+    b = blocks[0]
+    b["xs"] = np.concatenate([b["xs"], extra]).astype(np.float32)
+    b["ms"] = np.concatenate([b["ms"], np.full(len(extra), mass, np.float32)])
+    # the crafted particles do hit the condition (ring 0 of the 3-ring set is the z ring and its
+    # rotation is the identity in float32, so the ring-frame coordinates are x - origin)
+    d = (extra - c.astype(np.float32)).astype(np.float64)
+    events = 0
+    for i in (32, 96, 160, 224):
+        phi = float(i) / 256.0 * (2 * np.pi)
+        bb = d[:, 1] * np.cos(phi) - d[:, 0] * np.sin(phi)
+        events += int(np.count_nonzero(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] - bb * bb < 0))
+    assert events >= 4, events
+    ctx, coeffs, status, ref = run_both(halos, blocks, mass, rings=3)   # rings == 3: axis normals, ring 0 = z
+    assert_parity(ctx, coeffs, status, ref, 1)
+    # and they show: those LoS keep rho out to rMax, which a complete chord of a particle at
+    # r < 0.2 R200m never does -- the outermost bin of LoS 32 sits above the background
+    prof = ctx.profiles(0)
+    assert prof[0, 32, -1] > 1.5 * prof[0, :, -1].min() or prof[0, 160, -1] > 1.5 * prof[0, :, -1].min()
