@@ -123,13 +123,13 @@ __device__ __forceinline__ uint16_t clamp_idx(long long v, int n) {
 // round below zero, the distance becomes NaN and ProfileRing.Insert then adds
 // rho to bin 0 and never subtracts it (profile_ring.go:93-110).  Only the LoS
 // nearest to phiC +- pi/2 can qualify; they are evaluated literally.
-__device__ bool has_nan_los(double cx, double cy, double projDist2, double phiC, double dPhi,
+__device__ bool has_nan_los(double cx, double cy, double projDist2, double phiC, double dPhi, double invDPhi,
                             int n, const double *ringCos, const double *ringSin) {
     bool any = false;
     for (int sgn = -1; sgn <= 1; sgn += 2) {
         double ph = phiC + sgn * (kPi / 2);
         if (ph < 0) ph += kTwoPi;
-        const double t = ph / dPhi, ft = floor(t);
+        const double t = ph * invDPhi, ft = floor(t);   // approximate on purpose: four neighbours are tested
         // b^2 can round above dist2 only for a LoS within ~3e-8 rad of the perpendicular; phiC
         // is good to 1e-6, so unless a LoS lies within 1e-5 rad there is nothing to test
         if (fmin(t - ft, ft + 1.0 - t) * dPhi > 1e-5) continue;
@@ -156,7 +156,7 @@ __device__ bool has_nan_los(double cx, double cy, double projDist2, double phiC,
 // a superset of the LoS whose far intersection exceeds rMin.  Both prunings
 // only drop work the reference does to no effect; the per-LoS evaluation in
 // bin_kernel stays literal.
-__device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, double dPhi, int n,
+__device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, double dPhi, double invDPhi, int n,
                          const double *ringCos, const double *ringSin, HitRec &r) {
     rotate_vec(rot, c.vx, c.vy, c.vz, r.cx, r.cy, r.cz);
     const double cx = r.cx, cy = r.cy, cz = r.cz;
@@ -175,15 +175,17 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
         const double cosT = (h.rMin * h.rMin + projDist2 - projRad2) / (2.0 * h.rMin * D);
         const bool full = !(D > 1e-9 * h.rMin) || !(cosT > -1.0);
         if (!dead && full) return true;
-        if (has_nan_los(cx, cy, projDist2, phiC, dPhi, n, ringCos, ringSin)) return true;
+        if (has_nan_los(cx, cy, projDist2, phiC, dPhi, invDPhi, n, ringCos, ringSin)) return true;
         if (dead) return false;
         // rHi(theta) > rMin  <=>  cos(theta) > cosT, theta = angle(LoS, projected position)
         const double theta = static_cast<double>(acosf(static_cast<float>(fmin(cosT, 1.0)))) + 2.0 * dPhi + 1e-5;
         if (theta >= kPi) return true;
         double a = phiC - theta;
-        a -= kTwoPi * floor(a / kTwoPi);
-        const long long iLo = min(static_cast<long long>(n - 1), __double2ll_rd(a / dPhi));
-        const long long iHi = __double2ll_rd((a + 2.0 * theta) / dPhi) + 1;
+        a -= kTwoPi * floor(a * (1.0 / kTwoPi));
+        if (a < 0) a = 0;
+        // guarded by theta's two LoS spacings: the reciprocal is exact enough
+        const long long iLo = min(static_cast<long long>(n - 1), __double2ll_rd(a * invDPhi));
+        const long long iHi = __double2ll_rd((a + 2.0 * theta) * invDPhi) + 1;
         if (iHi <= n) {
             r.r01 = static_cast<uint32_t>(iLo) | static_cast<uint32_t>(iHi) << 16;
         } else if (iHi - n < iLo) {
@@ -199,6 +201,7 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
     // below asin(sqrt(0.98))) decides them unless a truncated value lies within kTrigEps of a
     // LoS boundary or the branch point phiLo = 0; those few hits take the float64 functions.
     double alpha, projPhi;
+    bool literal;   // alpha, projPhi are the reference's float64 values
     {
         const float qf = static_cast<float>(projRad2) / static_cast<float>(projDist2);
         bool fast = qf < 0.98f;
@@ -206,7 +209,7 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
             alpha = static_cast<double>(asinf(sqrtf(qf)));
             projPhi = static_cast<double>(atan2f(r.cy, r.cx));
             const double lo = projPhi - alpha, hi = projPhi + alpha;
-            const double tlo = (lo < 0 ? lo + kTwoPi : lo) / dPhi, thi = hi / dPhi;
+            const double tlo = (lo < 0 ? lo + kTwoPi : lo) * invDPhi, thi = hi * invDPhi;
             const double tol = kTrigEps / dPhi;
             if (fabs(lo) < kTrigEps || fabs(tlo - rint(tlo)) < tol || fabs(thi - rint(thi)) < tol) fast = false;
         }
@@ -214,6 +217,7 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
             alpha = asin(sqrt(projRad2 / projDist2));
             projPhi = atan2(cy, cx);
         }
+        literal = !fast;
     }
     // Radial trimming.  Along a LoS at angle delta from the projected position the chord is
     // [rLo, rHi](delta), rLo increasing and rHi decreasing in |delta| up to the tangent length
@@ -233,18 +237,26 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
             dStar = acosf(fminf(fmaxf(static_cast<float>((projDist2 + h.rMax * h.rMax - projRad2) / (2.0 * D * h.rMax)), -1.f), 1.f));
         else if (T2 < rMinSafe * rMinSafe && D + P > h.rMin)
             dStar = acosf(fminf(fmaxf(static_cast<float>((projDist2 + h.rMin * h.rMin - projRad2) / (2.0 * D * h.rMin)), -1.f), 1.f));
-        if (dStar + 2.0 * dPhi + 1e-3 < alpha) { half = dStar + 2.0 * dPhi + 1e-3; edge = half; }
+        if (dStar + 2.0 * dPhi + 1e-3 < alpha) { half = dStar + 2.0 * dPhi + 1e-3; edge = half; literal = false; }
     }
     const double phiLo = projPhi - half, phiHi = projPhi + half;
     // idxRange, halo.go:284-310 (literal when half == alpha; otherwise a subset of the literal
     // ranges that still holds every LoS within `half` of the projected position)
+    // The reference divides by dPhi; where the angles are not its float64 values anyway (float32
+    // trig, kept away from LoS boundaries by kTrigEps, or a guarded trim) the reciprocal serves.
     long long i0, i1, i2, i3;
-    if (phiHi > kTwoPi) {
-        i0 = go_int(phiLo / dPhi); i1 = n; i2 = 0; i3 = go_int((phiHi - kTwoPi) / dPhi) + 1;
+    if (literal) {
+        if (phiHi > kTwoPi) {
+            i0 = go_int(phiLo / dPhi); i1 = n; i2 = 0; i3 = go_int((phiHi - kTwoPi) / dPhi) + 1;
+        } else if (phiLo < 0) {
+            i0 = go_int((phiLo + kTwoPi) / dPhi); i1 = n; i2 = 0; i3 = go_int(phiHi / dPhi) + 1;
+        } else {
+            i0 = go_int(phiLo / dPhi); i1 = go_int(phiHi / dPhi) + 1; i2 = 0; i3 = 0;
+        }
     } else if (phiLo < 0) {
-        i0 = go_int((phiLo + kTwoPi) / dPhi); i1 = n; i2 = 0; i3 = go_int(phiHi / dPhi) + 1;
+        i0 = go_int((phiLo + kTwoPi) * invDPhi); i1 = n; i2 = 0; i3 = go_int(phiHi * invDPhi) + 1;
     } else {
-        i0 = go_int(phiLo / dPhi); i1 = go_int(phiHi / dPhi) + 1; i2 = 0; i3 = 0;
+        i0 = go_int(phiLo * invDPhi); i1 = go_int(phiHi * invDPhi) + 1; i2 = 0; i3 = 0;
     }
     r.r01 = clamp_idx(i0, n) | static_cast<uint32_t>(clamp_idx(i1, n)) << 16;
     r.r23 = clamp_idx(i2, n) | static_cast<uint32_t>(clamp_idx(i3, n)) << 16;
@@ -262,8 +274,8 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
         const double phiC = projPhi + kTwoPi;
         const double a1 = phiC + edge, a2 = phiC + kPi - edge;
         if (a1 < a2) {
-            const long long deadLo = __double2ll_rd(a1 / dPhi) + 1;   // first dead LoS
-            const long long deadHi = __double2ll_rd(a2 / dPhi);       // last dead LoS
+            const long long deadLo = __double2ll_rd(a1 * invDPhi) + 1;   // first dead LoS
+            const long long deadHi = __double2ll_rd(a2 * invDPhi);       // last dead LoS
             if (deadLo < n && deadLo > i0 && deadHi >= deadLo) {
                 r.r01 = clamp_idx(i0, n) | static_cast<uint32_t>(clamp_idx(deadLo, n)) << 16;
                 r.r23 = deadHi + 1 < n ? (clamp_idx(deadHi + 1, n) | static_cast<uint32_t>(n) << 16) : 0u;
@@ -338,6 +350,7 @@ hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const 
     if (live) c = cands[pc.start + threadIdx.x];
     sCand[threadIdx.x] = c;
     const double rad = h.rad;
+    const double invDPhi = 1.0 / dPhi;
     for (int r0 = 0; r0 < rings; r0 += kHitRingChunk) {
         const int r1 = min(rings, r0 + kHitRingChunk);
         if (threadIdx.x == 0) qCount = 0;
@@ -361,7 +374,7 @@ hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const 
             const uint32_t q = e < nq ? queue[e] : 0u;
             const int ring = static_cast<int>(q >> 8);
             HitRec rec;
-            const bool alive = e < nq && make_hit(rots + 9 * ring, sCand[q & 0xffu], h, dPhi, spokes,
+            const bool alive = e < nq && make_hit(rots + 9 * ring, sCand[q & 0xffu], h, dPhi, invDPhi, spokes,
                                                   ringCos, ringSin, rec);
             // one slot claim per (warp, ring): queue order keeps a ring's hits together
             const unsigned peers = __match_any_sync(0xffffffffu, alive ? ring : -1 - static_cast<int>(lane_id()));
