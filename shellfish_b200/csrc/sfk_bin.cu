@@ -10,7 +10,8 @@
 // counter.  For a group, lanes first clip the 32 records' LoS ranges against
 // the tile in parallel, a warp scan turns the clipped lengths into a list of
 // (record, LoS) pairs, and the pairs are then processed 32 at a time with one
-// pair per lane, so every lane does useful work whatever the range widths.
+// pair per lane (each lane finds its record by a shuffle binary search over the
+// scan), so every lane does useful work whatever the range widths.
 //
 // Arithmetic.  Everything that DECIDES something is evaluated literally, in
 // the reference's operation order with no FMA contraction (-fmad=false): the
@@ -135,10 +136,9 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     unsigned int *nextGroup = reinterpret_cast<unsigned int *>(empty + kBinStages);   // 8-byte slot
     double2 *sTrig = reinterpret_cast<double2 *>(empty + kBinStages + 2);         // [32] (cos, sin), 16-byte aligned
     double *sInvG = reinterpret_cast<double *>(sTrig + kTileLos);                 // [bins + 1]
-    uint32_t *sPair = reinterpret_cast<uint32_t *>(sInvG + bins + 1);             // [consumers][32]: record heads
     // accumulators are bin-major, [stride][32]: a warp's lanes are different LoS of (mostly) one
     // record, so the bank is the LoS and the atomics are conflict-free whatever the bins are
-    uint32_t *lo = sPair + kBinConsumers * 32;
+    uint32_t *lo = reinterpret_cast<uint32_t *>(sInvG + bins + 1);
     uint32_t *hi = lo + kTileLos * stride;
 
     const int nTiles = (a.spokes + kTileLos - 1) / kTileLos;
@@ -195,7 +195,6 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
         const double rMin = h.rMin, rMax = h.rMax, invRMin = h.invRMin, rad2 = h.rad2;
         const double invDr = a.invDr;
         const float cK = a.cK;
-        uint32_t *sHead = sPair + warp * 32;
         const size_t tapRing = (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes;
 
         // 32-record groups are handed out in order from a shared counter, so a
@@ -237,22 +236,18 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
                                   static_cast<unsigned>(st2 - t0) << 16;
 
             for (unsigned p0 = 0; p0 < nPairs; p0 += 32) {
-                // pair p0 + lane -> record: lanes whose record starts inside this chunk
-                // plant their lane number at the start position; every pair lane then
-                // takes the nearest planted record at or below its position
-                const unsigned rAtP0 = __popc(__ballot_sync(0xffffffffu, incl <= p0));
-                __syncwarp();
-                sHead[lane] = lane == 0 ? rAtP0 : 0xffu;
-                __syncwarp();
-                if (nMine > 0 && first > p0 && first < p0 + 32) sHead[first - p0] = lane;
-                __syncwarp();
-                const unsigned hv = sHead[lane];
-                const unsigned heads = __ballot_sync(0xffffffffu, hv != 0xffu);
-                const int hpos = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-                const int r = static_cast<int>(__shfl_sync(0xffffffffu, hv, hpos));
+                // pair p -> record: the number of records whose pairs end at or before p, by
+                // binary search over the (non-decreasing) inclusive scan held one per lane
+                const unsigned p = p0 + lane;
+                unsigned r = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const unsigned v = __shfl_sync(0xffffffffu, incl, (r + step - 1) & 31);
+                    if (v <= p) r += step;
+                }
+                r &= 31;   // lanes past nPairs (r == 32) are dropped below
                 const unsigned before = __shfl_sync(0xffffffffu, first, r);
                 const unsigned rmeta = __shfl_sync(0xffffffffu, meta, r);
-                const unsigned p = p0 + lane;
                 if (p >= nPairs) continue;
                 const int off = static_cast<int>(p - before);
                 const int l1 = static_cast<int>((rmeta >> 8) & 0xffu);
@@ -340,7 +335,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
 
 size_t bin_smem_bytes(int bins) {
     return sizeof(HitRec) * kBinStages * kStageRecs + (2 * kBinStages + 2) * sizeof(uint64_t) +
-           sizeof(double2) * kTileLos + sizeof(double) * (bins + 1) + sizeof(uint32_t) * kBinConsumers * 32 +
+           sizeof(double2) * kTileLos + sizeof(double) * (bins + 1) +
            sizeof(uint32_t) * 2 * kTileLos * (bins + 1);
 }
 
