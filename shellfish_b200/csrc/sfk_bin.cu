@@ -125,16 +125,23 @@ __device__ __forceinline__ void acc_add(uint32_t *lo, uint32_t *hi, int idx, lon
     atomicAdd(&hi[idx * kTileLos], add);
 }
 
+constexpr int kRawBufs = 2;     // TMA landing buffers of the producer warp
+constexpr int kRawRecs = 128;   // raw records per landing buffer (4 KB)
+
 template <bool TAPS>
 __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const int bins = a.bins;
     const int stride = bins + 1;   // +1: slot for a start/end edge that lands exactly on rMax
-    HitRec *stage = reinterpret_cast<HitRec *>(smemRaw);                          // [kBinStages][kStageRecs]
-    uint64_t *full = reinterpret_cast<uint64_t *>(stage + kBinStages * kStageRecs);   // [kBinStages]
+    HitRec *stage = reinterpret_cast<HitRec *>(smemRaw);                          // [kBinStages][kStageRecs] filtered records
+    HitRec *raw = stage + kBinStages * kStageRecs;                                // [kRawBufs][kRawRecs] TMA landing ring
+    uint64_t *full = reinterpret_cast<uint64_t *>(raw + kRawBufs * kRawRecs);     // [kBinStages]
     uint64_t *empty = full + kBinStages;                                          // [kBinStages]
-    unsigned int *nextGroup = reinterpret_cast<unsigned int *>(empty + kBinStages);   // 8-byte slot
-    double2 *sTrig = reinterpret_cast<double2 *>(empty + kBinStages + 2);         // [32] (cos, sin), 16-byte aligned
+    uint64_t *rawFull = empty + kBinStages;                                       // [kRawBufs]
+    int *sCnt = reinterpret_cast<int *>(rawFull + kRawBufs);                      // [kBinStages] records in the stage
+    int *sTerm = sCnt + kBinStages;                                               // [kBinStages] 1: no more stages
+    unsigned int *nextGroup = reinterpret_cast<unsigned int *>(sTerm + kBinStages);   // + pad to 16 bytes
+    double2 *sTrig = reinterpret_cast<double2 *>(nextGroup + 4);                  // [32] (cos, sin), 16-byte aligned
     double *sInvG = reinterpret_cast<double *>(sTrig + kTileLos);                 // [bins + 1]
     // accumulators are bin-major, [stride][32]: a warp's lanes are different LoS of (mostly) one
     // record, so the bank is the LoS and the atomics are conflict-free whatever the bins are
@@ -164,32 +171,73 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kBinConsumers);
         }
+        for (int s = 0; s < kRawBufs; s++) mbar_init(&rawFull[s], 1);
         fence_barrier_init();
     }
     __syncthreads();
 
-    // this CTA's share of the ring's records, in whole stages
+    // this CTA's share of the ring's records
     const size_t hr = static_cast<size_t>(slot) * a.rings + ring;
     const int64_t total = a.hitCount[hr];
-    const int64_t nStages = (total + kStageRecs - 1) / kStageRecs;
-    const int64_t s0 = nStages * chunk / a.chunks, s1 = nStages * (chunk + 1) / a.chunks;
+    const int64_t rec0 = (total * chunk / a.chunks) & ~int64_t(31);
+    const int64_t rec1 = chunk + 1 == a.chunks ? total : (total * (chunk + 1) / a.chunks) & ~int64_t(31);
     const HitRec *src = a.recs + a.hitOffset[hr];
     unsigned nIns = 0;
 
     if (warp == kBinConsumers) {
-        // ---- producer: keep the TMA ring full
-        if (lane == 0) {
-            for (int64_t s = s0; s < s1; s++) {
-                const int64_t t = s - s0;
-                const int buf = static_cast<int>(t % kBinStages);
-                if (t >= kBinStages) mbar_wait(&empty[buf], static_cast<uint32_t>((t / kBinStages - 1) & 1));
-                const int64_t first = s * kStageRecs;
-                const uint32_t cnt = static_cast<uint32_t>(min(static_cast<int64_t>(kStageRecs), total - first));
-                const uint32_t bytes = cnt * static_cast<uint32_t>(sizeof(HitRec));
-                mbar_expect_tx(&full[buf], bytes);
-                tma_load_1d(stage + buf * kStageRecs, src + first, bytes, &full[buf]);
+        // ---- producer warp.  Lane 0 keeps a small ring of TMA bulk copies of the ring's raw
+        // records in flight; the whole warp then keeps only the records whose LoS ranges touch
+        // this tile (about one in four) and packs them into the stages the consumers read, so a
+        // consumer group holds 32 useful records instead of 8.
+        const int64_t nRaw = (rec1 - rec0 + kRawRecs - 1) / kRawRecs;
+        auto issue = [&](int64_t rc) {
+            const int b = static_cast<int>(rc % kRawBufs);
+            const int64_t first = rec0 + rc * kRawRecs;
+            const uint32_t bytes = static_cast<uint32_t>(min(static_cast<int64_t>(kRawRecs), rec1 - first)) *
+                                   static_cast<uint32_t>(sizeof(HitRec));
+            mbar_expect_tx(&rawFull[b], bytes);
+            tma_load_1d(raw + b * kRawRecs, src + first, bytes, &rawFull[b]);
+        };
+        if (lane == 0)
+            for (int64_t rc = 0; rc < min(nRaw, static_cast<int64_t>(kRawBufs)); rc++) issue(rc);
+        int fill = 0, cbuf = 0;
+        int64_t t = 0;   // sequence number of the stage being filled
+        auto publish = [&](int count, int term) {
+            __syncwarp();
+            if (lane == 0) { sCnt[cbuf] = count; sTerm[cbuf] = term; mbar_arrive(&full[cbuf]); }
+            t++;
+            cbuf = static_cast<int>(t % kBinStages);
+            if (t >= kBinStages) mbar_wait(&empty[cbuf], static_cast<uint32_t>((t / kBinStages - 1) & 1));
+            fill = 0;
+        };
+        for (int64_t rc = 0; rc < nRaw; rc++) {
+            const int b = static_cast<int>(rc % kRawBufs);
+            mbar_wait(&rawFull[b], static_cast<uint32_t>((rc / kRawBufs) & 1));
+            const int cnt = static_cast<int>(min(static_cast<int64_t>(kRawRecs), rec1 - (rec0 + rc * kRawRecs)));
+            const uint4 *rp = reinterpret_cast<const uint4 *>(raw + b * kRawRecs);
+#pragma unroll
+            for (int sub = 0; sub < kRawRecs / 32; sub++) {
+                const int idx = sub * 32 + lane;
+                uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+                bool ov = false;
+                if (idx < cnt) {
+                    v0 = rp[2 * idx]; v1 = rp[2 * idx + 1];   // (cx, cy, cz, caseA), (r01, r23, rhoS)
+                    ov = (static_cast<int>(v1.x & 0xffffu) < t1 && static_cast<int>(v1.x >> 16) > t0) ||
+                         (static_cast<int>(v1.y & 0xffffu) < t1 && static_cast<int>(v1.y >> 16) > t0);
+                }
+                if (fill > kStageRecs - 32) publish(fill, 0);
+                const unsigned m = __ballot_sync(0xffffffffu, ov);
+                if (ov) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(stage + cbuf * kStageRecs + fill + __popc(m & ((1u << lane) - 1u)));
+                    dst[0] = v0; dst[1] = v1;
+                }
+                fill += __popc(m);
             }
+            __syncwarp();   // everyone is done with raw buffer b
+            if (lane == 0 && rc + kRawBufs < nRaw) issue(rc + kRawBufs);
         }
+        publish(fill, 0);
+        publish(0, 1);   // terminal stage: consumers that reach it leave
     } else {
         // ---- consumers
         const double rMin = h.rMin, rMax = h.rMax, invRMin = h.invRMin, rad2 = h.rad2;
@@ -199,18 +247,16 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
 
         // 32-record groups are handed out in order from a shared counter, so a
         // warp that drew light groups simply takes more of them
-        const unsigned nGroups = static_cast<unsigned>((s1 - s0) * kBinConsumers);
         for (;;) {
             unsigned g = 0;
             if (lane == 0) g = atomicAdd(nextGroup, 1u);
             g = __shfl_sync(0xffffffffu, g, 0);
-            if (g >= nGroups) break;
             const unsigned t = g / kBinConsumers;          // stage sequence number
             const int gi = static_cast<int>(g - t * kBinConsumers);
-            const int64_t s = s0 + t;
             const int buf = static_cast<int>(t % kBinStages);
             mbar_wait(&full[buf], (t / kBinStages) & 1u);
-            const int cnt = static_cast<int>(min(static_cast<int64_t>(kStageRecs), total - s * kStageRecs));
+            if (sTerm[buf]) break;
+            const int cnt = sCnt[buf];
             const HitRec *grp = stage + buf * kStageRecs + gi * 32;
 
             // clip my record's two LoS ranges to the tile
@@ -334,7 +380,8 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
 }  // namespace
 
 size_t bin_smem_bytes(int bins) {
-    return sizeof(HitRec) * kBinStages * kStageRecs + (2 * kBinStages + 2) * sizeof(uint64_t) +
+    return sizeof(HitRec) * (kBinStages * kStageRecs + kRawBufs * kRawRecs) +
+           (2 * kBinStages + kRawBufs) * sizeof(uint64_t) + 2 * kBinStages * sizeof(int) + 16 +
            sizeof(double2) * kTileLos + sizeof(double) * (bins + 1) +
            sizeof(uint32_t) * 2 * kTileLos * (bins + 1);
 }
