@@ -140,8 +140,12 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     uint64_t *rawFull = empty + kBinStages;                                       // [kRawBufs]
     int *sCnt = reinterpret_cast<int *>(rawFull + kRawBufs);                      // [kBinStages] records in the stage
     int *sTerm = sCnt + kBinStages;                                               // [kBinStages] 1: no more stages
-    unsigned int *nextGroup = reinterpret_cast<unsigned int *>(sTerm + kBinStages);   // + pad to 16 bytes
-    double2 *sTrig = reinterpret_cast<double2 *>(nextGroup + 4);                  // [32] (cos, sin), 16-byte aligned
+    unsigned int *nextGroup = reinterpret_cast<unsigned int *>(sTerm + kBinStages);
+    // byte offsets, not pointer casts: the compiler must keep seeing shared-memory addresses
+    constexpr size_t kTrigOff = (sizeof(HitRec) * (kBinStages * kStageRecs + kRawBufs * kRawRecs) +
+                                 sizeof(uint64_t) * (2 * kBinStages + kRawBufs) + sizeof(int) * 2 * kBinStages + 4 + 15) &
+                                ~size_t(15);
+    double2 *sTrig = reinterpret_cast<double2 *>(smemRaw + kTrigOff);             // [32] (cos, sin), 16-byte aligned
     double *sInvG = reinterpret_cast<double *>(sTrig + kTileLos);                 // [bins + 1]
     // accumulators are bin-major, [stride][32]: a warp's lanes are different LoS of (mostly) one
     // record, so the bank is the LoS and the atomics are conflict-free whatever the bins are
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
 
 size_t bin_smem_bytes(int bins) {
     return sizeof(HitRec) * (kBinStages * kStageRecs + kRawBufs * kRawRecs) +
-           (2 * kBinStages + kRawBufs) * sizeof(uint64_t) + 2 * kBinStages * sizeof(int) + 16 +
+           (2 * kBinStages + kRawBufs) * sizeof(uint64_t) + 2 * kBinStages * sizeof(int) + 32 +
            sizeof(double2) * kTileLos + sizeof(double) * (bins + 1) +
            sizeof(uint32_t) * 2 * kTileLos * (bins + 1);
 }
