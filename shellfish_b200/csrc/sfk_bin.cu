@@ -125,8 +125,9 @@ __device__ __forceinline__ void acc_add(uint32_t *lo, uint32_t *hi, int idx, lon
     atomicAdd(&hi[idx * kTileLos], add);
 }
 
+constexpr int kGroupsPerStage = kStageRecs / 32;   // consumer work items (and arrivals) per stage
 constexpr int kRawBufs = 2;     // TMA landing buffers of the producer warp
-constexpr int kRawRecs = 128;   // raw records per landing buffer (4 KB)
+constexpr int kRawRecs = 256;   // raw records per landing buffer (4 KB)
 
 template <bool TAPS>
 __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
         *nextGroup = 0;
         for (int s = 0; s < kBinStages; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kBinConsumers);
+            mbar_init(&empty[s], kGroupsPerStage);
         }
         for (int s = 0; s < kRawBufs; s++) mbar_init(&rawFull[s], 1);
         fence_barrier_init();
@@ -206,12 +207,14 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
             for (int64_t rc = 0; rc < min(nRaw, static_cast<int64_t>(kRawBufs)); rc++) issue(rc);
         int fill = 0, cbuf = 0;
         int64_t t = 0;   // sequence number of the stage being filled
-        auto publish = [&](int count, int term) {
+        // hands the stage being filled to the consumers and, unless it was the very last one,
+        // waits until the next buffer has been released by all groups of its previous use
+        auto publish = [&](int count, int term, bool more) {
             __syncwarp();
             if (lane == 0) { sCnt[cbuf] = count; sTerm[cbuf] = term; mbar_arrive(&full[cbuf]); }
             t++;
             cbuf = static_cast<int>(t % kBinStages);
-            if (t >= kBinStages) mbar_wait(&empty[cbuf], static_cast<uint32_t>((t / kBinStages - 1) & 1));
+            if (more && t >= kBinStages) mbar_wait(&empty[cbuf], static_cast<uint32_t>((t / kBinStages - 1) & 1));
             fill = 0;
         };
         for (int64_t rc = 0; rc < nRaw; rc++) {
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
                     ov = (static_cast<int>(v1.x & 0xffffu) < t1 && static_cast<int>(v1.x >> 16) > t0) ||
                          (static_cast<int>(v1.y & 0xffffu) < t1 && static_cast<int>(v1.y >> 16) > t0);
                 }
-                if (fill > kStageRecs - 32) publish(fill, 0);
+                if (fill > kStageRecs - 32) publish(fill, 0, true);
                 const unsigned m = __ballot_sync(0xffffffffu, ov);
                 if (ov) {
                     uint4 *dst = reinterpret_cast<uint4 *>(stage + cbuf * kStageRecs + fill + __popc(m & ((1u << lane) - 1u)));
@@ -240,8 +243,13 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
             __syncwarp();   // everyone is done with raw buffer b
             if (lane == 0 && rc + kRawBufs < nRaw) issue(rc + kRawBufs);
         }
-        publish(fill, 0);
-        publish(0, 1);   // terminal stage: consumers that reach it leave
+        publish(fill, 0, true);
+        // Terminal stages: a consumer that draws a group of one leaves without arriving.  Groups are
+        // drawn in order and every warp holds one at a time, so kBinConsumers terminal groups are
+        // enough for all warps to see one; their buffers only wait for real stages.
+        constexpr int kTerminal = (kBinConsumers + kGroupsPerStage - 1) / kGroupsPerStage;
+        static_assert(kTerminal < kBinStages, "terminal stages must not reuse the buffer of the last real stage");
+        for (int k = 0; k < kTerminal; k++) publish(0, 1, k + 1 < kTerminal);
     } else {
         // ---- consumers
         const double rMin = h.rMin, rMax = h.rMax, invRMin = h.invRMin, rad2 = h.rad2;
@@ -255,8 +263,8 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
             unsigned g = 0;
             if (lane == 0) g = atomicAdd(nextGroup, 1u);
             g = __shfl_sync(0xffffffffu, g, 0);
-            const unsigned t = g / kBinConsumers;          // stage sequence number
-            const int gi = static_cast<int>(g - t * kBinConsumers);
+            const unsigned t = g / kGroupsPerStage;          // stage sequence number
+            const int gi = static_cast<int>(g - t * kGroupsPerStage);
             const int buf = static_cast<int>(t % kBinStages);
             mbar_wait(&full[buf], (t / kBinStages) & 1u);
             if (sTerm[buf]) break;

@@ -15,8 +15,8 @@ constexpr int kTileLos = 32;
 // owns one 32-record group of each stage.
 constexpr int kBinConsumers = 16;
 constexpr int kBinThreads = (kBinConsumers + 1) * 32;
-constexpr int kStageRecs = kBinConsumers * 32;   // hit records per TMA stage (32 B each)
-constexpr int kBinStages = 2;
+constexpr int kStageRecs = 256;   // filtered hit records per consumer stage (32 B each)
+constexpr int kBinStages = 3;
 constexpr int kKdeKnots = 100;   // rn and the KDE knot count, kde.go:70,99
 constexpr int kMaxLevels = 6;    // KDE tree depth supported on the device
 constexpr int kMaxOrder = 4;     // Penna order (2*order^2 <= 32 coefficients)
