@@ -4,14 +4,17 @@
 // One CTA per (LoS tile of 32, ring, halo[, chunk of the hit list]).  The
 // tile's 32 x bins accumulators are 64-bit fixed point, split into lo/hi
 // 32-bit words in shared memory so that native 32-bit shared atomics can be
-// used (64-bit shared atomics are CAS loops on sm_100).  One producer warp
-// streams the ring's hit records through a 2-stage TMA (cp.async.bulk +
-// mbarrier) ring; 16 consumer warps draw 32-record groups from a shared
-// counter.  For a group, lanes first clip the 32 records' LoS ranges against
-// the tile in parallel, a warp scan turns the clipped lengths into a list of
-// (record, LoS) pairs, and the pairs are then processed 32 at a time with one
-// pair per lane (each lane finds its record by a shuffle binary search over the
-// scan), so every lane does useful work whatever the range widths.
+// used (64-bit shared atomics are CAS loops on sm_100).
+//
+// Every warp does the same job.  It draws 128-record chunks of the ring's hit
+// list from a shared counter, reads only the LoS ranges of those records
+// (prefetched one chunk ahead), and copies the records that touch this tile --
+// about one in four -- into its private 64-slot ring in shared memory with
+// cp.async.  Whenever 32 records are waiting, their ranges are clipped to the
+// tile, a warp scan turns the clipped lengths into a list of (record, LoS)
+// pairs, and the pairs are processed 32 at a time with one pair per lane (each
+// lane finds its record by a shuffle binary search over the scan), so every
+// lane does useful work whatever the range widths.
 //
 // Arithmetic.  Everything that DECIDES something is evaluated literally, in
 // the reference's operation order with no FMA contraction (-fmad=false): the
@@ -34,41 +37,11 @@ namespace {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+// 16-byte asynchronous copy global -> shared (LDGSTS): the data never visits registers
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep, do not spin
-            : "memory");
-    } while (!done);
-}
-// 1-D bulk copy global -> shared through the TMA unit, completion on mbarrier.
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // sqrt for x >= 0: MUFU.RSQ64H seed (~2^-22), one Newton step on 1/sqrt
 // (~2^-44), one residual correction of the root (<= 1 ulp), branch free.
@@ -125,32 +98,121 @@ __device__ __forceinline__ void acc_add(uint32_t *lo, uint32_t *hi, int idx, lon
     atomicAdd(&hi[idx * kTileLos], add);
 }
 
-constexpr int kGroupsPerStage = kStageRecs / 32;   // consumer work items (and arrivals) per stage
-constexpr int kRawBufs = 2;     // TMA landing buffers of the producer warp
-constexpr int kRawRecs = 256;   // raw records per landing buffer (4 KB)
+constexpr int kChunkRecs = 128;   // raw records a warp draws at a time (4 x 32)
+constexpr int kRingSlots = 64;    // per-warp ring of records that touch the tile
+
+// One round: up to 32 records of the warp's ring (slots head .. head + cnt - 1): clip to the
+// tile, expand to (record, LoS) pairs, evaluate the chords and add them to the tile.
+template <bool TAPS>
+__device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring, int head, int cnt, int lane, int t0,
+                                          int t1, int bins, double rMin, double rMax, double invRMin, double rad2,
+                                          double invDr, float cK, const double2 *sTrig, const double *sInvG,
+                                          uint32_t *lo, uint32_t *hi, size_t tapRing, unsigned &nIns) {
+    // clip my record's two LoS ranges to the tile
+    int len1 = 0, len2 = 0, st1 = 0, st2 = 0;
+    if (lane < cnt) {
+        const uint32_t r01 = wring[(head + lane) & (kRingSlots - 1)].r01, r23 = wring[(head + lane) & (kRingSlots - 1)].r23;
+        st1 = max(static_cast<int>(r01 & 0xffffu), t0);
+        len1 = max(min(static_cast<int>(r01 >> 16), t1) - st1, 0);
+        st2 = max(static_cast<int>(r23 & 0xffffu), t0);
+        len2 = max(min(static_cast<int>(r23 >> 16), t1) - st2, 0);
+        if (len1 == 0) st1 = t0;   // keep the packed start offsets within 0..31
+        if (len2 == 0) st2 = t0;
+    }
+    const unsigned nMine = static_cast<unsigned>(len1 + len2);
+    unsigned incl = nMine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const unsigned nPairs = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned first = incl - nMine;   // index of my record's first pair
+    const unsigned meta = static_cast<unsigned>(st1 - t0) | static_cast<unsigned>(len1) << 8 |
+                          static_cast<unsigned>(st2 - t0) << 16;
+
+    for (unsigned p0 = 0; p0 < nPairs; p0 += 32) {
+        // pair p -> record: the number of records whose pairs end at or before p, by
+        // binary search over the (non-decreasing) inclusive scan held one per lane
+        const unsigned p = p0 + lane;
+        unsigned r = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const unsigned v = __shfl_sync(0xffffffffu, incl, (r + step - 1) & 31);
+            if (v <= p) r += step;
+        }
+        r &= 31;   // lanes past nPairs (r == 32) are dropped below
+        const unsigned before = __shfl_sync(0xffffffffu, first, r);
+        const unsigned rmeta = __shfl_sync(0xffffffffu, meta, r);
+        if (p >= nPairs) continue;
+        const int off = static_cast<int>(p - before);
+        const int l1 = static_cast<int>((rmeta >> 8) & 0xffu);
+        const int ll = off < l1 ? static_cast<int>(rmeta & 0xffu) + off
+                                : static_cast<int>(rmeta >> 16) + (off - l1);   // LoS within the tile
+        const HitRec rec = wring[(head + r) & (kRingSlots - 1)];
+        const double2 cs = sTrig[ll];
+        const bool isA = rec.caseA != 0;
+        // literal geometry of insertToRing, los/halo.go:233-262
+        const double cx = rec.cx, cy = rec.cy, cz = rec.cz;
+        const double projDist2 = cx * cx + cy * cy;
+        double projRad2 = rad2 - cz * cz;
+        if (projRad2 < 0) projRad2 = 0;
+        const double b = cy * cs.x - cx * cs.y;
+        const double b2 = b * b;
+        const double m2 = projDist2 - b2;   // radicand of midDist / cMidDist
+        const double d2 = projRad2 - b2;    // radicand of diff / radMidDist
+        const bool bad = !(m2 >= 0) || !(d2 >= 0);   // a sqrt of the reference returns NaN
+        // twoValIntrDist skips NaN (halo.go:262); oneValIntrDist's NaN goes into Insert
+        if (bad && !isA) continue;
+        const double dir = cx * cs.x + cy * cs.y;
+        const double mid = sqrt_pos(m2), diff = sqrt_pos(d2);
+        const double rLo = mid - diff;
+        // mid + diff, or diff - mid on the far side of a centre-containing circle
+        const double rHi = fma((isA && !(dir > 0)) ? -1.0 : 1.0, mid, diff);
+        const bool endNaN = bad;            // only reachable with isA
+        // ProfileRing.Insert, profile_ring.go:92-120, with ln monotone:
+        // end <= lowR <=> rHi <= rMin, start >= highR <=> rLo >= rMax, ...
+        if (!endNaN && rHi <= rMin) continue;
+        if (!isA && rLo >= rMax) continue;
+        nIns++;
+        uint32_t *rowLo = lo + ll, *rowHi = hi + ll;
+        const size_t tapRow = tapRing + t0 + ll;
+        if (TAPS) atomicAdd(&a.tapInsert[tapRow], 1u);
+        const long long Q = __double2ll_rn(rec.rhoS);
+        if (!isA && rLo > rMin) {
+            int idx; double rem;
+            bin_of(rLo, invRMin, cK, invDr, sInvG, bins, idx, rem);
+            const long long q1 = __double2ll_rn(rec.rhoS * rem);
+            acc_add(rowLo, rowHi, idx, Q - q1);
+            if (idx < bins - 1) acc_add(rowLo, rowHi, idx + 1, q1);
+            if (TAPS && idx < bins) atomicAdd(&a.tapStart[tapRow * bins + idx], 1u);
+        } else {
+            acc_add(rowLo, rowHi, 0, Q);
+            if (TAPS) atomicAdd(&a.tapStart[tapRow * bins], 1u);
+        }
+        if (!endNaN && rHi < rMax) {
+            int idx; double rem;
+            bin_of(rHi, invRMin, cK, invDr, sInvG, bins, idx, rem);
+            const long long q1 = __double2ll_rn(rec.rhoS * rem);
+            acc_add(rowLo, rowHi, idx, q1 - Q);
+            if (idx < bins - 1) acc_add(rowLo, rowHi, idx + 1, -q1);
+            if (TAPS && idx < bins) atomicAdd(&a.tapEnd[tapRow * bins + idx], 1u);
+        }
+    }
+}
 
 template <bool TAPS>
 __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const int bins = a.bins;
     const int stride = bins + 1;   // +1: slot for a start/end edge that lands exactly on rMax
-    HitRec *stage = reinterpret_cast<HitRec *>(smemRaw);                          // [kBinStages][kStageRecs] filtered records
-    HitRec *raw = stage + kBinStages * kStageRecs;                                // [kRawBufs][kRawRecs] TMA landing ring
-    uint64_t *full = reinterpret_cast<uint64_t *>(raw + kRawBufs * kRawRecs);     // [kBinStages]
-    uint64_t *empty = full + kBinStages;                                          // [kBinStages]
-    uint64_t *rawFull = empty + kBinStages;                                       // [kRawBufs]
-    int *sCnt = reinterpret_cast<int *>(rawFull + kRawBufs);                      // [kBinStages] records in the stage
-    int *sTerm = sCnt + kBinStages;                                               // [kBinStages] 1: no more stages
-    unsigned int *nextGroup = reinterpret_cast<unsigned int *>(sTerm + kBinStages);
-    // byte offsets, not pointer casts: the compiler must keep seeing shared-memory addresses
-    constexpr size_t kTrigOff = (sizeof(HitRec) * (kBinStages * kStageRecs + kRawBufs * kRawRecs) +
-                                 sizeof(uint64_t) * (2 * kBinStages + kRawBufs) + sizeof(int) * 2 * kBinStages + 4 + 15) &
-                                ~size_t(15);
-    double2 *sTrig = reinterpret_cast<double2 *>(smemRaw + kTrigOff);             // [32] (cos, sin), 16-byte aligned
+    // byte offsets from the one dynamic array: the compiler must keep seeing shared addresses
+    HitRec *rings = reinterpret_cast<HitRec *>(smemRaw);                          // [warps][kRingSlots]
+    double2 *sTrig = reinterpret_cast<double2 *>(rings + kBinConsumers * kRingSlots);   // [32] (cos, sin)
     double *sInvG = reinterpret_cast<double *>(sTrig + kTileLos);                 // [bins + 1]
+    unsigned int *nextChunk = reinterpret_cast<unsigned int *>(sInvG + bins + 1);     // 8-byte slot
     // accumulators are bin-major, [stride][32]: a warp's lanes are different LoS of (mostly) one
     // record, so the bank is the LoS and the atomics are conflict-free whatever the bins are
-    uint32_t *lo = reinterpret_cast<uint32_t *>(sInvG + bins + 1);
+    uint32_t *lo = nextChunk + 2;
     uint32_t *hi = lo + kTileLos * stride;
 
     const int nTiles = (a.spokes + kTileLos - 1) / kTileLos;
@@ -170,15 +232,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
         const int l = min(t0 + static_cast<int>(threadIdx.x), a.spokes - 1);
         sTrig[threadIdx.x] = make_double2(a.ringCos[l], a.ringSin[l]);
     }
-    if (threadIdx.x == 0) {
-        *nextGroup = 0;
-        for (int s = 0; s < kBinStages; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kGroupsPerStage);
-        }
-        for (int s = 0; s < kRawBufs; s++) mbar_init(&rawFull[s], 1);
-        fence_barrier_init();
-    }
+    if (threadIdx.x == 0) *nextChunk = 0;
     __syncthreads();
 
     // this CTA's share of the ring's records
@@ -186,183 +240,76 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     const int64_t total = a.hitCount[hr];
     const int64_t rec0 = (total * chunk / a.chunks) & ~int64_t(31);
     const int64_t rec1 = chunk + 1 == a.chunks ? total : (total * (chunk + 1) / a.chunks) & ~int64_t(31);
-    const HitRec *src = a.recs + a.hitOffset[hr];
+    const HitRec *src = a.recs + a.hitOffset[hr] + rec0;
+    const int nRecs = static_cast<int>(rec1 - rec0);
+    const unsigned nChunks = static_cast<unsigned>((nRecs + kChunkRecs - 1) / kChunkRecs);
     unsigned nIns = 0;
 
-    if (warp == kBinConsumers) {
-        // ---- producer warp.  Lane 0 keeps a small ring of TMA bulk copies of the ring's raw
-        // records in flight; the whole warp then keeps only the records whose LoS ranges touch
-        // this tile (about one in four) and packs them into the stages the consumers read, so a
-        // consumer group holds 32 useful records instead of 8.
-        const int64_t nRaw = (rec1 - rec0 + kRawRecs - 1) / kRawRecs;
-        auto issue = [&](int64_t rc) {
-            const int b = static_cast<int>(rc % kRawBufs);
-            const int64_t first = rec0 + rc * kRawRecs;
-            const uint32_t bytes = static_cast<uint32_t>(min(static_cast<int64_t>(kRawRecs), rec1 - first)) *
-                                   static_cast<uint32_t>(sizeof(HitRec));
-            mbar_expect_tx(&rawFull[b], bytes);
-            tma_load_1d(raw + b * kRawRecs, src + first, bytes, &rawFull[b]);
-        };
-        if (lane == 0)
-            for (int64_t rc = 0; rc < min(nRaw, static_cast<int64_t>(kRawBufs)); rc++) issue(rc);
-        int fill = 0, cbuf = 0;
-        int64_t t = 0;   // sequence number of the stage being filled
-        // hands the stage being filled to the consumers and, unless it was the very last one,
-        // waits until the next buffer has been released by all groups of its previous use
-        auto publish = [&](int count, int term, bool more) {
-            __syncwarp();
-            if (lane == 0) { sCnt[cbuf] = count; sTerm[cbuf] = term; mbar_arrive(&full[cbuf]); }
-            t++;
-            cbuf = static_cast<int>(t % kBinStages);
-            if (more && t >= kBinStages) mbar_wait(&empty[cbuf], static_cast<uint32_t>((t / kBinStages - 1) & 1));
-            fill = 0;
-        };
-        for (int64_t rc = 0; rc < nRaw; rc++) {
-            const int b = static_cast<int>(rc % kRawBufs);
-            mbar_wait(&rawFull[b], static_cast<uint32_t>((rc / kRawBufs) & 1));
-            const int cnt = static_cast<int>(min(static_cast<int64_t>(kRawRecs), rec1 - (rec0 + rc * kRawRecs)));
-            const uint4 *rp = reinterpret_cast<const uint4 *>(raw + b * kRawRecs);
-#pragma unroll
-            for (int sub = 0; sub < kRawRecs / 32; sub++) {
-                const int idx = sub * 32 + lane;
-                uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-                bool ov = false;
-                if (idx < cnt) {
-                    v0 = rp[2 * idx]; v1 = rp[2 * idx + 1];   // (cx, cy, cz, caseA), (r01, r23, rhoS)
-                    ov = (static_cast<int>(v1.x & 0xffffu) < t1 && static_cast<int>(v1.x >> 16) > t0) ||
-                         (static_cast<int>(v1.y & 0xffffu) < t1 && static_cast<int>(v1.y >> 16) > t0);
-                }
-                if (fill > kStageRecs - 32) publish(fill, 0, true);
-                const unsigned m = __ballot_sync(0xffffffffu, ov);
-                if (ov) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(stage + cbuf * kStageRecs + fill + __popc(m & ((1u << lane) - 1u)));
-                    dst[0] = v0; dst[1] = v1;
-                }
-                fill += __popc(m);
-            }
-            __syncwarp();   // everyone is done with raw buffer b
-            if (lane == 0 && rc + kRawBufs < nRaw) issue(rc + kRawBufs);
-        }
-        publish(fill, 0, true);
-        // Terminal stages: a consumer that draws a group of one leaves without arriving.  Groups are
-        // drawn in order and every warp holds one at a time, so kBinConsumers terminal groups are
-        // enough for all warps to see one; their buffers only wait for real stages.
-        constexpr int kTerminal = (kBinConsumers + kGroupsPerStage - 1) / kGroupsPerStage;
-        static_assert(kTerminal < kBinStages, "terminal stages must not reuse the buffer of the last real stage");
-        for (int k = 0; k < kTerminal; k++) publish(0, 1, k + 1 < kTerminal);
-    } else {
-        // ---- consumers
+    {
         const double rMin = h.rMin, rMax = h.rMax, invRMin = h.invRMin, rad2 = h.rad2;
         const double invDr = a.invDr;
         const float cK = a.cK;
         const size_t tapRing = (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes;
+        HitRec *wring = rings + warp * kRingSlots;
+        int head = 0, count = 0;   // records waiting in the ring: slots head .. head + count - 1 (mod 64)
 
-        // 32-record groups are handed out in order from a shared counter, so a
-        // warp that drew light groups simply takes more of them
-        for (;;) {
-            unsigned g = 0;
-            if (lane == 0) g = atomicAdd(nextGroup, 1u);
-            g = __shfl_sync(0xffffffffu, g, 0);
-            const unsigned t = g / kGroupsPerStage;          // stage sequence number
-            const int gi = static_cast<int>(g - t * kGroupsPerStage);
-            const int buf = static_cast<int>(t % kBinStages);
-            mbar_wait(&full[buf], (t / kBinStages) & 1u);
-            if (sTerm[buf]) break;
-            const int cnt = sCnt[buf];
-            const HitRec *grp = stage + buf * kStageRecs + gi * 32;
-
-            // clip my record's two LoS ranges to the tile
-            int len1 = 0, len2 = 0, st1 = 0, st2 = 0;
-            if (gi * 32 + lane < cnt) {
-                const uint32_t r01 = grp[lane].r01, r23 = grp[lane].r23;
-                st1 = max(static_cast<int>(r01 & 0xffffu), t0);
-                len1 = max(min(static_cast<int>(r01 >> 16), t1) - st1, 0);
-                st2 = max(static_cast<int>(r23 & 0xffffu), t0);
-                len2 = max(min(static_cast<int>(r23 >> 16), t1) - st2, 0);
-                if (len1 == 0) st1 = t0;   // keep the packed start offsets within 0..31
-                if (len2 == 0) st2 = t0;
-            }
-            const unsigned nMine = static_cast<unsigned>(len1 + len2);
-            unsigned incl = nMine;
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += up;
-            }
-            const unsigned nPairs = __shfl_sync(0xffffffffu, incl, 31);
-            const unsigned first = incl - nMine;   // index of my record's first pair
-            const unsigned meta = static_cast<unsigned>(st1 - t0) | static_cast<unsigned>(len1) << 8 |
-                                  static_cast<unsigned>(st2 - t0) << 16;
-
-            for (unsigned p0 = 0; p0 < nPairs; p0 += 32) {
-                // pair p -> record: the number of records whose pairs end at or before p, by
-                // binary search over the (non-decreasing) inclusive scan held one per lane
-                const unsigned p = p0 + lane;
-                unsigned r = 0;
+        // (r01, r23) of record c * 128 + sub * 32 + lane of the drawn chunk; (0, 0) past the end
+        auto load_ranges = [&](unsigned c, uint2 (&rr)[kChunkRecs / 32]) {
 #pragma unroll
-                for (int step = 16; step > 0; step >>= 1) {
-                    const unsigned v = __shfl_sync(0xffffffffu, incl, (r + step - 1) & 31);
-                    if (v <= p) r += step;
-                }
-                r &= 31;   // lanes past nPairs (r == 32) are dropped below
-                const unsigned before = __shfl_sync(0xffffffffu, first, r);
-                const unsigned rmeta = __shfl_sync(0xffffffffu, meta, r);
-                if (p >= nPairs) continue;
-                const int off = static_cast<int>(p - before);
-                const int l1 = static_cast<int>((rmeta >> 8) & 0xffu);
-                const int ll = off < l1 ? static_cast<int>(rmeta & 0xffu) + off
-                                        : static_cast<int>(rmeta >> 16) + (off - l1);   // LoS within the tile
-                const HitRec rec = grp[r];
-                const double2 cs = sTrig[ll];
-                const bool isA = rec.caseA != 0;
-                // literal geometry of insertToRing, los/halo.go:233-262
-                const double cx = rec.cx, cy = rec.cy, cz = rec.cz;
-                const double projDist2 = cx * cx + cy * cy;
-                double projRad2 = rad2 - cz * cz;
-                if (projRad2 < 0) projRad2 = 0;
-                const double b = cy * cs.x - cx * cs.y;
-                const double b2 = b * b;
-                const double m2 = projDist2 - b2;   // radicand of midDist / cMidDist
-                const double d2 = projRad2 - b2;    // radicand of diff / radMidDist
-                const bool bad = !(m2 >= 0) || !(d2 >= 0);   // a sqrt of the reference returns NaN
-                // twoValIntrDist skips NaN (halo.go:262); oneValIntrDist's NaN goes into Insert
-                if (bad && !isA) continue;
-                const double dir = cx * cs.x + cy * cs.y;
-                const double mid = sqrt_pos(m2), diff = sqrt_pos(d2);
-                const double rLo = mid - diff;
-                // mid + diff, or diff - mid on the far side of a centre-containing circle
-                const double rHi = fma((isA && !(dir > 0)) ? -1.0 : 1.0, mid, diff);
-                const bool endNaN = bad;            // only reachable with isA
-                // ProfileRing.Insert, profile_ring.go:92-120, with ln monotone:
-                // end <= lowR <=> rHi <= rMin, start >= highR <=> rLo >= rMax, ...
-                if (!endNaN && rHi <= rMin) continue;
-                if (!isA && rLo >= rMax) continue;
-                nIns++;
-                uint32_t *rowLo = lo + ll, *rowHi = hi + ll;
-                const size_t tapRow = tapRing + t0 + ll;
-                if (TAPS) atomicAdd(&a.tapInsert[tapRow], 1u);
-                const long long Q = __double2ll_rn(rec.rhoS);
-                if (!isA && rLo > rMin) {
-                    int idx; double rem;
-                    bin_of(rLo, invRMin, cK, invDr, sInvG, bins, idx, rem);
-                    const long long q1 = __double2ll_rn(rec.rhoS * rem);
-                    acc_add(rowLo, rowHi, idx, Q - q1);
-                    if (idx < bins - 1) acc_add(rowLo, rowHi, idx + 1, q1);
-                    if (TAPS && idx < bins) atomicAdd(&a.tapStart[tapRow * bins + idx], 1u);
-                } else {
-                    acc_add(rowLo, rowHi, 0, Q);
-                    if (TAPS) atomicAdd(&a.tapStart[tapRow * bins], 1u);
-                }
-                if (!endNaN && rHi < rMax) {
-                    int idx; double rem;
-                    bin_of(rHi, invRMin, cK, invDr, sInvG, bins, idx, rem);
-                    const long long q1 = __double2ll_rn(rec.rhoS * rem);
-                    acc_add(rowLo, rowHi, idx, q1 - Q);
-                    if (idx < bins - 1) acc_add(rowLo, rowHi, idx + 1, -q1);
-                    if (TAPS && idx < bins) atomicAdd(&a.tapEnd[tapRow * bins + idx], 1u);
-                }
+            for (int sub = 0; sub < kChunkRecs / 32; sub++) {
+                const int idx = static_cast<int>(c) * kChunkRecs + sub * 32 + lane;
+                rr[sub] = make_uint2(0u, 0u);
+                if (c < nChunks && idx < nRecs) rr[sub] = *reinterpret_cast<const uint2 *>(&src[idx].r01);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[buf]);
+        };
+        auto draw = [&]() {
+            unsigned c = 0;
+            if (lane == 0) c = atomicAdd(nextChunk, 1u);
+            return __shfl_sync(0xffffffffu, c, 0);
+        };
+        unsigned cur = draw();
+        uint2 rr[kChunkRecs / 32];
+        load_ranges(cur, rr);
+        for (;;) {
+            const bool flush = cur >= nChunks;   // nothing left to draw: work off what is waiting
+            if (flush && count == 0) break;
+            if (!flush) {
+                // draw the next chunk and start its range loads before working on this one
+                const unsigned nxt = draw();
+                uint2 nr[kChunkRecs / 32];
+                load_ranges(nxt, nr);
+#pragma unroll
+                for (int sub = 0; sub < kChunkRecs / 32; sub++) {
+                    const bool ov = (static_cast<int>(rr[sub].x & 0xffffu) < t1 && static_cast<int>(rr[sub].x >> 16) > t0) ||
+                                    (static_cast<int>(rr[sub].y & 0xffffu) < t1 && static_cast<int>(rr[sub].y >> 16) > t0);
+                    const unsigned m = __ballot_sync(0xffffffffu, ov);
+                    if (ov) {
+                        const int at = (head + count + __popc(m & ((1u << lane) - 1u))) & (kRingSlots - 1);
+                        const HitRec *from = src + static_cast<int>(cur) * kChunkRecs + sub * 32 + lane;
+                        cp_async16(&wring[at], from);
+                        cp_async16(reinterpret_cast<char *>(&wring[at]) + 16, reinterpret_cast<const char *>(from) + 16);
+                    }
+                    count += __popc(m);
+                    if (count >= 32) {
+                        cp_async_wait_all();
+                        __syncwarp();
+                        bin_round<TAPS>(a, wring, head, 32, lane, t0, t1, bins, rMin, rMax, invRMin, rad2, invDr, cK,
+                                        sTrig, sInvG, lo, hi, tapRing, nIns);
+                        __syncwarp();   // the slots may be overwritten from here on
+                        head = (head + 32) & (kRingSlots - 1);
+                        count -= 32;
+                    }
+                }
+                cur = nxt;
+#pragma unroll
+                for (int sub = 0; sub < kChunkRecs / 32; sub++) rr[sub] = nr[sub];
+            } else {
+                cp_async_wait_all();
+                __syncwarp();
+                bin_round<TAPS>(a, wring, head, count, lane, t0, t1, bins, rMin, rMax, invRMin, rad2, invDr, cK,
+                                sTrig, sInvG, lo, hi, tapRing, nIns);
+                count = 0;
+            }
         }
         // the "particle-ray intersections" metric
         unsigned tot = nIns;
@@ -392,10 +339,8 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
 }  // namespace
 
 size_t bin_smem_bytes(int bins) {
-    return sizeof(HitRec) * (kBinStages * kStageRecs + kRawBufs * kRawRecs) +
-           (2 * kBinStages + kRawBufs) * sizeof(uint64_t) + 2 * kBinStages * sizeof(int) + 32 +
-           sizeof(double2) * kTileLos + sizeof(double) * (bins + 1) +
-           sizeof(uint32_t) * 2 * kTileLos * (bins + 1);
+    return sizeof(HitRec) * kBinConsumers * kRingSlots + sizeof(double2) * kTileLos + sizeof(double) * (bins + 1) +
+           2 * sizeof(unsigned int) + sizeof(uint32_t) * 2 * kTileLos * (bins + 1);
 }
 
 cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s) {

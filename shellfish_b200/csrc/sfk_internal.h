@@ -11,12 +11,9 @@ namespace sfk {
 
 // LoS per binning tile: one lane per LoS, one warp pass per (particle, ring).
 constexpr int kTileLos = 32;
-// Binning CTA: consumer warps + one TMA producer warp; every consumer warp
-// owns one 32-record group of each stage.
+// Binning CTA: every warp filters the ring's hit records into a private ring and bins them.
 constexpr int kBinConsumers = 16;
-constexpr int kBinThreads = (kBinConsumers + 1) * 32;
-constexpr int kStageRecs = 256;   // filtered hit records per consumer stage (32 B each)
-constexpr int kBinStages = 3;
+constexpr int kBinThreads = kBinConsumers * 32;
 constexpr int kKdeKnots = 100;   // rn and the KDE knot count, kde.go:70,99
 constexpr int kMaxLevels = 6;    // KDE tree depth supported on the device
 constexpr int kMaxOrder = 4;     // Penna order (2*order^2 <= 32 coefficients)
