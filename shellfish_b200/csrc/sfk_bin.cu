@@ -108,10 +108,12 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
                                           int t1, int bins, double rMin, double rMax, double invRMin, double rad2,
                                           double invDr, float cK, const double2 *sTrig, const double *sInvG,
                                           uint32_t *lo, uint32_t *hi, size_t tapRing, unsigned &nIns) {
+    // rounds take 32 records at a time, so head is 0 or 32 and the round never wraps
+    const HitRec *grp = wring + head;
     // clip my record's two LoS ranges to the tile
     int len1 = 0, len2 = 0, st1 = 0, st2 = 0;
     if (lane < cnt) {
-        const uint32_t r01 = wring[(head + lane) & (kRingSlots - 1)].r01, r23 = wring[(head + lane) & (kRingSlots - 1)].r23;
+        const uint32_t r01 = grp[lane].r01, r23 = grp[lane].r23;
         st1 = max(static_cast<int>(r01 & 0xffffu), t0);
         len1 = max(min(static_cast<int>(r01 >> 16), t1) - st1, 0);
         st2 = max(static_cast<int>(r23 & 0xffffu), t0);
@@ -148,7 +150,7 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
         const int l1 = static_cast<int>((rmeta >> 8) & 0xffu);
         const int ll = off < l1 ? static_cast<int>(rmeta & 0xffu) + off
                                 : static_cast<int>(rmeta >> 16) + (off - l1);   // LoS within the tile
-        const HitRec rec = wring[(head + r) & (kRingSlots - 1)];
+        const HitRec rec = grp[r];
         const double2 cs = sTrig[ll];
         const bool isA = rec.caseA != 0;
         // literal geometry of insertToRing, los/halo.go:233-262
