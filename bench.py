@@ -145,7 +145,7 @@ def run_reference(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one bin_kernel launch over its algorithmic bytes
-NCU_TRAFFIC_RATIO = (2.202771 + 0.803971) / 1.704478
+NCU_TRAFFIC_RATIO = (2.206682 + 0.804353) / 1.704478
 
 
 def main():
@@ -263,16 +263,16 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "bin_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          # DRAM bytes of one launch = NCU_TRAFFIC_RATIO x its algorithmic bytes (ncu --set
-                         # full capture of a 16-halo launch: dram read 2.203 GB + write 0.804 GB against
-                         # 1.704 GB algorithmic, profiles/r01e_bin_kernel_v5_by_line.txt)
+                         # full capture of a 16-halo launch: dram read 2.207 GB + write 0.804 GB against
+                         # 1.704 GB algorithmic, profiles/r01g_bin_kernel_v6_by_line.txt)
                          "traffic": NCU_TRAFFIC_RATIO * alg_bytes / launches / 1e9,
                          "traffic_unit": "GB per launch (ncu ratio x algorithmic bytes)",
                          "peak_source": peak_src,
                          "alg_bytes_per_launch": alg_bytes / launches,
                          "ms_per_launch": agg["ms_bin"] / launches,
                          "note": "bin_kernel is instruction-issue bound (FP64 chord geometry + shared-memory "
-                                 "atomics), not HBM bound: ncu issue-active 78%, FP64 pipe 35%, DRAM 2.5% "
-                                 "(profiles/r01e_bin_kernel_v5_by_line.txt, DESIGN.md)"},
+                                 "atomics), not HBM bound: ncu issue-active 73%, FP64 pipe 40%, DRAM 3% "
+                                 "(profiles/r01g_bin_kernel_v6_by_line.txt, DESIGN.md)"},
             "clocks": clocks, "e2e": e2e,
         }
         if world == 1 and not args.no_cpu:
