@@ -775,12 +775,15 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(FilterArgs a) {
     const size_t ringBase = (static_cast<size_t>(slot) * a.rings + ring) * a.spokes;
     const double *rsp = a.rsp + (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes;
 
-    // valid points in LoS order (ring_buffer.go OkPolarCoords)
+    // valid points in LoS order (ring_buffer.go OkPolarCoords): staged through shared memory so
+    // that the ordered compaction does not wait on one global load per LoS (n <= i: in place)
+    for (int i = tid; i < a.spokes; i += kFilterThreads) pR[i] = rsp[i];
+    __syncthreads();
     if (tid == 0) {
         int n = 0;
         double high = 0;
         for (int i = 0; i < a.spokes; i++) {
-            const double r = rsp[i];
+            const double r = pR[i];
             if (!isnan(r)) {
                 pR[n] = r; pIdx[n] = i;
                 if (n == 0 || r > high) high = r;
