@@ -106,3 +106,49 @@ def write_box_lgadget2(dirname, fmt, blocks, snap=100, n_total=None):
         write_lgadget2(name, b["xs"], b["TotalWidth"], cosmo, n_total=n_total)
         names.append(name)
     return names
+
+
+def write_box_gadget2(dirname, fmt, blocks, snap=100, pos_units=1e-3, mass_units=1e10):
+    """Writes synth.make_box blocks as one Gadget-2 file per block: all particles are
+    type 1 (dark matter) with the mass in the header table; positions are stored in
+    1/pos_units (kpc/h for 1e-3), masses in 1/mass_units (1e10 Msun/h)."""
+    import os
+    names = []
+    for i, b in enumerate(blocks):
+        name = os.path.join(dirname, fmt % (snap, i))
+        cosmo = dict(z=b["Z"], omega_m=b["OmegaM"], omega_l=b["OmegaL"], h100=b["H100"])
+        m = float(b["ms"][0]) / mass_units
+        write_gadget2(name, [None, b["xs"] / np.float32(pos_units), None, None, None, None],
+                      b["TotalWidth"] / pos_units, cosmo, [0.0, m, 0.0, 0.0, 0.0, 0.0])
+        names.append(name)
+    return names
+
+
+def write_box_gotetra(dirname, blocks, cells, segment_width, fmt="sheet%d%d%d.dat"):
+    """Writes the particles of synth.make_box blocks as cells^3 gotetra sheet files of
+    segment_width^3 particles each (the total must be exactly (cells*segment_width)^3).
+    Particles are dealt to files in block order; each header carries the bounding box of
+    its own particles, as gotetra's do for a Lagrangian segment.  Returns the file names
+    in the reference's block order (Block0 fastest, cmd/env/env.go:187-234)."""
+    import os
+    sw, gw = segment_width, segment_width + 1
+    xs = np.concatenate([b["xs"] for b in blocks]).astype(np.float32)
+    assert len(xs) == (cells * sw) ** 3, (len(xs), (cells * sw) ** 3)
+    b0 = blocks[0]
+    cosmo = dict(z=b0["Z"], omega_m=b0["OmegaM"], omega_l=b0["OmegaL"], h100=b0["H100"])
+    names = []
+    per = sw ** 3
+    k = 0
+    for iz in range(cells):
+        for iy in range(cells):
+            for ix in range(cells):
+                part = xs[k * per:(k + 1) * per]
+                grid = np.zeros((gw, gw, gw, 3), np.float32)
+                grid[:sw, :sw, :sw] = part.reshape(sw, sw, sw, 3)   # [z][y][x] like gotetra.go:73-85
+                lo, hi = part.min(0), part.max(0)
+                name = os.path.join(dirname, fmt % (ix, iy, iz))
+                write_gotetra(name, grid.reshape(-1, 3), k, cells, sw, cells * sw, b0["TotalWidth"], cosmo,
+                              origin=lo, width=hi - lo)
+                names.append(name)
+                k += 1
+    return names
