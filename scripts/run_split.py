@@ -43,6 +43,8 @@ def run(my_blocks, split):
     for b in my_blocks:
         ctx.push_block(b)
     torch.cuda.synchronize()
+    if split:
+        dist.barrier()   # every rank has pushed its blocks: time only the exchange + analysis
     t = time.time()
     out = shard.split_halo_finish(ctx, dist if split else None)
     torch.cuda.synchronize()
