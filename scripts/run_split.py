@@ -5,8 +5,9 @@ the GPUs of one box, bin grids all-reduced over NCCL.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
       --master-port 29511 scripts/run_split.py [--particles 10000000] [--rings 24]
 
-Every rank builds the same synthetic snapshot, pushes blocks rank::world, and
-the result is compared (bitwise) with rank 0's single-GPU run of all blocks."""
+Every rank builds the same synthetic snapshot and pushes its contiguous 1/N share of
+every block's particle list (BASELINE config 3: "particle list split contiguous-equal");
+the result is compared (bitwise) with rank 0's single-GPU run of all particles."""
 import argparse
 import json
 import os
@@ -51,8 +52,17 @@ def run(my_blocks, split):
     return out, time.time() - t, ctx.stats()
 
 
-run(blocks[rank::world], world > 1)   # warm-up
-(coeffs, status), dt, st = run(blocks[rank::world], world > 1)
+
+
+def share(b):
+    n = len(b["ms"])
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    return dict(b, xs=np.ascontiguousarray(b["xs"][lo:hi]), ms=np.ascontiguousarray(b["ms"][lo:hi]))
+
+
+mine = [share(b) for b in blocks] if world > 1 else blocks
+run(mine, world > 1)   # warm-up
+(coeffs, status), dt, st = run(mine, world > 1)
 if rank == 0:
     (c1, s1), dt1, st1 = run(blocks, False)
     print(json.dumps({"config": "configs[2]: one halo, %d particles, %d rings x 256 LoS x 256 bins" %
