@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--cpu-halos", type=int, default=6, help="halos in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--order", type=int, default=3, help="Penna order (BASELINE config 5 sweeps 2, 3, 4)")
+    ap.add_argument("--subsample", type=int, default=1, help="SubsampleFactor (config 5: 1, 2)")
     return ap.parse_args()
 
 
@@ -53,7 +55,7 @@ def workload(args, rank):
                         "default shell.config 100 rings x 256 LoS x 256 bins" %
                         (args.halos, args.n_total, args.box, args.cells),
             "halos": args.halos, "n_particles": int(args.n_total), "blocks": len(blocks),
-            "order": 3, "subsample": 1, "setup_s": round(time.time() - t, 1)}
+            "order": args.order, "subsample": args.subsample, "setup_s": round(time.time() - t, 1)}
     return halos, blocks, mass, desc
 
 
@@ -107,7 +109,7 @@ def cpu_sample(args, halos, blocks, mass, n_halos, threads):
     """Oracle (C restatement of the Go algorithm, strided workers + Split/Join
     like cmd/shell.go:423-500) on the first n_halos halos of the workload."""
     from oracle import pyoracle as po
-    cfg = po.ShellConfig.default(threads=threads, seed=1337)
+    cfg = po.ShellConfig.default(threads=threads, seed=1337, order=args.order, subsampleFactor=args.subsample)
     sub = halos[:n_halos]
     t = time.time()
     out = po.shell_run(cfg, mass, sub, blocks, taps=("nIntersections",))
@@ -165,7 +167,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     halos, blocks, mass, desc = workload(args, rank)
-    params = api.default_params(seed=1337, device=local)
+    params = api.default_params(seed=1337, device=local, order=args.order, subsample_factor=args.subsample)
     ctx = api.ShellContext(params)
     R, n, B = int(params.rings), int(params.spokes), int(params.radial_bins)
 
