@@ -258,16 +258,25 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
     ctx.GadgetDMSingleMassIndices = g.GadgetSingleMassIndices;
     ctx.GadgetMassUnits = g.GadgetMassUnits;
     ctx.GadgetPositionUnits = g.GadgetPositionUnits;
-    std::unique_ptr<VectorBuffer> buf;
-    if (!(err = NewVectorBuffer(g.SnapshotType, cat.ParticleCatalog(static_cast<int>(snaps[0]), 0), g.Endianness, ctx, buf)).empty())
-        return err;
-
     // loop(), cmd/shell.go:288-372
     std::map<int64_t, std::vector<size_t>> idxBins;   // binBySnap, sorted like sort.Ints
     for (size_t i = 0; i < snaps.size(); i++) idxBins[snaps[i]].push_back(i);
+    // The reference opens snaps[0] (:234) and reads the headers of sortedSnaps[0] (:305) before it
+    // skips Snap == -1 rows (:325), i.e. it indexes the file table with -1 and panics whenever such
+    // a row is present.  Here the first real snapshot serves both purposes.
+    int64_t firstSnap = -1;
+    for (const auto &kv : idxBins)
+        if (kv.first != -1) { firstSnap = kv.first; break; }
+    if (firstSnap == -1) return "Every row of the halo table has Snapshot = -1: nothing to do.";
+    if (firstSnap < g.particle.SnapMin || firstSnap > g.particle.SnapMax)
+        return "Snapshot " + std::to_string(firstSnap) + " is outside [SnapMin, SnapMax] = [" +
+               std::to_string(g.particle.SnapMin) + ", " + std::to_string(g.particle.SnapMax) + "].";
+    std::unique_ptr<VectorBuffer> buf;
+    if (!(err = NewVectorBuffer(g.SnapshotType, cat.ParticleCatalog(static_cast<int>(firstSnap), 0), g.Endianness, ctx, buf)).empty())
+        return err;
     std::vector<Header> hds0;
     std::vector<std::string> files;
-    if (!(err = ReadHeaders(static_cast<int>(idxBins.begin()->first), *buf, cat, g.MemoDir, hds0, files)).empty()) return err;
+    if (!(err = ReadHeaders(static_cast<int>(firstSnap), *buf, cat, g.MemoDir, hds0, files)).empty()) return err;
     if (hds0.empty()) return "The snapshot has no blocks.";
     const float minMass = buf->MinMass();
 
@@ -287,6 +296,9 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
     for (const auto &kv : idxBins) {
         const int64_t snap = kv.first;
         if (snap == -1) continue;
+        if (snap < g.particle.SnapMin || snap > g.particle.SnapMax)
+            return "Snapshot " + std::to_string(snap) + " is outside [SnapMin, SnapMax] = [" +
+                   std::to_string(g.particle.SnapMin) + ", " + std::to_string(g.particle.SnapMax) + "].";
         const std::vector<size_t> &idxs = kv.second;
         std::vector<double> x(idxs.size()), y(idxs.size()), z(idxs.size()), r(idxs.size());
         for (size_t i = 0; i < idxs.size(); i++) {

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <fstream>
 #include <iostream>
 #include <iterator>
@@ -123,7 +124,12 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "RNG Seed is %llu\n", static_cast<unsigned long long>(seed));
     }
     std::vector<std::string> lines;
-    if (!(err = RunShell(g, c, stdinData, seed, device, lines)).empty()) die(mode, err);
+    try {
+        err = RunShell(g, c, stdinData, seed, device, lines);
+    } catch (const std::exception &e) {   // a Go panic ends the same way: message, then the pipe sentinel
+        err = std::string("internal error: ") + e.what();
+    }
+    if (!err.empty()) die(mode, err);
     for (const std::string &l : lines) std::printf("%s\n", l.c_str());
     return 0;
 }

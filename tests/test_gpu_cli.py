@@ -199,3 +199,27 @@ def test_cli_gotetra_snapshot(tmp_path):
     for h in range(len(halos)):
         scale = np.max(np.abs(ref["coeffs"][h]))
         assert np.all(np.abs(coeffs[h] - ref["coeffs"][h]) <= 1e-5 * scale)
+
+
+def test_cli_two_snapshots_in_one_table(tmp_path):
+    """Rows of several snapshots in one halo table (binBySnap, cmd/shell.go:299-303,322-344):
+    snapshots are processed in ascending order, each with its own header memo, and the rows come
+    back in input order."""
+    halos, blocks, mass = synth.make_box(15, 62.5, 2, 20000, 8000, 2, margin=10.0)
+    for snap in (100, 101):
+        snapio.write_box_lgadget2(str(tmp_path), "snap_%03d.%d", blocks, snap=snap)
+    cfg = tmp_path / "g.config"
+    cfg.write_text((GLOBAL % (tmp_path, len(blocks) - 1, tmp_path)).replace("SnapMax = 100", "SnapMax = 101"))
+    rows = [(0, 101, halos[0]), (1, 100, halos[1]), (2, 100, halos[0]), (3, 101, halos[1]), (4, -1, halos[0])]
+    stdin = "".join("%d %d %.17g %.17g %.17g %.17g\n" % (i, s, *h[:4]) for i, s, h in rows)
+    env = dict(os.environ, SHELLFISH_GLOBAL_CONFIG=str(cfg), SHELLFISH_SEED="1337")
+    r = subprocess.run([H.cli_path(), "shell", "--Rings", "6"], input=stdin, capture_output=True, text=True, env=env,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr
+    out = [l.split() for l in r.stdout.split("\n")[1:-1]]
+    assert [int(l[0]) for l in out] == [0, 1, 2, 3, 4] and [int(l[1]) for l in out] == [101, 100, 100, 101, -1]
+    assert out[0][6:] == out[2][6:] and out[1][6:] == out[3][6:]      # same particles in both snapshots
+    assert out[0][6:] != out[1][6:]
+    assert all(float(v) == 0.0 for v in out[4][6:])                   # Snap == -1 rows are skipped, cmd/shell.go:325
+    for snap in (100, 101):
+        assert os.path.getsize(tmp_path / "memo" / ("hd_snap%d.dat" % snap)) == 72 * len(blocks)

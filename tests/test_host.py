@@ -383,3 +383,16 @@ def test_cli_no_gpu_fails_loudly(tmp_path):
     z, om, ol, h, n, tw = struct.unpack("<4dqd", hd[:48])
     assert (om, ol, h, n, tw) == (blocks[0]["OmegaM"], blocks[0]["OmegaL"], blocks[0]["H100"], n_total, 62.5)
     assert (tmp_path / "memo" / "memo.config").exists()
+
+
+def test_cli_snapshot_column_checks(tmp_path):
+    """Snap == -1 rows are skipped (cmd/shell.go:325); the reference indexes its file table with -1
+    before it gets there and panics, the C++ host reports instead."""
+    cfg = tmp_path / "g.config"
+    cfg.write_text(GLOBAL % (tmp_path, tmp_path / "memo"))
+    env = {"SHELLFISH_GLOBAL_CONFIG": str(cfg)}
+    r = _cli(["shell"], stdin="1 -1 1 1 1 1\n2 -1 2 2 2 1\n", env=env)
+    assert r.returncode == 1 and "Every row of the halo table has Snapshot = -1" in r.stderr
+    assert r.stdout == "Shellfish terminating.\n"
+    r = _cli(["shell"], stdin="1 7 1 1 1 1\n", env=env)
+    assert r.returncode == 1 and "Snapshot 7 is outside [SnapMin, SnapMax] = [100, 100]." in r.stderr
