@@ -126,10 +126,10 @@ class LGadget2Buffer : public VectorBuffer {
 public:
     LGadget2Buffer(bool swap, Context ctx) : swap_(swap), ctx_(std::move(ctx)) {}
     std::string init(const std::string &path) {   // NewLGadget2Buffer, io/lgadget2.go:188-223
-        LGadget2Header hd;
+        LGadget2Header hd{};
         std::string err = header(path, hd);
         if (!err.empty()) return err;
-        int64_t tot;
+        int64_t tot = 0;
         err = TotalParticles(path, tot);
         if (!err.empty()) return err;
         mass_ = calcUniformMass(tot, hd.BoxSize, Cosmology{hd.Redshift, hd.Omega0, hd.OmegaLambda, hd.HubbleParam});
@@ -143,7 +143,7 @@ public:
         c.get<int32_t>();
         LGadget2Header gh = parse_lgadget(c, true);   // the header is always little endian, :100
         c.get<int32_t>();
-        int64_t count;
+        int64_t count = 0;
         err = particle_num(gh.NPart, count);
         if (!err.empty()) return err;
         xs_.resize(3 * count);
@@ -156,7 +156,7 @@ public:
         return "";
     }
     std::string ReadHeader(const std::string &fname, Header &out) override {   // :259-273 + postprocess :25-40
-        LGadget2Header hd;
+        LGadget2Header hd{};
         std::string err = header(fname, hd);
         if (!err.empty()) return err;
         const float *xs, *ms;
@@ -172,7 +172,7 @@ public:
     }
     float MinMass() const override { return mass_; }
     std::string TotalParticles(const std::string &fname, int64_t &n) override {
-        LGadget2Header hd;
+        LGadget2Header hd{};
         std::string err = header(fname, hd);
         if (!err.empty()) return err;
         return particle_num(hd.NPartTotal, n);
@@ -258,7 +258,7 @@ public:
         return "";
     }
     std::string ReadHeader(const std::string &fname, Header &out) override {   // :386-400 + postprocess :29-48
-        Gadget2Header hd;
+        Gadget2Header hd{};
         std::string err = header(fname, hd);
         if (!err.empty()) return err;
         const float *xs, *ms;
@@ -274,7 +274,7 @@ public:
     }
     float MinMass() const override { return 0.f; }   // never assigned in the reference, io/gadget2.go:327,402
     std::string TotalParticles(const std::string &fname, int64_t &n) override {
-        Gadget2Header hd;
+        Gadget2Header hd{};
         std::string err = header(fname, hd);
         if (!err.empty()) return err;
         n = 0;
