@@ -41,6 +41,7 @@ def main():
     src = list(csv.reader(io.StringIO(sh("ncu -i %s --page source --csv" % rep))))
     h2, data = src[1], src[2:]
     iI, iS, iSm = h2.index("Instructions Executed"), h2.index("Source"), h2.index("# Samples")
+    iT = h2.index("Thread Instructions Executed")
     with tempfile.TemporaryDirectory() as td:
         sh("cuobjdump -xelf all %s" % os.path.join(ROOT, "shellfish_b200", "libsfk.so"), cwd=td)
         sass = sh("nvdisasm -g -c %s.sm_100a.cubin" % unit, cwd=td).split("\n")
@@ -57,9 +58,10 @@ def main():
         if m:
             seq.append((cur, m.group(2)))
     assert len(seq) == len(data), (len(seq), len(data))
-    per, smp, mix = collections.Counter(), collections.Counter(), collections.Counter()
+    per, smp, mix, thr = collections.Counter(), collections.Counter(), collections.Counter(), collections.Counter()
     for (ln, _), r in zip(seq, data):
         per[ln] += int(r[iI])
+        thr[ln] += int(r[iT])
         smp[ln] += int(r[iSm])
         t = r[iS].strip().split()
         mix[(t[1] if t[0].startswith("@") else t[0]).split(".")[0]] += int(r[iI])
@@ -68,10 +70,10 @@ def main():
     for k, v in mix.most_common(16):
         print("  %-10s %14d %5.1f%%" % (k, v, 100.0 * v / tot))
     text = open(os.path.join(ROOT, "shellfish_b200", "csrc", unit + ".cu")).read().split("\n")
-    print("\nby source line (warp instructions, share, stall samples):")
+    print("\nby source line (warp instructions, share, stall samples, mean active lanes):")
     for ln, v in sorted(per.items(), key=lambda kv: -kv[1])[:top]:
         t = text[ln - 1].strip()[:88] if ln and ln > 0 else "<inlined from a header>"
-        print("%5s %9.1fM %5.1f%% %7d | %s" % (ln, v / 1e6, 100.0 * v / tot, smp[ln], t))
+        print("%5s %9.1fM %5.1f%% %7d %5.1f | %s" % (ln, v / 1e6, 100.0 * v / tot, smp[ln], thr[ln] / max(v, 1), t))
 
 
 if __name__ == "__main__":
