@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include "sfk_kernels.cuh"
+#include "sfk_device.cuh"
 
 namespace sfk {
 
@@ -939,26 +940,6 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(FilterArgs a) {
 }
 
 // ------------------------------------------------------------------ fit --
-
-// Go's math.Pow for small non-negative integer exponents (src/math/pow.go):
-// repeated squaring on frexp mantissas.
-__device__ double go_pow_int(double x, int yi) {
-    if (yi == 0 || x == 1) return 1;
-    if (yi == 1) return x;
-    if (isnan(x)) return x;
-    if (x == 0) return 0;   // y > 0
-    if (isinf(x)) return pow(x, static_cast<double>(yi));
-    double a1 = 1.0;
-    int ae = 0, xe;
-    double x1 = frexp(x, &xe);
-    for (int i = yi; i != 0; i >>= 1) {
-        if (i & 1) { a1 *= x1; ae += xe; }
-        x1 *= x1;
-        xe <<= 1;
-        if (x1 < .5) { x1 += x1; xe--; }
-    }
-    return ldexp(a1, ae);
-}
 
 // gonum Dgetf2 + Dtrti2 + Dgetri (unblocked, row-major) == LAPACK
 // DGETF2/DTRTI2/DGETRI: the inverse mat64.Dense.Inverse computes in pinv,

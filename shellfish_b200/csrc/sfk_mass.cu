@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "sfk_device.cuh"
 #include "sfk_kernels.cuh"
 
 namespace sfk {
@@ -22,26 +23,6 @@ namespace {
 constexpr int kMassThreads = 256;
 constexpr int kMassPerThread = 4;
 constexpr int kMassHaloChunk = 256;
-
-// Go's math.Pow for small non-negative integer exponents (src/math/pow.go):
-// repeated squaring on frexp mantissas.
-__device__ double go_pow_small(double x, int yi) {
-    if (yi == 0 || x == 1) return 1;
-    if (yi == 1) return x;
-    if (isnan(x)) return x;
-    if (x == 0) return 0;
-    if (isinf(x)) return pow(x, static_cast<double>(yi));
-    double a1 = 1.0;
-    int ae = 0, xe;
-    double x1 = frexp(x, &xe);
-    for (int i = yi; i != 0; i >>= 1) {
-        if (i & 1) { a1 *= x1; ae += xe; }
-        x1 *= x1;
-        xe <<= 1;
-        if (x1 < .5) { x1 += x1; xe--; }
-    }
-    return ldexp(a1, ae);
-}
 
 // PennaFunc(cs, order, order, 2)(phi, theta) > r, penna.go:62-82 + shell.go:349-354
 __device__ bool shell_contains(const double *cs, int order, double x, double y, double z) {
@@ -54,12 +35,12 @@ __device__ bool shell_contains(const double *cs, int order, double x, double y, 
     int idx = 0;
     double sum = 0.0;
     for (int k = 0; k < 2; k++) {
-        const double cosK = go_pow_small(cosTh, k);
+        const double cosK = go_pow_int(cosTh, k);
         for (int j = 0; j < order; j++) {
-            const double sinJ = go_pow_small(sinPhi, j);
+            const double sinJ = go_pow_int(sinPhi, j);
             for (int i = 0; i < order; i++) {
-                const double cosI = go_pow_small(cosPhi, i);
-                const double sinIJ = go_pow_small(sinTh, i + j);
+                const double cosI = go_pow_int(cosPhi, i);
+                const double sinIJ = go_pow_int(sinTh, i + j);
                 sum += cs[idx] * sinIJ * cosK * sinJ * cosI;
                 idx++;
             }
