@@ -138,11 +138,15 @@ const char *sfh_catalog_name(const char *format, const char *meanings, const int
 }
 
 // Reads one block with the named reader.  Returns N or -1; data copied to xs/ms (cap entries).
+// dmTypes / singleMass: GadgetDMTypeIndices / GadgetSingleMassIndices as bit masks over the six species
+// (0 = the reference's defaults, {1} and {1})
 int64_t sfh_read_block(const char *type, const char *fname, const char *endianness, int64_t npartNum, double posUnits,
                        double massUnits, float *xs, float *ms, int64_t cap, void *header72, float *minMass,
-                       int64_t *total) {
+                       int64_t *total, int dmTypes, int singleMass) {
     Context ctx;
     ctx.LGadgetNPartNum = npartNum; ctx.GadgetPositionUnits = posUnits; ctx.GadgetMassUnits = massUnits;
+    if (dmTypes) { ctx.GadgetDMTypeIndices.clear(); for (int i = 0; i < 6; i++) if (dmTypes >> i & 1) ctx.GadgetDMTypeIndices.push_back(i); }
+    if (singleMass) { ctx.GadgetDMSingleMassIndices.clear(); for (int i = 0; i < 6; i++) if (singleMass >> i & 1) ctx.GadgetDMSingleMassIndices.push_back(i); }
     std::unique_ptr<VectorBuffer> buf;
     std::string err = NewVectorBuffer(type, fname, endianness, ctx, buf);
     if (!err.empty()) { keep(err); return -1; }

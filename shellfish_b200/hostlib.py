@@ -109,8 +109,10 @@ def catalog_name(fmt, meanings, block_mins, block_maxes, snap_min, snap_max, sna
     return out, nb.value
 
 
-def read_block(kind, fname, endianness="SystemOrder", npart_num=2, pos_units=1.0, mass_units=1.0, cap=1 << 22):
-    """Returns (xyz, mass, header dict, min_mass, total_particles)."""
+def read_block(kind, fname, endianness="SystemOrder", npart_num=2, pos_units=1.0, mass_units=1.0, cap=1 << 22,
+               dm_types=(), single_mass=()):
+    """Returns (xyz, mass, header dict, min_mass, total_particles).  dm_types / single_mass:
+    GadgetDMTypeIndices / GadgetSingleMassIndices (empty = the reference's defaults, [1] and [1])."""
     xs = np.zeros((cap, 3), np.float32)
     ms = np.zeros(cap, np.float32)
     hd = np.zeros(72, np.uint8)
@@ -118,7 +120,8 @@ def read_block(kind, fname, endianness="SystemOrder", npart_num=2, pos_units=1.0
     n = lib().sfh_read_block(kind.encode(), fname.encode(), endianness.encode(), C.c_int64(npart_num),
                              C.c_double(pos_units), C.c_double(mass_units), xs.ctypes.data_as(C.c_void_p),
                              ms.ctypes.data_as(C.c_void_p), C.c_int64(cap), hd.ctypes.data_as(C.c_void_p),
-                             C.byref(mm), C.byref(tot))
+                             C.byref(mm), C.byref(tot), C.c_int(sum(1 << i for i in dm_types)),
+                             C.c_int(sum(1 << i for i in single_mass)))
     if n < 0:
         raise ValueError(lib().sfh_last_text().decode())
     h = dict(zip(["z", "omega_m", "omega_l", "h100"], hd[:32].view(np.float64)))

@@ -70,3 +70,51 @@ def test_sphere_sheet_intersect():   # cmd/stats.go:685-692
     assert po.sphere_sheet_intersect([5, 5, 5], 1.0, [4, 4, 4], [2, 2, 2], 100.0)
     assert not po.sphere_sheet_intersect([5, 5, 5], 1.0, [7, 4, 4], [2, 2, 2], 100.0)
     assert po.sphere_sheet_intersect([0.5, 5, 5], 1.0, [98, 4, 4], [2, 2, 2], 100.0)   # periodic neighbour
+
+
+def penna_numpy(cs, order, phi, th):
+    """PennaFunc, penna.go:62-82, written independently with numpy broadcasting."""
+    r = np.zeros_like(phi)
+    idx = 0
+    for k in range(2):
+        for j in range(order):
+            for i in range(order):
+                r = r + cs[idx] * np.sin(th) ** (i + j) * np.cos(th) ** k * np.sin(phi) ** j * np.cos(phi) ** i
+                idx += 1
+    return r
+
+
+def test_contains_general_shell_against_numpy():
+    rng = np.random.default_rng(11)
+    for order in (2, 3, 4):
+        cs = np.zeros(2 * order * order)
+        cs[0] = 1.0
+        cs[1:] = rng.normal(0, 0.08, len(cs) - 1)
+        pts = rng.normal(size=(4000, 3)) * 0.7
+        r = np.linalg.norm(pts, axis=1)
+        phi = np.arctan2(pts[:, 1], pts[:, 0])
+        th = np.arccos(pts[:, 2] / r)
+        surf = penna_numpy(cs, order, phi, th)
+        want = surf > r
+        got = np.array([po.shell_contains(cs, *p) for p in pts])
+        sure = np.abs(surf - r) > 1e-9          # away from the surface both must agree
+        assert np.array_equal(got[sure], want[sure]) and sure.mean() > 0.999
+        assert 0.2 < want.mean() < 0.95         # the sample straddles the surface
+
+
+def test_mass_contained_general_shell_against_numpy():
+    rng = np.random.default_rng(12)
+    order, box = 3, 50.0
+    cs = np.zeros(18)
+    cs[0] = 2.0
+    cs[1:] = rng.normal(0, 0.15, 17)
+    c = np.array([25.0, 24.0, 26.0], np.float32)
+    xs = (c + rng.normal(size=(50000, 3)) * 1.5).astype(np.float32)
+    ms = rng.uniform(1, 2, len(xs)).astype(np.float32)
+    d = (xs - c).astype(np.float64)                      # no wrap needed: all within the box centre
+    r = np.linalg.norm(d, axis=1)
+    surf = penna_numpy(cs, order, np.arctan2(d[:, 1], d[:, 0]), np.arccos(d[:, 2] / r))
+    lo, hi = 0.9 * surf.min(), 1.1 * surf.max()
+    want = ms[(r < lo) | ((r < hi) & (surf > r))].astype(np.float64).sum()
+    got = po.mass_contained(box, xs, ms, cs, c, lo, hi)
+    assert abs(got - want) <= 1e-6 * want               # a particle within 1e-9 of the surface may flip
