@@ -183,6 +183,34 @@ int sfk_mass_finish(sfk_ctx *ctx, double *masses);
 int sfk_sphere_block_hit(const float center[3], float radius, const float origin[3],
                          const float width[3], double total_width);
 
+/* ---- `shellfish stats`, shell property integrals ------------------------------
+ * Shell.Volume / SurfaceArea / Axes / RadialRange (los/analyze/shell.go:58-283)
+ * of the Penna-Dines surface of every halo, as cmd/stats.go:274-289 computes
+ * them.  The reference samples MonteCarloSamples random solid angles per
+ * quantity from Go's unseeded global math/rand; this call integrates the same
+ * quantities over a fixed Gauss-Legendre(cos theta) x uniform(phi) rule of
+ * SFK_SHELL_RULE_THETA x SFK_SHELL_RULE_PHI nodes, so it is deterministic and
+ * agrees with the reference within the reference's own sampling noise.
+ *   coeffs [n_halo][2*order*order]   P_ijk columns of the `shell` catalog
+ *   props  [n_halo][SFK_SHELL_PROPS] = R_sp, Volume, SurfaceArea, a (major),
+ *          b, c (minor), Ax, Ay, Az, RMin, RMax -- the float columns of the
+ *          stats catalog after M_sp (cmd/stats.go:343-349); RMin / RMax are what
+ *          rangeSp (:445-449) feeds to massContained as r_low / r_high. */
+#define SFK_SHELL_PROPS 11
+#define SFK_SHELL_RULE_THETA 128
+#define SFK_SHELL_RULE_PHI 256
+#define SFK_SHELL_SUMS 13
+int sfk_shell_props(sfk_ctx *ctx, int64_t n_halo, int32_t order, const double *coeffs, double *props);
+/* Parity tap: the raw per-halo sums of the last sfk_shell_props call,
+ * [n_halo][SFK_SHELL_SUMS] = mean r^3, mean area (r^2 / cosNorm), area-weighted
+ * means of xx yy zz xy yz zx x y z (not yet divided by the mean area), min r,
+ * max r. */
+int sfk_shell_sums(sfk_ctx *ctx, int64_t n_halo, double *sums);
+/* Shell.Axes from los/analyze/shell.go:140 on (inertia tensor, eigenvalues,
+ * axis-ratio correction tables): moments = area-weighted means {xx, yy, zz, xy,
+ * yz, zx, x, y, z}, out = {a, b, c, Ax, Ay, Az}.  Host arithmetic, no context. */
+int sfk_axes_from_moments(const double moments[9], double out[6]);
+
 int sfk_get_stats(const sfk_ctx *ctx, sfk_stats *out);
 
 /* The cudaStream_t (as void*) every kernel of this context is launched on, so

@@ -336,3 +336,107 @@ def sphere_sheet_intersect(center, r, origin, width, total_width):
     o = np.ascontiguousarray(origin, np.float32)
     w = np.ascontiguousarray(width, np.float32)
     return bool(lib().orc_sphere_sheet_intersect(fp(c), float(r), fp(o), fp(w), total_width))
+
+
+# ---- `stats` shell property integrals (orc_shellprops.c) ------------------------------
+
+class _Stream(C.Structure):
+    _fields_ = [("w", C.c_uint32), ("x", C.c_uint32), ("y", C.c_uint32), ("z", C.c_uint32)]
+
+
+class _AxisTables(C.Structure):
+    _fields_ = [("n", C.c_int), ("acs", c_double_p), ("bcs", c_double_p),
+                ("acGrid", c_double_p), ("bcGrid", c_double_p), ("cGrid", c_double_p)]
+
+
+def _stream(seed):
+    L = lib()
+    st = _Stream()
+    L.orc_stream_init(C.byref(st), C.c_uint64(seed))
+    return st, C.cast(L.orc_stream_next, C.c_void_p)
+
+
+def _cs_order(cs):
+    cs = np.ascontiguousarray(cs, np.float64)
+    return cs, int(round((len(cs) / 2) ** 0.5))
+
+
+def shell_volume(cs, samples, seed=1):
+    """Shell.Volume, los/analyze/shell.go:59-68, on the xorshift stand-in stream."""
+    L = lib()
+    cs, order = _cs_order(cs)
+    st, fn = _stream(seed)
+    L.orc_shell_volume.restype = C.c_double
+    L.orc_shell_volume.argtypes = [c_double_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    return L.orc_shell_volume(dp(cs), order, samples, fn, C.byref(st))
+
+
+def shell_surface_area(cs, samples, seed=1):
+    """Shell.SurfaceArea, los/analyze/shell.go:229-237."""
+    L = lib()
+    cs, order = _cs_order(cs)
+    st, fn = _stream(seed)
+    L.orc_shell_surface_area.restype = C.c_double
+    L.orc_shell_surface_area.argtypes = [c_double_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    return L.orc_shell_surface_area(dp(cs), order, samples, fn, C.byref(st))
+
+
+def shell_radial_range(cs, samples, seed=1):
+    """Shell.RadialRange, los/analyze/shell.go:268-283."""
+    L = lib()
+    cs, order = _cs_order(cs)
+    st, fn = _stream(seed)
+    lo, hi = C.c_double(), C.c_double()
+    L.orc_shell_radial_range.argtypes = [c_double_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, c_double_p, c_double_p]
+    L.orc_shell_radial_range(dp(cs), order, samples, fn, C.byref(st), C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def cos_norm(cs, phi, theta):
+    """cosNorm, los/analyze/shell.go:201-226."""
+    L = lib()
+    cs, order = _cs_order(cs)
+    L.orc_cos_norm.restype = C.c_double
+    L.orc_cos_norm.argtypes = [c_double_p, C.c_int, C.c_double, C.c_double]
+    return L.orc_cos_norm(dp(cs), order, phi, theta)
+
+
+def penna_func(cs, phi, theta):
+    """PennaFunc(cs, order, order, 2)(phi, theta), los/analyze/penna.go:62-82."""
+    L = lib()
+    cs, order = _cs_order(cs)
+    L.orc_penna_func.restype = C.c_double
+    L.orc_penna_func.argtypes = [c_double_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+    return L.orc_penna_func(dp(cs), order, order, 2, phi, theta)
+
+
+def bicubic_eval(xs, ys, vals, x, y):
+    """BiCubic.Eval, math/interpolate/cubic_interpolators.go:92-103; None where Go panics."""
+    L = lib()
+    xs = np.ascontiguousarray(xs, np.float64)
+    ys = np.ascontiguousarray(ys, np.float64)
+    vals = np.ascontiguousarray(vals, np.float64)
+    out = C.c_double()
+    L.orc_bicubic_eval.argtypes = [c_double_p, C.c_int, c_double_p, C.c_int, c_double_p, C.c_double, C.c_double,
+                                   c_double_p]
+    rc = L.orc_bicubic_eval(dp(xs), len(xs), dp(ys), len(ys), dp(vals), x, y, C.byref(out))
+    return None if rc else out.value
+
+
+def shell_axes(cs, samples, seed=1, tables=None):
+    """Shell.Axes, los/analyze/shell.go:113-199 -> (a, b, c, aVec) or None where Go
+    panics.  tables = (ratios, acGrid, bcGrid, cGrid) or None for the uncorrected axes."""
+    L = lib()
+    cs, order = _cs_order(cs)
+    st, fn = _stream(seed)
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    vec = np.zeros(3)
+    tp = None
+    if tables is not None:
+        keep = [np.ascontiguousarray(t, np.float64) for t in tables]
+        tp = _AxisTables(len(keep[0]), dp(keep[0]), dp(keep[0]), dp(keep[1]), dp(keep[2]), dp(keep[3]))
+    L.orc_shell_axes.argtypes = [c_double_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 c_double_p, c_double_p, c_double_p, c_double_p]
+    rc = L.orc_shell_axes(dp(cs), order, samples, fn, C.byref(st), C.byref(tp) if tp is not None else None,
+                          C.byref(a), C.byref(b), C.byref(c), dp(vec))
+    return None if rc else (a.value, b.value, c.value, vec)

@@ -202,6 +202,26 @@ double orc_mass_contained(double totalWidth, const float *xs, const float *ms, i
 int orc_sphere_sheet_intersect(const float c[3], float r, const float origin[3],
                                const float width[3], double tw);
 
+/* ---- `stats` shell property integrals, los/analyze/shell.go:21-32,58-283 (orc_shellprops.c) */
+typedef double (*orc_uniform_fn)(void *state);    /* one rand.Float64() */
+typedef struct { uint32_t w, x, y, z; } orc_stream;   /* math/rand/xorshift.go */
+void orc_stream_init(orc_stream *s, uint64_t seed);
+double orc_stream_next(void *state);
+typedef struct {
+    int n;                                  /* knots per axis */
+    const double *acs, *bcs;                /* grid.ACRatios, grid.BCRatios */
+    const double *acGrid, *bcGrid, *cGrid;  /* [n*n], vals[n*yi + xi] */
+} orc_axis_tables;
+double orc_shell_volume(const double *cs, int order, int samples, orc_uniform_fn fn, void *st);
+double orc_cos_norm(const double *cs, int order, double phi, double theta);
+double orc_shell_surface_area(const double *cs, int order, int samples, orc_uniform_fn fn, void *st);
+void orc_shell_radial_range(const double *cs, int order, int samples, orc_uniform_fn fn, void *st,
+                            double *low, double *high);
+int orc_bicubic_eval(const double *xs, int nx, const double *ys, int ny, const double *vals,
+                     double x, double y, double *out);
+int orc_shell_axes(const double *cs, int order, int samples, orc_uniform_fn fn, void *st,
+                   const orc_axis_tables *tables, double *a, double *b, double *c, double aVec[3]);
+
 /* Resets the process-wide Savitzky-Golay kernel cache (smooth.go:9-12). */
 void orc_reset_kernel_cache(void);
 

@@ -51,8 +51,12 @@ EXPORTS = ["sfk_default_params", "sfk_create", "sfk_destroy", "sfk_last_error", 
            "sfk_add_halos", "sfk_set_owned", "sfk_block_halo_mask", "sfk_push_block", "sfk_push_block_device",
            "sfk_finish_snapshot", "sfk_row_length", "sfk_split_count", "sfk_split_bin", "sfk_split_buffer", "sfk_split_finish",
            "sfk_mass_begin", "sfk_mass_push_block", "sfk_mass_push_block_device", "sfk_mass_finish",
-           "sfk_sphere_block_hit", "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count",
+           "sfk_sphere_block_hit", "sfk_shell_props", "sfk_shell_sums", "sfk_axes_from_moments", "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count",
            "sfk_get_profiles", "sfk_get_counts", "sfk_get_ring_tables"]
+
+SHELL_PROPS = 11   # SFK_SHELL_PROPS
+SHELL_SUMS = 13    # SFK_SHELL_SUMS
+SHELL_RULE = (128, 256)   # SFK_SHELL_RULE_THETA, SFK_SHELL_RULE_PHI
 
 _lib = None
 
@@ -271,6 +275,27 @@ class ShellContext:
         self._ck(lib().sfk_mass_finish(self._h, out.ctypes.data_as(dp_)), "sfk_mass_finish")
         return out
 
+    # ---- stats mode: shell property integrals ----------------------------------------
+    def shell_props(self, coeffs):
+        """Shell.Volume / SurfaceArea / Axes / RadialRange (los/analyze/shell.go:58-283)
+        for every coefficient row: [n][SHELL_PROPS] = R_sp, Volume, SurfaceArea, a, b, c,
+        Ax, Ay, Az, RMin, RMax (the float columns of cmd/stats.go:343-349 after M_sp)."""
+        coeffs = np.ascontiguousarray(coeffs, np.float64)
+        n = len(coeffs)
+        order = int(round((coeffs.shape[1] / 2) ** 0.5))
+        out = np.zeros((n, SHELL_PROPS))
+        dp_ = C.POINTER(C.c_double)
+        self._ck(lib().sfk_shell_props(self._h, C.c_int64(n), C.c_int32(order), coeffs.ctypes.data_as(dp_),
+                                       out.ctypes.data_as(dp_)), "sfk_shell_props")
+        return out
+
+    def shell_sums(self, n):
+        """Parity tap: raw sums of the last shell_props call, [n][SHELL_SUMS]."""
+        out = np.zeros((n, SHELL_SUMS))
+        self._ck(lib().sfk_shell_sums(self._h, C.c_int64(n), out.ctypes.data_as(C.POINTER(C.c_double))),
+                 "sfk_shell_sums")
+        return out
+
     def stream_ptr(self):
         """cudaStream_t of this context as an integer (torch.cuda.ExternalStream)."""
         return lib().sfk_stream(self._h)
@@ -321,6 +346,17 @@ class ShellContext:
         self._ck(lib().sfk_get_ring_tables(self._h, norms.ctypes.data_as(fp), rot.ctypes.data_as(fp),
                                            irot.ctypes.data_as(fp)), "sfk_get_ring_tables")
         return norms, rot, irot
+
+
+def axes_from_moments(moments):
+    """Shell.Axes from los/analyze/shell.go:140 on: area-weighted means {xx, yy, zz, xy,
+    yz, zx, x, y, z} -> (a, b, c, Ax, Ay, Az).  Host arithmetic of libsfk.so."""
+    m = np.ascontiguousarray(moments, np.float64)
+    out = np.zeros(6)
+    dp_ = C.POINTER(C.c_double)
+    if lib().sfk_axes_from_moments(m.ctypes.data_as(dp_), out.ctypes.data_as(dp_)) != 0:
+        raise ShellfishError("sfk_axes_from_moments: bad arguments")
+    return out
 
 
 def run_shell(params, min_mass, halos, blocks):

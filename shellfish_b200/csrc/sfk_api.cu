@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include "sfk_kernels.cuh"
+#include "sfk_shellmath.cuh"
 
 using namespace sfk;
 
@@ -111,6 +112,9 @@ struct sfk_ctx {
     int64_t massHalos = 0;
     int massOrder = 0;
     bool massOpen = false;
+    // `stats` shell properties
+    DevBuf<double> dPropCoeffs, dPropSums, dGlX, dGlW;
+    int glTheta = 0;
     DevBuf<uint32_t> dTapInsert, dTapStart, dTapEnd;
 
     // batch scratch
@@ -906,6 +910,60 @@ int sfk_mass_finish(sfk_ctx *ctx, double *masses) {
         CU(cudaMemcpyAsync(masses, ctx->dMassSums.p, ctx->massHalos * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->massOpen = false;
+    return SFK_OK;
+}
+
+// ---- `stats` mode: shell property integrals --------------------------------------------
+
+static_assert(SS_COUNT == SFK_SHELL_SUMS, "sum layout");
+
+int sfk_shell_props(sfk_ctx *ctx, int64_t n_halo, int32_t order, const double *coeffs, double *props) {
+    if (!ctx || n_halo < 0 || order <= 0 || (n_halo > 0 && (!coeffs || !props)))
+        return fail(ctx, SFK_E_INVALID, "sfk_shell_props: bad arguments");
+    if (order > kMaxOrder) return fail(ctx, SFK_E_UNSUPPORTED, "Order above 4 is not supported.");
+    if (n_halo == 0) return SFK_OK;
+    if (n_halo > 0x7fffffff) return fail(ctx, SFK_E_INVALID, "sfk_shell_props: too many halos");
+    CU(cudaSetDevice(ctx->p.device));
+    const int nTheta = SFK_SHELL_RULE_THETA, nPhi = SFK_SHELL_RULE_PHI;
+    if (ctx->glTheta != nTheta) {
+        std::vector<double> x, w;
+        gauss_legendre(nTheta, x, w);
+        CU(ctx->dGlX.upload(x, ctx->stream));
+        CU(ctx->dGlW.upload(w, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->glTheta = nTheta;
+    }
+    const size_t P2 = 2 * static_cast<size_t>(order) * order;
+    CU(ctx->dPropCoeffs.ensure(P2 * n_halo));
+    CU(ctx->dPropSums.ensure(static_cast<size_t>(SS_COUNT) * n_halo));
+    CU(cudaMemcpyAsync(ctx->dPropCoeffs.p, coeffs, P2 * n_halo * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ShellPropArgs a{};
+    a.coeffs = ctx->dPropCoeffs.p; a.glX = ctx->dGlX.p; a.glW = ctx->dGlW.p; a.sums = ctx->dPropSums.p;
+    a.nHalo = static_cast<int>(n_halo); a.order = order; a.nTheta = nTheta; a.nPhi = nPhi;
+    CU(launch_shell_props(a, ctx->stream));
+    ctx->stats.launches += 1;
+    std::vector<double> sums(static_cast<size_t>(SS_COUNT) * n_halo);
+    CU(cudaMemcpyAsync(sums.data(), ctx->dPropSums.p, sums.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int64_t h = 0; h < n_halo; h++)
+        shell_props_finalize(sums.data() + h * SS_COUNT, props + h * SFK_SHELL_PROPS);
+    return SFK_OK;
+}
+
+int sfk_shell_sums(sfk_ctx *ctx, int64_t n_halo, double *sums) {
+    if (!ctx || n_halo < 0 || (n_halo > 0 && !sums) || static_cast<size_t>(n_halo) * SS_COUNT > ctx->dPropSums.cap)
+        return fail(ctx, SFK_E_INVALID, "sfk_shell_sums: call sfk_shell_props with at least n_halo halos first");
+    CU(cudaSetDevice(ctx->p.device));
+    if (n_halo)
+        CU(cudaMemcpyAsync(sums, ctx->dPropSums.p, static_cast<size_t>(n_halo) * SS_COUNT * sizeof(double),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SFK_OK;
+}
+
+int sfk_axes_from_moments(const double moments[9], double out[6]) {
+    if (!moments || !out) return SFK_E_INVALID;
+    axes_from_moments(moments, out);
     return SFK_OK;
 }
 

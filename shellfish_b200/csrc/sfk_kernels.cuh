@@ -104,6 +104,15 @@ struct MassArgs {
     int nHalo, order, P2;
 };
 cudaError_t launch_mass(const MassArgs &a, cudaStream_t s);
+
+// `stats` shell property integrals, los/analyze/shell.go:58-283
+struct ShellPropArgs {
+    const double *coeffs;        // [nHalo][2*order*order]
+    const double *glX, *glW;     // [nTheta] Gauss-Legendre nodes / weights in cos(theta)
+    double *sums;                // [nHalo][SS_COUNT], see sfk_shellmath.cuh
+    int nHalo, order, nTheta, nPhi;
+};
+cudaError_t launch_shell_props(const ShellPropArgs &a, cudaStream_t s);
 cudaError_t launch_cull(const CullArgs &a, bool fill, cudaStream_t s);
 cudaError_t launch_hit_count(const Piece *pieces, int nPieces, const Cand *cands, const HaloDev *halos,
                              const float *norms, int rings, uint32_t *hitCount,

@@ -1,0 +1,47 @@
+// hostcheck.cpp -- TEST INFRASTRUCTURE.  Compiles the host/device-shared
+// arithmetic of shellfish_b200/csrc/sfk_shellmath.cuh (the per-node code of
+// shell_props_kernel) and the closing arithmetic of sfk_axes.cpp with g++, so the
+// CPU test suite can check them against the oracle without a GPU.  Never loaded by
+// the product path: libsfk.so runs this arithmetic only inside its CUDA kernel.
+#include <cmath>
+#include <vector>
+
+#include "../../shellfish_b200/csrc/sfk_internal.h"
+#include "../../shellfish_b200/csrc/sfk_shellmath.cuh"
+
+extern "C" {
+
+double hc_penna_radius(const double *cs, int order, double phi, double theta) {
+    return sfk::penna_radius(cs, order, phi, theta);
+}
+
+double hc_cos_norm(const double *cs, int order, double phi, double theta) {
+    return sfk::shell_cos_norm(cs, order, phi, theta);
+}
+
+// The sums shell_props_kernel produces for one halo, nodes visited in index order.
+void hc_shell_sums(const double *cs, int order, int nTheta, int nPhi, double *sums) {
+    std::vector<double> x, w;
+    sfk::gauss_legendre(nTheta, x, w);
+    for (int i = 0; i < sfk::SS_COUNT; i++) sums[i] = 0.0;
+    sums[sfk::SS_RMIN] = INFINITY; sums[sfk::SS_RMAX] = -INFINITY;
+    for (int q = 0; q < nTheta * nPhi; q++) {
+        double phi, theta, wt;
+        sfk::shell_rule_node(q, nPhi, x.data(), w.data(), phi, theta, wt);
+        sfk::shell_node(cs, order, phi, theta, wt, sums);
+    }
+}
+
+void hc_shell_props(const double *cs, int order, int nTheta, int nPhi, double *props) {
+    double sums[sfk::SS_COUNT];
+    hc_shell_sums(cs, order, nTheta, nPhi, sums);
+    sfk::shell_props_finalize(sums, props);
+}
+
+void hc_gauss_legendre(int n, double *x, double *w) {
+    std::vector<double> xv, wv;
+    sfk::gauss_legendre(n, xv, wv);
+    for (int i = 0; i < n; i++) { x[i] = xv[i]; w[i] = wv[i]; }
+}
+
+}

@@ -1,0 +1,165 @@
+"""Shell property integrals of `shellfish stats` on the CPU tier.
+
+Three implementations meet here:
+  * the oracle's literal Monte-Carlo restatement of los/analyze/shell.go
+    (oracle/orc_shellprops.c; PARITY UNPINNED: the reference's sample stream is Go's
+    unseeded global math/rand),
+  * the product's per-node arithmetic, i.e. the source of shell_props_kernel compiled
+    for the host (tests/hostcheck), on the product's quadrature rule,
+  * closed forms / numpy / scipy.
+The GPU tier (tests/test_gpu_shellprops.py) then only has to show that the kernel
+returns what its host-compiled source returns."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+import hostcheck as hc
+import shell_cases as shells
+
+
+def test_gauss_legendre_rule_matches_numpy():
+    for n in (2, 7, 64, 128):
+        x, w = hc.gauss_legendre(n)
+        xr, wr = np.polynomial.legendre.leggauss(n)
+        assert np.allclose(x, xr, rtol=0, atol=2e-15) and np.allclose(w, wr, rtol=1e-10, atol=0)
+        assert abs(w.sum() - 2) < 1e-14
+        k = 2 * n - 2       # the highest even degree the rule integrates exactly
+        assert abs((w * x ** k).sum() * (k + 1) / 2 - 1) < 1e-12
+
+
+@pytest.mark.parametrize("order", [2, 3, 4])
+def test_penna_radius_and_cos_norm_equal_the_literal_restatement(order):
+    """Hoisting the math.Pow calls out of the term loop changes nothing: the same
+    products in the same association (penna.go:62-82)."""
+    rng = np.random.default_rng(order)
+    for _ in range(20):
+        cs = shells.random_shell(rng, order, radius=rng.uniform(0.5, 3))
+        for _ in range(20):
+            phi, th = rng.uniform(-0.1, 2 * np.pi + 0.1), rng.uniform(0, np.pi)
+            assert hc.penna_radius(cs, phi, th) == po.penna_func(cs, phi, th)
+            assert hc.cos_norm(cs, phi, th) == po.cos_norm(cs, phi, th)
+
+
+def test_sphere_closed_forms():
+    R = 1.7
+    p = hc.shell_props(shells.sphere(R))
+    vol = 4 * np.pi / 3 * R ** 3
+    assert abs(p[1] - vol) < 1e-13 * vol
+    assert abs(p[0] - (vol / (4 * np.pi / 3)) ** 0.33333) < 1e-13 * R      # cmd/stats.go:279
+    assert abs(p[2] - 4 * np.pi * R * R) < 1e-9 * R * R                     # finite-difference cosNorm
+    assert p[9] == R and p[10] == R
+    # Monte-Carlo restatement: every sample of a sphere gives the same value
+    assert abs(po.shell_volume(shells.sphere(R), 1000) - vol) < 1e-12 * vol
+    assert abs(po.shell_surface_area(shells.sphere(R), 1000) - 4 * np.pi * R * R) < 1e-8 * R * R
+    assert po.shell_radial_range(shells.sphere(R), 100) == (R, R)
+
+
+def test_offset_sphere_like_surface_closed_form():
+    """R = 1 + e cos(theta): mean R^3 = 1 + e^2 exactly (odd powers of cos vanish)."""
+    e = 0.3
+    cs = shells.sphere(1.0)
+    cs[9] = e
+    s = hc.shell_sums(cs)
+    assert abs(s[0] - (1 + e * e)) < 1e-14
+    assert abs(s[11] - (1 - e)) < 2e-4 and abs(s[12] - (1 + e)) < 2e-4   # poles are not nodes
+    assert s[11] >= 1 - e and s[12] <= 1 + e
+
+
+@pytest.mark.parametrize("order", [2, 3, 4])
+def test_rule_is_converged(order):
+    rng = np.random.default_rng(10 + order)
+    cs = shells.random_shell(rng, order, amp=0.4)
+    a, b = hc.shell_sums(cs, 64, 128), hc.shell_sums(cs, 128, 256)
+    assert np.allclose(a[:11], b[:11], rtol=1e-11, atol=1e-13)
+    assert abs(a[11] - b[11]) < 1e-3 and abs(a[12] - b[12]) < 1e-3
+
+
+@pytest.mark.parametrize("order", [2, 3, 4])
+def test_quadrature_agrees_with_monte_carlo_statistically(order):
+    """The deterministic rule must sit inside the scatter of the reference's estimator:
+    |rule - MC mean| < 5 sigma_mean over independent 50 000-sample runs (the
+    reference's MonteCarloSamples default, cmd/stats.go:111)."""
+    rng = np.random.default_rng(20 + order)
+    cs = shells.random_shell(rng, order, radius=1.3, amp=0.35)
+    p = hc.shell_props(cs)
+    seeds = range(1, 13)
+    vols = np.array([po.shell_volume(cs, 50000, s) for s in seeds])
+    sas = np.array([po.shell_surface_area(cs, 50000, 100 + s) for s in seeds])
+    for got, mc in ((p[1], vols), (p[2], sas)):
+        err = mc.std(ddof=1) / np.sqrt(len(mc))
+        assert abs(got - mc.mean()) < 5 * err, (got, mc.mean(), err)
+        assert err < 2e-3 * got
+    lo, hi = po.shell_radial_range(cs, 50000, 7)
+    # both estimates approach the true extrema from inside
+    assert abs(p[9] - lo) < 2e-3 and abs(p[10] - hi) < 2e-3
+
+
+def test_axes_agree_with_monte_carlo_statistically():
+    rng = np.random.default_rng(31)
+    tables = shells.axis_tables()
+    for order in (2, 3):
+        cs = shells.random_shell(rng, order, radius=1.0, amp=0.45)
+        p = hc.shell_props(cs)
+        runs = [po.shell_axes(cs, 50000, s, tables) for s in range(1, 9)]
+        assert all(r is not None for r in runs)
+        abc = np.array([r[:3] for r in runs])
+        err = abc.std(0, ddof=1) / np.sqrt(len(runs))
+        assert np.all(np.abs(p[3:6] - abc.mean(0)) < 5 * err + 1e-4), (p[3:6], abc.mean(0), err)
+        assert p[3] >= p[4] >= p[5] > 0
+        vec = np.array([r[3] for r in runs])
+        cosang = np.abs(vec @ p[6:9])
+        assert np.all(cosang > 0.98), cosang       # same major axis up to sign and noise
+        assert abs(np.linalg.norm(p[6:9]) - 1) < 1e-14 and p[6:9][np.abs(p[6:9]).argmax()] > 0
+
+
+def test_axes_closing_arithmetic_against_numpy():
+    """sfk_axes_from_moments (libsfk.so host code) vs shell.go:140-198 written out with
+    numpy.linalg.eigh and the oracle's BiCubic."""
+    from shellfish_b200 import api
+    ratios, acg, bcg, cg = shells.axis_tables()
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        # moments of a thin homoeoid with semi-axes s in a random orientation, off-centre
+        s = np.sort(rng.uniform(0.5, 1.5, 3))[::-1]
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        sec = q @ np.diag(s * s / 3) @ q.T
+        mu = rng.normal(size=3) * 0.05
+        sec = sec + np.outer(mu, mu)
+        m = [sec[0, 0], sec[1, 1], sec[2, 2], sec[0, 1], sec[1, 2], sec[2, 0], mu[0], mu[1], mu[2]]
+        got = api.axes_from_moments(m)
+        cen = sec - np.outer(mu, mu)
+        inertia = np.trace(cen) * np.eye(3) - cen
+        w, v = np.linalg.eigh(inertia)
+        ax2 = 3 * (w[1] + w[2] - w[0]) / 2
+        c, b, a = np.sqrt(sorted([ax2, 3 * w[1] - ax2, 3 * w[2] - ax2], reverse=True))
+        assert np.allclose([c, b, a], s, rtol=1e-12)         # the homoeoid relation recovers s
+        ac, bc = a / c, b / c
+        cr = po.bicubic_eval(ratios, ratios, cg, ac, bc)
+        exp = [cr * c, po.bicubic_eval(ratios, ratios, bcg, ac, bc) * bc * cr * c,
+               po.bicubic_eval(ratios, ratios, acg, ac, bc) * ac * cr * c]
+        assert np.allclose(got[:3], exp, rtol=1e-12), (got, exp)
+        assert abs(abs(got[3:] @ v[:, 0]) - 1) < 1e-10
+
+
+def test_bicubic_against_scipy_natural_splines():
+    from scipy.interpolate import CubicSpline
+    ratios, acg, _, cg = shells.axis_tables()
+    n = len(ratios)
+    rng = np.random.default_rng(9)
+    for grid in (acg, cg):
+        g = grid.reshape(n, n)     # [yi][xi]
+        for _ in range(10):
+            x, y = rng.uniform(ratios[0], 1, 2)
+            at_y = [CubicSpline(ratios, g[:, xi], bc_type="natural")(y) for xi in range(n)]
+            ref = CubicSpline(ratios, at_y, bc_type="natural")(x)
+            assert abs(po.bicubic_eval(ratios, ratios, grid, x, y) - ref) < 1e-13
+    assert po.bicubic_eval(ratios, ratios, acg, 0.1, 0.5) is None      # Spline.Eval panics, spline.go:80-90
+
+
+def test_elongated_shells_clamp_instead_of_panicking():
+    """Axis ratios below the first table knot: the reference panics, the product clamps."""
+    from shellfish_b200 import api
+    m = [1.0 / 3, 0.01 / 3, 0.01 / 3, 0, 0, 0, 0, 0, 0]     # a homoeoid with ratios 0.1
+    got = api.axes_from_moments(m)
+    assert np.all(np.isfinite(got)) and got[0] > got[1] >= got[2] > 0
+    assert abs(abs(got[3]) - 1) < 1e-12
