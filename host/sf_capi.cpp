@@ -7,6 +7,7 @@
 #include "sf_catalog.hpp"
 #include "sf_config.hpp"
 #include "sf_shell.hpp"
+#include "sf_stats.hpp"
 #include "sf_snapshot.hpp"
 
 using namespace sfhost;
@@ -106,6 +107,24 @@ const char *sfh_read_shell_config(const char *fname, const char *flags, int64_t 
     floats7[0] = c.rMaxMult; floats7[1] = c.rMinMult; floats7[2] = c.rKernelMult; floats7[3] = c.eta;
     floats7[4] = c.losSlopeCutoff; floats7[5] = c.backgroundRhoMult; floats7[6] = c.percentile;
     *pp = c.percentileProfile;
+    return keep(err);
+}
+
+const char *sfh_read_stats_config(const char *fname, const char *flags, int64_t *ints2, double *width, int *bools2,
+                                  char *strategy, int cap) {
+    StatsConfig c;
+    std::vector<std::string> args;
+    if (flags && *flags) {
+        std::string cur;
+        for (const char *p = flags; ; p++) {
+            if (*p == '\n' || !*p) { args.push_back(cur); cur.clear(); if (!*p) break; } else cur += *p;
+        }
+    }
+    std::string err = c.ReadConfig(fname ? fname : "", args);
+    ints2[0] = c.monteCarloSamples; ints2[1] = c.order;
+    *width = c.shellWidth;
+    bools2[0] = c.skipMass; bools2[1] = c.shellFilter;
+    std::strncpy(strategy, c.exclusionStrategy.c_str(), cap - 1); strategy[cap - 1] = 0;
     return keep(err);
 }
 

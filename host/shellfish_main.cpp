@@ -1,8 +1,11 @@
-// shellfish_main.cpp -- `shellfish shell [shell.config] [--Flag value ...]`:
-// the reference's CLI protocol (shellfish.go:305-450) for the one mode this
-// repository rebuilds.  stdin: halo table `ID Snap X Y Z R200m`; stdout: the
-// Penna coefficient catalog; errors go to stderr and "Shellfish terminating."
-// to stdout so that the next pipe stage aborts.
+// shellfish_main.cpp -- `shellfish shell [shell.config] [--Flag value ...]` and
+// `shellfish stats [stats.config] [--Flag value ...]`: the reference's CLI
+// protocol (shellfish.go:305-450) for the two modes this repository rebuilds, so
+// that `... | shellfish shell | shellfish stats` runs end to end.  shell: stdin is
+// the halo table `ID Snap X Y Z R200m`, stdout the Penna coefficient catalog;
+// stats: stdin is that catalog, stdout the M_sp / R_sp / shape catalog.  Errors
+// go to stderr and "Shellfish terminating." to stdout so that the next pipe stage
+// aborts.
 //
 // New knobs are environment variables (config files stay valid for the Go
 // binary): SHELLFISH_SEED pins cmd/cmd.go:658's wall-clock seed,
@@ -19,6 +22,7 @@
 
 #include "sf_config.hpp"
 #include "sf_shell.hpp"
+#include "sf_stats.hpp"
 
 using namespace sfhost;
 
@@ -74,12 +78,14 @@ int main(int argc, char **argv) {
     const std::string mode = argv[1];
     if (mode == "help") {
         if (argc == 3 && std::string(argv[2]) == "shell.config") std::printf("%s\n", ShellConfig::ExampleConfig());
-        else std::printf("shellfish shell [shell.config] [--Flag value ...]   (B200 build: only the shell mode is built)\n");
+        else if (argc == 3 && std::string(argv[2]) == "stats.config") std::printf("%s\n", StatsConfig::ExampleConfig());
+        else std::printf("shellfish shell [shell.config] [--Flag value ...]\n"
+                         "shellfish stats [stats.config] [--Flag value ...]   (B200 build: the shell and stats modes)\n");
         return 0;
     }
     if (mode == "version") { std::printf("Shellfish version %s\n", kSourceVersion); return 0; }
     if (mode == "hello") { std::printf("Hello back at you! Installation was successful.\n"); return 0; }
-    if (mode != "shell") {
+    if (mode != "shell" && mode != "stats") {
         std::fprintf(stderr, "You passed me the mode '%s', which this B200 build does not provide.\n"
                              "For help, type './shellfish help'\n", mode.c_str());
         std::printf("Shellfish terminating.\n");
@@ -105,7 +111,10 @@ int main(int argc, char **argv) {
     std::string err = g.ReadConfig(gName);
     if (!err.empty()) die(mode, err);
     ShellConfig c;
-    if (!(err = c.ReadConfig(configName, flags)).empty()) die(mode, err);
+    StatsConfig sc;
+    if (mode == "shell") err = c.ReadConfig(configName, flags);
+    else err = sc.ReadConfig(configName, flags);
+    if (!err.empty()) die(mode, err);
     if (!(err = check_memo_dir(g.MemoDir, gName)).empty()) die(mode, err);
     if (g.SnapshotType == "nil") {
         std::fprintf(stderr, "Cannot run mode %s with SnapshotType = nil\n", mode.c_str());
@@ -120,12 +129,13 @@ int main(int argc, char **argv) {
     if (const char *s = std::getenv("SHELLFISH_SEED")) seed = std::strtoull(s, nullptr, 10);
     const int device = std::getenv("SHELLFISH_GPU") ? std::atoi(std::getenv("SHELLFISH_GPU")) : 0;
     if (g.Logging != "nil") {
-        std::fprintf(stderr, "\n#####################\n## shellfish shell ##\n#####################\n");
-        std::fprintf(stderr, "RNG Seed is %llu\n", static_cast<unsigned long long>(seed));
+        std::fprintf(stderr, "\n#####################\n## shellfish %s ##\n#####################\n", mode.c_str());
+        if (mode == "shell") std::fprintf(stderr, "RNG Seed is %llu\n", static_cast<unsigned long long>(seed));
     }
     std::vector<std::string> lines;
     try {
-        err = RunShell(g, c, stdinData, seed, device, lines);
+        if (mode == "shell") err = RunShell(g, c, stdinData, seed, device, lines);
+        else err = RunStats(g, sc, stdinData, device, lines);
     } catch (const std::exception &e) {   // a Go panic ends the same way: message, then the pipe sentinel
         err = std::string("internal error: ") + e.what();
     }

@@ -18,7 +18,7 @@ def lib():
             raise RuntimeError("libsfhost.so is missing: run `make -C host` (or __graft_entry__.build())")
         _lib = C.CDLL(path)
         for name in ("sfh_go_g6", "sfh_comment_string", "sfh_format_cols", "sfh_last_text", "sfh_read_test_config",
-                     "sfh_read_shell_config", "sfh_read_global_config", "sfh_catalog_name"):
+                     "sfh_read_shell_config", "sfh_read_stats_config", "sfh_read_global_config", "sfh_catalog_name"):
             getattr(_lib, name).restype = C.c_char_p
         _lib.sfh_go_g6.argtypes = [C.c_double]
         _lib.sfh_read_block.restype = C.c_int64
@@ -89,6 +89,16 @@ def read_shell_config(fname=None, flags=()):
     out.update(zip(keys_f, list(floats)))
     out["PercentileProfile"] = bool(pp.value)
     return err, out
+
+
+def read_stats_config(fname=None, flags=()):
+    """StatsConfig.ReadConfig + validate, cmd/stats.go:109-172."""
+    ints, width, bools = (C.c_int64 * 2)(), C.c_double(), (C.c_int * 2)()
+    strat = C.create_string_buffer(64)
+    err = lib().sfh_read_stats_config(None if fname is None else fname.encode(), "\n".join(flags).encode(),
+                                      ints, C.byref(width), bools, strat, 64).decode()
+    return err, dict(MonteCarloSamples=ints[0], Order=ints[1], ShellWidth=width.value, SkipMass=bool(bools[0]),
+                     shellFilter=bool(bools[1]), ExclusionStrategy=strat.value.decode())
 
 
 def read_global_config(fname):

@@ -223,3 +223,52 @@ def test_cli_two_snapshots_in_one_table(tmp_path):
     assert all(float(v) == 0.0 for v in out[4][6:])                   # Snap == -1 rows are skipped, cmd/shell.go:325
     for snap in (100, 101):
         assert os.path.getsize(tmp_path / "memo" / ("hd_snap%d.dat" % snap)) == 72 * len(blocks)
+
+
+def test_shell_stats_pipeline(tmp_path):
+    """`shellfish shell | shellfish stats` (cmd/stats.go:174-360): the stats catalog printed by
+    the CLI is text-identical to the same two device passes driven through the ctypes binding,
+    M_sp agrees with the oracle's massContained on the blocks binSphereIntersections keeps, and
+    volume / area sit inside the scatter of the oracle's Monte-Carlo restatement."""
+    halos, blocks, min_mass, cfg = _setup(tmp_path, 15, 3, 30000, 20000, 2)
+    shell_lines = _run_cli(cfg, halos, ["--Rings", "12"])
+    env = dict(os.environ, SHELLFISH_GLOBAL_CONFIG=cfg)
+    r = subprocess.run([H.cli_path(), "stats"], input="\n".join(shell_lines) + "\n", capture_output=True, text=True,
+                       env=env, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.split("\n")[:-1]
+    assert lines[0] == ("# Column contents: ID(0) Snapshot(1) M_sp [M_sun/h](2) R_sp [cMpc/h](3) "
+                        "Volume [cMpc^3/h^3](4) Surface Area [cMpc^2/h^2](5) Major Axis [cMpc/h](6) "
+                        "Intermediate Axis [cMpc/h](7) Minor Axis [cMpc/h](8) Ax(9) Ay(10) Az(11) "
+                        "RMin [cMpc/h](12) RMax [cMpc/h](13)")
+    assert len(lines) == 1 + len(halos)
+
+    # the catalog text is the interface between the two modes: stats sees the %.6g coefficients
+    ic, fc = H.parse_catalog("\n".join(shell_lines) + "\n", [0, 1], list(range(2, 24)))
+    centers, r200, coeffs = fc[:3].T.copy(), fc[3].copy(), fc[4:].T.copy()
+    ctx = api.ShellContext(api.default_params(rings=3))
+    props = ctx.shell_props(coeffs)
+    masses = ctx.mass_contained(centers, coeffs, props[:, 9], props[:, 10], blocks, radii=r200.astype(np.float32))
+    want = H.format_cols([ic[0], ic[1]], [masses] + [props[:, k] for k in range(11)], list(range(14)))
+    assert lines[1:] == want
+
+    kept = [b for b in blocks if any(po.sphere_sheet_intersect(centers[h], np.float32(r200[h]), b["Origin"], b["Width"],
+                                                               b["TotalWidth"]) for h in range(len(halos)))]
+    for h in range(len(halos)):
+        m = sum(po.mass_contained(b["TotalWidth"], b["xs"], b["ms"], coeffs[h], centers[h].astype(np.float32),
+                                  props[h, 9], props[h, 10]) for b in kept)
+        assert m > 0 and abs(masses[h] - m) <= 1e-12 * m
+        vols = np.array([po.shell_volume(coeffs[h], 50000, s) for s in range(1, 7)])
+        assert abs(props[h, 1] - vols.mean()) < 5 * vols.std(ddof=1) / np.sqrt(len(vols))
+        assert props[h, 9] < halos[h, 3] * 3 and props[h, 10] > props[h, 9] > 0
+
+    # SkipMass leaves the mass column at zero and reads no particle file (cmd/stats.go:316)
+    r2 = subprocess.run([H.cli_path(), "stats", "--SkipMass", "true"], input="\n".join(shell_lines) + "\n",
+                        capture_output=True, text=True, env=env, timeout=600)
+    assert r2.returncode == 0, r2.stderr
+    rows = [l.split() for l in r2.stdout.split("\n")[1:-1]]
+    assert all(float(row[2]) == 0.0 for row in rows)
+    assert [row[3:] for row in rows] == [l.split()[3:] for l in lines[1:]]
+    # the pipe sentinel of a failed upstream stage is passed on (shellfish.go:366-373)
+    r3 = subprocess.run([H.cli_path(), "stats"], input="Shellfish terminating.\n", capture_output=True, text=True, env=env)
+    assert r3.returncode == 1 and r3.stdout == "Shellfish terminating.\n"

@@ -426,3 +426,53 @@ def test_gadget2_big_endian(tmp_path):
     except ValueError:
         return   # a swapped header may fail validation before the particles are reached: also the reference's fate
     assert np.array_equal(xs, dm) and np.all(ms == 2.0)
+
+
+# ---- `shellfish stats` host side ---------------------------------------------------------
+
+def test_stats_config_defaults_flags_and_validation(tmp_path):   # cmd/stats.go:109-172
+    err, c = H.read_stats_config()
+    assert err == ""
+    assert c == dict(MonteCarloSamples=50000, Order=3, ShellWidth=0.0, SkipMass=False, shellFilter=False,
+                     ExclusionStrategy="none")
+    f = tmp_path / "stats.config"
+    f.write_text("[stats.config]\nOrder = 4\nExclusionStrategy = overlap\nValues = m_sp, r_sp\n")
+    err, c = H.read_stats_config(str(f), ["--SkipMass", "true"])
+    assert err == "" and c["Order"] == 4 and c["ExclusionStrategy"] == "overlap" and c["SkipMass"]
+    # shellFilter needs both a width and a file (cmd/stats.go:129-130,143-144)
+    assert H.read_stats_config(None, ["--ShellWidth", "0.05"])[1]["shellFilter"] is False
+    assert H.read_stats_config(None, ["--ShellWidth", "0.05", "--ShellParticleFile", "p.dat"])[1]["shellFilter"] is True
+    err, _ = H.read_stats_config(None, ["--Values", "m_sp,volume"])
+    assert err == "Item 1 of variable 'Values' is set to 'volume', which I don't recognize."
+    err, _ = H.read_stats_config(None, ["--ExclusionStrategy", "all"])
+    assert err == "variable 'ExclusionStrategy' set to 'all', which I don't recognize."
+    err, _ = H.read_stats_config(None, ["--MonteCarloSamples", "0"])
+    assert err == "The variable 'MonteCarloSamples' was set to %!g(int64=0)"   # Go's %g on an int64 (:167-168)
+    f.write_text("[shell.config]\nOrder = 4\n")
+    err, _ = H.read_stats_config(str(f))
+    assert "stats.config" in err
+
+
+def test_stats_cli_protocol_without_gpu(tmp_path):
+    assert "MonteCarloSamples" in _cli(["help", "stats.config"]).stdout
+    assert _cli(["stats"], stdin="").returncode == 0
+    r = _cli(["stats"], stdin="Shellfish terminating.\n")
+    assert r.returncode == 1 and r.stdout == "Shellfish terminating.\n"
+    row = "0 100 1 1 1 1 " + " ".join(["0.5"] + ["0"] * 17) + "\n"
+    r = _cli(["stats"], stdin=row)
+    assert r.returncode == 1 and r.stderr.startswith("Error running mode stats:\n")
+    assert "$SHELLFISH_GLOBAL_CONFIG has not been set." in r.stderr and r.stdout == "Shellfish terminating.\n"
+    cfg = tmp_path / "g.config"
+    cfg.write_text(GLOBAL % (tmp_path, tmp_path / "memo"))
+    env = {"SHELLFISH_GLOBAL_CONFIG": str(cfg)}
+    r = _cli(["stats", "--ExclusionStrategy", "most"], stdin=row, env=env)
+    assert r.returncode == 1 and "which I don't recognize." in r.stderr
+    # a shell catalog of another order has the wrong number of columns (catalog.Parse, cmd/stats.go:197-202)
+    r = _cli(["stats", "--Order", "4"], stdin=row, env=env)
+    assert r.returncode == 1 and r.stdout == "Shellfish terminating.\n"
+    r = _cli(["stats", "--ShellWidth", "0.1", "--ShellParticleFile", "x.dat"], stdin=row, env=env)
+    assert r.returncode == 1 and "not supported by this build" in r.stderr
+    import torch
+    if not torch.cuda.is_available():   # no CPU path: the device library refuses
+        r = _cli(["stats", "--SkipMass", "true"], stdin=row, env=env)
+        assert r.returncode == 1 and "Error running mode stats:" in r.stderr and r.stdout == "Shellfish terminating.\n"
