@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -154,6 +156,12 @@ int fail(sfk_ctx *c, int code, const std::string &msg) {
         if (e_ != cudaSuccess)                                                         \
             return fail(ctx, SFK_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
+
+// No C++ exception may cross the C ABI: every entry point that takes a context is a
+// function-try-block ending in this handler.
+#define SFK_CATCH(ctx)                                                                        \
+    catch (const std::bad_alloc &) { return fail(ctx, SFK_E_NOMEM, "out of host memory"); }   \
+    catch (const std::exception &e) { return fail(ctx, SFK_E_INVALID, std::string("internal error: ") + e.what()); }
 
 // ShellConfig.validate, cmd/shell.go:143-187
 int validate(sfk_ctx *ctx, const sfk_params &p) {
@@ -579,11 +587,18 @@ void sfk_default_params(sfk_params *p) {
     p->seed = 0; p->device = 0; p->flags = 0;
 }
 
+static int create_impl(sfk_ctx *ctx, const sfk_params *params);
+
 int sfk_create(sfk_ctx **out, const sfk_params *params) {
     if (!out || !params) return SFK_E_INVALID;
     *out = nullptr;
-    sfk_ctx *ctx = new sfk_ctx();
+    sfk_ctx *ctx = new (std::nothrow) sfk_ctx();
+    if (!ctx) return SFK_E_NOMEM;
     *out = ctx;  // returned even on failure so the caller can read the error
+    return create_impl(ctx, params);
+}
+
+static int create_impl(sfk_ctx *ctx, const sfk_params *params) try {
     ctx->p = *params;
     int rc = validate(ctx, *params);
     if (rc) return rc;
@@ -616,7 +631,7 @@ int sfk_create(sfk_ctx **out, const sfk_params *params) {
     CU(ctx->dBinInvG.upload(ctx->tab.binInvG, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
 void sfk_destroy(sfk_ctx *ctx) {
     if (!ctx) return;
@@ -626,7 +641,7 @@ void sfk_destroy(sfk_ctx *ctx) {
 
 const char *sfk_last_error(const sfk_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-int sfk_begin_snapshot(sfk_ctx *ctx, const sfk_cosmo *cosmo, float min_mass) {
+int sfk_begin_snapshot(sfk_ctx *ctx, const sfk_cosmo *cosmo, float min_mass) try {
     if (!ctx || !cosmo) return SFK_E_INVALID;
     CU(cudaSetDevice(ctx->p.device));
     ctx->cosmo0 = *cosmo;
@@ -637,10 +652,10 @@ int sfk_begin_snapshot(sfk_ctx *ctx, const sfk_cosmo *cosmo, float min_mass) {
     ctx->inSnapshot = true; ctx->finished = false; ctx->splitPhase = 0;
     ctx->stats = sfk_stats{};
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
 int sfk_add_halos(sfk_ctx *ctx, int64_t n, const double *x, const double *y, const double *z,
-                  const double *r200m) {
+                  const double *r200m) try {
     if (!ctx || !ctx->inSnapshot || n < 0) return fail(ctx, SFK_E_INVALID, "sfk_add_halos: no snapshot open");
     if (!ctx->halos.empty()) return fail(ctx, SFK_E_INVALID, "sfk_add_halos: halos already set");
     const sfk_params &p = ctx->p;
@@ -683,9 +698,9 @@ int sfk_add_halos(sfk_ctx *ctx, int64_t n, const double *x, const double *y, con
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stats.n_halos = n;
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
-int sfk_set_owned(sfk_ctx *ctx, int64_t n, const uint8_t *owned) {
+int sfk_set_owned(sfk_ctx *ctx, int64_t n, const uint8_t *owned) try {
     if (!ctx || !ctx->inSnapshot || !owned || n != static_cast<int64_t>(ctx->halos.size()))
         return fail(ctx, SFK_E_INVALID, "sfk_set_owned: call after sfk_add_halos with one flag per halo");
     if (ctx->candCount != 0) return fail(ctx, SFK_E_INVALID, "sfk_set_owned: blocks were already pushed");
@@ -693,10 +708,10 @@ int sfk_set_owned(sfk_ctx *ctx, int64_t n, const uint8_t *owned) {
     CU(ctx->dHalos.upload(ctx->halos, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
 int sfk_block_halo_mask(sfk_ctx *ctx, const float origin[3], const float width[3],
-                        double total_width, uint8_t *hit, int64_t *n_hit) {
+                        double total_width, uint8_t *hit, int64_t *n_hit) try {
     if (!ctx || !ctx->inSnapshot) return fail(ctx, SFK_E_INVALID, "sfk_block_halo_mask: no snapshot open");
     int64_t cnt = 0;
     for (size_t i = 0; i < ctx->halos.size(); i++) {
@@ -706,11 +721,11 @@ int sfk_block_halo_mask(sfk_ctx *ctx, const float origin[3], const float width[3
     }
     if (n_hit) *n_hit = cnt;
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
 int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
                    const sfk_cosmo *cosmo, double total_width, const float origin[3],
-                   const float width[3]) {
+                   const float width[3]) try {
     if (!ctx || !ctx->inSnapshot || ctx->finished || !cosmo || n < 0 || (n > 0 && (!xyz || !mass)))
         return fail(ctx, SFK_E_INVALID, "sfk_push_block: bad arguments or no snapshot open");
     CU(cudaSetDevice(ctx->p.device));
@@ -722,22 +737,22 @@ int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
     CU(cudaMemcpyAsync(ctx->dXyz.p, xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->dMass.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     return push_block_impl(ctx, ctx->dXyz.p, ctx->dMass.p, n, cosmo, total_width, origin, width);
-}
+} SFK_CATCH(ctx)
 
 int sfk_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass, int64_t n,
                           const sfk_cosmo *cosmo, double total_width, const float origin[3],
-                          const float width[3]) {
+                          const float width[3]) try {
     if (!ctx || !ctx->inSnapshot || ctx->finished || !cosmo || n < 0 || (n > 0 && (!d_xyz || !d_mass)))
         return fail(ctx, SFK_E_INVALID, "sfk_push_block_device: bad arguments or no snapshot open");
     CU(cudaSetDevice(ctx->p.device));
     // the caller's buffers live on other streams: order after everything queued so far
     CU(cudaDeviceSynchronize());
     return push_block_impl(ctx, d_xyz, d_mass, n, cosmo, total_width, origin, width);
-}
+} SFK_CATCH(ctx)
 
 int64_t sfk_row_length(const sfk_ctx *ctx) { return ctx ? ctx->P2 : 0; }
 
-int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) {
+int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) try {
     if (!ctx || !ctx->inSnapshot) return fail(ctx, SFK_E_INVALID, "sfk_finish_snapshot: no snapshot open");
     if (ctx->splitPhase != 0) return fail(ctx, SFK_E_INVALID, "sfk_finish_snapshot: a split-halo pass is open");
     CU(cudaSetDevice(ctx->p.device));
@@ -765,11 +780,11 @@ int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) {
         if (rc) return rc;
     }
     return stage_collect(ctx, coeffs, status);
-}
+} SFK_CATCH(ctx)
 
 // ---- split-halo mode: one halo's particles spread over several GPUs -----------
 
-int sfk_split_count(sfk_ctx *ctx) {
+int sfk_split_count(sfk_ctx *ctx) try {
     if (!ctx || !ctx->inSnapshot || ctx->splitPhase != 0)
         return fail(ctx, SFK_E_INVALID, "sfk_split_count: no snapshot open or split pass already started");
     CU(cudaSetDevice(ctx->p.device));
@@ -781,9 +796,9 @@ int sfk_split_count(sfk_ctx *ctx) {
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->splitPhase = 1;
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
-int sfk_split_bin(sfk_ctx *ctx) {
+int sfk_split_bin(sfk_ctx *ctx) try {
     if (!ctx || ctx->splitPhase != 1) return fail(ctx, SFK_E_INVALID, "sfk_split_bin: call sfk_split_count first");
     CU(cudaSetDevice(ctx->p.device));
     CU(cudaDeviceSynchronize());   // the caller's collectives ran on other streams
@@ -796,9 +811,9 @@ int sfk_split_bin(sfk_ctx *ctx) {
     if (rc) return rc;
     ctx->splitPhase = 2;
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
-int sfk_split_buffer(sfk_ctx *ctx, int32_t which, void **d_ptr, int64_t *count) {
+int sfk_split_buffer(sfk_ctx *ctx, int32_t which, void **d_ptr, int64_t *count) try {
     if (!ctx || !d_ptr || !count) return SFK_E_INVALID;
     const int64_t nHalo = static_cast<int64_t>(ctx->halos.size());
     switch (which) {
@@ -816,16 +831,16 @@ int sfk_split_buffer(sfk_ctx *ctx, int32_t which, void **d_ptr, int64_t *count) 
     default: break;
     }
     return fail(ctx, SFK_E_INVALID, "sfk_split_buffer: buffer not available in this phase");
-}
+} SFK_CATCH(ctx)
 
-int sfk_split_finish(sfk_ctx *ctx, double *coeffs, int32_t *status) {
+int sfk_split_finish(sfk_ctx *ctx, double *coeffs, int32_t *status) try {
     if (!ctx || ctx->splitPhase != 2) return fail(ctx, SFK_E_INVALID, "sfk_split_finish: call sfk_split_bin first");
     CU(cudaSetDevice(ctx->p.device));
     CU(cudaDeviceSynchronize());   // the caller's all-reduce of the grid
     int rc = stage_analyze(ctx, static_cast<int>(ctx->order.size()));
     if (rc) return rc;
     return stage_collect(ctx, coeffs, status);
-}
+} SFK_CATCH(ctx)
 
 // ---- `stats` mode: splashback mass --------------------------------------------------
 
@@ -838,7 +853,7 @@ int sfk_sphere_block_hit(const float center[3], float radius, const float origin
 }
 
 int sfk_mass_begin(sfk_ctx *ctx, int64_t n_halo, int32_t order, const float *centers, const double *coeffs,
-                   const double *r_low, const double *r_high) {
+                   const double *r_low, const double *r_high) try {
     if (!ctx || n_halo < 0 || order <= 0 || (n_halo > 0 && (!centers || !coeffs || !r_low || !r_high)))
         return fail(ctx, SFK_E_INVALID, "sfk_mass_begin: bad arguments");
     if (order > kMaxOrder) return fail(ctx, SFK_E_UNSUPPORTED, "Order above 4 is not supported.");
@@ -861,9 +876,9 @@ int sfk_mass_begin(sfk_ctx *ctx, int64_t n_halo, int32_t order, const float *cen
     CU(cudaStreamSynchronize(ctx->stream));   // the host vectors die here
     ctx->massHalos = n_halo; ctx->massOrder = order; ctx->massOpen = true;
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
-static int mass_push_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, int64_t n, double total_width) {
+static int mass_push_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, int64_t n, double total_width) try {
     MassArgs a{};
     a.xyz = dxyz; a.mass = dmass; a.n = n;
     a.tw2 = static_cast<float>(total_width) / 2;
@@ -875,9 +890,9 @@ static int mass_push_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, i
     CU(launch_mass(a, ctx->stream));
     ctx->stats.launches += 3;
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
-int sfk_mass_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n, double total_width) {
+int sfk_mass_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n, double total_width) try {
     if (!ctx || !ctx->massOpen || n < 0 || (n > 0 && (!xyz || !mass)))
         return fail(ctx, SFK_E_INVALID, "sfk_mass_push_block: call sfk_mass_begin first");
     if (n == 0 || ctx->massHalos == 0) return SFK_OK;
@@ -890,19 +905,19 @@ int sfk_mass_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64
     if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));   // the caller may reuse its buffers (io.VectorBuffer does)
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
 int sfk_mass_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass, int64_t n,
-                               double total_width) {
+                               double total_width) try {
     if (!ctx || !ctx->massOpen || n < 0 || (n > 0 && (!d_xyz || !d_mass)))
         return fail(ctx, SFK_E_INVALID, "sfk_mass_push_block_device: call sfk_mass_begin first");
     if (n == 0 || ctx->massHalos == 0) return SFK_OK;
     CU(cudaSetDevice(ctx->p.device));
     CU(cudaDeviceSynchronize());   // the caller's buffers live on other streams
     return mass_push_impl(ctx, d_xyz, d_mass, n, total_width);
-}
+} SFK_CATCH(ctx)
 
-int sfk_mass_finish(sfk_ctx *ctx, double *masses) {
+int sfk_mass_finish(sfk_ctx *ctx, double *masses) try {
     if (!ctx || !ctx->massOpen || (ctx->massHalos > 0 && !masses))
         return fail(ctx, SFK_E_INVALID, "sfk_mass_finish: call sfk_mass_begin first");
     CU(cudaSetDevice(ctx->p.device));
@@ -911,13 +926,13 @@ int sfk_mass_finish(sfk_ctx *ctx, double *masses) {
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->massOpen = false;
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
 // ---- `stats` mode: shell property integrals --------------------------------------------
 
 static_assert(SS_COUNT == SFK_SHELL_SUMS, "sum layout");
 
-int sfk_shell_props(sfk_ctx *ctx, int64_t n_halo, int32_t order, const double *coeffs, double *props) {
+int sfk_shell_props(sfk_ctx *ctx, int64_t n_halo, int32_t order, const double *coeffs, double *props) try {
     if (!ctx || n_halo < 0 || order <= 0 || (n_halo > 0 && (!coeffs || !props)))
         return fail(ctx, SFK_E_INVALID, "sfk_shell_props: bad arguments");
     if (order > kMaxOrder) return fail(ctx, SFK_E_UNSUPPORTED, "Order above 4 is not supported.");
@@ -948,9 +963,9 @@ int sfk_shell_props(sfk_ctx *ctx, int64_t n_halo, int32_t order, const double *c
     for (int64_t h = 0; h < n_halo; h++)
         shell_props_finalize(sums.data() + h * SS_COUNT, props + h * SFK_SHELL_PROPS);
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
-int sfk_shell_sums(sfk_ctx *ctx, int64_t n_halo, double *sums) {
+int sfk_shell_sums(sfk_ctx *ctx, int64_t n_halo, double *sums) try {
     if (!ctx || n_halo < 0 || (n_halo > 0 && !sums) || static_cast<size_t>(n_halo) * SS_COUNT > ctx->dPropSums.cap)
         return fail(ctx, SFK_E_INVALID, "sfk_shell_sums: call sfk_shell_props with at least n_halo halos first");
     CU(cudaSetDevice(ctx->p.device));
@@ -959,7 +974,7 @@ int sfk_shell_sums(sfk_ctx *ctx, int64_t n_halo, double *sums) {
                            cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
 int sfk_axes_from_moments(const double moments[9], double out[6]) {
     if (!moments || !out) return SFK_E_INVALID;
@@ -982,31 +997,31 @@ static int check_halo(sfk_ctx *ctx, int64_t halo, bool needTaps) {
     return SFK_OK;
 }
 
-int sfk_get_rsp(sfk_ctx *ctx, int64_t halo, double *r) {
+int sfk_get_rsp(sfk_ctx *ctx, int64_t halo, double *r) try {
     int rc = check_halo(ctx, halo, false);
     if (rc) return rc;
     const size_t rn = static_cast<size_t>(ctx->rings) * ctx->spokes;
     CU(cudaMemcpy(r, ctx->dRsp.p + halo * rn, rn * sizeof(double), cudaMemcpyDeviceToHost));
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
-int sfk_get_candidate_count(sfk_ctx *ctx, int64_t halo, int64_t *n) {
+int sfk_get_candidate_count(sfk_ctx *ctx, int64_t halo, int64_t *n) try {
     int rc = check_halo(ctx, halo, false);
     if (rc) return rc;
     *n = ctx->candPerHalo[halo];
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
-int sfk_get_profiles(sfk_ctx *ctx, int64_t halo, double *rho) {
+int sfk_get_profiles(sfk_ctx *ctx, int64_t halo, double *rho) try {
     int rc = check_halo(ctx, halo, true);
     if (rc) return rc;
     const size_t rnb = static_cast<size_t>(ctx->rings) * ctx->spokes * ctx->bins;
     CU(cudaMemcpy(rho, ctx->dProfiles.p + halo * rnb, rnb * sizeof(double), cudaMemcpyDeviceToHost));
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
 int sfk_get_counts(sfk_ctx *ctx, int64_t halo, uint32_t *n_insert, uint32_t *start_edges,
-                   uint32_t *end_edges) {
+                   uint32_t *end_edges) try {
     int rc = check_halo(ctx, halo, true);
     if (rc) return rc;
     const size_t rn = static_cast<size_t>(ctx->rings) * ctx->spokes, rnb = rn * ctx->bins;
@@ -1014,7 +1029,7 @@ int sfk_get_counts(sfk_ctx *ctx, int64_t halo, uint32_t *n_insert, uint32_t *sta
     if (start_edges) CU(cudaMemcpy(start_edges, ctx->dTapStart.p + halo * rnb, rnb * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (end_edges) CU(cudaMemcpy(end_edges, ctx->dTapEnd.p + halo * rnb, rnb * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return SFK_OK;
-}
+} SFK_CATCH(ctx)
 
 int sfk_get_ring_tables(const sfk_ctx *ctx, float *norms, float *rot, float *irot) {
     if (!ctx) return SFK_E_INVALID;
