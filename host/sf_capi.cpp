@@ -128,6 +128,22 @@ const char *sfh_read_stats_config(const char *fname, const char *flags, int64_t 
     return keep(err);
 }
 
+const char *sfh_read_prof_config(const char *fname, const char *flags, int64_t *ints4, double *floats3, char *ptype, int cap) {
+    ProfConfig c;
+    std::vector<std::string> args;
+    if (flags && *flags) {
+        std::string cur;
+        for (const char *p = flags; ; p++) {
+            if (*p == '\n' || !*p) { args.push_back(cur); cur.clear(); if (!*p) break; } else cur += *p;
+        }
+    }
+    std::string err = c.ReadConfig(fname ? fname : "", args);
+    ints4[0] = c.bins; ints4[1] = c.order; ints4[2] = c.samples; ints4[3] = c.medianPixelLevel;
+    floats3[0] = c.rMaxMult; floats3[1] = c.rMinMult; floats3[2] = c.percentile;
+    std::strncpy(ptype, c.pType.c_str(), cap - 1); ptype[cap - 1] = 0;
+    return keep(err);
+}
+
 const char *sfh_read_global_config(const char *fname, char *snapType, int cap, int64_t *blocks) {
     GlobalConfig g;
     std::string err = g.ReadConfig(fname);

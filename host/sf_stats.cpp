@@ -189,4 +189,106 @@ std::string RunStats(const GlobalConfig &g, const StatsConfig &c, const std::str
     return "";
 }
 
+// ---- `shellfish prof`, angular-fraction profiles ----------------------------------------
+
+std::string ProfConfig::ReadConfig(const std::string &fname, const std::vector<std::string> &flags) {
+    ConfigVars vars("prof.config");   // cmd/prof.go:103-151
+    vars.Int(&bins, "Bins", 150);
+    vars.Int(&order, "Order", 3);
+    vars.Int(&samples, "Samples", 50 * 1000);
+    vars.Float(&rMaxMult, "RMaxMult", 3.0);
+    vars.Float(&rMinMult, "RMinMult", 0.03);
+    vars.Int(&medianPixelLevel, "MedianPixelLevel", 3);
+    vars.Float(&percentile, "Percentile", 50);
+    vars.String(&pType, "ProfileType", "");
+    std::string err;
+    if (fname.empty()) {
+        if (flags.empty()) return "";
+        if (!(err = vars.ReadFlags(flags)).empty()) return err;
+    } else {
+        if (!(err = vars.ReadConfig(fname)).empty()) return err;
+        if (!(err = vars.ReadFlags(flags)).empty()) return err;
+    }
+    if (pType.empty()) return "The variable 'ProfileType' was not set.";
+    if (pType != "density" && pType != "median-density" && pType != "median-error" && pType != "contained-density" &&
+        pType != "angular-fraction" && pType != "bound-density")
+        return "The varaiable 'ProfileType' was set to '" + pType + "'.";   // sic, cmd/prof.go:147
+    return validate();
+}
+
+std::string ProfConfig::validate() const {   // cmd/prof.go:153-169, with its copy-paste slips
+    char buf[200];
+    if (bins < 0) { snprintf(buf, sizeof buf, "The variable 'Bins' was set to %lld.", static_cast<long long>(bins)); return buf; }
+    if (rMinMult <= 0) { snprintf(buf, sizeof buf, "The variable 'RMinMult' was set to %s.", go_g6(rMinMult).c_str()); return buf; }
+    if (rMaxMult <= 0) { snprintf(buf, sizeof buf, "The variable 'RMinMult' was set to %s.", go_g6(rMinMult).c_str()); return buf; }
+    if (medianPixelLevel < 0)
+        return "The variable 'MedianPixelLevel' was set to %!g(int64=" + std::to_string(medianPixelLevel) + ").";
+    return "";
+}
+
+const char *ProfConfig::ExampleConfig() {
+    return "[prof.config]\n\n"
+           "# ProfileType is required.  This build provides angular-fraction, the one type for which\n"
+           "# the reference prints a catalog (cmd/prof.go:414 returns early for the particle-based types).\n"
+           "ProfileType = angular-fraction\n\n"
+           "# Optional (defaults shown, cmd/prof.go:106-112).  Samples is accepted for compatibility: the\n"
+           "# fractions count one direction per equal-area stratum (1024 x 256) instead of random samples.\n"
+           "Bins = 150\nOrder = 3\nSamples = 50000\nRMaxMult = 3.0\nRMinMult = 0.03";
+}
+
+std::string RunProf(const GlobalConfig &g, const ProfConfig &c, const std::string &stdinData, int device,
+                    std::vector<std::string> &outLines) {
+    (void)g;
+    if (c.pType != "angular-fraction")
+        return "ProfileType = " + c.pType + " is not provided by this build: the reference's prof mode returns "
+               "without output for the particle-based profile types (cmd/prof.go:414).";
+    // cmd/prof.go:227-262
+    const size_t P2 = static_cast<size_t>(2 * c.order * c.order);
+    std::vector<int> floatIdx(4 + P2);
+    for (size_t i = 0; i < floatIdx.size(); i++) floatIdx[i] = static_cast<int>(i) + 2;
+    std::vector<std::vector<int64_t>> intCols;
+    std::vector<std::vector<double>> floatCols;
+    std::string err = Parse(stdinData, {0, 1}, floatIdx, intCols, floatCols);
+    if (!err.empty()) return err;
+    if (intCols.empty() || intCols[0].empty()) return "No input IDs.";
+    const std::vector<int64_t> &ids = intCols[0], &snaps = intCols[1];
+    const size_t n = ids.size();
+    const int bins = static_cast<int>(c.bins);
+    if (c.order <= 0 || c.order > 4) return "Order above 4 is not supported.";
+
+    std::vector<double> coeffs(n * P2), rMin(n), rMax(n);
+    for (size_t i = 0; i < n; i++) {
+        for (size_t k = 0; k < P2; k++) coeffs[i * P2 + k] = floatCols[4 + k][i];
+        rMin[i] = floatCols[3][i] * c.rMinMult;   // cmd/prof.go:641-642
+        rMax[i] = floatCols[3][i] * c.rMaxMult;
+    }
+    std::vector<double> rs(n * std::max(bins, 0)), fs(rs.size());
+    if (bins > 0) {
+        sfk_params p;
+        sfk_default_params(&p);
+        p.rings = 3; p.device = device;
+        sfk_ctx *sfk = nullptr;
+        struct Guard { sfk_ctx *&c; ~Guard() { if (c) sfk_destroy(c); } } guard{sfk};
+        if (sfk_create(&sfk, &p) != 0) return sfk_last_error(sfk);
+        if (sfk_angular_fraction(sfk, static_cast<int64_t>(n), static_cast<int32_t>(c.order), coeffs.data(), rMin.data(),
+                                 rMax.data(), bins, rs.data(), fs.data()) != 0)
+            return sfk_last_error(sfk);
+    }
+    // angularFractionMain, cmd/prof.go:628-661
+    std::vector<std::vector<double>> cols(2 * static_cast<size_t>(std::max(bins, 0)), std::vector<double>(n));
+    for (int j = 0; j < bins; j++)
+        for (size_t i = 0; i < n; i++) {
+            cols[j][i] = rs[i * bins + j];
+            cols[bins + j][i] = fs[i * bins + j];
+        }
+    std::vector<int> ord(cols.size() + 2);
+    for (size_t i = 0; i < ord.size(); i++) ord[i] = static_cast<int>(i);
+    std::vector<std::string> lines = FormatCols({ids, snaps}, cols, ord);
+    outLines.clear();
+    outLines.push_back(CommentString({"ID", "Snapshot", "R [cMpc/h]", "Volume Fraction Contained"}, {}, {0, 1, 2, 3},
+                                     {1, 1, bins, bins}));
+    outLines.insert(outLines.end(), lines.begin(), lines.end());
+    return "";
+}
+
 }  // namespace sfhost

@@ -31,4 +31,25 @@ struct StatsConfig {
 std::string RunStats(const GlobalConfig &g, const StatsConfig &c, const std::string &stdinData, int device,
                      std::vector<std::string> &outLines);
 
+// ProfConfig, cmd/prof.go:23-186.  Only ProfileType = angular-fraction is built: it is
+// the one profile type for which the reference prints anything (Run returns nil, nil
+// after the first particle block for every other type, cmd/prof.go:414).
+struct ProfConfig {
+    int64_t bins, order, samples;
+    double rMaxMult, rMinMult;
+    int64_t medianPixelLevel;
+    double percentile;
+    std::string pType;
+
+    std::string ReadConfig(const std::string &fname, const std::vector<std::string> &flags);
+    std::string validate() const;
+    static const char *ExampleConfig();
+};
+
+// ProfConfig.Run for the angular-fraction type (cmd/prof.go:188-275, 628-661): stdin =
+// the `shell` catalog, output = bin radii and the fraction of solid angle in which the
+// shell lies beyond them.
+std::string RunProf(const GlobalConfig &g, const ProfConfig &c, const std::string &stdinData, int device,
+                    std::vector<std::string> &outLines);
+
 }  // namespace sfhost

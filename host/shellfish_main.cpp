@@ -79,13 +79,15 @@ int main(int argc, char **argv) {
     if (mode == "help") {
         if (argc == 3 && std::string(argv[2]) == "shell.config") std::printf("%s\n", ShellConfig::ExampleConfig());
         else if (argc == 3 && std::string(argv[2]) == "stats.config") std::printf("%s\n", StatsConfig::ExampleConfig());
+        else if (argc == 3 && std::string(argv[2]) == "prof.config") std::printf("%s\n", ProfConfig::ExampleConfig());
         else std::printf("shellfish shell [shell.config] [--Flag value ...]\n"
-                         "shellfish stats [stats.config] [--Flag value ...]   (B200 build: the shell and stats modes)\n");
+                         "shellfish stats [stats.config] [--Flag value ...]\n"
+                         "shellfish prof  [prof.config]  [--Flag value ...]   (B200 build: shell, stats and prof's angular-fraction)\n");
         return 0;
     }
     if (mode == "version") { std::printf("Shellfish version %s\n", kSourceVersion); return 0; }
     if (mode == "hello") { std::printf("Hello back at you! Installation was successful.\n"); return 0; }
-    if (mode != "shell" && mode != "stats") {
+    if (mode != "shell" && mode != "stats" && mode != "prof") {
         std::fprintf(stderr, "You passed me the mode '%s', which this B200 build does not provide.\n"
                              "For help, type './shellfish help'\n", mode.c_str());
         std::printf("Shellfish terminating.\n");
@@ -112,8 +114,10 @@ int main(int argc, char **argv) {
     if (!err.empty()) die(mode, err);
     ShellConfig c;
     StatsConfig sc;
+    ProfConfig pc;
     if (mode == "shell") err = c.ReadConfig(configName, flags);
-    else err = sc.ReadConfig(configName, flags);
+    else if (mode == "stats") err = sc.ReadConfig(configName, flags);
+    else err = pc.ReadConfig(configName, flags);
     if (!err.empty()) die(mode, err);
     if (!(err = check_memo_dir(g.MemoDir, gName)).empty()) die(mode, err);
     if (g.SnapshotType == "nil") {
@@ -135,7 +139,8 @@ int main(int argc, char **argv) {
     std::vector<std::string> lines;
     try {
         if (mode == "shell") err = RunShell(g, c, stdinData, seed, device, lines);
-        else err = RunStats(g, sc, stdinData, device, lines);
+        else if (mode == "stats") err = RunStats(g, sc, stdinData, device, lines);
+        else err = RunProf(g, pc, stdinData, device, lines);
     } catch (const std::exception &e) {   // a Go panic ends the same way: message, then the pipe sentinel
         err = std::string("internal error: ") + e.what();
     }

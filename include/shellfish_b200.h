@@ -206,6 +206,18 @@ int sfk_shell_props(sfk_ctx *ctx, int64_t n_halo, int32_t order, const double *c
  * means of xx yy zz xy yz zx x y z (not yet divided by the mean area), min r,
  * max r. */
 int sfk_shell_sums(sfk_ctx *ctx, int64_t n_halo, double *sums);
+/* Shell.AngularFractionProfile (los/analyze/shell.go:295-335), the quantity
+ * `shellfish prof` prints for ProfileType = angular-fraction (cmd/prof.go:628-661):
+ * for each halo the fraction of solid angle in which the shell lies beyond radius
+ * r, in `bins` log-radial bins of [r_min, r_max] = R200m * [RMinMult, RMaxMult].
+ * Instead of `Samples` random directions the histogram counts one direction per
+ * equal-area stratum, SFK_FRACTION_STRATA_THETA midpoints in cos(theta) x
+ * SFK_FRACTION_STRATA_PHI in phi (262 144 directions; the default Samples is 50 000).
+ *   rs, fs  [n_halo][bins]  bin centres and fractions */
+#define SFK_FRACTION_STRATA_THETA 1024
+#define SFK_FRACTION_STRATA_PHI 256
+int sfk_angular_fraction(sfk_ctx *ctx, int64_t n_halo, int32_t order, const double *coeffs,
+                         const double *r_min, const double *r_max, int32_t bins, double *rs, double *fs);
 /* Shell.Axes from los/analyze/shell.go:140 on (inertia tensor, eigenvalues,
  * axis-ratio correction tables): moments = area-weighted means {xx, yy, zz, xy,
  * yz, zx, x, y, z}, out = {a, b, c, Ax, Ay, Az}.  Host arithmetic, no context. */

@@ -17,6 +17,7 @@
 #include "shellfish_oracle.h"
 
 #include <math.h>
+#include <stdint.h>
 #include <stdlib.h>
 
 /* ---- a uniform stream: math/rand/xorshift.go:13-33 of the reference's own package */
@@ -261,4 +262,31 @@ int orc_shell_axes(const double *cs, int order, int samples, orc_uniform_fn fn, 
     c = cRatio * c;
     *aOut = c; *bOut = bcRatio * bc * c; *cOut = acRatio * ac * c;
     return 0;
+}
+
+/* shell.go:295-335.  rs, fs: [bins].  Go's int() conversion of a float64 truncates
+ * toward zero; NaN and out-of-range values become the most negative int64 on amd64. */
+void orc_angular_fraction_profile(const double *cs, int order, int samples, int bins, double rMin, double rMax,
+                                  orc_uniform_fn fn, void *st, double *rs, double *fs) {
+    int64_t *ns = calloc((size_t)bins, sizeof(int64_t));
+    double lrMin = log(rMin), lrMax = log(rMax);
+    double dlr = (lrMax - lrMin) / (double)bins;
+
+    for (int i = 0; i < bins; i++) rs[i] = exp(lrMin + ((double)i + 0.5) * dlr);
+
+    for (int i = 0; i < samples; i++) {
+        double phi, theta;
+        random_angle(fn, st, &phi, &theta);
+        double lr = log(shell(cs, order, phi, theta));
+        double t = (lr - lrMin) / dlr;
+        int64_t lri = (t != t || t >= 9.2e18 || t <= -9.2e18) ? INT64_MIN : (int64_t)t;
+        if (lri < 0 || lri >= bins) continue;
+        ns[lri]++;
+    }
+
+    /* reverse cumulative sum */
+    for (int i = bins - 2; i >= 0; i--) ns[i] += ns[i + 1];
+
+    for (int i = 0; i < bins; i++) fs[i] = (double)ns[i] / (double)ns[0];
+    free(ns);
 }

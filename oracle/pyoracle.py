@@ -440,3 +440,16 @@ def shell_axes(cs, samples, seed=1, tables=None):
     rc = L.orc_shell_axes(dp(cs), order, samples, fn, C.byref(st), C.byref(tp) if tp is not None else None,
                           C.byref(a), C.byref(b), C.byref(c), dp(vec))
     return None if rc else (a.value, b.value, c.value, vec)
+
+
+def angular_fraction_profile(cs, samples, bins, r_min, r_max, seed=1):
+    """Shell.AngularFractionProfile, los/analyze/shell.go:295-335 -> (rs, fs)."""
+    L = lib()
+    cs, order = _cs_order(cs)
+    st, fn = _stream(seed)
+    rs, fs = np.zeros(bins), np.zeros(bins)
+    L.orc_angular_fraction_profile.argtypes = [c_double_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                               C.c_void_p, C.c_void_p, c_double_p, c_double_p]
+    L.orc_angular_fraction_profile.restype = None
+    L.orc_angular_fraction_profile(dp(cs), order, samples, bins, r_min, r_max, fn, C.byref(st), dp(rs), dp(fs))
+    return rs, fs

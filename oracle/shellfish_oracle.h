@@ -219,6 +219,8 @@ void orc_shell_radial_range(const double *cs, int order, int samples, orc_unifor
                             double *low, double *high);
 int orc_bicubic_eval(const double *xs, int nx, const double *ys, int ny, const double *vals,
                      double x, double y, double *out);
+void orc_angular_fraction_profile(const double *cs, int order, int samples, int bins, double rMin, double rMax,
+                                  orc_uniform_fn fn, void *st, double *rs, double *fs);
 int orc_shell_axes(const double *cs, int order, int samples, orc_uniform_fn fn, void *st,
                    const orc_axis_tables *tables, double *a, double *b, double *c, double aVec[3]);
 

@@ -51,12 +51,13 @@ EXPORTS = ["sfk_default_params", "sfk_create", "sfk_destroy", "sfk_last_error", 
            "sfk_add_halos", "sfk_set_owned", "sfk_block_halo_mask", "sfk_push_block", "sfk_push_block_device",
            "sfk_finish_snapshot", "sfk_row_length", "sfk_split_count", "sfk_split_bin", "sfk_split_buffer", "sfk_split_finish",
            "sfk_mass_begin", "sfk_mass_push_block", "sfk_mass_push_block_device", "sfk_mass_finish",
-           "sfk_sphere_block_hit", "sfk_shell_props", "sfk_shell_sums", "sfk_axes_from_moments", "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count",
+           "sfk_sphere_block_hit", "sfk_shell_props", "sfk_shell_sums", "sfk_angular_fraction", "sfk_axes_from_moments", "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count",
            "sfk_get_profiles", "sfk_get_counts", "sfk_get_ring_tables"]
 
 SHELL_PROPS = 11   # SFK_SHELL_PROPS
 SHELL_SUMS = 13    # SFK_SHELL_SUMS
 SHELL_RULE = (128, 256)   # SFK_SHELL_RULE_THETA, SFK_SHELL_RULE_PHI
+FRACTION_STRATA = (1024, 256)   # SFK_FRACTION_STRATA_THETA, SFK_FRACTION_STRATA_PHI
 
 _lib = None
 
@@ -288,6 +289,21 @@ class ShellContext:
         self._ck(lib().sfk_shell_props(self._h, C.c_int64(n), C.c_int32(order), coeffs.ctypes.data_as(dp_),
                                        out.ctypes.data_as(dp_)), "sfk_shell_props")
         return out
+
+    def angular_fraction(self, coeffs, r_min, r_max, bins):
+        """Shell.AngularFractionProfile (los/analyze/shell.go:295-335) for every row:
+        (rs, fs), each [n][bins]."""
+        coeffs = np.ascontiguousarray(coeffs, np.float64)
+        n = len(coeffs)
+        order = int(round((coeffs.shape[1] / 2) ** 0.5))
+        r_min = np.ascontiguousarray(np.broadcast_to(r_min, (n,)), np.float64)
+        r_max = np.ascontiguousarray(np.broadcast_to(r_max, (n,)), np.float64)
+        rs, fs = np.zeros((n, bins)), np.zeros((n, bins))
+        dp_ = C.POINTER(C.c_double)
+        self._ck(lib().sfk_angular_fraction(self._h, C.c_int64(n), C.c_int32(order), coeffs.ctypes.data_as(dp_),
+                                            r_min.ctypes.data_as(dp_), r_max.ctypes.data_as(dp_), C.c_int32(bins),
+                                            rs.ctypes.data_as(dp_), fs.ctypes.data_as(dp_)), "sfk_angular_fraction")
+        return rs, fs
 
     def shell_sums(self, n):
         """Parity tap: raw sums of the last shell_props call, [n][SHELL_SUMS]."""

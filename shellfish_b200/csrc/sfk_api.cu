@@ -932,6 +932,18 @@ int sfk_mass_finish(sfk_ctx *ctx, double *masses) try {
 
 static_assert(SS_COUNT == SFK_SHELL_SUMS, "sum layout");
 
+// Gauss-Legendre nodes / weights of the solid-angle rule, built once per context.
+static int ensure_rule(sfk_ctx *ctx) {
+    if (ctx->glTheta == SFK_SHELL_RULE_THETA) return SFK_OK;
+    std::vector<double> x, w;
+    gauss_legendre(SFK_SHELL_RULE_THETA, x, w);
+    CU(ctx->dGlX.upload(x, ctx->stream));
+    CU(ctx->dGlW.upload(w, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->glTheta = SFK_SHELL_RULE_THETA;
+    return SFK_OK;
+}
+
 int sfk_shell_props(sfk_ctx *ctx, int64_t n_halo, int32_t order, const double *coeffs, double *props) try {
     if (!ctx || n_halo < 0 || order <= 0 || (n_halo > 0 && (!coeffs || !props)))
         return fail(ctx, SFK_E_INVALID, "sfk_shell_props: bad arguments");
@@ -940,14 +952,8 @@ int sfk_shell_props(sfk_ctx *ctx, int64_t n_halo, int32_t order, const double *c
     if (n_halo > 0x7fffffff) return fail(ctx, SFK_E_INVALID, "sfk_shell_props: too many halos");
     CU(cudaSetDevice(ctx->p.device));
     const int nTheta = SFK_SHELL_RULE_THETA, nPhi = SFK_SHELL_RULE_PHI;
-    if (ctx->glTheta != nTheta) {
-        std::vector<double> x, w;
-        gauss_legendre(nTheta, x, w);
-        CU(ctx->dGlX.upload(x, ctx->stream));
-        CU(ctx->dGlW.upload(w, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        ctx->glTheta = nTheta;
-    }
+    int rcRule = ensure_rule(ctx);
+    if (rcRule) return rcRule;
     const size_t P2 = 2 * static_cast<size_t>(order) * order;
     CU(ctx->dPropCoeffs.ensure(P2 * n_halo));
     CU(ctx->dPropSums.ensure(static_cast<size_t>(SS_COUNT) * n_halo));
@@ -962,6 +968,43 @@ int sfk_shell_props(sfk_ctx *ctx, int64_t n_halo, int32_t order, const double *c
     CU(cudaStreamSynchronize(ctx->stream));
     for (int64_t h = 0; h < n_halo; h++)
         shell_props_finalize(sums.data() + h * SS_COUNT, props + h * SFK_SHELL_PROPS);
+    return SFK_OK;
+} SFK_CATCH(ctx)
+
+int sfk_angular_fraction(sfk_ctx *ctx, int64_t n_halo, int32_t order, const double *coeffs, const double *r_min,
+                         const double *r_max, int32_t bins, double *rs, double *fs) try {
+    if (!ctx || n_halo < 0 || order <= 0 || bins < 0 ||
+        (n_halo > 0 && bins > 0 && (!coeffs || !r_min || !r_max || !rs || !fs)))
+        return fail(ctx, SFK_E_INVALID, "sfk_angular_fraction: bad arguments");
+    if (order > kMaxOrder) return fail(ctx, SFK_E_UNSUPPORTED, "Order above 4 is not supported.");
+    if (bins > 4096) return fail(ctx, SFK_E_UNSUPPORTED, "Bins above 4096 is not supported.");
+    if (n_halo == 0 || bins == 0) return SFK_OK;
+    if (n_halo > 0x7fffffff) return fail(ctx, SFK_E_INVALID, "sfk_angular_fraction: too many halos");
+    CU(cudaSetDevice(ctx->p.device));
+    const size_t P2 = 2 * static_cast<size_t>(order) * order;
+    // one staging buffer: coefficients, rMin, rMax, then the fractions
+    CU(ctx->dPropCoeffs.ensure((P2 + 2) * n_halo));
+    CU(ctx->dPropSums.ensure(std::max<size_t>(static_cast<size_t>(bins), SS_COUNT) * n_halo));
+    double *dMin = ctx->dPropCoeffs.p + P2 * n_halo, *dMax = dMin + n_halo;
+    CU(cudaMemcpyAsync(ctx->dPropCoeffs.p, coeffs, P2 * n_halo * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dMin, r_min, n_halo * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dMax, r_max, n_halo * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ShellFractionArgs a{};
+    a.coeffs = ctx->dPropCoeffs.p; a.rMin = dMin; a.rMax = dMax;
+    a.fs = ctx->dPropSums.p;
+    a.nHalo = static_cast<int>(n_halo); a.order = order; a.bins = bins;
+    a.nTheta = SFK_FRACTION_STRATA_THETA; a.nPhi = SFK_FRACTION_STRATA_PHI;
+    CU(launch_shell_fraction(a, ctx->stream));
+    ctx->stats.launches += 1;
+    CU(cudaMemcpyAsync(fs, ctx->dPropSums.p, static_cast<size_t>(bins) * n_halo * sizeof(double), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    // bin centres, shell.go:304-309
+    for (int64_t h = 0; h < n_halo; h++) {
+        const double lrMin = std::log(r_min[h]), lrMax = std::log(r_max[h]);
+        const double dlr = (lrMax - lrMin) / static_cast<double>(bins);
+        for (int i = 0; i < bins; i++) rs[h * bins + i] = std::exp(lrMin + (static_cast<double>(i) + 0.5) * dlr);
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
     return SFK_OK;
 } SFK_CATCH(ctx)
 

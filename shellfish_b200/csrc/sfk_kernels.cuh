@@ -113,6 +113,15 @@ struct ShellPropArgs {
     int nHalo, order, nTheta, nPhi;
 };
 cudaError_t launch_shell_props(const ShellPropArgs &a, cudaStream_t s);
+
+// `prof` angular-fraction profile, los/analyze/shell.go:295-335
+struct ShellFractionArgs {
+    const double *coeffs;        // [nHalo][2*order*order]
+    const double *rMin, *rMax;   // [nHalo] profile range, cmd/prof.go:641-642
+    double *fs;                  // [nHalo][bins]
+    int nHalo, order, bins, nTheta, nPhi;
+};
+cudaError_t launch_shell_fraction(const ShellFractionArgs &a, cudaStream_t s);
 cudaError_t launch_cull(const CullArgs &a, bool fill, cudaStream_t s);
 cudaError_t launch_hit_count(const Piece *pieces, int nPieces, const Cand *cands, const HaloDev *halos,
                              const float *norms, int rings, uint32_t *hitCount,

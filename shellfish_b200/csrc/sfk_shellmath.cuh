@@ -131,4 +131,25 @@ SFK_HD inline void shell_rule_node(int q, int nPhi, const double *glX, const dou
     w = glW[it] * 0.5 / nPhi;
 }
 
+// Bin of one sample of Shell.AngularFractionProfile (shell.go:311-318): Go's int()
+// truncates toward zero, so (lr - lrMin)/dlr in (-1, 0) lands in bin 0; NaN converts to
+// the most negative int64 on amd64 and is skipped.  Returns -1 for "continue".
+SFK_HD inline int shell_fraction_bin(double r, double lrMin, double dlr, int bins) {
+    const double lr = log(r);
+    const double t = (lr - lrMin) / dlr;
+    if (!(t > -1.0)) return -1;               // negative index or NaN
+    if (t >= static_cast<double>(bins)) return -1;
+    return static_cast<int>(t);
+}
+
+// Direction q of the angular-fraction profile's sample: a histogram is not a smooth
+// functional, so instead of the Gauss-Legendre rule it uses equal-area strata -- nTheta
+// midpoints in cos(theta) x nPhi midpoints in phi, every direction with the same weight,
+// so the histogram holds integer counts exactly like the reference's.
+SFK_HD inline void shell_stratum(int q, int nTheta, int nPhi, double &phi, double &theta) {
+    const int it = q / nPhi, ip = q - it * nPhi;
+    phi = 6.283185307179586 * ((ip + 0.5) / nPhi);
+    theta = acos(-1.0 + (it + 0.5) * (2.0 / nTheta));
+}
+
 }  // namespace sfk

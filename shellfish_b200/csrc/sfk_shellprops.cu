@@ -66,7 +66,44 @@ __global__ void __launch_bounds__(kPropThreads) shell_props_kernel(ShellPropArgs
     }
 }
 
+// Shell.AngularFractionProfile, shell.go:295-335, for `prof`'s angular-fraction type
+// (cmd/prof.go:628-661): histogram of ln R(phi, theta) over the rule's nodes in `bins`
+// log-radial bins of [rMin, rMax], reverse cumulative sum, normalised by its first entry.
+// The directions are nTheta x nPhi equal-area strata (shell_stratum), so the histogram
+// holds integer counts: independent of the atomic order.
+__global__ void __launch_bounds__(kPropThreads) shell_fraction_kernel(ShellFractionArgs a) {
+    extern __shared__ unsigned long long sHist[];
+    __shared__ double sCs[2 * kShellMaxOrder * kShellMaxOrder];
+    const int h = blockIdx.x;
+    const int P2 = 2 * a.order * a.order;
+    for (int i = threadIdx.x; i < P2; i += kPropThreads) sCs[i] = a.coeffs[static_cast<size_t>(h) * P2 + i];
+    for (int i = threadIdx.x; i < a.bins; i += kPropThreads) sHist[i] = 0ull;
+    __syncthreads();
+    const double lrMin = log(a.rMin[h]), lrMax = log(a.rMax[h]);
+    const double dlr = (lrMax - lrMin) / static_cast<double>(a.bins);
+    const int nNodes = a.nTheta * a.nPhi;
+    for (int q = threadIdx.x; q < nNodes; q += kPropThreads) {
+        double phi, theta;
+        shell_stratum(q, a.nTheta, a.nPhi, phi, theta);
+        const int b = shell_fraction_bin(penna_radius(sCs, a.order, phi, theta), lrMin, dlr, a.bins);
+        if (b >= 0) atomicAdd(&sHist[b], 1ull);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)   // reverse cumulative sum, shell.go:325-328
+        for (int i = a.bins - 2; i >= 0; i--) sHist[i] += sHist[i + 1];
+    __syncthreads();
+    const double n0 = static_cast<double>(sHist[0]);
+    for (int i = threadIdx.x; i < a.bins; i += kPropThreads)
+        a.fs[static_cast<size_t>(h) * a.bins + i] = static_cast<double>(sHist[i]) / n0;   // :330-332
+}
+
 }  // namespace
+
+cudaError_t launch_shell_fraction(const ShellFractionArgs &a, cudaStream_t s) {
+    if (a.nHalo <= 0 || a.bins <= 0) return cudaSuccess;
+    shell_fraction_kernel<<<static_cast<unsigned>(a.nHalo), kPropThreads, a.bins * sizeof(unsigned long long), s>>>(a);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_shell_props(const ShellPropArgs &a, cudaStream_t s) {
     if (a.nHalo <= 0) return cudaSuccess;

@@ -18,7 +18,7 @@ def lib():
             raise RuntimeError("libsfhost.so is missing: run `make -C host` (or __graft_entry__.build())")
         _lib = C.CDLL(path)
         for name in ("sfh_go_g6", "sfh_comment_string", "sfh_format_cols", "sfh_last_text", "sfh_read_test_config",
-                     "sfh_read_shell_config", "sfh_read_stats_config", "sfh_read_global_config", "sfh_catalog_name"):
+                     "sfh_read_shell_config", "sfh_read_stats_config", "sfh_read_prof_config", "sfh_read_global_config", "sfh_catalog_name"):
             getattr(_lib, name).restype = C.c_char_p
         _lib.sfh_go_g6.argtypes = [C.c_double]
         _lib.sfh_read_block.restype = C.c_int64
@@ -99,6 +99,16 @@ def read_stats_config(fname=None, flags=()):
                                       ints, C.byref(width), bools, strat, 64).decode()
     return err, dict(MonteCarloSamples=ints[0], Order=ints[1], ShellWidth=width.value, SkipMass=bool(bools[0]),
                      shellFilter=bool(bools[1]), ExclusionStrategy=strat.value.decode())
+
+
+def read_prof_config(fname=None, flags=()):
+    """ProfConfig.ReadConfig + validate, cmd/prof.go:103-169."""
+    ints, floats = (C.c_int64 * 4)(), (C.c_double * 3)()
+    ptype = C.create_string_buffer(64)
+    err = lib().sfh_read_prof_config(None if fname is None else fname.encode(), "\n".join(flags).encode(),
+                                     ints, floats, ptype, 64).decode()
+    return err, dict(Bins=ints[0], Order=ints[1], Samples=ints[2], MedianPixelLevel=ints[3], RMaxMult=floats[0],
+                     RMinMult=floats[1], Percentile=floats[2], ProfileType=ptype.value.decode())
 
 
 def read_global_config(fname):

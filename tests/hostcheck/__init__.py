@@ -26,6 +26,7 @@ def lib():
         L.hc_cos_norm.argtypes = [_dp, C.c_int, C.c_double, C.c_double]
         L.hc_shell_sums.argtypes = [_dp, C.c_int, C.c_int, C.c_int, _dp]
         L.hc_shell_props.argtypes = [_dp, C.c_int, C.c_int, C.c_int, _dp]
+        L.hc_angular_fraction.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _dp]
         L.hc_gauss_legendre.argtypes = [C.c_int, _dp, _dp]
         _LIB = L
     return _LIB
@@ -64,3 +65,10 @@ def gauss_legendre(n):
     x, w = np.zeros(n), np.zeros(n)
     lib().hc_gauss_legendre(n, x.ctypes.data_as(_dp), w.ctypes.data_as(_dp))
     return x, w
+
+
+def angular_fraction(cs, r_min, r_max, bins, n_theta=1024, n_phi=256):
+    cs, order = _cs(cs)
+    out = np.zeros(bins)
+    lib().hc_angular_fraction(cs.ctypes.data_as(_dp), order, n_theta, n_phi, r_min, r_max, bins, out.ctypes.data_as(_dp))
+    return out

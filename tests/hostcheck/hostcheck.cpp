@@ -38,6 +38,22 @@ void hc_shell_props(const double *cs, int order, int nTheta, int nPhi, double *p
     sfk::shell_props_finalize(sums, props);
 }
 
+// shell_fraction_kernel's histogram for one halo.
+void hc_angular_fraction(const double *cs, int order, int nTheta, int nPhi, double rMin, double rMax, int bins,
+                         double *fs) {
+    std::vector<unsigned long long> hist(bins, 0ull);
+    const double lrMin = std::log(rMin), lrMax = std::log(rMax);
+    const double dlr = (lrMax - lrMin) / static_cast<double>(bins);
+    for (int q = 0; q < nTheta * nPhi; q++) {
+        double phi, theta;
+        sfk::shell_stratum(q, nTheta, nPhi, phi, theta);
+        const int b = sfk::shell_fraction_bin(sfk::penna_radius(cs, order, phi, theta), lrMin, dlr, bins);
+        if (b >= 0) hist[b] += 1;
+    }
+    for (int i = bins - 2; i >= 0; i--) hist[i] += hist[i + 1];
+    for (int i = 0; i < bins; i++) fs[i] = static_cast<double>(hist[i]) / static_cast<double>(hist[0]);
+}
+
 void hc_gauss_legendre(int n, double *x, double *w) {
     std::vector<double> xv, wv;
     sfk::gauss_legendre(n, xv, wv);

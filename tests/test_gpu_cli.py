@@ -272,3 +272,22 @@ def test_shell_stats_pipeline(tmp_path):
     # the pipe sentinel of a failed upstream stage is passed on (shellfish.go:366-373)
     r3 = subprocess.run([H.cli_path(), "stats"], input="Shellfish terminating.\n", capture_output=True, text=True, env=env)
     assert r3.returncode == 1 and r3.stdout == "Shellfish terminating.\n"
+
+
+def test_prof_angular_fraction_cli(tmp_path):
+    """`shellfish shell | shellfish prof --ProfileType angular-fraction` (cmd/prof.go:628-661)."""
+    halos, blocks, min_mass, cfg = _setup(tmp_path, 16, 2, 20000, 10000, 1)
+    shell_lines = _run_cli(cfg, halos, ["--Rings", "8"])
+    env = dict(os.environ, SHELLFISH_GLOBAL_CONFIG=cfg)
+    r = subprocess.run([H.cli_path(), "prof", "--ProfileType", "angular-fraction", "--Bins", "40"],
+                       input="\n".join(shell_lines) + "\n", capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.split("\n")[:-1]
+    assert lines[0] == "# Column contents: ID(0) Snapshot(1) R [cMpc/h](2-41) Volume Fraction Contained(42-81)"
+    ic, fc = H.parse_catalog("\n".join(shell_lines) + "\n", [0, 1], list(range(2, 24)))
+    r200, coeffs = fc[3].copy(), fc[4:].T.copy()
+    ctx = api.ShellContext(api.default_params(rings=3))
+    rs, fs = ctx.angular_fraction(coeffs, 0.03 * r200, 3.0 * r200, 40)
+    want = H.format_cols([ic[0], ic[1]], [rs[:, j] for j in range(40)] + [fs[:, j] for j in range(40)], list(range(82)))
+    assert lines[1:] == want
+    assert np.all(fs[:, 0] == 1.0) and np.all(fs[:, -1] < 1.0)

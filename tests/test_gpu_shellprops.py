@@ -78,3 +78,26 @@ def test_radial_range_feeds_the_mass_pass():
     # and the range brackets the surface well enough that a 2 % wider one counts the same particles
     wide = ctx.mass_contained(centers, rows, 0.98 * lo, 1.02 * hi, blocks)
     np.testing.assert_allclose(wide, got, rtol=2e-4)
+
+
+def test_angular_fraction_kernel():
+    """sfk_angular_fraction = its host-compiled source (integer histogram: exactly), and the
+    Monte-Carlo restatement within noise; NaN rows where no direction falls in range."""
+    rng = np.random.default_rng(80)
+    ctx = api.ShellContext(api.default_params(rings=3))
+    for order in (2, 3, 4):
+        rows = np.array([shells.random_shell(rng, order, radius=rng.uniform(0.5, 2), amp=0.4) for _ in range(9)])
+        r200 = rng.uniform(0.4, 1.5, len(rows))
+        rs, fs = ctx.angular_fraction(rows, 0.03 * r200, 3.0 * r200, 150)
+        for h, cs in enumerate(rows):
+            want = hc.angular_fraction(cs, 0.03 * r200[h], 3.0 * r200[h], 150, *api.FRACTION_STRATA)
+            # a node within an ulp of a bin edge may fall either side (CUDA vs glibc log / sincos)
+            assert np.abs(fs[h] - want).max() < 1e-4
+            assert np.sum(fs[h] != want) <= 4
+            lr = np.log(0.03 * r200[h]) + (np.arange(150) + 0.5) * (np.log(3.0 * r200[h]) - np.log(0.03 * r200[h])) / 150
+            np.testing.assert_allclose(rs[h], np.exp(lr), rtol=1e-14)
+        fm = po.angular_fraction_profile(rows[0], 200000, 150, 0.03 * r200[0], 3.0 * r200[0], seed=9)[1]
+        assert np.abs(fs[0] - fm).max() < 5 * np.sqrt(0.25 / 200000)
+    _, fs = ctx.angular_fraction(np.array([shells.sphere(0.5)]), 1.0, 2.0, 10)
+    assert np.all(np.isnan(fs))
+    assert ctx.angular_fraction(np.zeros((0, 18)), 1.0, 2.0, 10)[1].shape == (0, 10)

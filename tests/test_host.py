@@ -476,3 +476,25 @@ def test_stats_cli_protocol_without_gpu(tmp_path):
     if not torch.cuda.is_available():   # no CPU path: the device library refuses
         r = _cli(["stats", "--SkipMass", "true"], stdin=row, env=env)
         assert r.returncode == 1 and "Error running mode stats:" in r.stderr and r.stdout == "Shellfish terminating.\n"
+
+
+def test_prof_config(tmp_path):   # cmd/prof.go:103-169
+    err, c = H.read_prof_config()
+    assert err == "" and c["Bins"] == 150 and c["RMinMult"] == 0.03 and c["RMaxMult"] == 3.0 and c["Samples"] == 50000
+    assert H.read_prof_config(None, ["--Bins", "10"])[0] == "The variable 'ProfileType' was not set."
+    assert H.read_prof_config(None, ["--ProfileType", "mean"])[0] == "The varaiable 'ProfileType' was set to 'mean'."
+    err, c = H.read_prof_config(None, ["--ProfileType", "angular-fraction", "--Bins", "40"])
+    assert err == "" and c["ProfileType"] == "angular-fraction" and c["Bins"] == 40
+    assert H.read_prof_config(None, ["--ProfileType", "density", "--Bins", "-2"])[0] == "The variable 'Bins' was set to -2."
+    # the reference reports RMinMult (name and value) when RMaxMult is the bad one (cmd/prof.go:160-162)
+    assert H.read_prof_config(None, ["--ProfileType", "density", "--RMaxMult", "-1"])[0] == \
+        "The variable 'RMinMult' was set to 0.03."
+    assert H.read_prof_config(None, ["--ProfileType", "density", "--MedianPixelLevel", "-1"])[0] == \
+        "The variable 'MedianPixelLevel' was set to %!g(int64=-1)."
+    r = _cli(["prof", "--ProfileType", "angular-fraction"], stdin="Shellfish terminating.\n")
+    assert r.returncode == 1 and r.stdout == "Shellfish terminating.\n"
+    cfg = tmp_path / "g.config"
+    cfg.write_text(GLOBAL % (tmp_path, tmp_path / "memo"))
+    row = "0 100 1 1 1 1 " + " ".join(["0.5"] + ["0"] * 17) + "\n"
+    r = _cli(["prof", "--ProfileType", "median-density"], stdin=row, env={"SHELLFISH_GLOBAL_CONFIG": str(cfg)})
+    assert r.returncode == 1 and "is not provided by this build" in r.stderr and r.stdout == "Shellfish terminating.\n"

@@ -209,3 +209,37 @@ def test_committed_tables_are_what_the_generator_writes(tmp_path):
     subprocess.run([sys.executable, os.path.join(shells.ROOT, "scripts", "make_axis_tables.py"), str(out)], check=True)
     committed = open(os.path.join(shells.ROOT, "shellfish_b200", "csrc", "sfk_axis_tables.inc")).read()
     assert out.read_text() == committed
+
+
+def test_angular_fraction_profile():
+    """Shell.AngularFractionProfile (shell.go:295-335): closed form for R = 1 + e cos(theta)
+    -- the fraction of directions with R > r is (1 - (r - 1)/e)/2 -- and the Monte-Carlo
+    restatement within its binomial noise."""
+    e = 0.3
+    cs = shells.sphere(1.0)
+    cs[9] = e
+    bins, r_min, r_max = 150, 0.3, 3.0
+    f = hc.angular_fraction(cs, r_min, r_max, bins)
+    edges = np.exp(np.log(r_min) + np.arange(bins) * (np.log(r_max) - np.log(r_min)) / bins)
+    exact = np.clip((1 - (edges - 1) / e) / 2, 0, 1)     # fs[i] counts directions whose bin is >= i
+    assert np.abs(f - exact).max() < 1.01 / 1024          # one stratum of cos(theta): the worst case, an axisymmetric shell
+    assert f[0] == 1.0 and np.all(np.diff(f) <= 0) and f[-1] == 0.0
+    rs, fm = po.angular_fraction_profile(cs, 200000, bins, r_min, r_max, seed=3)
+    assert np.allclose(rs, np.exp(np.log(r_min) + (np.arange(bins) + 0.5) * (np.log(r_max) - np.log(r_min)) / bins))
+    assert np.abs(f - fm).max() < 5 * np.sqrt(0.25 / 200000)
+    rng = np.random.default_rng(41)
+    for order in (2, 3, 4):
+        cs = shells.random_shell(rng, order, radius=1.0, amp=0.4)
+        f = hc.angular_fraction(cs, 0.5, 2.0, 60)
+        fm = po.angular_fraction_profile(cs, 200000, 60, 0.5, 2.0, seed=order)[1]
+        assert np.abs(f - fm).max() < 5 * np.sqrt(0.25 / 200000)
+
+
+def test_angular_fraction_bin_truncation():
+    """Go's int() truncates toward zero: a surface slightly inside rMin is still counted in
+    bin 0 (shell.go:313-318); one far inside is skipped and the profile is 0/0 = NaN."""
+    assert np.all(hc.angular_fraction(shells.sphere(0.999), 1.0, 2.0, 10)[:1] == 1.0)
+    rs, fm = po.angular_fraction_profile(shells.sphere(0.999), 100, 10, 1.0, 2.0)
+    assert fm[0] == 1.0 and fm[1] == 0.0
+    assert np.all(np.isnan(hc.angular_fraction(shells.sphere(0.5), 1.0, 2.0, 10)))
+    assert np.all(np.isnan(po.angular_fraction_profile(shells.sphere(0.5), 100, 10, 1.0, 2.0)[1]))
