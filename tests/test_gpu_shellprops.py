@@ -87,11 +87,16 @@ def test_angular_fraction_kernel():
     ctx = api.ShellContext(api.default_params(rings=3))
     for order in (2, 3, 4):
         rows = np.array([shells.random_shell(rng, order, radius=rng.uniform(0.5, 2), amp=0.4) for _ in range(9)])
-        r200 = rng.uniform(0.4, 1.5, len(rows))
+        r200 = rows[:, 0] * rng.uniform(0.5, 1.2, len(rows))     # R_sp / R200m between 0.8 and 2
+        r200[-1] = rows[-1, 0] / 8                               # a shell wholly beyond rMax: 0/0 rows
         rs, fs = ctx.angular_fraction(rows, 0.03 * r200, 3.0 * r200, 150)
+        assert np.all(np.isnan(fs[-1])) and not np.isnan(fs[:-1]).any()
         for h, cs in enumerate(rows):
             want = hc.angular_fraction(cs, 0.03 * r200[h], 3.0 * r200[h], 150, *api.FRACTION_STRATA)
             # a node within an ulp of a bin edge may fall either side (CUDA vs glibc log / sincos)
+            if h == len(rows) - 1:
+                assert np.all(np.isnan(want))
+                continue
             assert np.abs(fs[h] - want).max() < 1e-4
             assert np.sum(fs[h] != want) <= 4
             lr = np.log(0.03 * r200[h]) + (np.arange(150) + 0.5) * (np.log(3.0 * r200[h]) - np.log(0.03 * r200[h])) / 150
