@@ -42,6 +42,10 @@ extern "C" {
 
 /* sfk_params.flags */
 #define SFK_FLAG_TAPS 1u /* keep parity taps: profiles, integer edge counts */
+/* Experimental: evaluate the two Savitzky-Golay filters of Smooth (smooth.go:46-81)
+ * through five sliding polynomial moments instead of 2 x SmoothingWindow taps per bin.
+ * Same result to ~1e-13 (not bit-identical to the tap loop); off by default. */
+#define SFK_FLAG_LOS_MOMENTS 2u
 
 typedef struct sfk_ctx sfk_ctx;
 

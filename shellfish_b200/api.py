@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsfk.so")
 
 SFK_FLAG_TAPS = 1
+SFK_FLAG_LOS_MOMENTS = 2   # experimental, see include/shellfish_b200.h
 SPLIT_HIT_COUNTS, SPLIT_RHO_MAX, SPLIT_GRID = 0, 1, 2
 HALO_STATUS = {0: "ok", 1: "skipped", 2: "no_points", 3: "no_maximum", 4: "spline", 5: "singular",
                6: "not_owned"}

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "sfk_kernels.cuh"
+#include "sfk_sgmath.cuh"
 #include "sfk_shellmath.cuh"
 
 using namespace sfk;
@@ -80,6 +81,8 @@ struct sfk_ctx {
     DevBuf<float> dNorms, dRots, dIrots;
     DevBuf<double> dCos, dSin, dPhi, dTaps0, dTaps1, dBinInvG;
     bool tapsReady = false;  // Sav-Gol kernels cached for the process, smooth.go:84-96
+    SgPoly sg{};             // the same taps as polynomials of the offset (SFK_FLAG_LOS_MOMENTS)
+    bool sgReady = false;
 
     // snapshot state
     bool inSnapshot = false, finished = false;
@@ -342,6 +345,7 @@ int stage_prepare(sfk_ctx *ctx) {
             CU(ctx->dTaps1.upload(k1, st));
             CU(cudaStreamSynchronize(st));
             ctx->tapsReady = true;
+            ctx->sgReady = savgol_poly(k0, k1, ctx->sg);
             break;
         }
     }
@@ -505,8 +509,14 @@ int stage_analyze(sfk_ctx *ctx, int nb) {
     la.rsp = ctx->dRsp.p; la.profiles = ctx->taps ? ctx->dProfiles.p : nullptr;
     la.rings = R; la.spokes = n; la.bins = B; la.window = static_cast<int>(ctx->p.smoothing_window);
     la.dLim = ctx->p.los_slope_cutoff;
+    // Experimental sliding-moment smoothing: only when every ln(rho) is finite (rho_bg > 0; with
+    // Gadget-2's MinMass() == 0 the reference's -Inf / NaN propagation must stay sample-exact).
+    bool moments = (ctx->p.flags & SFK_FLAG_LOS_MOMENTS) && ctx->sgReady && los_moments_supported(la);
+    for (const HaloDev &h : ctx->halos)
+        if (h.valid && !(h.defaultRho > 0)) moments = false;
     ctx->timer.begin(ST_LOS, st);
-    CU(launch_los(la, nb, st));
+    if (moments) CU(launch_los_moments(la, ctx->sg, nb, st));
+    else CU(launch_los(la, nb, st));
     ctx->stats.launches++;
     ctx->timer.end(ST_LOS, st);
 

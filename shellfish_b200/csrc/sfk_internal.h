@@ -77,6 +77,8 @@ double rho_average(double H0, double omegaM, double omegaL, double z);
 // Savitzky-Golay value / first-derivative taps (order 4), smooth.go:84-96.
 bool savgol_taps(int order, int width, int ld, double dx, std::vector<double> &taps);
 double go_pow(double x, double y);
+struct SgPoly;   // sfk_sgmath.cuh
+bool savgol_poly(const std::vector<double> &taps0, const std::vector<double> &taps1, SgPoly &out);
 // `stats` shell properties (sfk_axes.cpp): quadrature rule and per-halo closing arithmetic.
 void gauss_legendre(int n, std::vector<double> &x, std::vector<double> &w);
 void axes_from_moments(const double m[9], double out[6]);

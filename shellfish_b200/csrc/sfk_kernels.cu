@@ -17,6 +17,7 @@
 
 #include "sfk_kernels.cuh"
 #include "sfk_device.cuh"
+#include "sfk_sgmath.cuh"
 
 namespace sfk {
 
@@ -517,6 +518,152 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
             }
         }
     }
+#pragma unroll
+    for (int c = 0; c < PER; c++) s0[c] = exp(s0[c]);   // vals; s1 = d ln rho / d ln r
+
+    // SplashbackRadius: rhoMin starts at vals[0]; i = 1 .. B-2 is a candidate when
+    // vals[i] < min(vals[0..i-1]) and derivs[i] is a strict local minimum below dLim.
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const double v0 = __shfl_sync(0xffffffffu, s0[0], 0);
+    double lmin = inf;
+#pragma unroll
+    for (int c = 0; c < PER; c++) { const double v = s0[c]; if (v < lmin) lmin = v; }
+    double excl = lmin;   // inclusive prefix min over lanes, then shifted
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, excl, o);
+        if (lane >= o && up < excl) excl = up;
+    }
+    excl = __shfl_up_sync(0xffffffffu, excl, 1);
+    if (lane == 0) excl = inf;
+    const double dPrev = __shfl_up_sync(0xffffffffu, s1[PER - 1], 1);
+    const double dNext = __shfl_down_sync(0xffffffffu, s1[0], 1);
+    double runMin = excl, best = a.dLim;
+    int bestI = -1;
+#pragma unroll
+    for (int c = 0; c < PER; c++) {
+        const int i = i0 + c;
+        const double v = s0[c];
+        if (i == 0) { runMin = v; continue; }           // rhoMin := rhos[0]
+        if (v < runMin) {
+            runMin = v;
+            const double dm = c == 0 ? dPrev : s1[c == 0 ? 0 : c - 1];
+            const double dp = c == PER - 1 ? dNext : s1[c == PER - 1 ? c : c + 1];
+            const double dd = s1[c];
+            if (i < B - 1 && dd < dp && dd < dm && dd < best) { best = dd; bestI = i; }
+        }
+    }
+    // vals[0] NaN poisons the running minimum: no candidate anywhere
+    if (v0 != v0) bestI = -1;
+    // arg-min over lanes, earliest index on ties (sequential update semantics)
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bestI, o);
+        const bool take = oi >= 0 && (bestI < 0 || ob < best || (ob == best && oi < bestI));
+        if (take) { best = ob; bestI = oi; }
+    }
+    if (lane == 0)
+        *out = bestI < 0 ? nan_f64() : exp(h.lrMin + h.dlr * (static_cast<double>(bestI) + 0.5));
+}
+
+// EXPERIMENTAL (SFK_FLAG_LOS_MOMENTS; not yet timed or run on a GPU -- its arithmetic is
+// checked on the host-compiled source, tests/test_sgmoments.py).  los_kernel_fast with the two
+// FIRs evaluated through the five sliding polynomial moments of sfk_sgmath.cuh: one direct
+// pass over the window for the lane's first output (window x 5 FMAs), PER - 1 binomial shifts
+// for the rest, instead of window x 2*PER FMAs.  Everything outside the marked block is
+// los_kernel_fast verbatim; the two are to be merged once this variant has been measured.
+template <int PER>
+__global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast_moments(LosArgs a, int nb, SgPoly sg) {
+    const int i0 = (threadIdx.x & 31) * PER;
+    extern __shared__ double sm[];
+    constexpr int B = 32 * PER;
+    const int window = a.window;
+    const int center = window / 2;
+    // ln(rho) with the Extension boundary (filter.go:104-161) materialised: sample i sits at
+    // position p = i + padL, padL = center + 1, the positions below / above hold sample 0 / B-1.
+    // Position p is stored at row p % PER, column p / PER, so the FIR below reads row jj at
+    // column (lane + const): conflict-free and with no index arithmetic.
+    const int padL = center + 1;
+    constexpr int rowLen = kLosFastRow;
+    double *ys = sm + 2 * window + (threadIdx.x >> 5) * (PER * rowLen);
+    double *upow = sm + 2 * window + kLosWarps * (PER * rowLen);   // [window][4]: u, u^2, u^3, u^4 of every tap
+    for (int k = threadIdx.x; k < window; k += blockDim.x) {
+        const double u = static_cast<double>(k - center) / static_cast<double>(center);
+        upow[4 * k] = u; upow[4 * k + 1] = u * u; upow[4 * k + 2] = u * u * u; upow[4 * k + 3] = (u * u) * (u * u);
+    }
+    __syncthreads();
+    const int lane = lane_id();
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kLosWarps + (threadIdx.x >> 5);
+    const int64_t perHalo = static_cast<int64_t>(a.rings) * a.spokes;
+    if (gw >= perHalo * nb) return;
+    const int slot = static_cast<int>(gw / perHalo);
+    const int64_t rl = gw - slot * perHalo;
+    const int haloIdx = a.batchHalos[slot];
+    const HaloDev &h = a.halos[haloIdx];
+    const longlong2 *g = reinterpret_cast<const longlong2 *>(a.grid + (static_cast<size_t>(slot) * perHalo + rl) * B);
+
+    // Retrieve + GetRhos: exact int64 prefix sum, clamp, ln
+    long long d[PER];
+#pragma unroll
+    for (int c = 0; c < PER; c += 2) {
+        const longlong2 v = g[(lane * PER + c) / 2];
+        d[c] = v.x; d[c + 1] = v.y;
+    }
+    long long run = 0;
+#pragma unroll
+    for (int c = 0; c < PER; c++) run += d[c];
+    long long incl = run;
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    long long acc = incl - run;
+    const double q = h.quantum, bg = h.defaultRho;
+    double yFirst = 0.0, yLast = 0.0;
+#pragma unroll
+    for (int c = 0; c < PER; c++) {
+        acc += d[c];
+        double rho = static_cast<double>(acc) * q;
+        if (rho < bg) rho = bg;
+        if (a.profiles) a.profiles[(static_cast<size_t>(haloIdx) * perHalo + rl) * B + lane * PER + c] = rho;
+        const double y = log(rho);
+        const int p = lane * PER + c + padL;
+        ys[(p % PER) * rowLen + p / PER] = y;
+        if (c == 0) yFirst = y;
+        if (c == PER - 1) yLast = y;
+    }
+    // Extension: repeat the end samples
+    yFirst = __shfl_sync(0xffffffffu, yFirst, 0);
+    yLast = __shfl_sync(0xffffffffu, yLast, 31);
+    for (int e = lane; e < padL; e += 32) ys[(e % PER) * rowLen + e / PER] = yFirst;
+    for (int e = B + padL + lane; e < PER * rowLen; e += 32) ys[(e % PER) * rowLen + e / PER] = yLast;
+    __syncwarp();
+
+    double *out = a.rsp + static_cast<size_t>(haloIdx) * perHalo + rl;
+    if (B <= window) {   // Smooth: ok = false, smooth.go:51-53
+        if (lane == 0) *out = nan_f64();
+        return;
+    }
+    // ---- sliding moments instead of the tap loop ----
+    // Output i0 + c reads positions lane*PER + c + 1 + j, j = 0 .. window-1; position
+    // lane*PER + q sits at row q % PER, column lane + q / PER.
+    const double *yl = ys + lane;
+    double s0[PER], s1[PER];
+    {
+        double M[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int j = 0; j < window; j++) {
+            const int q = 1 + j;
+            sg_accumulate(M, yl[(q % PER) * rowLen + q / PER], upow + 4 * j);
+        }
+#pragma unroll
+        for (int c = 0; c < PER; c++) {
+            sg_outputs(M, sg, s0[c], s1[c]);
+            if (c < PER - 1) {
+                const int qo = c + 1, qi = c + 1 + window;
+                sg_advance(M, sg, yl[(qo % PER) * rowLen + qo / PER], yl[(qi % PER) * rowLen + qi / PER]);
+            }
+        }
+    }
+    // ---- end of the block that differs from los_kernel_fast ----
 #pragma unroll
     for (int c = 0; c < PER; c++) s0[c] = exp(s0[c]);   // vals; s1 = d ln rho / d ln r
 
@@ -1340,6 +1487,18 @@ cudaError_t launch_percentile(const PercentileArgs &a, int nb, cudaStream_t s) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     percentile_kernel<<<dim3(a.bins, nb), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// Experimental sliding-moment variant of the fast path; false when the shape is not served.
+bool los_moments_supported(const LosArgs &a) { return a.bins == 256 && a.window <= kLosFastMaxWindow && a.window >= 7; }
+
+cudaError_t launch_los_moments(const LosArgs &a, const SgPoly &sg, int nb, cudaStream_t s) {
+    if (nb <= 0) return cudaSuccess;
+    const int64_t warps = static_cast<int64_t>(nb) * a.rings * a.spokes;
+    const unsigned grid = static_cast<unsigned>((warps + kLosWarps - 1) / kLosWarps);
+    const size_t fsmem = sizeof(double) * (2 * a.window + kLosWarps * 8 * kLosFastRow + 4 * a.window);
+    los_kernel_fast_moments<8><<<grid, kLosWarps * 32, fsmem, s>>>(a, nb, sg);
     return cudaGetLastError();
 }
 

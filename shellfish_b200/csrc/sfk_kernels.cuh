@@ -133,6 +133,9 @@ cudaError_t launch_hits(const Piece *pieces, int nPieces, const Cand *cands,
                         uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs, cudaStream_t s);
 cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s);
 cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s);
+struct SgPoly;   // sfk_sgmath.cuh
+bool los_moments_supported(const LosArgs &a);
+cudaError_t launch_los_moments(const LosArgs &a, const SgPoly &sg, int nb, cudaStream_t s);
 cudaError_t launch_filter(const FilterArgs &a, int nb, cudaStream_t s);
 cudaError_t launch_fit(const FitArgs &a, int nb, cudaStream_t s);
 size_t bin_smem_bytes(int bins);

@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "sfk_internal.h"
+#include "sfk_sgmath.cuh"
 
 namespace sfk {
 
@@ -256,6 +257,54 @@ bool savgol_taps(int order, int width, int ld, double dx, std::vector<double> &t
         for (int i = 2; i <= ld; i++) fact *= i;
         double scale = static_cast<double>(fact) / go_pow(dx, static_cast<double>(ld));
         for (double &c : taps) c *= scale;
+    }
+    return true;
+}
+
+// Polynomial form of the Savitzky-Golay taps for the sliding-moment path (sfk_sgmath.cuh):
+// least-squares fit of degree 4 in u_j = (j - center)/center through all taps (they are such
+// polynomials up to rounding), normal equations solved in long double.
+bool savgol_poly(const std::vector<double> &taps0, const std::vector<double> &taps1, SgPoly &out) {
+    const int window = static_cast<int>(taps0.size());
+    if (window < 7 || taps1.size() != taps0.size() || window % 2 != 1) return false;
+    const int center = window / 2;
+    long double A[5][5] = {}, b0[5] = {}, b1[5] = {};
+    for (int j = 0; j < window; j++) {
+        const long double u = static_cast<long double>(j - center) / center;
+        long double pw[9];
+        pw[0] = 1;
+        for (int k = 1; k < 9; k++) pw[k] = pw[k - 1] * u;
+        for (int k = 0; k < 5; k++) {
+            for (int l = 0; l < 5; l++) A[k][l] += pw[k + l];
+            b0[k] += pw[k] * taps0[j];
+            b1[k] += pw[k] * taps1[j];
+        }
+    }
+    for (int c = 0; c < 5; c++) {   // Gaussian elimination with partial pivoting, two right-hand sides
+        int piv = c;
+        for (int r = c + 1; r < 5; r++) if (fabsl(A[r][c]) > fabsl(A[piv][c])) piv = r;
+        if (A[piv][c] == 0) return false;
+        if (piv != c) {
+            for (int l = 0; l < 5; l++) std::swap(A[c][l], A[piv][l]);
+            std::swap(b0[c], b0[piv]); std::swap(b1[c], b1[piv]);
+        }
+        for (int r = c + 1; r < 5; r++) {
+            const long double f = A[r][c] / A[c][c];
+            for (int l = c; l < 5; l++) A[r][l] -= f * A[c][l];
+            b0[r] -= f * b0[c]; b1[r] -= f * b1[c];
+        }
+    }
+    for (int r = 4; r >= 0; r--) {
+        long double s0 = b0[r], s1 = b1[r];
+        for (int l = r + 1; l < 5; l++) { s0 -= A[r][l] * out.c0[l]; s1 -= A[r][l] * out.c1[l]; }
+        out.c0[r] = static_cast<double>(s0 / A[r][r]);
+        out.c1[r] = static_cast<double>(s1 / A[r][r]);
+    }
+    const long double d = -1.0L / center;
+    static const int binom[5][5] = {{1, 0, 0, 0, 0}, {1, 1, 0, 0, 0}, {1, 2, 1, 0, 0}, {1, 3, 3, 1, 0}, {1, 4, 6, 4, 1}};
+    for (int k = 0; k < 5; k++) {
+        for (int l = 0; l < 5; l++) out.T[k][l] = l <= k ? static_cast<double>(binom[k][l] * powl(d, k - l)) : 0.0;
+        out.lo[k] = static_cast<double>(powl(-1.0L + d, k));
     }
     return true;
 }

@@ -27,6 +27,7 @@ def lib():
         L.hc_shell_sums.argtypes = [_dp, C.c_int, C.c_int, C.c_int, _dp]
         L.hc_shell_props.argtypes = [_dp, C.c_int, C.c_int, C.c_int, _dp]
         L.hc_angular_fraction.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _dp]
+        L.hc_sg_moments.argtypes = [_dp, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, _dp]
         L.hc_gauss_legendre.argtypes = [C.c_int, _dp, _dp]
         _LIB = L
     return _LIB
@@ -72,3 +73,16 @@ def angular_fraction(cs, r_min, r_max, bins, n_theta=1024, n_phi=256):
     out = np.zeros(bins)
     lib().hc_angular_fraction(cs.ctypes.data_as(_dp), order, n_theta, n_phi, r_min, r_max, bins, out.ctypes.data_as(_dp))
     return out
+
+
+def sg_moments(ys, taps0, taps1, per=8):
+    """Savitzky-Golay value / derivative of one ln(rho) row by the kernel's sliding moments."""
+    ys = np.ascontiguousarray(ys, np.float64)
+    t0 = np.ascontiguousarray(taps0, np.float64)
+    t1 = np.ascontiguousarray(taps1, np.float64)
+    s0, s1 = np.zeros(len(ys)), np.zeros(len(ys))
+    rc = lib().hc_sg_moments(ys.ctypes.data_as(_dp), len(ys), t0.ctypes.data_as(_dp), t1.ctypes.data_as(_dp), len(t0),
+                             per, s0.ctypes.data_as(_dp), s1.ctypes.data_as(_dp))
+    if rc:
+        raise RuntimeError("savgol_poly failed")
+    return s0, s1

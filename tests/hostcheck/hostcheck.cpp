@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../shellfish_b200/csrc/sfk_internal.h"
+#include "../../shellfish_b200/csrc/sfk_sgmath.cuh"
 #include "../../shellfish_b200/csrc/sfk_shellmath.cuh"
 
 extern "C" {
@@ -52,6 +53,36 @@ void hc_angular_fraction(const double *cs, int order, int nTheta, int nPhi, doub
     }
     for (int i = bins - 2; i >= 0; i--) hist[i] += hist[i + 1];
     for (int i = 0; i < bins; i++) fs[i] = static_cast<double>(hist[i]) / static_cast<double>(hist[0]);
+}
+
+// The sliding-moment Savitzky-Golay path of los_kernel_fast<PER> for one line of sight:
+// ys[bins] = ln(rho); lane L evaluates outputs L*per .. L*per + per - 1 (one direct anchor,
+// per - 1 shifts) on the Extension-padded row, exactly as the kernel's lanes do.
+int hc_sg_moments(const double *ys, int bins, const double *taps0, const double *taps1, int window, int per,
+                  double *s0, double *s1) {
+    std::vector<double> t0(taps0, taps0 + window), t1(taps1, taps1 + window);
+    sfk::SgPoly poly;
+    if (!sfk::savgol_poly(t0, t1, poly)) return -1;
+    const int center = window / 2, padL = center + 1;
+    std::vector<double> pos(bins + 2 * window + 2 * per + 2);
+    for (size_t p = 0; p < pos.size(); p++) {
+        long i = static_cast<long>(p) - padL;
+        pos[p] = ys[i < 0 ? 0 : (i >= bins ? bins - 1 : i)];
+    }
+    std::vector<double> upow(4 * static_cast<size_t>(window));
+    for (int j = 0; j < window; j++) {
+        const double u = static_cast<double>(j - center) / static_cast<double>(center);
+        upow[4 * j] = u; upow[4 * j + 1] = u * u; upow[4 * j + 2] = u * u * u; upow[4 * j + 3] = (u * u) * (u * u);
+    }
+    for (int i0 = 0; i0 < bins; i0 += per) {
+        double M[5] = {0, 0, 0, 0, 0};
+        for (int j = 0; j < window; j++) sfk::sg_accumulate(M, pos[i0 + 1 + j], &upow[4 * j]);
+        for (int c = 0; c < per && i0 + c < bins; c++) {
+            sfk::sg_outputs(M, poly, s0[i0 + c], s1[i0 + c]);
+            sfk::sg_advance(M, poly, pos[i0 + c + 1], pos[i0 + c + 1 + window]);
+        }
+    }
+    return 0;
 }
 
 void hc_gauss_legendre(int n, double *x, double *w) {
