@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--order", type=int, default=3, help="Penna order (BASELINE config 5 sweeps 2, 3, 4)")
     ap.add_argument("--subsample", type=int, default=1, help="SubsampleFactor (config 5: 1, 2)")
+    ap.add_argument("--los-moments", action="store_true",
+                    help="A/B switch: SFK_FLAG_LOS_MOMENTS (experimental sliding-moment Savitzky-Golay)")
     return ap.parse_args()
 
 
@@ -56,6 +58,8 @@ def workload(args, rank):
                         (args.halos, args.n_total, args.box, args.cells),
             "halos": args.halos, "n_particles": int(args.n_total), "blocks": len(blocks),
             "order": args.order, "subsample": args.subsample, "setup_s": round(time.time() - t, 1)}
+    if args.los_moments:
+        desc["los_moments"] = True   # experimental kernel variant: not the default product path
     return halos, blocks, mass, desc
 
 
@@ -167,7 +171,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     halos, blocks, mass, desc = workload(args, rank)
-    params = api.default_params(seed=1337, device=local, order=args.order, subsample_factor=args.subsample)
+    params = api.default_params(seed=1337, device=local, order=args.order, subsample_factor=args.subsample,
+                                flags=api.SFK_FLAG_LOS_MOMENTS if args.los_moments else 0)
     ctx = api.ShellContext(params)
     R, n, B = int(params.rings), int(params.spokes), int(params.radial_bins)
 
