@@ -498,3 +498,16 @@ def test_prof_config(tmp_path):   # cmd/prof.go:103-169
     row = "0 100 1 1 1 1 " + " ".join(["0.5"] + ["0"] * 17) + "\n"
     r = _cli(["prof", "--ProfileType", "median-density"], stdin=row, env={"SHELLFISH_GLOBAL_CONFIG": str(cfg)})
     assert r.returncode == 1 and "is not provided by this build" in r.stderr and r.stdout == "Shellfish terminating.\n"
+
+
+def test_example_configs_parse(tmp_path):
+    """cmd/config_file_test.go:9-39 (TestExampleFiles): every mode's ExampleConfig() is a file its
+    own ReadConfig accepts."""
+    for name, reader in (("shell.config", H.read_shell_config), ("stats.config", H.read_stats_config),
+                         ("prof.config", H.read_prof_config)):
+        text = _cli(["help", name]).stdout
+        assert text.startswith("[%s]" % name)
+        f = tmp_path / name
+        f.write_text(text)
+        err, _ = reader(str(f))
+        assert err == "", (name, err)
