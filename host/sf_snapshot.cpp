@@ -146,6 +146,8 @@ public:
         int64_t count = 0;
         err = particle_num(gh.NPart, count);
         if (!err.empty()) return err;
+        // a header that promises more particles than the file holds must not size the buffers
+        if (!c.ok || count < 0 || 12 * count > static_cast<int64_t>(img.size())) return "read " + fname + ": unexpected EOF";
         xs_.resize(3 * count);
         c.get<int32_t>();
         c.array(xs_.data(), 3 * count);
@@ -223,6 +225,8 @@ public:
             if (isDM(i)) dmN += gh.NPart[i];
             if (isMulti(i)) multiN += gh.NPart[i];
         }
+        // a header that promises more particles than the file holds must not size the buffers
+        if (!c.ok || totalN < 0 || 24 * totalN > static_cast<int64_t>(img.size())) return "read " + fname + ": unexpected EOF";
         xs_.resize(3 * totalN);
         ms_.assign(totalN, 0.f);
         std::vector<float> multi(multiN);
@@ -331,6 +335,7 @@ public:
                      static_cast<long long>(gw_ * gw_ * gw_), fname.c_str(), static_cast<long long>(hd.GridCount));
             return buf;
         }
+        if (hd.GridCount < 0 || 12 * hd.GridCount > static_cast<int64_t>(img.size())) return "read " + fname + ": unexpected EOF";
         std::vector<float> sheet(3 * hd.GridCount);
         c.array(sheet.data(), sheet.size());
         if (!c.ok) return "read " + fname + ": unexpected EOF";

@@ -511,3 +511,20 @@ def test_example_configs_parse(tmp_path):
         f.write_text(text)
         err, _ = reader(str(f))
         assert err == "", (name, err)
+
+
+def test_truncated_snapshots_are_reported(tmp_path):
+    """A header that promises more particles than the file holds ends in the reader's error
+    text (io.ReadFull's unexpected EOF in the reference), not in an allocation failure."""
+    dm = _box(9, 1000, 100.0)
+    f = str(tmp_path / "g2.0")
+    snapio.write_gadget2(f, [None, dm, None, None, None, None], 100.0, COSMO, [0, 1.0, 0, 0, 0, 0])
+    raw = open(f, "rb").read()
+    open(f, "wb").write(raw[:4 + 256 + 4 + 4 + 1200])          # header + 100 of the 1000 positions
+    with pytest.raises(ValueError, match="unexpected EOF"):
+        H.read_block("Gadget-2", f)
+    hdr = bytearray(raw)
+    struct.pack_into("<I", hdr, 4 + 4, 0x7fffffff)             # NPart[1] := 2^31 - 1 in an otherwise intact file
+    open(f, "wb").write(bytes(hdr))
+    with pytest.raises(ValueError, match="unexpected EOF"):
+        H.read_block("Gadget-2", f)
