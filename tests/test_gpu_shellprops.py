@@ -106,3 +106,14 @@ def test_angular_fraction_kernel():
     _, fs = ctx.angular_fraction(np.array([shells.sphere(0.5)]), 1.0, 2.0, 10)
     assert np.all(np.isnan(fs))
     assert ctx.angular_fraction(np.zeros((0, 18)), 1.0, 2.0, 10)[1].shape == (0, 10)
+
+
+def test_golden_stats_fixture_on_the_gpu():
+    """The committed rule values of tests/golden/stats_small.json (no oracle, no host build needed)."""
+    import json
+    import os
+    g = json.load(open(os.path.join(shells.ROOT, "tests", "golden", "stats_small.json")))
+    ctx = api.ShellContext(api.default_params(rings=3))
+    for name, case in g["cases"].items():
+        got = ctx.shell_props(np.array([case["coeffs"]]))[0]
+        np.testing.assert_allclose(got, case["rule_128x256"], rtol=1e-9, atol=1e-12)

@@ -243,3 +243,23 @@ def test_angular_fraction_bin_truncation():
     assert fm[0] == 1.0 and fm[1] == 0.0
     assert np.all(np.isnan(hc.angular_fraction(shells.sphere(0.5), 1.0, 2.0, 10)))
     assert np.all(np.isnan(po.angular_fraction_profile(shells.sphere(0.5), 100, 10, 1.0, 2.0)[1]))
+
+
+def test_golden_stats_fixture():
+    """tests/golden/stats_small.json (tests/golden/make_golden_stats.py): the oracle's Monte-Carlo
+    values at fixed seeds and the rule's values do not drift."""
+    import json
+    import os
+    g = json.load(open(os.path.join(shells.ROOT, "tests", "golden", "stats_small.json")))
+    tables = shells.axis_tables()
+    for name, case in g["cases"].items():
+        cs, mc, n = case["coeffs"], case["monte_carlo"], g["samples"]
+        assert po.shell_volume(cs, n, 1) == pytest.approx(mc["volume_seed1"], rel=1e-13)
+        assert po.shell_surface_area(cs, n, 2) == pytest.approx(mc["area_seed2"], rel=1e-13)
+        a, b, c, vec = po.shell_axes(cs, n, 3, tables)
+        assert [a, b, c] == pytest.approx(mc["axes_seed3"], rel=1e-11)
+        assert list(po.shell_radial_range(cs, n, 4)) == pytest.approx(mc["range_seed4"], rel=1e-14)
+        np.testing.assert_allclose(hc.shell_props(cs), case["rule_128x256"], rtol=1e-12, atol=1e-14)
+        # the two estimates of the same integrals agree within the Monte-Carlo scatter (~1e-3)
+        assert abs(mc["volume_seed1"] / case["rule_128x256"][1] - 1) < 3e-3
+        assert abs(mc["area_seed2"] / case["rule_128x256"][2] - 1) < 3e-3
