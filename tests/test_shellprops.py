@@ -263,3 +263,12 @@ def test_golden_stats_fixture():
         # the two estimates of the same integrals agree within the Monte-Carlo scatter (~1e-3)
         assert abs(mc["volume_seed1"] / case["rule_128x256"][1] - 1) < 3e-3
         assert abs(mc["area_seed2"] / case["rule_128x256"][2] - 1) < 3e-3
+
+
+def test_degenerate_rows_do_not_crash():
+    """An all-zero coefficient row (what `shell` prints for a halo whose fit failed) gives
+    volume 0 and NaN shape columns; the reference's Axes would panic in mat64.Eigen there
+    (los/analyze/shell.go:151-154)."""
+    p = hc.shell_props(np.zeros(18))
+    assert p[0] == 0 and p[1] == 0 and np.all(np.isnan(p[2:9])) and p[9] == 0 and p[10] == 0
+    assert np.all(np.isnan(hc.shell_props(np.full(18, np.nan))[:9]))
