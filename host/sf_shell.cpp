@@ -2,6 +2,7 @@
 #include "sf_shell.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -293,6 +294,14 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
     if (sfk_create(&sfk, &p) != 0) return sfk_last_error(sfk);
     const sfk_cosmo cosmo0{hds0[0].Cosmo.Z, hds0[0].Cosmo.OmegaM, hds0[0].Cosmo.OmegaL, hds0[0].Cosmo.H100};
 
+    // Logging = performance (cmd/shell.go:352-367): elapsed time after sphereLoop and after
+    // haloAnalysis of every snapshot, on stderr like Go's log package; the time spent inside
+    // buf.Read (file I/O) and the device stage times are reported next to it.
+    const bool perf = g.Logging == "performance";
+    const auto tStart = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    };
     for (const auto &kv : idxBins) {
         const int64_t snap = kv.first;
         if (snap == -1) continue;
@@ -300,6 +309,8 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
             return "Snapshot " + std::to_string(snap) + " is outside [SnapMin, SnapMax] = [" +
                    std::to_string(g.particle.SnapMin) + ", " + std::to_string(g.particle.SnapMax) + "].";
         const std::vector<size_t> &idxs = kv.second;
+        double readSeconds = 0.0;
+        int64_t blocksRead = 0, particlesRead = 0;
         std::vector<double> x(idxs.size()), y(idxs.size()), z(idxs.size()), r(idxs.size());
         for (size_t i = 0; i < idxs.size(); i++) {
             x[i] = coords[0][idxs[i]]; y[i] = coords[1][idxs[i]]; z[i] = coords[2][idxs[i]]; r[i] = coords[3][idxs[i]];
@@ -317,10 +328,17 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
             if (nHit == 0) continue;
             const float *xs, *ms;
             int64_t n;
+            const auto tRead = std::chrono::steady_clock::now();
             if (!(err = buf->Read(files[i], &xs, &ms, &n)).empty()) return err;
+            readSeconds += since(tRead); blocksRead++; particlesRead += n;
             const sfk_cosmo hc{hds[i].Cosmo.Z, hds[i].Cosmo.OmegaM, hds[i].Cosmo.OmegaL, hds[i].Cosmo.H100};
             if (sfk_push_block(sfk, xs, ms, n, &hc, hds[i].TotalWidth, hds[i].Origin, hds[i].Width) != 0)
                 return sfk_last_error(sfk);
+        }
+        if (perf) {
+            std::fprintf(stderr, "Snap %lld, sphereLoop ended\nTime: %.6gs\n", static_cast<long long>(snap), since(tStart));
+            std::fprintf(stderr, "Read: %.6gs in buf.Read (%lld blocks, %lld particles)\n", readSeconds,
+                         static_cast<long long>(blocksRead), static_cast<long long>(particlesRead));
         }
         // haloAnalysis, cmd/shell.go:502-528: a failed fit leaves the zero row
         std::vector<double> cs(idxs.size() * rowLen);
@@ -328,6 +346,16 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
         if (sfk_finish_snapshot(sfk, cs.data(), status.data()) != 0) return sfk_last_error(sfk);
         for (size_t i = 0; i < idxs.size(); i++)
             std::copy(cs.begin() + i * rowLen, cs.begin() + (i + 1) * rowLen, out[idxs[i]].begin());
+        if (perf) {
+            std::fprintf(stderr, "Snap %lld, haloAnalysis ended\nTime: %.6gs\n", static_cast<long long>(snap), since(tStart));
+            sfk_stats st{};
+            if (sfk_get_stats(sfk, &st) == 0)
+                std::fprintf(stderr, "Device: cull %.3f ms, hits %.3f ms, bin %.3f ms, los %.3f ms, filter %.3f ms, fit %.3f ms; "
+                                     "%lld candidates, %lld intersections, %lld launches\n",
+                             st.ms_cull, st.ms_hits, st.ms_bin, st.ms_los, st.ms_filter, st.ms_fit,
+                             static_cast<long long>(st.n_candidates), static_cast<long long>(st.n_intersections),
+                             static_cast<long long>(st.launches));
+        }
     }
 
     // cmd/shell.go:246-262

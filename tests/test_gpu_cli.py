@@ -291,3 +291,20 @@ def test_prof_angular_fraction_cli(tmp_path):
     want = H.format_cols([ic[0], ic[1]], [rs[:, j] for j in range(40)] + [fs[:, j] for j in range(40)], list(range(82)))
     assert lines[1:] == want
     assert np.all(fs[:, 0] == 1.0) and np.all(fs[:, -1] < 1.0)
+
+
+def test_cli_performance_logging(tmp_path):
+    """Logging = performance (cmd/shell.go:352-367): stage times on stderr, the file-read time
+    separately; the catalog on stdout is unchanged."""
+    halos, blocks, min_mass, cfg = _setup(tmp_path, 17, 1, 10000, 4000, 1)
+    quiet = _run_cli(cfg, halos, ["--Rings", "4"])
+    open(cfg, "a").write("Logging = performance\n")
+    env = dict(os.environ, SHELLFISH_GLOBAL_CONFIG=cfg, SHELLFISH_SEED="1337")
+    stdin = "".join("%d 100 %.17g %.17g %.17g %.17g\n" % (i, *h[:4]) for i, h in enumerate(halos))
+    os.remove(os.path.join(os.path.dirname(cfg), "memo", "memo.config"))   # the config changed on purpose
+    r = subprocess.run([H.cli_path(), "shell", "--Rings", "4"], input=stdin, capture_output=True, text=True, env=env,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.split("\n")[:-1] == quiet
+    for needle in ("RNG Seed is 1337", "Snap 100, sphereLoop ended", "Read: ", "Snap 100, haloAnalysis ended", "Device: cull"):
+        assert needle in r.stderr, r.stderr
