@@ -32,6 +32,19 @@ if [ -f $OUT/${TAG}_bin.ncu-rep ]; then
     python profiles/ncu_by_line.py $OUT/${TAG}_bin.ncu-rep sfk_bin bin_kernelILb0 > $OUT/${TAG}_bin_kernel_by_line.txt 2>&1 || true
 fi
 
+# A/B of the experimental sliding-moment los kernel on the same 64-halo sample (stage_ms_per_step.ms_los)
+timeout 200 $B64 --no-e2e --los-moments > $OUT/${TAG}_bench64_los_moments.json 2> $OUT/${TAG}_bench64_los_moments.err
+python - <<PY
+import json
+try:
+    a = json.loads(open("$OUT/${TAG}_bench64.json").read().strip().splitlines()[-1])
+    b = json.loads(open("$OUT/${TAG}_bench64_los_moments.json").read().strip().splitlines()[-1])
+    print("los A/B: ms_los %.2f -> %.2f, halos/s %.1f -> %.1f" % (a["stage_ms_per_step"]["ms_los"],
+          b["stage_ms_per_step"]["ms_los"], a["value"], b["value"]))
+except Exception as e:
+    print("los A/B: no comparison (%s)" % e)
+PY
+
 if [ "${2:-}" = "full" ]; then
     timeout 600 python bench.py > $OUT/${TAG}_bench_full.json 2> $OUT/${TAG}_bench_full.err
     echo "bench full rc=$? $(cut -c1-200 $OUT/${TAG}_bench_full.json)"
