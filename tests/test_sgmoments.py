@@ -86,3 +86,6 @@ def test_splashback_decisions_do_not_change():
     assert np.allclose(rs[i_d[ok]], rsp[ok], rtol=1e-12)
     assert np.array_equal(i_d, i_m)
     assert np.abs(dm - dd).max() < 1e-11 and np.abs(vm - vd).max() < 1e-11
+    # exp is monotone and SplashbackRadius only compares the smoothed densities
+    # (splashback_radius.go:36-41): the search can run on the smoothed logarithms
+    assert np.array_equal(splashback_index(vd, dd), i_d)
