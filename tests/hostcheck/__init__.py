@@ -75,14 +75,15 @@ def angular_fraction(cs, r_min, r_max, bins, n_theta=1024, n_phi=256):
     return out
 
 
-def sg_moments(ys, taps0, taps1, per=8):
-    """Savitzky-Golay value / derivative of one ln(rho) row by the kernel's sliding moments."""
+def sg_moments(ys, taps0, taps1, per=8, paired=False):
+    """Savitzky-Golay value / derivative of one ln(rho) row by the kernel's sliding moments
+    (paired: the anchor folds the taps at +-u, sg_accumulate_pair)."""
     ys = np.ascontiguousarray(ys, np.float64)
     t0 = np.ascontiguousarray(taps0, np.float64)
     t1 = np.ascontiguousarray(taps1, np.float64)
     s0, s1 = np.zeros(len(ys)), np.zeros(len(ys))
     rc = lib().hc_sg_moments(ys.ctypes.data_as(_dp), len(ys), t0.ctypes.data_as(_dp), t1.ctypes.data_as(_dp), len(t0),
-                             per, s0.ctypes.data_as(_dp), s1.ctypes.data_as(_dp))
+                             -per if paired else per, s0.ctypes.data_as(_dp), s1.ctypes.data_as(_dp))
     if rc:
         raise RuntimeError("savgol_poly failed")
     return s0, s1

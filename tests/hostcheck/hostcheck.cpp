@@ -58,8 +58,11 @@ void hc_angular_fraction(const double *cs, int order, int nTheta, int nPhi, doub
 // The sliding-moment Savitzky-Golay path of los_kernel_fast<PER> for one line of sight:
 // ys[bins] = ln(rho); lane L evaluates outputs L*per .. L*per + per - 1 (one direct anchor,
 // per - 1 shifts) on the Extension-padded row, exactly as the kernel's lanes do.
-int hc_sg_moments(const double *ys, int bins, const double *taps0, const double *taps1, int window, int per,
+// per < 0: |per| outputs per lane with the paired anchor (sg_accumulate_pair).
+int hc_sg_moments(const double *ys, int bins, const double *taps0, const double *taps1, int window, int perArg,
                   double *s0, double *s1) {
+    const bool paired = perArg < 0;
+    const int per = paired ? -perArg : perArg;
     std::vector<double> t0(taps0, taps0 + window), t1(taps1, taps1 + window);
     sfk::SgPoly poly;
     if (!sfk::savgol_poly(t0, t1, poly)) return -1;
@@ -76,7 +79,13 @@ int hc_sg_moments(const double *ys, int bins, const double *taps0, const double 
     }
     for (int i0 = 0; i0 < bins; i0 += per) {
         double M[5] = {0, 0, 0, 0, 0};
-        for (int j = 0; j < window; j++) sfk::sg_accumulate(M, pos[i0 + 1 + j], &upow[4 * j]);
+        if (paired) {   // paired anchor: taps center +- m share one update
+            M[0] = pos[i0 + 1 + center];
+            for (int m = 1; m <= center; m++)
+                sfk::sg_accumulate_pair(M, pos[i0 + 1 + center + m], pos[i0 + 1 + center - m], &upow[4 * (center + m)]);
+        } else {
+            for (int j = 0; j < window; j++) sfk::sg_accumulate(M, pos[i0 + 1 + j], &upow[4 * j]);
+        }
         for (int c = 0; c < per && i0 + c < bins; c++) {
             sfk::sg_outputs(M, poly, s0[i0 + c], s1[i0 + c]);
             sfk::sg_advance(M, poly, pos[i0 + c + 1], pos[i0 + c + 1 + window]);

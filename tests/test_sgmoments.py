@@ -29,6 +29,8 @@ def test_moments_equal_the_tap_loop(window):
         v, d = direct(ys, k0, k1)
         s0, s1 = hc.sg_moments(ys, k0, k1)
         worst = max(worst, np.abs(s0 - v).max() / np.abs(v).max(), np.abs(s1 - d).max() / np.abs(d).max())
+        p0, p1 = hc.sg_moments(ys, k0, k1, paired=True)     # taps at +-u folded (sg_accumulate_pair)
+        worst = max(worst, np.abs(p0 - v).max() / np.abs(v).max(), np.abs(p1 - d).max() / np.abs(d).max())
     assert worst < 2e-11, worst     # relative to the curve; the rows carry offsets of up to 20
 
 
