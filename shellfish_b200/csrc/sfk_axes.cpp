@@ -75,19 +75,28 @@ struct NaturalSpline {
     }
 };
 
-// BiCubic.Eval, math/interpolate/cubic_interpolators.go:71-103: one spline in y
-// per x knot (vals[nx*yi + xi]), then a spline in x through their values at y.
-double bicubic_eval(const double *knots, const double *vals, int n, double x, double y) {
-    std::vector<double> col(n), atY(n);
-    NaturalSpline sp;
-    for (int xi = 0; xi < n; xi++) {
-        for (int yi = 0; yi < n; yi++) col[yi] = vals[n * yi + xi];
-        sp.init(knots, col.data(), n);
-        atY[xi] = sp.eval(y);
+// BiCubic, math/interpolate/cubic_interpolators.go:22-103: one spline in y per x knot
+// (vals[nx*yi + xi]) built once (initSplines :71-90), then per evaluation a spline in x through
+// their values at y (Eval :92-103).
+struct BiCubic {
+    std::vector<NaturalSpline> ySplines;
+    const double *knots;
+    int n;
+    BiCubic(const double *kn, const double *vals, int count) : ySplines(count), knots(kn), n(count) {
+        std::vector<double> col(n);
+        for (int xi = 0; xi < n; xi++) {
+            for (int yi = 0; yi < n; yi++) col[yi] = vals[n * yi + xi];
+            ySplines[xi].init(knots, col.data(), n);
+        }
     }
-    sp.init(knots, atY.data(), n);
-    return sp.eval(x);
-}
+    double eval(double x, double y) const {
+        std::vector<double> atY(n);
+        for (int xi = 0; xi < n; xi++) atY[xi] = ySplines[xi].eval(y);
+        NaturalSpline sp;
+        sp.init(knots, atY.data(), n);
+        return sp.eval(x);
+    }
+};
 
 // Cyclic Jacobi for a symmetric 3x3 matrix; eigenvectors in the columns of v.
 void jacobi3(double a[3][3], double w[3], double v[3][3]) {
@@ -192,9 +201,12 @@ void axes_from_moments(const double m[9], double out[6]) {
     trisort(std::sqrt(ax2), std::sqrt(ay2), std::sqrt(az2), c, b, a, aIdx);
     (void)aIdx;
     const double ac = a / c, bc = b / c;
-    const double acRatio = bicubic_eval(kAxisRatios, kACGrid, kAxisN, ac, bc);
-    const double bcRatio = bicubic_eval(kAxisRatios, kBCGrid, kAxisN, ac, bc);
-    const double cRatio = bicubic_eval(kAxisRatios, kCGrid, kAxisN, ac, bc);
+    // axisInterpolators, shell.go:356-374: built once per process
+    static const BiCubic acTable(kAxisRatios, kACGrid, kAxisN), bcTable(kAxisRatios, kBCGrid, kAxisN),
+        cTable(kAxisRatios, kCGrid, kAxisN);
+    const double acRatio = acTable.eval(ac, bc);
+    const double bcRatio = bcTable.eval(ac, bc);
+    const double cRatio = cTable.eval(ac, bc);
     double v[3] = {vecs[0][ord[0]], vecs[1][ord[0]], vecs[2][ord[0]]};
     const double norm = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     int big = 0;
