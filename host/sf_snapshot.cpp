@@ -29,6 +29,44 @@ bool read_file(const std::string &path, std::vector<unsigned char> &out, std::st
     return true;
 }
 
+// The first `want` bytes of a file (fewer if it is shorter): headers are parsed from these.
+bool read_prefix(const std::string &path, size_t want, std::vector<unsigned char> &out, std::string &err) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) { err = "open " + path + ": " + std::strerror(errno); return false; }
+    out.resize(want);
+    out.resize(std::fread(out.data(), 1, want, f));
+    std::fclose(f);
+    return true;
+}
+
+// An open snapshot file read in pieces: only the blocks the shell path needs (positions,
+// masses) are transferred, the velocity and id blocks are skipped with a seek.
+struct FileReader {
+    FILE *f = nullptr;
+    int64_t size = 0;
+    ~FileReader() { if (f) std::fclose(f); }
+    bool open(const std::string &path, std::string &err) {
+        f = std::fopen(path.c_str(), "rb");
+        if (!f) { err = "open " + path + ": " + std::strerror(errno); return false; }
+        std::fseek(f, 0, SEEK_END);
+        size = std::ftell(f);
+        std::fseek(f, 0, SEEK_SET);
+        return true;
+    }
+    bool read_at(int64_t offset, void *dst, size_t bytes) {
+        if (offset < 0 || offset + static_cast<int64_t>(bytes) > size) return false;
+        if (std::fseek(f, static_cast<long>(offset), SEEK_SET) != 0) return false;
+        return bytes == 0 || std::fread(dst, 1, bytes, f) == bytes;
+    }
+};
+
+template <typename T> void swap_array(T *dst, size_t n) {
+    for (size_t k = 0; k < n; k++) {
+        unsigned char *b = reinterpret_cast<unsigned char *>(&dst[k]);
+        for (size_t i = 0; i < sizeof(T) / 2; i++) std::swap(b[i], b[sizeof(T) - 1 - i]);
+    }
+}
+
 // A cursor over a file image; `swap` = the file's byte order differs from the host's.
 struct Cursor {
     const unsigned char *p, *end;
@@ -62,6 +100,8 @@ bool needs_swap(const std::string &flag) {   // io/lgadget2.go:194-203 (host is 
 }
 
 // ---- (L)Gadget-2 headers, io/lgadget2.go:12-23 and io/gadget2.go:11-25 (256 bytes each)
+// Fortran framing: [i32 256][header][i32 256][i32 bytes of the position block] -> positions start here
+constexpr int64_t kGadgetPosOffset = 4 + 256 + 4 + 4;
 struct LGadget2Header {
     uint32_t NPart[6]; double Mass[6]; double Time, Redshift; int32_t FlagSfr, FlagFeedback;
     uint32_t NPartTotal[6]; int32_t FlagCooling, NumFiles; double BoxSize, Omega0, OmegaLambda, HubbleParam;
@@ -136,22 +176,24 @@ public:
         return "";
     }
     std::string Read(const std::string &fname, const float **xs, const float **ms, int64_t *n) override {
-        std::vector<unsigned char> img;
+        // file = [i32 hdr(256) i32] [i32 pos(12 N) i32] [i32 vel(12 N) i32] [i32 ids(8 N) i32]: only the
+        // header and the position block are transferred (readLGadget2Particles, io/lgadget2.go:84-150)
+        FileReader fr;
         std::string err;
-        if (!read_file(fname, img, err)) return err;
-        Cursor c{img.data(), img.data() + img.size(), swap_};
+        if (!fr.open(fname, err)) return err;
+        unsigned char head[kGadgetPosOffset];
+        if (!fr.read_at(0, head, sizeof head)) return "read " + fname + ": unexpected EOF";
+        Cursor c{head, head + sizeof head, swap_};
         c.get<int32_t>();
         LGadget2Header gh = parse_lgadget(c, true);   // the header is always little endian, :100
-        c.get<int32_t>();
         int64_t count = 0;
         err = particle_num(gh.NPart, count);
         if (!err.empty()) return err;
         // a header that promises more particles than the file holds must not size the buffers
-        if (!c.ok || count < 0 || 12 * count > static_cast<int64_t>(img.size())) return "read " + fname + ": unexpected EOF";
+        if (count < 0 || kGadgetPosOffset + 12 * count > fr.size) return "read " + fname + ": unexpected EOF";
         xs_.resize(3 * count);
-        c.get<int32_t>();
-        c.array(xs_.data(), 3 * count);
-        if (!c.ok) return "read " + fname + ": unexpected EOF";
+        if (!fr.read_at(kGadgetPosOffset, xs_.data(), 12 * static_cast<size_t>(count))) return "read " + fname + ": unexpected EOF";
+        if (swap_) swap_array(xs_.data(), xs_.size());
         if (!fix_positions(xs_.data(), count, static_cast<float>(gh.BoxSize))) return corrupt(fname);
         ms_.assign(count, mass_);
         *xs = xs_.data(); *ms = ms_.data(); *n = count;
@@ -183,7 +225,7 @@ private:
     std::string header(const std::string &path, LGadget2Header &hd) {   // readLGadget2Header, :70-82
         std::vector<unsigned char> img;
         std::string err;
-        if (!read_file(path, img, err)) return err;
+        if (!read_prefix(path, kGadgetPosOffset, img, err)) return err;
         Cursor c{img.data(), img.data() + img.size(), swap_};
         c.get<int32_t>();
         hd = parse_lgadget(c, true);
@@ -212,13 +254,16 @@ public:
     Gadget2Buffer(bool swap, Context ctx) : swap_(swap), ctx_(std::move(ctx)) {}
     std::string init(const std::string &path) { Gadget2Header hd; return header(path, hd); }
     std::string Read(const std::string &fname, const float **xs, const float **ms, int64_t *n) override {
-        std::vector<unsigned char> img;
         std::string err;
-        if (!read_file(fname, img, err)) return err;
-        Cursor c{img.data(), img.data() + img.size(), swap_};
+        // file = [i32 hdr i32] [i32 pos i32] [i32 vel i32] [i32 ids i32] [i32 masses i32]: header, positions and
+        // the mass block are transferred, velocities and ids are skipped (readGadget2Particles, io/gadget2.go:74-130)
+        FileReader fr;
+        if (!fr.open(fname, err)) return err;
+        unsigned char head[kGadgetPosOffset];
+        if (!fr.read_at(0, head, sizeof head)) return "read " + fname + ": unexpected EOF";
+        Cursor c{head, head + sizeof head, swap_};
         c.get<int32_t>();
         Gadget2Header gh = parse_gadget(c, false);   // honours Endianness here, io/gadget2.go:83
-        c.get<int32_t>();
         int64_t totalN = 0, dmN = 0, multiN = 0;
         for (int i = 0; i < 6; i++) {
             totalN += gh.NPart[i];
@@ -226,17 +271,25 @@ public:
             if (isMulti(i)) multiN += gh.NPart[i];
         }
         // a header that promises more particles than the file holds must not size the buffers
-        if (!c.ok || totalN < 0 || 24 * totalN > static_cast<int64_t>(img.size())) return "read " + fname + ": unexpected EOF";
+        if (totalN < 0 || kGadgetPosOffset + 24 * totalN > fr.size) return "read " + fname + ": unexpected EOF";
         xs_.resize(3 * totalN);
         ms_.assign(totalN, 0.f);
         std::vector<float> multi(multiN);
-        c.get<int32_t>(); c.array(xs_.data(), 3 * totalN); c.get<int32_t>();
-        c.get<int32_t>(); c.p += 12 * totalN; c.get<int32_t>();                 // velocities
-        const int32_t idBytes = c.get<int32_t>();                               // ids: 8 or 4 bytes each, :110-120
-        if (totalN > 0) c.p += (idBytes / totalN == 8 ? 8 : (idBytes / totalN == 4 ? 4 : 0)) * totalN;
-        c.get<int32_t>();
-        c.get<int32_t>(); c.array(multi.data(), multiN); c.get<int32_t>();      // read unconditionally, :123-125
-        if (!c.ok || c.p > c.end) return "read " + fname + ": unexpected EOF";
+        int64_t at = kGadgetPosOffset;
+        if (!fr.read_at(at, xs_.data(), 12 * static_cast<size_t>(totalN))) return "read " + fname + ": unexpected EOF";
+        if (swap_) swap_array(xs_.data(), xs_.size());
+        at += 12 * totalN + 4;                 // positions + their end marker
+        at += 4 + 12 * totalN + 4;             // velocities
+        int32_t idBytes = 0;                   // ids: 8 or 4 bytes each, :110-120
+        if (!fr.read_at(at, &idBytes, 4)) return "read " + fname + ": unexpected EOF";
+        if (swap_) swap_array(&idBytes, 1);
+        at += 4;
+        if (totalN > 0) at += (idBytes / totalN == 8 ? 8 : (idBytes / totalN == 4 ? 4 : 0)) * totalN;
+        at += 4;
+        at += 4;                               // start marker of the mass block, read unconditionally, :123-125
+        if (!fr.read_at(at, multi.data(), 4 * static_cast<size_t>(multiN))) return "read " + fname + ": unexpected EOF";
+        if (swap_) swap_array(multi.data(), multi.size());
+        if (at + 4 * multiN + 4 > fr.size) return "read " + fname + ": unexpected EOF";   // its end marker
         // unpackMass :202-233, then packVec / packFloat32 :235-295 keep the DM species
         int64_t off = 0, moff = 0, dst = 0;
         for (int i = 0; i < 6; i++) {
@@ -292,7 +345,7 @@ private:
     std::string header(const std::string &path, Gadget2Header &hd) {   // readGadget2Header: always little endian, :60
         std::vector<unsigned char> img;
         std::string err;
-        if (!read_file(path, img, err)) return err;
+        if (!read_prefix(path, kGadgetPosOffset, img, err)) return err;
         Cursor c{img.data(), img.data() + img.size(), swap_};
         c.get<int32_t>();
         hd = parse_gadget(c, true);
@@ -370,7 +423,8 @@ private:
     // loadSheetHeader, io/gotetra.go:177-211
     std::string load(const std::string &fname, RawGotetraHeader &hd, std::vector<unsigned char> &img, Cursor *rest) {
         std::string err;
-        if (!read_file(fname, img, err)) return err;
+        // without `rest` only the header is wanted: 8 bytes of flags + the 152-byte struct
+        if (!(rest ? read_file(fname, img, err) : read_prefix(fname, 8 + sizeof(RawGotetraHeader), img, err))) return err;
         Cursor c{img.data(), img.data() + img.size(), false};
         const int32_t flag = c.get<int32_t>();
         if (flag == -1) c.swap = true;          // endianness(): 0 little, -1 big, :145-153
