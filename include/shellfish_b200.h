@@ -46,6 +46,13 @@ extern "C" {
  * through five sliding polynomial moments instead of 2 x SmoothingWindow taps per bin.
  * Same result to ~1e-13 (not bit-identical to the tap loop); off by default. */
 #define SFK_FLAG_LOS_MOMENTS 2u
+/* Tests only: build the ring-frame hit records exactly as insertToRing / idxRange do
+ * (los/halo.go:241-310: all n LoS for a centre-containing circle, float64 asin / atan2,
+ * nothing dropped), i.e. without the exact pruning of the product path, so that a test
+ * can show pruned and unpruned integer bins are identical. */
+#define SFK_FLAG_NO_PRUNE 4u
+/* Tests only: keep every halo's int64 fixed-point bin grid for sfk_get_grid. */
+#define SFK_FLAG_KEEP_GRID 8u
 
 typedef struct sfk_ctx sfk_ctx;
 
@@ -240,12 +247,19 @@ void *sfk_stream(const sfk_ctx *ctx);
 int sfk_get_rsp(sfk_ctx *ctx, int64_t halo, double *r);
 /* Number of particles queued for the halo (passing Halo.Intersect). */
 int sfk_get_candidate_count(sfk_ctx *ctx, int64_t halo, int64_t *n);
+/* ProfileRing.Insert calls of the halo that passed the early-out (profile_ring.go:92-95):
+ * the halo's share of sfk_stats.n_intersections.  Always available. */
+int sfk_get_intersection_count(sfk_ctx *ctx, int64_t halo, int64_t *n);
 /* Halo.GetRhos for every LoS: [rings][spokes][bins].  Needs SFK_FLAG_TAPS. */
 int sfk_get_profiles(sfk_ctx *ctx, int64_t halo, double *rho);
 /* Integer taps, need SFK_FLAG_TAPS: inserts per LoS [rings][spokes] and the
  * number of start / end edges landing in each bin [rings][spokes][bins]. */
 int sfk_get_counts(sfk_ctx *ctx, int64_t halo, uint32_t *n_insert,
                    uint32_t *start_edges, uint32_t *end_edges);
+/* The halo's bin grid as the binning kernel left it: ProfileRing.derivs
+ * (profile_ring.go:34-40) of every ring, [rings][spokes][bins], as int64 multiples of
+ * *quantum (either output may be NULL).  Needs SFK_FLAG_KEEP_GRID. */
+int sfk_get_grid(sfk_ctx *ctx, int64_t halo, int64_t *grid, double *quantum);
 /* Host-side tables the context was built with: normals [rings][3], rotation
  * matrices rot / irot [rings][9]. */
 int sfk_get_ring_tables(const sfk_ctx *ctx, float *norms, float *rot, float *irot);

@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libsfk.so")
 
 SFK_FLAG_TAPS = 1
 SFK_FLAG_LOS_MOMENTS = 2   # experimental, see include/shellfish_b200.h
+SFK_FLAG_NO_PRUNE = 4      # tests only: literal insertToRing / idxRange records
+SFK_FLAG_KEEP_GRID = 8     # tests only: keep the int64 bin grids for ShellContext.grid
 SPLIT_HIT_COUNTS, SPLIT_RHO_MAX, SPLIT_GRID = 0, 1, 2
 HALO_STATUS = {0: "ok", 1: "skipped", 2: "no_points", 3: "no_maximum", 4: "spline", 5: "singular",
                6: "not_owned"}
@@ -52,8 +54,8 @@ EXPORTS = ["sfk_default_params", "sfk_create", "sfk_destroy", "sfk_last_error", 
            "sfk_add_halos", "sfk_set_owned", "sfk_block_halo_mask", "sfk_push_block", "sfk_push_block_device",
            "sfk_finish_snapshot", "sfk_row_length", "sfk_split_count", "sfk_split_bin", "sfk_split_buffer", "sfk_split_finish",
            "sfk_mass_begin", "sfk_mass_push_block", "sfk_mass_push_block_device", "sfk_mass_finish",
-           "sfk_sphere_block_hit", "sfk_shell_props", "sfk_shell_sums", "sfk_angular_fraction", "sfk_axes_from_moments", "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count",
-           "sfk_get_profiles", "sfk_get_counts", "sfk_get_ring_tables"]
+           "sfk_sphere_block_hit", "sfk_shell_props", "sfk_shell_sums", "sfk_angular_fraction", "sfk_axes_from_moments", "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count", "sfk_get_intersection_count",
+           "sfk_get_profiles", "sfk_get_counts", "sfk_get_grid", "sfk_get_ring_tables"]
 
 SHELL_PROPS = 11   # SFK_SHELL_PROPS
 SHELL_SUMS = 13    # SFK_SHELL_SUMS
@@ -95,10 +97,12 @@ def lib():
         L.sfk_stream.restype = C.c_void_p
         L.sfk_get_rsp.argtypes = [vp, C.c_int64, dp]
         L.sfk_get_candidate_count.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64)]
+        L.sfk_get_intersection_count.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64)]
         L.sfk_get_profiles.argtypes = [vp, C.c_int64, dp]
         u32p = C.POINTER(C.c_uint32)
         L.sfk_get_counts.argtypes = [vp, C.c_int64, u32p, u32p, u32p]
         L.sfk_get_ring_tables.argtypes = [vp, fp, fp, fp]
+        L.sfk_get_grid.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64), dp]
         for name in EXPORTS:
             if getattr(L, name).restype is not None and name not in ("sfk_last_error", "sfk_stream"):
                 getattr(L, name).restype = C.c_int
@@ -338,6 +342,11 @@ class ShellContext:
         self._ck(lib().sfk_get_candidate_count(self._h, halo, C.byref(n)), "sfk_get_candidate_count")
         return n.value
 
+    def intersection_count(self, halo):
+        n = C.c_int64()
+        self._ck(lib().sfk_get_intersection_count(self._h, halo, C.byref(n)), "sfk_get_intersection_count")
+        return n.value
+
     def profiles(self, halo):
         R, n, B = self._shape()
         out = np.zeros((R, n, B))
@@ -354,6 +363,14 @@ class ShellContext:
         self._ck(lib().sfk_get_counts(self._h, halo, ins.ctypes.data_as(u32p), st.ctypes.data_as(u32p),
                                       en.ctypes.data_as(u32p)), "sfk_get_counts")
         return ins, st, en
+
+    def grid(self, halo):
+        """(int64 [rings][spokes][bins], quantum): ProfileRing.derivs in fixed point (SFK_FLAG_KEEP_GRID)."""
+        R, n, B = self._shape()
+        g = np.zeros((R, n, B), np.int64)
+        q = C.c_double()
+        self._ck(lib().sfk_get_grid(self._h, halo, g.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(q)), "sfk_get_grid")
+        return g, q.value
 
     def ring_tables(self):
         R = int(self.params.rings)

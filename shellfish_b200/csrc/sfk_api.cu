@@ -95,6 +95,7 @@ struct sfk_ctx {
     int64_t candCount = 0;
     std::vector<Seg> segs;
     std::vector<int64_t> candPerHalo;
+    std::vector<int64_t> interPerHalo;   // ProfileRing.Insert calls per halo (after finish)
 
     // block staging
     DevBuf<float> dXyz, dMass;
@@ -121,6 +122,8 @@ struct sfk_ctx {
     DevBuf<double> dPropCoeffs, dPropSums, dGlX, dGlW;
     int glTheta = 0;
     DevBuf<uint32_t> dTapInsert, dTapStart, dTapEnd;
+    DevBuf<unsigned long long> dGridTap;   // SFK_FLAG_KEEP_GRID: [nHalo][rings][spokes][bins]
+    bool keepGrid = false;
 
     // batch scratch
     DevBuf<Piece> dPieces;
@@ -328,6 +331,10 @@ int stage_prepare(sfk_ctx *ctx) {
         CU(cudaMemsetAsync(ctx->dTapStart.p, 0, nHalo * rnb * sizeof(uint32_t), st));
         CU(cudaMemsetAsync(ctx->dTapEnd.p, 0, nHalo * rnb * sizeof(uint32_t), st));
     }
+    if (ctx->keepGrid) {
+        CU(ctx->dGridTap.ensure(nHalo * rnb));
+        CU(cudaMemsetAsync(ctx->dGridTap.p, 0, nHalo * rnb * sizeof(unsigned long long), st));
+    }
 
     // Savitzky-Golay taps: built once per process from the first smoothed
     // profile's dx = ln r1 - ln r0 (smooth.go:63,84-96)
@@ -457,7 +464,8 @@ int stage_bin(sfk_ctx *ctx, const std::vector<int32_t> &batch) {
     ctx->timer.begin(ST_HITS, st);
     CU(launch_hits(ctx->dPieces.p, static_cast<int>(pieces.size()), ctx->dCands.p, ctx->dHalos.p,
                    ctx->dNorms.p, ctx->dRots.p, ctx->dCos.p, ctx->dSin.p, R, n, ctx->tab.dPhi,
-                   ctx->dHitOffset.p, ctx->dHitCursor.p, ctx->dHaloSlot.p, ctx->dRecs.p, st));
+                   ctx->dHitOffset.p, ctx->dHitCursor.p, ctx->dHaloSlot.p, ctx->dRecs.p,
+                   !(ctx->p.flags & SFK_FLAG_NO_PRUNE), st));
     ctx->stats.launches++;
     ctx->timer.end(ST_HITS, st);
 
@@ -478,6 +486,10 @@ int stage_bin(sfk_ctx *ctx, const std::vector<int32_t> &batch) {
     CU(launch_bin(ba, nb, ctx->taps, st));
     ctx->stats.launches++; ctx->stats.bin_launches++;
     ctx->timer.end(ST_BIN, st);
+    if (ctx->keepGrid)
+        for (int s = 0; s < nb; s++)
+            CU(cudaMemcpyAsync(ctx->dGridTap.p + static_cast<size_t>(batch[s]) * rnb, ctx->dGrid.p + static_cast<size_t>(s) * rnb,
+                               rnb * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
     // host vectors of this batch are read by async copies: drain before they die
     CU(cudaStreamSynchronize(st));
     return SFK_OK;
@@ -559,6 +571,7 @@ int stage_collect(sfk_ctx *ctx, double *coeffs, int32_t *status) {
     CU(cudaMemcpyAsync(nInter.data(), ctx->dNInter.p, nHalo * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(nPts.data(), ctx->dNPoints.p, nHalo * sizeof(long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    ctx->interPerHalo.assign(nInter.begin(), nInter.end());
     for (int64_t i = 0; i < nHalo; i++) {
         if (ctx->hStatus[i] == SFK_HALO_OK) ctx->hStatus[i] = dstat[i];
         if (ctx->hStatus[i] != SFK_HALO_OK)
@@ -631,6 +644,7 @@ static int create_impl(sfk_ctx *ctx, const sfk_params *params) try {
     ctx->P2 = params->percentile_profile ? static_cast<int>(2 * params->radial_bins)
                                          : static_cast<int>(2 * params->order * params->order);
     ctx->taps = (params->flags & SFK_FLAG_TAPS) != 0;
+    ctx->keepGrid = (params->flags & SFK_FLAG_KEEP_GRID) != 0;
     build_tables(*params, ctx->tab);
     CU(ctx->dNorms.upload(ctx->tab.norms, ctx->stream));
     CU(ctx->dRots.upload(ctx->tab.rots, ctx->stream));
@@ -1065,6 +1079,13 @@ int sfk_get_candidate_count(sfk_ctx *ctx, int64_t halo, int64_t *n) try {
     return SFK_OK;
 } SFK_CATCH(ctx)
 
+int sfk_get_intersection_count(sfk_ctx *ctx, int64_t halo, int64_t *n) try {
+    int rc = check_halo(ctx, halo, false);
+    if (rc) return rc;
+    *n = halo < static_cast<int64_t>(ctx->interPerHalo.size()) ? ctx->interPerHalo[halo] : 0;
+    return SFK_OK;
+} SFK_CATCH(ctx)
+
 int sfk_get_profiles(sfk_ctx *ctx, int64_t halo, double *rho) try {
     int rc = check_halo(ctx, halo, true);
     if (rc) return rc;
@@ -1081,6 +1102,16 @@ int sfk_get_counts(sfk_ctx *ctx, int64_t halo, uint32_t *n_insert, uint32_t *sta
     if (n_insert) CU(cudaMemcpy(n_insert, ctx->dTapInsert.p + halo * rn, rn * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (start_edges) CU(cudaMemcpy(start_edges, ctx->dTapStart.p + halo * rnb, rnb * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (end_edges) CU(cudaMemcpy(end_edges, ctx->dTapEnd.p + halo * rnb, rnb * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return SFK_OK;
+} SFK_CATCH(ctx)
+
+int sfk_get_grid(sfk_ctx *ctx, int64_t halo, int64_t *grid, double *quantum) try {
+    int rc = check_halo(ctx, halo, false);
+    if (rc) return rc;
+    if (!ctx->keepGrid) return fail(ctx, SFK_E_INVALID, "context was created without SFK_FLAG_KEEP_GRID");
+    const size_t rnb = static_cast<size_t>(ctx->rings) * ctx->spokes * ctx->bins;
+    if (grid) CU(cudaMemcpy(grid, ctx->dGridTap.p + halo * rnb, rnb * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (quantum) *quantum = ctx->halos[halo].quantum;
     return SFK_OK;
 } SFK_CATCH(ctx)
 

@@ -158,6 +158,11 @@ __device__ bool has_nan_los(double cx, double cy, double projDist2, double phiC,
 // a superset of the LoS whose far intersection exceeds rMin.  Both prunings
 // only drop work the reference does to no effect; the per-LoS evaluation in
 // bin_kernel stays literal.
+//
+// PRUNE == false (SFK_FLAG_NO_PRUNE, tests only) is the reference verbatim: all n LoS for a
+// centre-containing hit, float64 asin / atan2 and idxRange as written for the others, nothing
+// dropped.  tests/test_gpu_parity.py shows that both instantiations give identical integer bins.
+template <bool PRUNE>
 __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, double dPhi, double invDPhi, int n,
                          const double *ringCos, const double *ringSin, HitRec &r) {
     rotate_vec(rot, c.vx, c.vy, c.vz, r.cx, r.cy, r.cz);
@@ -166,6 +171,25 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
     double projRad2 = h.rad2 - cz * cz;
     if (projRad2 < 0) projRad2 = 0;
     r.rhoS = c.rho * h.scale;
+    if (!PRUNE) {
+        r.caseA = projRad2 > projDist2 ? 1u : 0u;
+        r.r01 = static_cast<uint32_t>(n) << 16; r.r23 = 0;
+        if (r.caseA) return true;
+        const double alpha = asin(sqrt(projRad2 / projDist2));   // halfAngularWidth, halo.go:315-318
+        const double projPhi = atan2(cy, cx);
+        const double phiLo = projPhi - alpha, phiHi = projPhi + alpha;
+        long long i0, i1, i2, i3;   // idxRange, halo.go:284-310
+        if (phiHi > kTwoPi) {
+            i0 = go_int(phiLo / dPhi); i1 = n; i2 = 0; i3 = go_int((phiHi - kTwoPi) / dPhi) + 1;
+        } else if (phiLo < 0) {
+            i0 = go_int((phiLo + kTwoPi) / dPhi); i1 = n; i2 = 0; i3 = go_int(phiHi / dPhi) + 1;
+        } else {
+            i0 = go_int(phiLo / dPhi); i1 = go_int(phiHi / dPhi) + 1; i2 = 0; i3 = 0;
+        }
+        r.r01 = clamp_idx(i0, n) | static_cast<uint32_t>(clamp_idx(i1, n)) << 16;
+        r.r23 = clamp_idx(i2, n) | static_cast<uint32_t>(clamp_idx(i3, n)) << 16;
+        return true;
+    }
     const double D = sqrt(projDist2), P = sqrt(projRad2);
     const double rMinSafe = h.rMin * (1.0 - 1e-9), rMaxSafe = h.rMax * (1.0 + 1e-9);
     if (projRad2 > projDist2) {
@@ -332,6 +356,7 @@ constexpr int kHitRingChunk = 64;   // rings per queue pass: 256 x 64 entries of
 // walks the queue with all lanes busy (the hit rate is ~1/3, so computing the
 // geometry in place would idle two lanes out of three), builds the record and
 // claims a slot of the (halo, ring) list.
+template <bool PRUNE>
 __global__ void __launch_bounds__(kHitThreads)
 hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const float *norms,
             const float *rots, const double *ringCos, const double *ringSin, int rings, int spokes,
@@ -376,7 +401,7 @@ hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const 
             const uint32_t q = e < nq ? queue[e] : 0u;
             const int ring = static_cast<int>(q >> 8);
             HitRec rec;
-            const bool alive = e < nq && make_hit(rots + 9 * ring, sCand[q & 0xffu], h, dPhi, invDPhi, spokes,
+            const bool alive = e < nq && make_hit<PRUNE>(rots + 9 * ring, sCand[q & 0xffu], h, dPhi, invDPhi, spokes,
                                                   ringCos, ringSin, rec);
             // one slot claim per (warp, ring): queue order keeps a ring's hits together
             const unsigned peers = __match_any_sync(0xffffffffu, alive ? ring : -1 - static_cast<int>(lane_id()));
@@ -1395,16 +1420,21 @@ cudaError_t launch_hits(const Piece *pieces, int nPieces, const Cand *cands,
                         const HaloDev *halos, const float *norms, const float *rots,
                         const double *ringCos, const double *ringSin,
                         int rings, int spokes, double dPhi, const int64_t *hitOffset,
-                        uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs, cudaStream_t s) {
+                        uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs, bool prune, cudaStream_t s) {
     if (nPieces <= 0) return cudaSuccess;
     const size_t smem = sizeof(Cand) * kHitThreads + sizeof(float) * 3 * rings +
                         sizeof(uint32_t) * kHitThreads * kHitRingChunk;
     {   // per device, so set it on every launch (a second GPU in the same process must get it too)
-        cudaError_t e = cudaFuncSetAttribute(hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = prune ? cudaFuncSetAttribute(hits_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                              : cudaFuncSetAttribute(hits_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
     }
-    hits_kernel<<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rots, ringCos, ringSin, rings,
-                                                   spokes, dPhi, hitOffset, hitCursor, haloSlot, recs);
+    if (prune)
+        hits_kernel<true><<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rots, ringCos, ringSin, rings,
+                                                             spokes, dPhi, hitOffset, hitCursor, haloSlot, recs);
+    else
+        hits_kernel<false><<<nPieces, kHitThreads, smem, s>>>(pieces, cands, halos, norms, rots, ringCos, ringSin, rings,
+                                                              spokes, dPhi, hitOffset, hitCursor, haloSlot, recs);
     return cudaGetLastError();
 }
 

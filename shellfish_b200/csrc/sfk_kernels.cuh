@@ -130,7 +130,7 @@ cudaError_t launch_hits(const Piece *pieces, int nPieces, const Cand *cands,
                         const HaloDev *halos, const float *norms, const float *rots,
                         const double *ringCos, const double *ringSin,
                         int rings, int spokes, double dPhi, const int64_t *hitOffset,
-                        uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs, cudaStream_t s);
+                        uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs, bool prune, cudaStream_t s);
 cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s);
 cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s);
 struct SgPoly;   // sfk_sgmath.cuh

@@ -10,24 +10,60 @@ the CPU tests).
 import numpy as np
 
 
-def partition_halos(weights, n_ranks):
+def partition_halos(weights, n_ranks, groups=None):
     """Longest-processing-time greedy partition.
 
     weights: per-halo cost estimate (particle count within the LoS sphere, or
-    R200m**3 as a proxy before the first pass).  Returns a list of n_ranks
-    index arrays; each keeps catalog order so that Transform's cumulative
-    in-place wrap (los/halo.go:168-197) sees the rank's halos in the same
-    relative order as the reference loop does.
+    R200m**3 as a proxy before the first pass).  groups: optional integer label
+    per halo (the snapshot block holding its centre, `block_of`); halos of one
+    group go to the same rank, so a rank reads few particle blocks -- it only
+    needs the blocks its own halos touch (`blocks_needed`).  Returns a list of
+    n_ranks index arrays; each keeps catalog order so that Transform's
+    cumulative in-place wrap (los/halo.go:168-197) sees the rank's halos in the
+    same relative order as the reference loop does.
     """
     weights = np.asarray(weights, np.float64)
-    order = np.argsort(-weights, kind="stable")
+    if groups is None:
+        groups = np.arange(len(weights))
+    groups = np.asarray(groups, np.int64)
+    labels, inv = np.unique(groups, return_inverse=True)
+    gw = np.bincount(inv, weights=weights, minlength=len(labels))
+    order = np.argsort(-gw, kind="stable")
     loads = np.zeros(n_ranks)
-    parts = [[] for _ in range(n_ranks)]
-    for i in order:
+    owner = np.zeros(len(labels), np.int64)
+    for g in order:
         r = int(np.argmin(loads))
-        parts[r].append(int(i))
-        loads[r] += weights[i]
-    return [np.array(sorted(p), np.int64) for p in parts]
+        owner[g] = r
+        loads[r] += gw[g]
+    halo_owner = owner[inv]
+    return [np.flatnonzero(halo_owner == r).astype(np.int64) for r in range(n_ranks)]
+
+
+def block_of(halos, blocks):
+    """Index of the block whose [Origin, Origin + Width) holds each halo centre
+    (-1 if none does): the affinity label for partition_halos."""
+    xyz = np.asarray(halos, np.float64)[:, :3]
+    out = np.full(len(xyz), -1, np.int64)
+    for bi, b in enumerate(blocks):
+        o = np.asarray(b["Origin"], np.float64)
+        w = np.asarray(b["Width"], np.float64)
+        m = np.all((xyz >= o) & (xyz < o + w), axis=1) & (out < 0)
+        out[m] = bi
+    return out
+
+
+def blocks_needed(ctx, blocks, owned):
+    """Indices of the blocks this rank has to push: those a halo it owns touches
+    (binIntersections, cmd/shell.go:599-611, restricted to the rank's halos).
+    A pushed block still replays Transform for every halo touching it, owned or
+    not (sfk_set_owned), so results do not depend on the partition."""
+    owned = np.asarray(owned, bool)
+    need = []
+    for bi, b in enumerate(blocks):
+        hit = ctx.block_halo_mask(b["Origin"], b["Width"], b["TotalWidth"])
+        if np.any(hit & owned):
+            need.append(bi)
+    return need
 
 
 def estimate_weights(halos, r_max_mult=3.0, r_kernel_mult=0.2):
@@ -70,6 +106,30 @@ def gather_rows(local_idx, local_rows, n_total, dist=None, device="cpu"):
         m = i_np >= 0
         full[i_np[m]] = r_np[m]
     return full
+
+
+def gather_table(parts, rank, local_rows, n_total, dist=None, device="cpu"):
+    """gather_rows when every rank knows the whole partition (`parts` from
+    partition_halos): one fixed-size all-gather, no size or index exchange.
+    local_rows: (len(parts[rank]), k).  Returns the (n_total, k) table."""
+    local_rows = np.asarray(local_rows, np.float64)
+    k = local_rows.shape[1]
+    table = np.zeros((n_total, k))
+    world = len(parts)
+    if world == 1 or dist is None or not dist.is_initialized():
+        table[parts[rank]] = local_rows
+        return table
+    import torch
+    n_max = max(1, max(len(p) for p in parts))
+    loc = torch.zeros((n_max, k), dtype=torch.float64)
+    loc[:len(local_rows)] = torch.from_numpy(local_rows)
+    loc = loc.to(device)
+    full = torch.empty((world * n_max, k), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(full, loc)
+    full = full.cpu().numpy().reshape(world, n_max, k)
+    for r, p in enumerate(parts):
+        table[p] = full[r, :len(p)]
+    return table
 
 
 def split_halo_finish(ctx, dist):

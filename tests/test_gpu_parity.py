@@ -393,3 +393,68 @@ def test_experimental_los_moments_flag():
     _, cz0, _ = api.run_shell(api.default_params(rings=6, seed=1337), 0.0, halos, blocks)
     _, cz1, _ = api.run_shell(api.default_params(rings=6, seed=1337, flags=api.SFK_FLAG_LOS_MOMENTS), 0.0, halos, blocks)
     assert np.array_equal(cz0, cz1, equal_nan=True)
+
+
+def _taps_of(flags, halos, blocks, mass, **kw):
+    ctx, c, s = api.run_shell(api.default_params(seed=1337, flags=flags, **kw), mass, halos, blocks)
+    return ctx, c, s
+
+
+def test_pruned_and_literal_hit_records_give_identical_integer_bins():
+    """Differential test of the exact pruning in make_hit (sfk_kernels.cu) on > 1e7 ring hits.
+    SFK_FLAG_NO_PRUNE builds every record as insertToRing / idxRange write it (los/halo.go:
+    241-310: all n LoS for a centre-containing circle, float64 asin / atan2, the scan up to LoS
+    n - 1 of a wedge that atan2 puts below zero); the default path trims LoS ranges and drops
+    hits.  Inserts per LoS, start / end edges per (LoS, bin), the int64 bin grid and every
+    downstream number must be identical: the pruning only removes work that reaches no bin."""
+    rng = np.random.default_rng(5)
+    halos, blocks, mass = synth.single_halo(seed=41, n=260000, n_background=30000)
+    c = halos[0, :3]
+    # a dense core (centre-containing circles) and a sheet of particles around phi = +-pi of
+    # the z axis frame (wedges that wrap), on top of the NFW + infall halo
+    n_core = 40000
+    v = rng.normal(size=(n_core, 3))
+    v *= (0.3 * rng.random(n_core) ** (1 / 3) / np.linalg.norm(v, axis=1))[:, None]
+    ang = np.pi + rng.normal(scale=0.05, size=20000)
+    rad = rng.uniform(0.25, 3.1, 20000)
+    sheet = np.stack([rad * np.cos(ang), rad * np.sin(ang), rng.normal(scale=0.3, size=20000)], axis=1)
+    extra = (c + np.concatenate([v, sheet])).astype(np.float32)
+    b = blocks[0]
+    b["xs"] = np.concatenate([b["xs"], extra]).astype(np.float32)
+    b["ms"] = np.concatenate([b["ms"], np.full(len(extra), mass, np.float32)])
+    T, K, N = api.SFK_FLAG_TAPS, api.SFK_FLAG_KEEP_GRID, api.SFK_FLAG_NO_PRUNE
+    a, ca, sa = _taps_of(T | K, halos, blocks, mass)
+    l, cl, sl = _taps_of(T | K | N, halos, blocks, mass)
+    assert a.stats()["n_ring_hits"] > 10_000_000
+    assert a.stats()["n_ring_hits"] == l.stats()["n_ring_hits"]   # raw sphereIntersectRing successes
+    assert a.stats()["n_intersections"] == l.stats()["n_intersections"]
+    for x, y in zip(a.counts(0), l.counts(0)):
+        assert np.array_equal(x, y)
+    ga, qa = a.grid(0)
+    gl, ql = l.grid(0)
+    assert qa == ql and np.array_equal(ga, gl)
+    assert np.array_equal(a.rsp(0), l.rsp(0), equal_nan=True)
+    assert np.array_equal(ca, cl) and np.array_equal(sa, sl)
+
+
+@pytest.mark.parametrize("rings,n", [(100, 50000), (7, 30000)])
+def test_product_bin_kernel_writes_the_grid_whose_taps_are_checked(rings, n):
+    """The integer taps (inserts, edges) are read from bin_kernel<TAPS = true>; the product
+    runs bin_kernel<false>.  Both must leave the same int64 grid, and the grid must be the
+    prefix-differenced profile the oracle holds: sum over bins of grid * quantum == GetRhos
+    before the clamp."""
+    halos, blocks, mass = synth.single_halo(seed=43, n=n, n_background=8000)
+    K = api.SFK_FLAG_KEEP_GRID
+    prod, cp, sp_ = _taps_of(K, halos, blocks, mass, rings=rings)
+    taps, ct, st = _taps_of(K | api.SFK_FLAG_TAPS, halos, blocks, mass, rings=rings)
+    gp, qp = prod.grid(0)
+    gt, qt = taps.grid(0)
+    assert qp == qt and np.array_equal(gp, gt)
+    assert np.array_equal(cp, ct) and np.array_equal(prod.rsp(0), taps.rsp(0), equal_nan=True)
+    ref = po.shell_run(po.ShellConfig.default(seed=1337, threads=4, rings=rings), mass, halos, blocks,
+                       taps=("profiles",))
+    rho = np.cumsum(gp, axis=2).astype(np.float64) * qp
+    rp = ref["profiles"][0]
+    bg = rp.min()
+    rho = np.maximum(rho, bg)
+    assert np.max(np.abs(rho - rp) / np.maximum(np.abs(rp), bg)) <= RTOL
