@@ -49,8 +49,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--order", type=int, default=3, help="Penna order (BASELINE config 5 sweeps 2, 3, 4)")
     ap.add_argument("--subsample", type=int, default=1, help="SubsampleFactor (config 5: 1, 2)")
-    ap.add_argument("--los-moments", action="store_true",
-                    help="A/B switch: SFK_FLAG_LOS_MOMENTS (experimental sliding-moment Savitzky-Golay)")
+    ap.add_argument("--los-taploop", action="store_true",
+                    help="A/B switch: SFK_FLAG_LOS_TAPLOOP (literal Savitzky-Golay tap loop instead of sliding moments)")
     return ap.parse_args()
 
 
@@ -66,8 +66,8 @@ def workload(args):
               "order": args.order, "subsample": args.subsample,
               "l2": "inputs larger than L2: %.1f GB of particle blocks and > 100 MB of hit records per halo each step"
                     % (16.0 * args.n_total / 1e9)}
-    if args.los_moments:
-        config["los_moments"] = True   # experimental kernel variant: not the default product path
+    if args.los_taploop:
+        config["los_taploop"] = True   # A/B variant: not the default product path
     meta = {"setup_s": round(time.time() - t, 1)}
     return halos, blocks, mass, config, meta
 
@@ -206,7 +206,7 @@ def main():
     halos, blocks, mass, config, meta = workload(args)
     nH = len(halos)
     params = api.default_params(seed=1337, device=local, order=args.order, subsample_factor=args.subsample,
-                                flags=api.SFK_FLAG_LOS_MOMENTS if args.los_moments else 0)
+                                flags=api.SFK_FLAG_LOS_TAPLOOP if args.los_taploop else 0)
     ctx = api.ShellContext(params)
     R, n, B = int(params.rings), int(params.spokes), int(params.radial_bins)
     P2 = ctx.P2

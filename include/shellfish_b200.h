@@ -42,10 +42,12 @@ extern "C" {
 
 /* sfk_params.flags */
 #define SFK_FLAG_TAPS 1u /* keep parity taps: profiles, integer edge counts */
-/* Experimental: evaluate the two Savitzky-Golay filters of Smooth (smooth.go:46-81)
- * through five sliding polynomial moments instead of 2 x SmoothingWindow taps per bin.
- * Same result to ~1e-13 (not bit-identical to the tap loop); off by default. */
-#define SFK_FLAG_LOS_MOMENTS 2u
+/* A/B and tests: evaluate the two Savitzky-Golay filters of Smooth (smooth.go:46-81) with
+ * the literal 2 x SmoothingWindow tap loop of ConvolveAt (filter.go:104-161) and libm's log.
+ * The default evaluates them through five sliding polynomial moments (same values to
+ * ~1e-13, same R_sp) whenever RadialBins = 256, SmoothingWindow <= 231 and the background
+ * density is positive; every other configuration always takes the tap loop. */
+#define SFK_FLAG_LOS_TAPLOOP 2u
 /* Tests only: build the ring-frame hit records exactly as insertToRing / idxRange do
  * (los/halo.go:241-310: all n LoS for a centre-containing circle, float64 asin / atan2,
  * nothing dropped), i.e. without the exact pruning of the product path, so that a test

@@ -4,6 +4,10 @@ lines.  ncu's CSV source page lists SASS only, so the line table comes from
 `nvdisasm -g` on the cubin embedded in libsfk.so (same instruction order).
 
   python profiles/ncu_by_line.py gpurun_out/prof.ncu-rep sfk_bin bin_kernelILb0 [top]
+
+For a report holding several kernels set NCU_KERNEL (a name regex; the first matching launch
+is used).  SFK_LIB / SFK_SRC point at the libsfk.so and csrc/ the report was captured from when
+the tree has moved on since.
 """
 import collections
 import csv
@@ -24,7 +28,10 @@ def sh(cmd, **kw):
 def main():
     rep, unit, func = sys.argv[1], sys.argv[2], sys.argv[3]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    raw = list(csv.reader(io.StringIO(sh("ncu -i %s --page raw --csv" % rep))))
+    sel = ""
+    if os.environ.get("NCU_KERNEL"):
+        sel = " -k regex:%s -c 1" % os.environ["NCU_KERNEL"]
+    raw = list(csv.reader(io.StringIO(sh("ncu -i %s%s --page raw --csv" % (rep, sel)))))
     hdr, units, vals = raw[0], raw[1], raw[2]
     keys = ["gpu__time_duration.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
             "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -38,12 +45,16 @@ def main():
     for h, u, v in zip(hdr, units, vals):
         if h in keys:
             print("%s [%s] = %s" % (h, u, v))
-    src = list(csv.reader(io.StringIO(sh("ncu -i %s --page source --csv" % rep))))
+    src = list(csv.reader(io.StringIO(sh("ncu -i %s%s --page source --csv" % (rep, sel)))))
     h2, data = src[1], src[2:]
+    for i, r in enumerate(data):   # several launches in the report: keep the first
+        if r and r[0] == "Kernel Name":
+            data = data[:i]
+            break
     iI, iS, iSm = h2.index("Instructions Executed"), h2.index("Source"), h2.index("# Samples")
     iT = h2.index("Thread Instructions Executed")
     with tempfile.TemporaryDirectory() as td:
-        sh("cuobjdump -xelf all %s" % os.path.join(ROOT, "shellfish_b200", "libsfk.so"), cwd=td)
+        sh("cuobjdump -xelf all %s" % os.environ.get("SFK_LIB", os.path.join(ROOT, "shellfish_b200", "libsfk.so")), cwd=td)
         sass = sh("nvdisasm -g -c %s.sm_100a.cubin" % unit, cwd=td).split("\n")
     start = next(i for i, l in enumerate(sass) if l.startswith(".text.") and func in l)
     cur, seq = None, []
@@ -69,7 +80,7 @@ def main():
     print("\nSASS mix (warp instructions):")
     for k, v in mix.most_common(16):
         print("  %-10s %14d %5.1f%%" % (k, v, 100.0 * v / tot))
-    text = open(os.path.join(ROOT, "shellfish_b200", "csrc", unit + ".cu")).read().split("\n")
+    text = open(os.path.join(os.environ.get("SFK_SRC", os.path.join(ROOT, "shellfish_b200", "csrc")), unit + ".cu")).read().split("\n")
     print("\nby source line (warp instructions, share, stall samples, mean active lanes):")
     for ln, v in sorted(per.items(), key=lambda kv: -kv[1])[:top]:
         t = text[ln - 1].strip()[:88] if ln and ln > 0 else "<inlined from a header>"

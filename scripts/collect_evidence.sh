@@ -46,7 +46,7 @@ if [ "${2:-}" = "full" ]; then
     timeout 600 python bench.py > $OUT/${TAG}_bench_full.json 2> $OUT/${TAG}_bench_full.err
     echo "bench full rc=$? $(cut -c1-200 $OUT/${TAG}_bench_full.json)"
 fi
-if [ "${3:-}" = "moments" ]; then
-    timeout 400 python bench.py --no-cpu --no-e2e --los-moments > $OUT/${TAG}_bench_full_los_moments.json 2> $OUT/${TAG}_bench_full_los_moments.err
-    echo "bench full (los moments) rc=$? $(cut -c1-200 $OUT/${TAG}_bench_full_los_moments.json)"
+if [ "${3:-}" = "taploop" ]; then
+    timeout 400 python bench.py --no-cpu --no-e2e --los-taploop > $OUT/${TAG}_bench_full_los_taploop.json 2> $OUT/${TAG}_bench_full_los_taploop.err
+    echo "bench full (los tap loop) rc=$? $(cut -c1-200 $OUT/${TAG}_bench_full_los_taploop.json)"
 fi

@@ -9,7 +9,7 @@ from shellfish_b200 import api, synth  # noqa: E402
 
 halos, blocks, mass = synth.single_halo(seed=3, n=20000, n_background=5000)
 out = {}
-for name, flags in (("taps", 0), ("moments", api.SFK_FLAG_LOS_MOMENTS)):
+for name, flags in (("taps", api.SFK_FLAG_LOS_TAPLOOP), ("moments", 0)):
     best = None
     for _ in range(3):
         ctx, coeffs, status = api.run_shell(api.default_params(seed=1337, flags=flags), mass, halos, blocks)

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsfk.so")
 
 SFK_FLAG_TAPS = 1
-SFK_FLAG_LOS_MOMENTS = 2   # experimental, see include/shellfish_b200.h
+SFK_FLAG_LOS_TAPLOOP = 2   # A/B: literal Savitzky-Golay tap loop instead of sliding moments
 SFK_FLAG_NO_PRUNE = 4      # tests only: literal insertToRing / idxRange records
 SFK_FLAG_KEEP_GRID = 8     # tests only: keep the int64 bin grids for ShellContext.grid
 SPLIT_HIT_COUNTS, SPLIT_RHO_MAX, SPLIT_GRID = 0, 1, 2

@@ -79,9 +79,9 @@ struct sfk_ctx {
     bool taps = false;
 
     DevBuf<float> dNorms, dRots, dIrots;
-    DevBuf<double> dCos, dSin, dPhi, dTaps0, dTaps1, dBinInvG;
+    DevBuf<double> dCos, dSin, dPhi, dTaps0, dTaps1, dBinInvG, dLogTab;
     bool tapsReady = false;  // Sav-Gol kernels cached for the process, smooth.go:84-96
-    SgPoly sg{};             // the same taps as polynomials of the offset (SFK_FLAG_LOS_MOMENTS)
+    SgPoly sg{};             // the same taps as polynomials of the offset (sliding-moment smoothing)
     bool sgReady = false;
 
     // snapshot state
@@ -131,7 +131,8 @@ struct sfk_ctx {
     DevBuf<int64_t> dHitOffset;
     DevBuf<uint32_t> dHitCursor, dBatchHitCount;
     DevBuf<int32_t> dBatchHalos, dHaloSlot;
-    DevBuf<unsigned long long> dGrid;
+    DevBuf<unsigned long long> dGrid, dOvfList;
+    DevBuf<unsigned> dOvfCount;
     DevBuf<double> dFR;
     DevBuf<int32_t> dFIdx, dFCount;
 
@@ -459,7 +460,6 @@ int stage_bin(sfk_ctx *ctx, const std::vector<int32_t> &batch) {
     CU(ctx->dHaloSlot.upload(haloSlot, st));
     CU(ctx->dHitOffset.upload(hitOffset, st));
     CU(cudaMemsetAsync(ctx->dHitCursor.p, 0, static_cast<size_t>(nb) * R * sizeof(uint32_t), st));
-    CU(cudaMemsetAsync(ctx->dGrid.p, 0, static_cast<size_t>(nb) * rnb * sizeof(unsigned long long), st));
 
     ctx->timer.begin(ST_HITS, st);
     CU(launch_hits(ctx->dPieces.p, static_cast<int>(pieces.size()), ctx->dCands.p, ctx->dHalos.p,
@@ -482,6 +482,16 @@ int stage_bin(sfk_ctx *ctx, const std::vector<int32_t> &batch) {
     // split long hit lists when there are too few CTAs to fill 148 SMs x 2 for a few waves
     const int64_t ctas = static_cast<int64_t>((n + kTileLos - 1) / kTileLos) * R * nb;
     ba.chunks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(64, (148 * 2 * 4 + ctas - 1) / ctas)));
+    constexpr unsigned kOvfCap = 1u << 16;
+    if (!ctx->dOvfCount.p) {
+        CU(ctx->dOvfList.ensure(2 * kOvfCap));
+        CU(ctx->dOvfCount.ensure(2));
+        CU(cudaMemsetAsync(ctx->dOvfCount.p, 0, 2 * sizeof(unsigned), st));
+    }
+    ba.ovfList = ctx->dOvfList.p; ba.ovfCount = ctx->dOvfCount.p; ba.ovfCap = kOvfCap;
+    // partial tiles are added with RED.64 and need a zeroed grid; whole tiles are stored
+    if (!bin_stores_whole_grid(ba))
+        CU(cudaMemsetAsync(ctx->dGrid.p, 0, static_cast<size_t>(nb) * rnb * sizeof(unsigned long long), st));
     ctx->timer.begin(ST_BIN, st);
     CU(launch_bin(ba, nb, ctx->taps, st));
     ctx->stats.launches++; ctx->stats.bin_launches++;
@@ -517,18 +527,17 @@ int stage_analyze(sfk_ctx *ctx, int nb) {
     }
     LosArgs la{};
     la.grid = ctx->dGrid.p; la.halos = ctx->dHalos.p; la.batchHalos = ctx->dBatchHalos.p;
-    la.valTaps = ctx->dTaps0.p; la.derivTaps = ctx->dTaps1.p;
+    la.valTaps = ctx->dTaps0.p; la.derivTaps = ctx->dTaps1.p; la.logTab = ctx->dLogTab.p;
     la.rsp = ctx->dRsp.p; la.profiles = ctx->taps ? ctx->dProfiles.p : nullptr;
     la.rings = R; la.spokes = n; la.bins = B; la.window = static_cast<int>(ctx->p.smoothing_window);
     la.dLim = ctx->p.los_slope_cutoff;
-    // Experimental sliding-moment smoothing: only when every ln(rho) is finite (rho_bg > 0; with
+    // Sliding-moment smoothing only when every ln(rho) is finite and normal (rho_bg > 0; with
     // Gadget-2's MinMass() == 0 the reference's -Inf / NaN propagation must stay sample-exact).
-    bool moments = (ctx->p.flags & SFK_FLAG_LOS_MOMENTS) && ctx->sgReady && los_moments_supported(la);
+    bool moments = !(ctx->p.flags & SFK_FLAG_LOS_TAPLOOP) && ctx->sgReady && los_moments_supported(la);
     for (const HaloDev &h : ctx->halos)
-        if (h.valid && !(h.defaultRho > 0)) moments = false;
+        if (h.valid && !(h.defaultRho >= 1e-290 && h.defaultRho <= 1e290 && h.quantum >= 1e-290)) moments = false;
     ctx->timer.begin(ST_LOS, st);
-    if (moments) CU(launch_los_moments(la, ctx->sg, nb, st));
-    else CU(launch_los(la, nb, st));
+    CU(launch_los(la, moments ? &ctx->sg : nullptr, nb, st));
     ctx->stats.launches++;
     ctx->timer.end(ST_LOS, st);
 
@@ -566,11 +575,17 @@ int stage_collect(sfk_ctx *ctx, double *coeffs, int32_t *status) {
     std::vector<int32_t> dstat(nHalo);
     std::vector<unsigned long long> nInter(nHalo);
     std::vector<long long> nPts(nHalo);
+    unsigned ovf[2] = {0, 0};
+    if (ctx->dOvfCount.p) CU(cudaMemcpyAsync(ovf, ctx->dOvfCount.p, sizeof ovf, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ctx->hCoeffs.data(), ctx->dCoeffs.p, ctx->hCoeffs.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(dstat.data(), ctx->dStatus.p, nHalo * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(nInter.data(), ctx->dNInter.p, nHalo * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(nPts.data(), ctx->dNPoints.p, nHalo * sizeof(long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (ovf[1] != 0) {
+        CU(cudaMemsetAsync(ctx->dOvfCount.p, 0, 2 * sizeof(unsigned), st));
+        return fail(ctx, SFK_E_UNSUPPORTED, "bin_kernel: side list of edges on rMax exhausted");
+    }
     ctx->interPerHalo.assign(nInter.begin(), nInter.end());
     for (int64_t i = 0; i < nHalo; i++) {
         if (ctx->hStatus[i] == SFK_HALO_OK) ctx->hStatus[i] = dstat[i];
@@ -653,6 +668,9 @@ static int create_impl(sfk_ctx *ctx, const sfk_params *params) try {
     CU(ctx->dSin.upload(ctx->tab.ringSin, ctx->stream));
     CU(ctx->dPhi.upload(ctx->tab.ringPhi, ctx->stream));
     CU(ctx->dBinInvG.upload(ctx->tab.binInvG, ctx->stream));
+    std::vector<double> logTab;
+    build_log_table(logTab);
+    CU(ctx->dLogTab.upload(logTab, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SFK_OK;
 } SFK_CATCH(ctx)

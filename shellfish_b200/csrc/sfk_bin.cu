@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 
 #include "sfk_kernels.cuh"
+#include "sfk_device.cuh"
 
 namespace sfk {
 
@@ -42,21 +43,6 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// sqrt for x >= 0: MUFU.RSQ64H seed (~2^-22), one Newton step on 1/sqrt
-// (~2^-44), one residual correction of the root (<= 1 ulp), branch free.
-// Callers test the sign first.
-__device__ __forceinline__ double sqrt_pos(double x) {
-    x += 1e-300;   // 0 -> 1e-150 (still far below every rMin); exact no-op for x > 1e-284
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double hx = 0.5 * x;
-    const double e = fma(-hx * y, y, 0.5);
-    y = fma(y, e, y);
-    const double s = x * y;
-    const double r = fma(-s, s, x);
-    return fma(r, 0.5 * y, s);
-}
 
 // Bin index and fractional position of radius r, rMin < r < rMax
 // (profile_ring.go:100-101: Modf((ln r - lowR)/dr)).
@@ -133,16 +119,14 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
                           static_cast<unsigned>(st2 - t0) << 16;
 
     for (unsigned p0 = 0; p0 < nPairs; p0 += 32) {
-        // pair p -> record: the number of records whose pairs end at or before p, by
-        // binary search over the (non-decreasing) inclusive scan held one per lane
+        // pair p -> record.  Every record of the round owns >= 1 pair, so the first-pair indices
+        // are strictly increasing: one REDUX.OR marks the records that start inside this window
+        // of 32 pairs, and pair p belongs to the last record starting at or before it.
         const unsigned p = p0 + lane;
-        unsigned r = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            const unsigned v = __shfl_sync(0xffffffffu, incl, (r + step - 1) & 31);
-            if (v <= p) r += step;
-        }
-        r &= 31;   // lanes past nPairs (r == 32) are dropped below
+        const unsigned rel = first - p0;   // wraps for records that started earlier
+        const unsigned starts = __reduce_or_sync(0xffffffffu, (nMine && rel < 32u) ? 1u << rel : 0u);
+        const unsigned nBefore = __popc(__ballot_sync(0xffffffffu, nMine && first < p0));
+        const unsigned r = (nBefore + __popc(starts & (0xffffffffu >> (31 - lane))) - 1u) & 31u;
         const unsigned before = __shfl_sync(0xffffffffu, first, r);
         const unsigned rmeta = __shfl_sync(0xffffffffu, meta, r);
         if (p >= nPairs) continue;
@@ -282,8 +266,9 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
                 load_ranges(nxt, nr);
 #pragma unroll
                 for (int sub = 0; sub < kChunkRecs / 32; sub++) {
-                    const bool ov = (static_cast<int>(rr[sub].x & 0xffffu) < t1 && static_cast<int>(rr[sub].x >> 16) > t0) ||
-                                    (static_cast<int>(rr[sub].y & 0xffffu) < t1 && static_cast<int>(rr[sub].y >> 16) > t0);
+                    // a kept record has at least one LoS in the tile (bin_round relies on it)
+                    const bool ov = min(static_cast<int>(rr[sub].x >> 16), t1) > max(static_cast<int>(rr[sub].x & 0xffffu), t0) ||
+                                    min(static_cast<int>(rr[sub].y >> 16), t1) > max(static_cast<int>(rr[sub].y & 0xffffu), t0);
                     const unsigned m = __ballot_sync(0xffffffffu, ov);
                     if (ov) {
                         const int at = (head + count + __popc(m & ((1u << lane) - 1u))) & (kRingSlots - 1);
@@ -320,8 +305,39 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     }
     __syncthreads();
 
-    // flush the tile: [LoS][bin] rows, coalesced over bins
+    // flush the tile into the [LoS][bin] rows of the grid
     unsigned long long *g = a.grid + (static_cast<size_t>(slot) * a.rings + ring) * a.spokes * bins;
+    if (a.chunks == 1 && (bins & 3) == 0) {
+        // This CTA is the only writer of its 32 rows: plain stores of every cell, zeros included,
+        // so the grid needs no memset and no read-modify-write.  Lane = LoS (conflict-free reads
+        // of the bin-major tile), four consecutive bins = one full 32-byte sector per lane.
+        const int gl = t0 + lane;
+        for (int b0 = warp * 4; b0 < bins; b0 += kBinConsumers * 4) {
+            unsigned long long v[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                v[c] = (static_cast<unsigned long long>(hi[(b0 + c) * kTileLos + lane]) << 32) | lo[(b0 + c) * kTileLos + lane];
+            if (gl < a.spokes) {
+                ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(g + static_cast<size_t>(gl) * bins + b0);
+                dst[0] = make_ulonglong2(v[0], v[1]);
+                dst[1] = make_ulonglong2(v[2], v[3]);
+            }
+        }
+        // index == bins lands in the next LoS's first bin (derivs is one slice), which may belong
+        // to another CTA: such edges (start or end within an ulp of rMax) go to a side list that
+        // bin_overflow_kernel adds once every tile is stored
+        if (warp == 0 && gl + 1 < a.spokes) {
+            const unsigned long long v = (static_cast<unsigned long long>(hi[bins * kTileLos + lane]) << 32) | lo[bins * kTileLos + lane];
+            if (v != 0) {
+                const unsigned at = atomicAdd(a.ovfCount, 1u);
+                if (at < a.ovfCap) {
+                    a.ovfList[2 * at] = static_cast<unsigned long long>((g - a.grid) + static_cast<size_t>(gl + 1) * bins);
+                    a.ovfList[2 * at + 1] = v;
+                }
+            }
+        }
+        return;
+    }
     for (int k = threadIdx.x; k < kTileLos * stride; k += kBinThreads) {
         const int l = k / stride, bin = k - l * stride;
         const int gl = tile * kTileLos + l;
@@ -338,7 +354,21 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     }
 }
 
+// Adds the side list of the plain-store flush (edges that land in the next LoS's first bin) and
+// re-arms it; ovfCount[1] counts entries that did not fit (sfk_finish_snapshot fails on it).
+__global__ void bin_overflow_kernel(unsigned long long *grid, const unsigned long long *list, unsigned *count, unsigned cap) {
+    const unsigned n = count[0];
+    for (unsigned e = threadIdx.x; e < min(n, cap); e += blockDim.x) atomicAdd(&grid[list[2 * e]], list[2 * e + 1]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (n > cap) count[1] += n - cap;
+        count[0] = 0;
+    }
+}
+
 }  // namespace
+
+bool bin_stores_whole_grid(const BinArgs &a) { return a.chunks == 1 && (a.bins & 3) == 0; }
 
 size_t bin_smem_bytes(int bins) {
     return sizeof(HitRec) * kBinConsumers * kRingSlots + sizeof(double2) * kTileLos + sizeof(double) * (bins + 1) +
@@ -357,6 +387,7 @@ cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s) {
     dim3 grid(nTiles * a.chunks, a.rings, nb);
     if (taps) bin_kernel<true><<<grid, kBinThreads, smem, s>>>(a);
     else bin_kernel<false><<<grid, kBinThreads, smem, s>>>(a);
+    if (bin_stores_whole_grid(a)) bin_overflow_kernel<<<1, 256, 0, s>>>(a.grid, a.ovfList, a.ovfCount, a.ovfCap);
     return cudaGetLastError();
 }
 

@@ -5,6 +5,21 @@
 
 namespace sfk {
 
+// sqrt for x >= 0: MUFU.RSQ64H seed (~2^-22), one Newton step on 1/sqrt
+// (~2^-44), one residual correction of the root (<= 1 ulp), branch free.
+// Callers test the sign first.
+__device__ __forceinline__ double sqrt_pos(double x) {
+    x += 1e-300;   // 0 -> 1e-150 (still far below every rMin); exact no-op for x > 1e-284
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    const double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    const double s = x * y;
+    const double r = fma(-s, s, x);
+    return fma(r, 0.5 * y, s);
+}
+
 // Go's math.Pow for small non-negative integer exponents (src/math/pow.go):
 // repeated squaring on frexp mantissas.
 __device__ inline double go_pow_int(double x, int yi) {

@@ -78,6 +78,7 @@ double rho_average(double H0, double omegaM, double omegaL, double z);
 bool savgol_taps(int order, int width, int ld, double dx, std::vector<double> &taps);
 double go_pow(double x, double y);
 struct SgPoly;   // sfk_sgmath.cuh
+void build_log_table(std::vector<double> &tab);
 bool savgol_poly(const std::vector<double> &taps0, const std::vector<double> &taps1, SgPoly &out);
 // `stats` shell properties (sfk_axes.cpp): quadrature rule and per-halo closing arithmetic.
 void gauss_legendre(int n, std::vector<double> &x, std::vector<double> &w);

@@ -190,7 +190,9 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
         r.r23 = clamp_idx(i2, n) | static_cast<uint32_t>(clamp_idx(i3, n)) << 16;
         return true;
     }
-    const double D = sqrt(projDist2), P = sqrt(projRad2);
+    // D, P only enter comparisons guarded by 1e-9 relative margins or LoS-spacing guards: the
+    // <= 1 ulp branch-free root serves
+    const double D = sqrt_pos(projDist2), P = sqrt_pos(projRad2);
     const double rMinSafe = h.rMin * (1.0 - 1e-9), rMaxSafe = h.rMax * (1.0 + 1e-9);
     if (projRad2 > projDist2) {
         // circle contains the centre: Insert(-Inf, ln rHi) on every LoS, halo.go:241-250
@@ -356,6 +358,12 @@ constexpr int kHitRingChunk = 64;   // rings per queue pass: 256 x 64 entries of
 // walks the queue with all lanes busy (the hit rate is ~1/3, so computing the
 // geometry in place would idle two lanes out of three), builds the record and
 // claims a slot of the (halo, ring) list.
+// The queue has two ends.  Whether the projected circle contains the centre
+// (insertToRing's first branch) is |v|^2 < rad^2 up to the rounding of the
+// rotation, i.e. a property of the PARTICLE, and the two branches of make_hit
+// share almost no code; so hits of particles inside the kernel radius grow from
+// the bottom of the queue and all others from the top, and a warp of phase 2
+// runs one branch (the few misfiled entries at |v| ~ rad only cost divergence).
 template <bool PRUNE>
 __global__ void __launch_bounds__(kHitThreads)
 hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const float *norms,
@@ -366,7 +374,8 @@ hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const 
     Cand *sCand = reinterpret_cast<Cand *>(smemRaw);                          // [256]
     float *sNorm = reinterpret_cast<float *>(sCand + kHitThreads);            // [rings][3]
     uint32_t *queue = reinterpret_cast<uint32_t *>(sNorm + 3 * rings);        // [256 * kHitRingChunk]
-    __shared__ uint32_t qCount;
+    __shared__ uint32_t qCount[2];
+    constexpr uint32_t qCap = kHitThreads * kHitRingChunk;
     const Piece pc = pieces[blockIdx.x];
     const HaloDev &h = halos[pc.halo];
     const int slot = haloSlot[pc.halo];
@@ -378,9 +387,10 @@ hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const 
     sCand[threadIdx.x] = c;
     const double rad = h.rad;
     const double invDPhi = 1.0 / dPhi;
+    const bool inner = static_cast<double>((c.vx * c.vx + c.vy * c.vy) + c.vz * c.vz) < h.rad2;
     for (int r0 = 0; r0 < rings; r0 += kHitRingChunk) {
         const int r1 = min(rings, r0 + kHitRingChunk);
-        if (threadIdx.x == 0) qCount = 0;
+        if (threadIdx.x < 2) qCount[threadIdx.x] = 0;
         __syncthreads();
         for (int ring = r0; ring < r1; ring++) {
             const float d = (sNorm[3 * ring] * c.vx + sNorm[3 * ring + 1] * c.vy) + sNorm[3 * ring + 2] * c.vz;
@@ -388,17 +398,26 @@ hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const 
             const bool hit = live && dot < rad && dot > -rad;
             const unsigned mask = __ballot_sync(0xffffffffu, hit);
             if (mask == 0) continue;
-            const int leader = __ffs(mask) - 1;
+            const unsigned maskIn = __ballot_sync(0xffffffffu, hit && inner);
+            const unsigned mine = inner ? maskIn : mask & ~maskIn;   // the hits of my end of the queue
+            // lanes 0 and 1 claim the slots of the bottom and top end
             uint32_t base = 0;
-            if (lane_id() == leader) base = atomicAdd(&qCount, __popc(mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (hit) queue[base + __popc(mask & ((1u << lane_id()) - 1u))] = threadIdx.x | (ring << 8);
+            if (lane_id() < 2) {
+                const int cnt = __popc(lane_id() == 0 ? maskIn : mask & ~maskIn);
+                if (cnt) base = atomicAdd(&qCount[lane_id()], cnt);
+            }
+            base = __shfl_sync(0xffffffffu, base, inner ? 0 : 1);
+            if (hit) {
+                const uint32_t at = base + __popc(mine & ((1u << lane_id()) - 1u));
+                queue[inner ? at : qCap - 1 - at] = threadIdx.x | (ring << 8);
+            }
         }
         __syncthreads();
-        const uint32_t nq = qCount;
+        for (int end = 0; end < 2; end++) {
+        const uint32_t nq = qCount[end];
         for (uint32_t e0 = threadIdx.x & ~31u; e0 < nq; e0 += kHitThreads) {
             const uint32_t e = e0 + lane_id();
-            const uint32_t q = e < nq ? queue[e] : 0u;
+            const uint32_t q = e < nq ? queue[end == 0 ? e : qCap - 1 - e] : 0u;
             const int ring = static_cast<int>(q >> 8);
             HitRec rec;
             const bool alive = e < nq && make_hit<PRUNE>(rots + 9 * ring, sCand[q & 0xffu], h, dPhi, invDPhi, spokes,
@@ -414,6 +433,7 @@ hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const 
                 recs[hitOffset[hr] + base + __popc(peers & ((1u << lane_id()) - 1u))] = rec;
             }
         }
+        }
         __syncthreads();
     }
 }
@@ -428,14 +448,46 @@ constexpr int kLosFastMaxWindow = 8 * kLosFastRow - 256 - 24;
 
 __device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8000000000000ll); }
 
+// ln(x) for a normal x > 0: x = 2^e m, m in [1, 2); the top 7 mantissa bits pick
+// c = 1 + (idx + 1/2)/128 from a table of (1/c rounded, -ln of that rounded value), so that
+// ln m = tab.y + log1p(m * tab.x - 1) holds exactly, and |m * tab.x - 1| < 2^-8 leaves a
+// degree-6 series (truncation 2e-18).  Absolute error ~2e-16, as libm's log for |ln x| > 1;
+// used only where the value decides nothing beyond tie level (the smoothed profile).
+__device__ __forceinline__ double fast_log(double x, const double2 *tab) {
+    const int hi = __double2hiint(x);
+    const int e = (hi >> 20) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    const double2 t = tab[(hi >> 13) & 127];
+    const double r = fma(m, t.x, -1.0);
+    double L = fma(r, -1.0 / 6.0, 0.2);
+    L = fma(L, r, -0.25);
+    L = fma(L, r, 1.0 / 3.0);
+    L = fma(L, r, -0.5);
+    L = fma(L, r, 1.0);
+    return fma(static_cast<double>(e), 0.693147180559945309417232121458, fma(L, r, t.y));
+}
+
 // Fast path of los_kernel for bins == 32 * PER: every lane keeps its PER
-// consecutive bins in registers.  The two Savitzky-Golay FIRs run as a sliding
-// window: per tap one shared-memory read of ln(rho) per lane (conflict-free
-// permuted layout) and one broadcast read of the tap pair feed 2*PER FMAs.
-// The steepest-slope search is the running-minimum scan of
-// splashback_radius.go:30-58 done as a warp prefix-min plus an arg-min.
-template <int PER>
-__global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int nb) {
+// consecutive bins in registers.
+//
+// Smooth (smooth.go:46-81) returns vals = exp(K0 * ln rho) and derivs = K1 * ln rho, and
+// SplashbackRadius (splashback_radius.go:30-58) only COMPARES vals with each other, so the
+// running minimum is taken on K0 * ln rho itself: exp is monotone, NaN and +-Inf order the
+// same way, and the 256 exp() per line of sight are gone.
+//
+// MOMENTS == true (default whenever every ln rho is finite, i.e. rho_bg > 0): the two
+// Savitzky-Golay FIRs are evaluated through the five sliding polynomial moments of
+// sfk_sgmath.cuh -- one direct pass over the window for the lane's first output (taps +-k
+// paired: 7 operations per two taps), PER - 1 binomial shifts for the rest -- and ln() is
+// fast_log.  Same values as the tap loop to ~1e-13 (tests/test_sgmoments.py), same R_sp.
+// MOMENTS == false: ConvolveAt verbatim (filter.go:104-161) as a register sliding window:
+// per tap one shared-memory read of ln(rho) per lane (conflict-free permuted layout) and one
+// broadcast read of the tap pair feed 2*PER FMAs; libm log, so that the -Inf / NaN
+// propagation of Gadget-2's MinMass() == 0 stays sample-exact.
+// The steepest-slope search is the running-minimum scan of splashback_radius.go:30-58 done
+// as a warp prefix-min plus an arg-min.
+template <int PER, bool MOMENTS>
+__global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int nb, SgPoly sg) {
     const int i0 = (threadIdx.x & 31) * PER;
     extern __shared__ double sm[];
     constexpr int B = 32 * PER;
@@ -447,9 +499,20 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
     // column (lane + const): conflict-free and with no index arithmetic.
     const int padL = center + 1;
     constexpr int rowLen = kLosFastRow;
-    double2 *taps = reinterpret_cast<double2 *>(sm);                       // [window] (value, deriv)
-    double *ys = sm + 2 * window + (threadIdx.x >> 5) * (PER * rowLen);
-    for (int k = threadIdx.x; k < window; k += blockDim.x) taps[k] = make_double2(a.valTaps[k], a.derivTaps[k]);
+    double2 *taps = reinterpret_cast<double2 *>(sm);                       // tap loop: [window] (value, deriv)
+    double *upow = sm;                                                     // moments: [center + 1][4] u, u^2, u^3, u^4
+    const int tabOff = MOMENTS ? 4 * (center + 1) : 2 * window;
+    const double2 *logTab = reinterpret_cast<const double2 *>(sm + tabOff);   // moments: [128]
+    double *ys = sm + tabOff + (MOMENTS ? 256 : 0) + (threadIdx.x >> 5) * (PER * rowLen);
+    if (MOMENTS) {
+        for (int k = threadIdx.x; k <= center; k += blockDim.x) {
+            const double u = static_cast<double>(k) / static_cast<double>(center);
+            upow[4 * k] = u; upow[4 * k + 1] = u * u; upow[4 * k + 2] = u * u * u; upow[4 * k + 3] = (u * u) * (u * u);
+        }
+        for (int k = threadIdx.x; k < 256; k += blockDim.x) sm[tabOff + k] = a.logTab[k];
+    } else {
+        for (int k = threadIdx.x; k < window; k += blockDim.x) taps[k] = make_double2(a.valTaps[k], a.derivTaps[k]);
+    }
     __syncthreads();
     const int lane = lane_id();
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * kLosWarps + (threadIdx.x >> 5);
@@ -485,7 +548,7 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
         double rho = static_cast<double>(acc) * q;
         if (rho < bg) rho = bg;
         if (a.profiles) a.profiles[(static_cast<size_t>(haloIdx) * perHalo + rl) * B + lane * PER + c] = rho;
-        const double y = log(rho);
+        const double y = MOMENTS ? fast_log(rho, logTab) : log(rho);
         const int p = lane * PER + c + padL;
         ys[(p % PER) * rowLen + p / PER] = y;
         if (c == 0) yFirst = y;
@@ -503,35 +566,37 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
         if (lane == 0) *out = nan_f64();
         return;
     }
-    // ConvolveAt with Extension (filter.go:104-161), taps ascending.  Output i0 + c needs
-    // sample i0 + c - center + j for tap j, i.e. position lane*PER + (c + j + 1): w[m % PER]
-    // holds position lane*PER + 1 + m for m = j .. j + PER - 1.
+    // Output i0 + c reads positions lane*PER + c + 1 + j, j = 0 .. window-1 (tap j, sample
+    // i0 + c - center + j); position lane*PER + q sits at row q % PER, column lane + q / PER.
     const double *yl = ys + lane;
-    double w[PER], s0[PER], s1[PER];
+    double s0[PER], s1[PER];
+    if (MOMENTS) {
+        double M[5] = {yl[((1 + center) % PER) * rowLen + (1 + center) / PER], 0.0, 0.0, 0.0, 0.0};
+        for (int k = 1; k <= center; k++) {
+            const int qp = 1 + center + k, qm = 1 + center - k;
+            sg_accumulate_pair(M, yl[(qp % PER) * rowLen + qp / PER], yl[(qm % PER) * rowLen + qm / PER], upow + 4 * k);
+        }
 #pragma unroll
-    for (int c = 0; c < PER; c++) { s0[c] = 0.0; s1[c] = 0.0; }
-#pragma unroll
-    for (int m = 0; m < PER - 1; m++) w[m] = yl[(1 + m) * rowLen];
-    int jb = 0;
-    for (; jb + PER <= window; jb += PER) {
-        const double *yj = yl + jb / PER + 1;   // position lane*PER + jb + PER + jj: row jj, column lane + jb/PER + 1
-#pragma unroll
-        for (int jj = 0; jj < PER; jj++) {
-            w[(jj + PER - 1) % PER] = yj[jj * rowLen];
-            const double2 tp = taps[jb + jj];
-#pragma unroll
-            for (int c = 0; c < PER; c++) {
-                const double x = w[(c + jj) % PER];
-                s0[c] = fma(x, tp.x, s0[c]);
-                s1[c] = fma(x, tp.y, s1[c]);
+        for (int c = 0; c < PER; c++) {
+            sg_outputs(M, sg, s0[c], s1[c]);
+            if (c < PER - 1) {
+                const int qo = c + 1, qi = c + 1 + window;
+                sg_advance(M, sg, yl[(qo % PER) * rowLen + qo / PER], yl[(qi % PER) * rowLen + qi / PER]);
             }
         }
-    }
-    {   // the last window % PER taps
-        const double *yj = yl + jb / PER + 1;
+    } else {
+        // ConvolveAt with Extension (filter.go:104-161), taps ascending: w[m % PER] holds
+        // position lane*PER + 1 + m for m = j .. j + PER - 1.
+        double w[PER];
 #pragma unroll
-        for (int jj = 0; jj < PER; jj++) {
-            if (jb + jj < window) {
+        for (int c = 0; c < PER; c++) { s0[c] = 0.0; s1[c] = 0.0; }
+#pragma unroll
+        for (int m = 0; m < PER - 1; m++) w[m] = yl[(1 + m) * rowLen];
+        int jb = 0;
+        for (; jb + PER <= window; jb += PER) {
+            const double *yj = yl + jb / PER + 1;   // position lane*PER + jb + PER + jj: row jj, column lane + jb/PER + 1
+#pragma unroll
+            for (int jj = 0; jj < PER; jj++) {
                 w[(jj + PER - 1) % PER] = yj[jj * rowLen];
                 const double2 tp = taps[jb + jj];
 #pragma unroll
@@ -542,155 +607,24 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
                 }
             }
         }
-    }
+        {   // the last window % PER taps
+            const double *yj = yl + jb / PER + 1;
 #pragma unroll
-    for (int c = 0; c < PER; c++) s0[c] = exp(s0[c]);   // vals; s1 = d ln rho / d ln r
-
-    // SplashbackRadius: rhoMin starts at vals[0]; i = 1 .. B-2 is a candidate when
-    // vals[i] < min(vals[0..i-1]) and derivs[i] is a strict local minimum below dLim.
-    const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    const double v0 = __shfl_sync(0xffffffffu, s0[0], 0);
-    double lmin = inf;
+            for (int jj = 0; jj < PER; jj++) {
+                if (jb + jj < window) {
+                    w[(jj + PER - 1) % PER] = yj[jj * rowLen];
+                    const double2 tp = taps[jb + jj];
 #pragma unroll
-    for (int c = 0; c < PER; c++) { const double v = s0[c]; if (v < lmin) lmin = v; }
-    double excl = lmin;   // inclusive prefix min over lanes, then shifted
-    for (int o = 1; o < 32; o <<= 1) {
-        const double up = __shfl_up_sync(0xffffffffu, excl, o);
-        if (lane >= o && up < excl) excl = up;
-    }
-    excl = __shfl_up_sync(0xffffffffu, excl, 1);
-    if (lane == 0) excl = inf;
-    const double dPrev = __shfl_up_sync(0xffffffffu, s1[PER - 1], 1);
-    const double dNext = __shfl_down_sync(0xffffffffu, s1[0], 1);
-    double runMin = excl, best = a.dLim;
-    int bestI = -1;
-#pragma unroll
-    for (int c = 0; c < PER; c++) {
-        const int i = i0 + c;
-        const double v = s0[c];
-        if (i == 0) { runMin = v; continue; }           // rhoMin := rhos[0]
-        if (v < runMin) {
-            runMin = v;
-            const double dm = c == 0 ? dPrev : s1[c == 0 ? 0 : c - 1];
-            const double dp = c == PER - 1 ? dNext : s1[c == PER - 1 ? c : c + 1];
-            const double dd = s1[c];
-            if (i < B - 1 && dd < dp && dd < dm && dd < best) { best = dd; bestI = i; }
-        }
-    }
-    // vals[0] NaN poisons the running minimum: no candidate anywhere
-    if (v0 != v0) bestI = -1;
-    // arg-min over lanes, earliest index on ties (sequential update semantics)
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bestI, o);
-        const bool take = oi >= 0 && (bestI < 0 || ob < best || (ob == best && oi < bestI));
-        if (take) { best = ob; bestI = oi; }
-    }
-    if (lane == 0)
-        *out = bestI < 0 ? nan_f64() : exp(h.lrMin + h.dlr * (static_cast<double>(bestI) + 0.5));
-}
-
-// EXPERIMENTAL (SFK_FLAG_LOS_MOMENTS; not yet timed or run on a GPU -- its arithmetic is
-// checked on the host-compiled source, tests/test_sgmoments.py).  los_kernel_fast with the two
-// FIRs evaluated through the five sliding polynomial moments of sfk_sgmath.cuh: one direct
-// pass over the window for the lane's first output (window x 5 FMAs), PER - 1 binomial shifts
-// for the rest, instead of window x 2*PER FMAs.  Everything outside the marked block is
-// los_kernel_fast verbatim; the two are to be merged once this variant has been measured.
-template <int PER>
-__global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast_moments(LosArgs a, int nb, SgPoly sg) {
-    const int i0 = (threadIdx.x & 31) * PER;
-    extern __shared__ double sm[];
-    constexpr int B = 32 * PER;
-    const int window = a.window;
-    const int center = window / 2;
-    // ln(rho) with the Extension boundary (filter.go:104-161) materialised: sample i sits at
-    // position p = i + padL, padL = center + 1, the positions below / above hold sample 0 / B-1.
-    // Position p is stored at row p % PER, column p / PER, so the FIR below reads row jj at
-    // column (lane + const): conflict-free and with no index arithmetic.
-    const int padL = center + 1;
-    constexpr int rowLen = kLosFastRow;
-    double *ys = sm + 2 * window + (threadIdx.x >> 5) * (PER * rowLen);
-    double *upow = sm + 2 * window + kLosWarps * (PER * rowLen);   // [window][4]: u, u^2, u^3, u^4 of every tap
-    for (int k = threadIdx.x; k < window; k += blockDim.x) {
-        const double u = static_cast<double>(k - center) / static_cast<double>(center);
-        upow[4 * k] = u; upow[4 * k + 1] = u * u; upow[4 * k + 2] = u * u * u; upow[4 * k + 3] = (u * u) * (u * u);
-    }
-    __syncthreads();
-    const int lane = lane_id();
-    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kLosWarps + (threadIdx.x >> 5);
-    const int64_t perHalo = static_cast<int64_t>(a.rings) * a.spokes;
-    if (gw >= perHalo * nb) return;
-    const int slot = static_cast<int>(gw / perHalo);
-    const int64_t rl = gw - slot * perHalo;
-    const int haloIdx = a.batchHalos[slot];
-    const HaloDev &h = a.halos[haloIdx];
-    const longlong2 *g = reinterpret_cast<const longlong2 *>(a.grid + (static_cast<size_t>(slot) * perHalo + rl) * B);
-
-    // Retrieve + GetRhos: exact int64 prefix sum, clamp, ln
-    long long d[PER];
-#pragma unroll
-    for (int c = 0; c < PER; c += 2) {
-        const longlong2 v = g[(lane * PER + c) / 2];
-        d[c] = v.x; d[c + 1] = v.y;
-    }
-    long long run = 0;
-#pragma unroll
-    for (int c = 0; c < PER; c++) run += d[c];
-    long long incl = run;
-    for (int o = 1; o < 32; o <<= 1) {
-        const long long up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
-    }
-    long long acc = incl - run;
-    const double q = h.quantum, bg = h.defaultRho;
-    double yFirst = 0.0, yLast = 0.0;
-#pragma unroll
-    for (int c = 0; c < PER; c++) {
-        acc += d[c];
-        double rho = static_cast<double>(acc) * q;
-        if (rho < bg) rho = bg;
-        if (a.profiles) a.profiles[(static_cast<size_t>(haloIdx) * perHalo + rl) * B + lane * PER + c] = rho;
-        const double y = log(rho);
-        const int p = lane * PER + c + padL;
-        ys[(p % PER) * rowLen + p / PER] = y;
-        if (c == 0) yFirst = y;
-        if (c == PER - 1) yLast = y;
-    }
-    // Extension: repeat the end samples
-    yFirst = __shfl_sync(0xffffffffu, yFirst, 0);
-    yLast = __shfl_sync(0xffffffffu, yLast, 31);
-    for (int e = lane; e < padL; e += 32) ys[(e % PER) * rowLen + e / PER] = yFirst;
-    for (int e = B + padL + lane; e < PER * rowLen; e += 32) ys[(e % PER) * rowLen + e / PER] = yLast;
-    __syncwarp();
-
-    double *out = a.rsp + static_cast<size_t>(haloIdx) * perHalo + rl;
-    if (B <= window) {   // Smooth: ok = false, smooth.go:51-53
-        if (lane == 0) *out = nan_f64();
-        return;
-    }
-    // ---- sliding moments instead of the tap loop ----
-    // Output i0 + c reads positions lane*PER + c + 1 + j, j = 0 .. window-1; position
-    // lane*PER + q sits at row q % PER, column lane + q / PER.
-    const double *yl = ys + lane;
-    double s0[PER], s1[PER];
-    {
-        double M[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-        for (int j = 0; j < window; j++) {
-            const int q = 1 + j;
-            sg_accumulate(M, yl[(q % PER) * rowLen + q / PER], upow + 4 * j);
-        }
-#pragma unroll
-        for (int c = 0; c < PER; c++) {
-            sg_outputs(M, sg, s0[c], s1[c]);
-            if (c < PER - 1) {
-                const int qo = c + 1, qi = c + 1 + window;
-                sg_advance(M, sg, yl[(qo % PER) * rowLen + qo / PER], yl[(qi % PER) * rowLen + qi / PER]);
+                    for (int c = 0; c < PER; c++) {
+                        const double x = w[(c + jj) % PER];
+                        s0[c] = fma(x, tp.x, s0[c]);
+                        s1[c] = fma(x, tp.y, s1[c]);
+                    }
+                }
             }
         }
     }
-    // ---- end of the block that differs from los_kernel_fast ----
-#pragma unroll
-    for (int c = 0; c < PER; c++) s0[c] = exp(s0[c]);   // vals; s1 = d ln rho / d ln r
+    // s0 = ln vals, s1 = d ln rho / d ln r.
 
     // SplashbackRadius: rhoMin starts at vals[0]; i = 1 .. B-2 is a candidate when
     // vals[i] < min(vals[0..i-1]) and derivs[i] is a strict local minimum below dLim.
@@ -799,7 +733,7 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel(LosArgs a, int nb) 
             s0 += x * taps0[j];
             s1 += x * taps1[j];
         }
-        vals[i] = exp(s0);
+        vals[i] = s0;   // ln of Smooth's vals: only compared below, exp is monotone
         ders[i] = s1;
     }
     __syncwarp();
@@ -1004,17 +938,38 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(FilterArgs a) {
         // so each KDE still sums its own points in the reference's order.
         for (int t = tid; t < nKde * kKdeKnots; t += kFilterThreads) Y[t] = 0.0;
         __syncthreads();
+        // The points are in LoS order, so a point's node index is non-decreasing at every level:
+        // each node's sum is one contiguous run of points and lives in a register until the node
+        // changes (the change depends on p only: no divergence).
         for (int i = tid; i < kKdeKnots; i += kFilterThreads) {
             const double xi = sm.X[i];
             double acc0 = 0.0;
+            double accL[kMaxLevels];
+            int nodeL[kMaxLevels];
+#pragma unroll
+            for (int l = 0; l < kMaxLevels; l++) { accL[l] = 0.0; nodeL[l] = 0; }
             for (int p = 0; p < nv; p++) {
+#pragma unroll
+                for (int l = 0; l < kMaxLevels; l++) {
+                    if (l < a.levels) {
+                        const int node = pNode[l * a.spokes + p];
+                        if (node != nodeL[l]) {
+                            Y[((2 << l) - 1 + nodeL[l]) * kKdeKnots + i] = accL[l];
+                            accL[l] = 0.0;
+                            nodeL[l] = node;
+                        }
+                    }
+                }
                 if (i < pLo[p] || i > pHi[p]) continue;
                 const double udx = (xi - pR[p]) / hk;
                 const double e = exp(-udx * udx);
                 acc0 += e;
-                for (int l = 1; l <= a.levels; l++)
-                    Y[((1 << l) - 1 + pNode[(l - 1) * a.spokes + p]) * kKdeKnots + i] += e;
+#pragma unroll
+                for (int l = 0; l < kMaxLevels; l++) accL[l] += e;
             }
+#pragma unroll
+            for (int l = 0; l < kMaxLevels; l++)
+                if (l < a.levels) Y[((2 << l) - 1 + nodeL[l]) * kKdeKnots + i] = accL[l];
             Y[i] = acc0;
         }
         __syncthreads();
@@ -1520,31 +1475,24 @@ cudaError_t launch_percentile(const PercentileArgs &a, int nb, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-// Experimental sliding-moment variant of the fast path; false when the shape is not served.
+// Sliding-moment form of the fast path; false when the shape is not served.
 bool los_moments_supported(const LosArgs &a) { return a.bins == 256 && a.window <= kLosFastMaxWindow && a.window >= 7; }
 
-cudaError_t launch_los_moments(const LosArgs &a, const SgPoly &sg, int nb, cudaStream_t s) {
+cudaError_t launch_los(const LosArgs &a, const SgPoly *sg, int nb, cudaStream_t s) {
     if (nb <= 0) return cudaSuccess;
     const int64_t warps = static_cast<int64_t>(nb) * a.rings * a.spokes;
     const unsigned grid = static_cast<unsigned>((warps + kLosWarps - 1) / kLosWarps);
-    const size_t fsmem = sizeof(double) * (2 * a.window + kLosWarps * 8 * kLosFastRow + 4 * a.window);
-    los_kernel_fast_moments<8><<<grid, kLosWarps * 32, fsmem, s>>>(a, nb, sg);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s) {
-    if (nb <= 0) return cudaSuccess;
-    const size_t smem = sizeof(double) * (2 * a.window + kLosWarps * 3 * a.bins);
-    {   // per device, so set it on every launch (a second GPU in the same process must get it too)
+    if (sg && los_moments_supported(a)) {
+        const size_t fsmem = sizeof(double) * (4 * (a.window / 2 + 1) + 256 + kLosWarps * 8 * kLosFastRow);
+        los_kernel_fast<8, true><<<grid, kLosWarps * 32, fsmem, s>>>(a, nb, *sg);
+    } else if (a.bins == 256 && a.window <= kLosFastMaxWindow) {
+        const size_t fsmem = sizeof(double) * (2 * a.window + kLosWarps * 8 * kLosFastRow);
+        los_kernel_fast<8, false><<<grid, kLosWarps * 32, fsmem, s>>>(a, nb, SgPoly{});
+    } else {
+        const size_t smem = sizeof(double) * (2 * a.window + kLosWarps * 3 * a.bins);
+        // per device, so set it on every launch (a second GPU in the same process must get it too)
         cudaError_t e = cudaFuncSetAttribute(los_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-    }
-    const int64_t warps = static_cast<int64_t>(nb) * a.rings * a.spokes;
-    const unsigned grid = static_cast<unsigned>((warps + kLosWarps - 1) / kLosWarps);
-    if (a.bins == 256 && a.window <= kLosFastMaxWindow) {
-        const size_t fsmem = sizeof(double) * (2 * a.window + kLosWarps * 8 * kLosFastRow);
-        los_kernel_fast<8><<<grid, kLosWarps * 32, fsmem, s>>>(a, nb);
-    } else {
         los_kernel<<<grid, kLosWarps * 32, smem, s>>>(a, nb);
     }
     return cudaGetLastError();

@@ -36,13 +36,20 @@ struct BinArgs {
     double invDr;               // 1/dr
     float cK;                   // bins per octave: ln 2 / dr
     int rings, spokes, bins, chunks;
+    // chunks == 1: tiles are stored, not added; edges falling into the next LoS's bin 0 go here
+    unsigned long long *ovfList;   // [ovfCap][2] (grid cell, value)
+    unsigned *ovfCount;            // [2] entries of this launch, entries ever dropped
+    unsigned ovfCap;
 };
+// true when launch_bin writes every cell of the grid itself (no memset needed)
+bool bin_stores_whole_grid(const BinArgs &a);
 
 struct LosArgs {
     const unsigned long long *grid;
     const HaloDev *halos;
     const int32_t *batchHalos;
     const double *valTaps, *derivTaps;
+    const double *logTab;   // [128][2] fast_log table (1/c, -ln(1/c)), sfk_tables.cpp
     double *rsp;        // [nHalo][rings][spokes]
     double *profiles;   // TAPS: [nHalo][rings][spokes][bins], else null
     int rings, spokes, bins, window;
@@ -132,10 +139,10 @@ cudaError_t launch_hits(const Piece *pieces, int nPieces, const Cand *cands,
                         int rings, int spokes, double dPhi, const int64_t *hitOffset,
                         uint32_t *hitCursor, const int32_t *haloSlot, HitRec *recs, bool prune, cudaStream_t s);
 cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s);
-cudaError_t launch_los(const LosArgs &a, int nb, cudaStream_t s);
 struct SgPoly;   // sfk_sgmath.cuh
 bool los_moments_supported(const LosArgs &a);
-cudaError_t launch_los_moments(const LosArgs &a, const SgPoly &sg, int nb, cudaStream_t s);
+// sg != null: sliding-moment Savitzky-Golay where the shape allows it; null: the literal tap loop
+cudaError_t launch_los(const LosArgs &a, const SgPoly *sg, int nb, cudaStream_t s);
 cudaError_t launch_filter(const FilterArgs &a, int nb, cudaStream_t s);
 cudaError_t launch_fit(const FitArgs &a, int nb, cudaStream_t s);
 size_t bin_smem_bytes(int bins);

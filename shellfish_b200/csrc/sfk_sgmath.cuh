@@ -1,5 +1,5 @@
 // sfk_sgmath.cuh -- Savitzky-Golay smoothing by sliding polynomial moments
-// (experimental path of los_kernel_fast, SFK_FLAG_LOS_MOMENTS).
+// (default path of los_kernel_fast; SFK_FLAG_LOS_TAPLOOP selects the literal tap loop).
 //
 // The taps of an order-4 Savitzky-Golay kernel (math/interpolate/filter.go:218-318) are,
 // exactly, polynomials of degree 4 in the tap offset: k[j] = sum_k c_k u_j^k with
@@ -48,8 +48,8 @@ SFK_SG_HD inline void sg_accumulate(double M[5], double x, const double *up) {
 }
 
 // The same for the two taps at offsets +u and -u at once (yp, ym their samples): even moments
-// take the sum, odd ones the difference -- 7 operations instead of 10.  Not used by a kernel
-// yet (next step for los_kernel_fast_moments); checked in tests/test_sgmoments.py.
+// take the sum, odd ones the difference -- 7 operations instead of 10 (los_kernel_fast's anchor pass);
+// checked in tests/test_sgmoments.py.
 SFK_SG_HD inline void sg_accumulate_pair(double M[5], double yp, double ym, const double *up) {
     const double s = yp + ym, d = yp - ym;
     M[0] += s;

@@ -309,4 +309,17 @@ bool savgol_poly(const std::vector<double> &taps0, const std::vector<double> &ta
     return true;
 }
 
+// Table of fast_log (sfk_kernels.cu): for c_i = 1 + (i + 1/2)/128 the pair (1/c_i rounded to
+// double, -ln of that rounded value), so that ln m = tab[2i+1] + log1p(m * tab[2i] - 1) is an
+// identity and the rounding of 1/c_i costs nothing.
+void build_log_table(std::vector<double> &tab) {
+    tab.resize(256);
+    for (int i = 0; i < 128; i++) {
+        const long double c = 1.0L + (static_cast<long double>(i) + 0.5L) / 128.0L;
+        const double invc = static_cast<double>(1.0L / c);
+        tab[2 * i] = invc;
+        tab[2 * i + 1] = static_cast<double>(-logl(static_cast<long double>(invc)));
+    }
+}
+
 }  // namespace sfk

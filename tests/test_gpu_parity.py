@@ -377,21 +377,21 @@ def test_nan_line_of_sight_is_reproduced():
     assert prof[0, 32, -1] > 1.5 * prof[0, :, -1].min() or prof[0, 160, -1] > 1.5 * prof[0, :, -1].min()
 
 
-def test_experimental_los_moments_flag():
-    """SFK_FLAG_LOS_MOMENTS (sliding-moment Savitzky-Golay, los_kernel_fast_moments): same
-    R_sp per line of sight as the default tap loop -- and hence as the oracle -- and the same
-    coefficients to rounding; with MinMass = 0 (rho_bg = 0) the flag is ignored."""
+def test_sliding_moment_smoothing_equals_the_tap_loop():
+    """The default los kernel evaluates Smooth's two Savitzky-Golay filters through sliding
+    polynomial moments and a table logarithm; SFK_FLAG_LOS_TAPLOOP selects ConvolveAt's literal
+    tap loop (filter.go:104-161).  Same R_sp for every line of sight -- and hence as the oracle
+    -- and the same coefficients to rounding; with MinMass = 0 (rho_bg = 0) both run the tap loop."""
     halos, blocks, mass = synth.single_halo(seed=21, n=30000, n_background=8000)
-    base, c0, s0 = api.run_shell(api.default_params(rings=20, seed=1337), mass, halos, blocks)
-    exp, c1, s1 = api.run_shell(api.default_params(rings=20, seed=1337, flags=api.SFK_FLAG_LOS_MOMENTS),
-                                mass, halos, blocks)
+    base, c0, s0 = api.run_shell(api.default_params(rings=20, seed=1337, flags=api.SFK_FLAG_LOS_TAPLOOP), mass, halos, blocks)
+    exp, c1, s1 = api.run_shell(api.default_params(rings=20, seed=1337), mass, halos, blocks)
     assert s0[0] == 0 and s1[0] == 0
     r0, r1 = base.rsp(0), exp.rsp(0)
     assert np.array_equal(np.isnan(r0), np.isnan(r1))
     assert np.array_equal(r0[~np.isnan(r0)], r1[~np.isnan(r1)])
     np.testing.assert_allclose(c1, c0, rtol=0, atol=1e-9 * np.abs(c0).max())
-    _, cz0, _ = api.run_shell(api.default_params(rings=6, seed=1337), 0.0, halos, blocks)
-    _, cz1, _ = api.run_shell(api.default_params(rings=6, seed=1337, flags=api.SFK_FLAG_LOS_MOMENTS), 0.0, halos, blocks)
+    _, cz0, _ = api.run_shell(api.default_params(rings=6, seed=1337, flags=api.SFK_FLAG_LOS_TAPLOOP), 0.0, halos, blocks)
+    _, cz1, _ = api.run_shell(api.default_params(rings=6, seed=1337), 0.0, halos, blocks)
     assert np.array_equal(cz0, cz1, equal_nan=True)
 
 

@@ -1,5 +1,5 @@
 """Sliding-moment Savitzky-Golay smoothing (experimental los_kernel_fast_moments,
-SFK_FLAG_LOS_MOMENTS): the host/device-shared arithmetic of
+the default los_kernel_fast path): the host/device-shared arithmetic of
 shellfish_b200/csrc/sfk_sgmath.cuh, compiled for the CPU (tests/hostcheck), against the
 tap loop of Kernel.ConvolveAt (math/interpolate/filter.go:104-161) that the oracle and the
 default kernel evaluate."""
