@@ -57,6 +57,13 @@ int sfh_parse_catalog(const char *data, const int *icols, int nI, const int *fco
 }
 const char *sfh_last_text() { return g_text.c_str(); }
 
+// PartitionHalos of sf_shell.cpp (the multi-GPU CLI's halo partition)
+void sfh_partition_halos(const double *weights, const int64_t *groups, int n, int nRanks, int *owner) {
+    std::vector<int> own;
+    PartitionHalos(std::vector<double>(weights, weights + n), std::vector<int64_t>(groups, groups + n), nRanks, own);
+    for (int i = 0; i < n; i++) owner[i] = own[i];
+}
+
 // makeTestConfig of parse/config_test.go:300-321: one variable of every kind
 // under the header [config].  text == NULL skips the file step; flags is
 // '\n'-separated.  Lists come back joined by ','.

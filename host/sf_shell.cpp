@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <thread>
 #include <sys/stat.h>
 
 #include "../include/shellfish_b200.h"
@@ -237,8 +238,31 @@ const char *ShellConfig::ExampleConfig() {
            "BackgroundRhoMult = 0.5";
 }
 
+void PartitionHalos(const std::vector<double> &weights, const std::vector<int64_t> &groups, int nRanks,
+                    std::vector<int> &owner) {
+    // group weights, groups in ascending label order (numpy.unique)
+    std::map<int64_t, double> gw;
+    for (size_t i = 0; i < weights.size(); i++) gw[groups[i]] += weights[i];
+    std::vector<std::pair<int64_t, double>> gs(gw.begin(), gw.end());
+    std::vector<size_t> order(gs.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return gs[a].second > gs[b].second; });
+    std::vector<double> loads(std::max(nRanks, 1), 0.0);
+    std::map<int64_t, int> gOwner;
+    for (size_t k : order) {
+        int r = 0;
+        for (int q = 1; q < nRanks; q++) if (loads[q] < loads[r]) r = q;   // first minimum, like argmin
+        gOwner[gs[k].first] = r;
+        loads[r] += gs[k].second;
+    }
+    owner.resize(weights.size());
+    for (size_t i = 0; i < weights.size(); i++) owner[i] = gOwner[groups[i]];
+}
+
 std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::string &stdinData, uint64_t seed,
-                     int device, std::vector<std::string> &outLines) {
+                     const std::vector<int> &devices, std::vector<std::string> &outLines) {
+    if (devices.empty()) return "No GPU selected.";
+    const int G = static_cast<int>(devices.size());
     // catalog.Parse(stdin, {0,1}, {2,3,4,5}), cmd/shell.go:209-218
     std::vector<std::vector<int64_t>> intCols;
     std::vector<std::vector<double>> coords;
@@ -288,10 +312,14 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
     p.eta = c.eta; p.order = c.order; p.smoothing_window = c.smoothingWindow; p.levels = c.levels;
     p.subsample_factor = c.subsampleFactor; p.los_slope_cutoff = c.losSlopeCutoff;
     p.background_rho_mult = c.backgroundRhoMult; p.percentile_profile = c.percentileProfile;
-    p.percentile = c.percentile; p.seed = seed; p.device = device;
-    sfk_ctx *sfk = nullptr;
-    struct Guard { sfk_ctx *&c; ~Guard() { if (c) sfk_destroy(c); } } guard{sfk};
-    if (sfk_create(&sfk, &p) != 0) return sfk_last_error(sfk);
+    p.percentile = c.percentile; p.seed = seed;
+    std::vector<sfk_ctx *> ctxs(G, nullptr);
+    struct Guard { std::vector<sfk_ctx *> &c; ~Guard() { for (sfk_ctx *x : c) if (x) sfk_destroy(x); } } guard{ctxs};
+    for (int d = 0; d < G; d++) {
+        p.device = devices[d];
+        if (sfk_create(&ctxs[d], &p) != 0) return sfk_last_error(ctxs[d]);
+    }
+    sfk_ctx *sfk = ctxs[0];
     const sfk_cosmo cosmo0{hds0[0].Cosmo.Z, hds0[0].Cosmo.OmegaM, hds0[0].Cosmo.OmegaL, hds0[0].Cosmo.H100};
 
     // Logging = performance (cmd/shell.go:352-367): elapsed time after sphereLoop and after
@@ -315,25 +343,58 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
         for (size_t i = 0; i < idxs.size(); i++) {
             x[i] = coords[0][idxs[i]]; y[i] = coords[1][idxs[i]]; z[i] = coords[2][idxs[i]]; r[i] = coords[3][idxs[i]];
         }
-        if (sfk_begin_snapshot(sfk, &cosmo0, minMass) != 0) return sfk_last_error(sfk);
-        if (sfk_add_halos(sfk, static_cast<int64_t>(idxs.size()), x.data(), y.data(), z.data(), r.data()) != 0)
-            return sfk_last_error(sfk);
+        for (sfk_ctx *cx : ctxs) {
+            if (sfk_begin_snapshot(cx, &cosmo0, minMass) != 0) return sfk_last_error(cx);
+            if (sfk_add_halos(cx, static_cast<int64_t>(idxs.size()), x.data(), y.data(), z.data(), r.data()) != 0)
+                return sfk_last_error(cx);
+        }
         // sphereLoop, cmd/shell.go:376-415
         std::vector<Header> hds;
         if (!(err = ReadHeaders(static_cast<int>(snap), *buf, cat, g.MemoDir, hds, files)).empty()) return err;
+        // several GPUs: halos partitioned by estimated particle count (R200m^3 plus a constant
+        // for the per-halo analysis), the halos of one block kept on one GPU
+        std::vector<int> owner(idxs.size(), 0);
+        if (G > 1) {
+            std::vector<double> w(idxs.size());
+            std::vector<int64_t> grp(idxs.size(), -1);
+            double mean = 0;
+            for (size_t i = 0; i < idxs.size(); i++) { w[i] = r[i] > 0 ? r[i] * r[i] * r[i] : 0.0; mean += w[i]; }
+            mean = idxs.empty() ? 1.0 : std::max(mean / static_cast<double>(idxs.size()), 1e-300);
+            for (size_t i = 0; i < idxs.size(); i++) {
+                w[i] = w[i] / mean + 0.25;
+                for (size_t b = 0; b < hds.size() && grp[i] < 0; b++) {
+                    const Header &h = hds[b];
+                    if (x[i] >= h.Origin[0] && x[i] < static_cast<double>(h.Origin[0]) + h.Width[0] &&
+                        y[i] >= h.Origin[1] && y[i] < static_cast<double>(h.Origin[1]) + h.Width[1] &&
+                        z[i] >= h.Origin[2] && z[i] < static_cast<double>(h.Origin[2]) + h.Width[2])
+                        grp[i] = static_cast<int64_t>(b);
+                }
+            }
+            PartitionHalos(w, grp, G, owner);
+            std::vector<uint8_t> mine(idxs.size());
+            for (int d = 0; d < G; d++) {
+                for (size_t i = 0; i < idxs.size(); i++) mine[i] = owner[i] == d;
+                if (sfk_set_owned(ctxs[d], static_cast<int64_t>(mine.size()), mine.data()) != 0) return sfk_last_error(ctxs[d]);
+            }
+        }
+        std::vector<uint8_t> hit(idxs.size());
         for (size_t i = 0; i < hds.size(); i++) {
             int64_t nHit = 0;
-            if (sfk_block_halo_mask(sfk, hds[i].Origin, hds[i].Width, hds[i].TotalWidth, nullptr, &nHit) != 0)
+            if (sfk_block_halo_mask(sfk, hds[i].Origin, hds[i].Width, hds[i].TotalWidth, hit.data(), &nHit) != 0)
                 return sfk_last_error(sfk);
             if (nHit == 0) continue;
+            // the block is read once and pushed to every GPU that owns a halo touching it
+            std::vector<char> wants(G, 0);
+            for (size_t k = 0; k < hit.size(); k++) if (hit[k]) wants[owner[k]] = 1;
             const float *xs, *ms;
             int64_t n;
             const auto tRead = std::chrono::steady_clock::now();
             if (!(err = buf->Read(files[i], &xs, &ms, &n)).empty()) return err;
             readSeconds += since(tRead); blocksRead++; particlesRead += n;
             const sfk_cosmo hc{hds[i].Cosmo.Z, hds[i].Cosmo.OmegaM, hds[i].Cosmo.OmegaL, hds[i].Cosmo.H100};
-            if (sfk_push_block(sfk, xs, ms, n, &hc, hds[i].TotalWidth, hds[i].Origin, hds[i].Width) != 0)
-                return sfk_last_error(sfk);
+            for (int d = 0; d < G; d++)
+                if (wants[d] && sfk_push_block(ctxs[d], xs, ms, n, &hc, hds[i].TotalWidth, hds[i].Origin, hds[i].Width) != 0)
+                    return sfk_last_error(ctxs[d]);
         }
         if (perf) {
             std::fprintf(stderr, "Snap %lld, sphereLoop ended\nTime: %.6gs\n", static_cast<long long>(snap), since(tStart));
@@ -341,15 +402,27 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
                          static_cast<long long>(blocksRead), static_cast<long long>(particlesRead));
         }
         // haloAnalysis, cmd/shell.go:502-528: a failed fit leaves the zero row
-        std::vector<double> cs(idxs.size() * rowLen);
-        std::vector<int32_t> status(idxs.size());
-        if (sfk_finish_snapshot(sfk, cs.data(), status.data()) != 0) return sfk_last_error(sfk);
-        for (size_t i = 0; i < idxs.size(); i++)
-            std::copy(cs.begin() + i * rowLen, cs.begin() + (i + 1) * rowLen, out[idxs[i]].begin());
+        std::vector<std::vector<double>> cs(G, std::vector<double>(idxs.size() * rowLen));
+        std::vector<std::vector<int32_t>> status(G, std::vector<int32_t>(idxs.size()));
+        std::vector<int> rcs(G, 0);
+        if (G == 1) {
+            rcs[0] = sfk_finish_snapshot(sfk, cs[0].data(), status[0].data());
+        } else {   // one host thread per GPU
+            std::vector<std::thread> th;
+            for (int d = 0; d < G; d++)
+                th.emplace_back([&, d] { rcs[d] = sfk_finish_snapshot(ctxs[d], cs[d].data(), status[d].data()); });
+            for (std::thread &t : th) t.join();
+        }
+        for (int d = 0; d < G; d++) if (rcs[d] != 0) return sfk_last_error(ctxs[d]);
+        for (size_t i = 0; i < idxs.size(); i++) {
+            const std::vector<double> &src = cs[owner[i]];
+            std::copy(src.begin() + i * rowLen, src.begin() + (i + 1) * rowLen, out[idxs[i]].begin());
+        }
         if (perf) {
             std::fprintf(stderr, "Snap %lld, haloAnalysis ended\nTime: %.6gs\n", static_cast<long long>(snap), since(tStart));
             sfk_stats st{};
-            if (sfk_get_stats(sfk, &st) == 0)
+            for (int d = 0; d < G; d++)
+            if (sfk_get_stats(ctxs[d], &st) == 0)
                 std::fprintf(stderr, "Device: cull %.3f ms, hits %.3f ms, bin %.3f ms, los %.3f ms, filter %.3f ms, fit %.3f ms; "
                                      "%lld candidates, %lld intersections, %lld launches\n",
                              st.ms_cull, st.ms_hits, st.ms_bin, st.ms_los, st.ms_filter, st.ms_fit,

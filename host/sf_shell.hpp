@@ -48,8 +48,19 @@ struct ShellConfig {
 };
 
 // ShellConfig.Run: stdin halo table -> catalog lines (header comment first).
-// seed replaces cmd/cmd.go:658 randSeed; device is the CUDA ordinal.
+// seed replaces cmd/cmd.go:658 randSeed; devices are the CUDA ordinals to use, one context
+// (and, for haloAnalysis, one host thread) per entry.  With several entries the halos of a
+// snapshot are partitioned by estimated particle count (PartitionHalos) -- the reference
+// spreads each halo's particles over all cores instead (cmd/shell.go:311-314, 427-431) --
+// every block is read once and pushed to the contexts whose halos touch it, and the rows
+// come back in input order.  The catalog does not depend on the device list.
 std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::string &stdinData, uint64_t seed,
-                     int device, std::vector<std::string> &outLines);
+                     const std::vector<int> &devices, std::vector<std::string> &outLines);
+
+// Longest-processing-time partition of halos over nRanks: weights[i] is the cost estimate of
+// halo i, groups[i] an affinity label (the block holding its centre); halos of one group go
+// to one rank.  Same result as shellfish_b200/shard.py partition_halos.  owner[i] in [0, nRanks).
+void PartitionHalos(const std::vector<double> &weights, const std::vector<int64_t> &groups, int nRanks,
+                    std::vector<int> &owner);
 
 }  // namespace sfhost

@@ -9,7 +9,7 @@
 //
 // New knobs are environment variables (config files stay valid for the Go
 // binary): SHELLFISH_SEED pins cmd/cmd.go:658's wall-clock seed,
-// SHELLFISH_GPU picks the CUDA device.
+// SHELLFISH_GPUS / SHELLFISH_GPU pick the CUDA devices (default: all of the node).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -20,6 +20,9 @@
 #include <iterator>
 #include <sstream>
 
+#include <algorithm>
+
+#include "../include/shellfish_b200.h"
 #include "sf_config.hpp"
 #include "sf_shell.hpp"
 #include "sf_stats.hpp"
@@ -131,14 +134,33 @@ int main(int argc, char **argv) {
     }
     uint64_t seed = static_cast<uint64_t>(std::chrono::system_clock::now().time_since_epoch().count());
     if (const char *s = std::getenv("SHELLFISH_SEED")) seed = std::strtoull(s, nullptr, 10);
-    const int device = std::getenv("SHELLFISH_GPU") ? std::atoi(std::getenv("SHELLFISH_GPU")) : 0;
+    // SHELLFISH_GPUS = comma-separated CUDA ordinals (or "all"), one context per entry;
+    // SHELLFISH_GPU = one ordinal.  Default: every GPU of the node, as the reference uses every
+    // core (Threads = -1, cmd/shell.go:311-314).  `stats` and `prof` use the first entry.
+    std::vector<int> devices;
+    if (const char *s = std::getenv("SHELLFISH_GPUS")) {
+        if (std::string(s) != "all")
+            for (const char *q = s; *q;) {
+                char *end = nullptr;
+                const long v = std::strtol(q, &end, 10);
+                if (end == q) die(mode, std::string("Cannot parse $SHELLFISH_GPUS = '") + s + "'.");
+                devices.push_back(static_cast<int>(v));
+                q = *end == ',' ? end + 1 : end;
+                if (*end && *end != ',') die(mode, std::string("Cannot parse $SHELLFISH_GPUS = '") + s + "'.");
+            }
+    } else if (const char *s1 = std::getenv("SHELLFISH_GPU")) {
+        devices.push_back(std::atoi(s1));
+    }
+    if (devices.empty())
+        for (int d = 0; d < std::max(1, sfk_device_count()); d++) devices.push_back(d);
+    const int device = devices[0];
     if (g.Logging != "nil") {
         std::fprintf(stderr, "\n#####################\n## shellfish %s ##\n#####################\n", mode.c_str());
         if (mode == "shell") std::fprintf(stderr, "RNG Seed is %llu\n", static_cast<unsigned long long>(seed));
     }
     std::vector<std::string> lines;
     try {
-        if (mode == "shell") err = RunShell(g, c, stdinData, seed, device, lines);
+        if (mode == "shell") err = RunShell(g, c, stdinData, seed, devices, lines);
         else if (mode == "stats") err = RunStats(g, sc, stdinData, device, lines);
         else err = RunProf(g, pc, stdinData, device, lines);
     } catch (const std::exception &e) {   // a Go panic ends the same way: message, then the pipe sentinel

@@ -90,6 +90,9 @@ typedef struct {
     int64_t launches;        /* kernel launches of this library since begin_snapshot */
 } sfk_stats;
 
+/* Number of CUDA devices visible to the process (0 when there is none). */
+int sfk_device_count(void);
+
 /* Fills *p with the defaults of cmd/shell.go:105-119. */
 void sfk_default_params(sfk_params *p);
 
@@ -171,6 +174,24 @@ int sfk_split_count(sfk_ctx *ctx);
 int sfk_split_bin(sfk_ctx *ctx);
 int sfk_split_buffer(sfk_ctx *ctx, int32_t which, void **d_ptr, int64_t *count);
 int sfk_split_finish(sfk_ctx *ctx, double *coeffs, int32_t *status);
+
+/* The same exchange inside the library, over NCCL (opened with dlopen on first use: a
+ * libnccl.so.2 already in the process, $SFK_NCCL_LIB, or the loader path).  One context per
+ * GPU, one rank per context:
+ *   sfk_comm_unique_id  on one rank; the SFK_COMM_ID_BYTES are handed to the others by the host
+ *   sfk_comm_init       on every rank (collective; ncclCommInitRank on the context's GPU)
+ *   sfk_split_finish_comm  on every rank after it pushed its share of the blocks (collective):
+ *     all-reduce of the per-ring hit counts and of rho_max -> private grids (Halo.Split) ->
+ *     reduce-scatter(SUM) of the int64 grid by (halo, ring) row (Halo.Join): rank g receives
+ *     rows g*ceil(rows/G) ... -> RingBuffer.Splashback + FilterPoints on those rings only ->
+ *     all-gather of R_sp and of the filtered points -> PennaVolumeFit of all points on every
+ *     rank, in the single-GPU summation order.  Coefficients, status and taps are identical on
+ *     every rank and bitwise equal to a single-GPU run.  sfk_stats.n_intersections is the
+ *     halo-wide count. */
+#define SFK_COMM_ID_BYTES 128
+int sfk_comm_unique_id(void *id128);
+int sfk_comm_init(sfk_ctx *ctx, const void *id128, int32_t rank, int32_t nranks);
+int sfk_split_finish_comm(sfk_ctx *ctx, double *coeffs, int32_t *status);
 
 /* ---- `shellfish stats`, splashback mass M_sp ---------------------------------
  * massContained (cmd/stats.go:451-543) for every halo of a snapshot: the mass of

@@ -1,18 +1,21 @@
 #!/usr/bin/env python
 """BASELINE config 3: one cluster-mass halo whose particles are split across
-the GPUs of one box, bin grids all-reduced over NCCL.
+the GPUs of one box; the bin grids are summed over NCCL inside libsfk.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
       --master-port 29511 scripts/run_split.py [--particles 10000000] [--rings 24]
 
 Every rank builds the same synthetic snapshot and pushes its contiguous 1/N share of
-every block's particle list (BASELINE config 3: "particle list split contiguous-equal");
-the result is compared (bitwise) with rank 0's single-GPU run of all particles."""
+every block's particle list (BASELINE config 3: "particle list split contiguous-equal").
+Two exchanges are timed (CUDA events on the library's stream, max over ranks, best of
+--reps): `in_library` = sfk_split_finish_comm (reduce-scatter by ring, ring-partitioned
+analysis, all-gather of the filtered points) and `allreduce` = round 1's three
+torch.distributed all-reduces with the analysis replicated on every rank.  Both are compared
+(bitwise) with rank 0's single-GPU run of all particles."""
 import argparse
 import json
 import os
 import sys
-import time
 
 import numpy as np
 import torch
@@ -25,6 +28,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--particles", type=int, default=10_000_000)
 ap.add_argument("--rings", type=int, default=24)
 ap.add_argument("--cells", type=int, default=4)
+ap.add_argument("--reps", type=int, default=5)
 args = ap.parse_args()
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
@@ -35,23 +39,10 @@ box = 60.0
 halos, blocks, mass = synth.make_box(3, box, 1, args.particles, args.particles // 10, args.cells,
                                      centers=[[box / 2] * 3], radii=[2.0])
 params = api.default_params(seed=1337, rings=args.rings, device=local)
-
-
-def run(my_blocks, split):
-    ctx = api.ShellContext(params)
-    ctx.begin_snapshot(blocks[0], mass)
-    ctx.add_halos(halos)
-    for b in my_blocks:
-        ctx.push_block(b)
-    torch.cuda.synchronize()
-    if split:
-        dist.barrier()   # every rank has pushed its blocks: time only the exchange + analysis
-    t = time.time()
-    out = shard.split_halo_finish(ctx, dist if split else None)
-    torch.cuda.synchronize()
-    return out, time.time() - t, ctx.stats()
-
-
+ctx = api.ShellContext(params)
+if world > 1:
+    shard.comm_init(ctx, dist, "cuda")
+stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=local)
 
 
 def share(b):
@@ -60,15 +51,58 @@ def share(b):
     return dict(b, xs=np.ascontiguousarray(b["xs"][lo:hi]), ms=np.ascontiguousarray(b["ms"][lo:hi]))
 
 
-mine = [share(b) for b in blocks] if world > 1 else blocks
-run(mine, world > 1)   # warm-up
-(coeffs, status), dt, st = run(mine, world > 1)
-if rank == 0:
-    (c1, s1), dt1, st1 = run(blocks, False)
-    print(json.dumps({"config": "configs[2]: one halo, %d particles, %d rings x 256 LoS x 256 bins" %
-                      (args.particles, args.rings), "n_gpus": world, "split_seconds": dt,
-                      "single_gpu_seconds": dt1, "bitwise_equal_to_single_gpu": bool(np.array_equal(coeffs, c1)),
-                      "status": int(status[0]), "intersections_rank0": st["n_intersections"],
-                      "intersections_single": st1["n_intersections"], "allreduce_bytes": args.rings * 256 * 256 * 8}))
+def run(my_blocks, mode):
+    """mode: 'single' | 'in_library' | 'allreduce'.  Returns (coeffs, status), ms of the push
+    of the blocks, ms of the exchange + analysis."""
+    dev = [(torch.from_numpy(b["xs"]).cuda(), torch.from_numpy(b["ms"]).cuda()) for b in my_blocks]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize()
+    if mode != "single":
+        dist.barrier()
+        torch.cuda.synchronize()
+    ev[0].record(stream)
+    ctx.begin_snapshot(blocks[0], mass)
+    ctx.add_halos(halos)
+    for b, (dx, dm) in zip(my_blocks, dev):
+        ctx.push_block_device(b, dx, dm)
+    ev[1].record(stream)
+    if mode == "single":
+        out = ctx.finish_snapshot()
+    else:
+        out = shard.split_halo_finish(ctx, dist, in_library=(mode == "in_library"))
+    ev[2].record(stream)
+    torch.cuda.synchronize()
+    t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], device="cuda", dtype=torch.float64)
+    if mode != "single":
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return out, float(t[0]), float(t[1]), ctx.stats()
+
+
+def best(my_blocks, mode):
+    res = [run(my_blocks, mode) for _ in range(args.reps + 1)][1:]   # first pass = warm-up
+    k = int(np.argmin([r[1] + r[2] for r in res]))
+    return res[k]
+
+
+line = {"config": "configs[2]: one halo, %d particles, %d rings x 256 LoS x 256 bins" % (args.particles, args.rings),
+        "n_gpus": world, "grid_bytes": args.rings * 256 * 256 * 8}
 if world > 1:
+    mine = [share(b) for b in blocks]
+    for mode in ("in_library", "allreduce"):
+        (coeffs, status), ms_push, ms_fin, st = best(mine, mode)
+        line[mode] = {"push_ms": ms_push, "finish_ms": ms_fin, "coeffs": coeffs.tolist(), "status": int(status[0]),
+                      "n_intersections": st["n_intersections"]}
+if rank == 0:
+    (c1, s1), ms_push, ms_fin, st1 = best(blocks, "single")
+    line["single_gpu"] = {"push_ms": ms_push, "finish_ms": ms_fin, "n_intersections": st1["n_intersections"]}
+    for mode in ("in_library", "allreduce"):
+        if mode in line:
+            d = line[mode]
+            d["bitwise_equal_to_single_gpu"] = bool(np.array_equal(np.array(d.pop("coeffs")), c1)) and d["status"] == int(s1[0])
+    if "in_library" in line:
+        line["in_library"]["intersections_equal"] = line["in_library"]["n_intersections"] == st1["n_intersections"]
+        line["speedup_finish_in_library"] = ms_fin / line["in_library"]["finish_ms"]
+    print(json.dumps(line))
+if world > 1:
+    dist.barrier()
     dist.destroy_process_group()

@@ -50,9 +50,10 @@ class Stats(C.Structure):
 
 
 # every symbol include/shellfish_b200.h declares
-EXPORTS = ["sfk_default_params", "sfk_create", "sfk_destroy", "sfk_last_error", "sfk_begin_snapshot",
+EXPORTS = ["sfk_device_count", "sfk_default_params", "sfk_create", "sfk_destroy", "sfk_last_error", "sfk_begin_snapshot",
            "sfk_add_halos", "sfk_set_owned", "sfk_block_halo_mask", "sfk_push_block", "sfk_push_block_device",
            "sfk_finish_snapshot", "sfk_row_length", "sfk_split_count", "sfk_split_bin", "sfk_split_buffer", "sfk_split_finish",
+           "sfk_comm_unique_id", "sfk_comm_init", "sfk_split_finish_comm",
            "sfk_mass_begin", "sfk_mass_push_block", "sfk_mass_push_block_device", "sfk_mass_finish",
            "sfk_sphere_block_hit", "sfk_shell_props", "sfk_shell_sums", "sfk_angular_fraction", "sfk_axes_from_moments", "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count", "sfk_get_intersection_count",
            "sfk_get_profiles", "sfk_get_counts", "sfk_get_grid", "sfk_get_ring_tables"]
@@ -92,6 +93,9 @@ def lib():
         L.sfk_split_bin.argtypes = [vp]
         L.sfk_split_buffer.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_int64)]
         L.sfk_split_finish.argtypes = [vp, dp, C.POINTER(C.c_int32)]
+        L.sfk_comm_unique_id.argtypes = [vp]
+        L.sfk_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
+        L.sfk_split_finish_comm.argtypes = [vp, dp, C.POINTER(C.c_int32)]
         L.sfk_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.sfk_stream.argtypes = [vp]
         L.sfk_stream.restype = C.c_void_p
@@ -244,6 +248,22 @@ class ShellContext:
                                         status.ctypes.data_as(C.POINTER(C.c_int32))), "sfk_split_finish")
         return coeffs, status
 
+    # ---- split-halo mode with the exchange inside the library (NCCL)
+    def comm_init(self, unique_id, rank, nranks):
+        """Collective: joins this context to the NCCL communicator named by `unique_id`
+        (comm_unique_id() of one rank, handed to the others by the host)."""
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self._ck(lib().sfk_comm_init(self._h, buf, rank, nranks), "sfk_comm_init")
+
+    def split_finish_comm(self):
+        """Collective: hit-count / rho_max all-reduce, private grids, reduce-scatter by ring,
+        ring-partitioned analysis, all-gather, fit (sfk_split_finish_comm)."""
+        coeffs = np.zeros((self.n_halos, self.P2))
+        status = np.zeros(self.n_halos, np.int32)
+        self._ck(lib().sfk_split_finish_comm(self._h, coeffs.ctypes.data_as(C.POINTER(C.c_double)),
+                                             status.ctypes.data_as(C.POINTER(C.c_int32))), "sfk_split_finish_comm")
+        return coeffs, status
+
     # ---- stats mode: M_sp ----------------------------------------------------------
     def mass_contained(self, centers, coeffs, r_low, r_high, blocks, radii=None, device_blocks=None):
         """massContained (cmd/stats.go:451-543) for every halo over `blocks`
@@ -380,6 +400,17 @@ class ShellContext:
         self._ck(lib().sfk_get_ring_tables(self._h, norms.ctypes.data_as(fp), rot.ctypes.data_as(fp),
                                            irot.ctypes.data_as(fp)), "sfk_get_ring_tables")
         return norms, rot, irot
+
+
+COMM_ID_BYTES = 128   # SFK_COMM_ID_BYTES
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library: bytes to hand to every rank's comm_init."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    if lib().sfk_comm_unique_id(buf) != 0:
+        raise ShellfishError("sfk_comm_unique_id: NCCL is not available (set SFK_NCCL_LIB)")
+    return buf.raw
 
 
 def axes_from_moments(moments):

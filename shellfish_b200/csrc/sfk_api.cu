@@ -12,6 +12,7 @@
 
 #include <cuda_runtime.h>
 
+#include "sfk_comm.h"
 #include "sfk_kernels.cuh"
 #include "sfk_sgmath.cuh"
 #include "sfk_shellmath.cuh"
@@ -143,6 +144,11 @@ struct sfk_ctx {
     std::vector<int32_t> order;
     DevBuf<uint32_t> dHitCountGlobal;
     int splitPhase = 0;
+    // NCCL communicator of this context (sfk_comm_init) and the row-indexed R_sp scratch of the
+    // ring-partitioned analysis
+    ncclComm_t comm = nullptr;
+    int commRank = 0, commSize = 1;
+    DevBuf<double> dRspRows;
 
     sfk_stats stats{};
     StageTimer timer;
@@ -505,11 +511,17 @@ int stage_bin(sfk_ctx *ctx, const std::vector<int32_t> &batch) {
     return SFK_OK;
 }
 
+int stage_fit(sfk_ctx *ctx, int nb);
+
 // haloAnalysis for the batch whose grid is resident: RingBuffer.Splashback,
-// FilterPoints, PennaVolumeFit (cmd/shell.go:613-627).
-int stage_analyze(sfk_ctx *ctx, int nb) {
+// FilterPoints, PennaVolumeFit (cmd/shell.go:613-627).  With rowCount >= 0 only the (slot,
+// ring) rows [rowBegin, rowBegin + rowCount) are analysed, R_sp goes to the row-indexed
+// scratch and the fit is left to the caller (ring-partitioned split-halo analysis).
+int stage_analyze(sfk_ctx *ctx, int nb, int rowBegin = 0, int rowCount = -1) {
     cudaStream_t st = ctx->stream;
     const int R = ctx->rings, n = ctx->spokes, B = ctx->bins;
+    const bool part = rowCount >= 0;
+    if (!part) { rowBegin = 0; rowCount = nb * R; }
     if (ctx->p.percentile_profile) {
         // calcPercentile replaces calcCoeffs, cmd/shell.go:515-517
         PercentileArgs pa{};
@@ -528,9 +540,11 @@ int stage_analyze(sfk_ctx *ctx, int nb) {
     LosArgs la{};
     la.grid = ctx->dGrid.p; la.halos = ctx->dHalos.p; la.batchHalos = ctx->dBatchHalos.p;
     la.valTaps = ctx->dTaps0.p; la.derivTaps = ctx->dTaps1.p; la.logTab = ctx->dLogTab.p;
-    la.rsp = ctx->dRsp.p; la.profiles = ctx->taps ? ctx->dProfiles.p : nullptr;
+    la.rsp = part ? ctx->dRspRows.p : ctx->dRsp.p; la.profiles = ctx->taps ? ctx->dProfiles.p : nullptr;
     la.rings = R; la.spokes = n; la.bins = B; la.window = static_cast<int>(ctx->p.smoothing_window);
     la.dLim = ctx->p.los_slope_cutoff;
+    la.losBegin = static_cast<int64_t>(rowBegin) * n; la.losCount = static_cast<int64_t>(rowCount) * n;
+    la.rspBySlot = part ? 1 : 0;
     // Sliding-moment smoothing only when every ln(rho) is finite and normal (rho_bg > 0; with
     // Gadget-2's MinMass() == 0 the reference's -Inf / NaN propagation must stay sample-exact).
     bool moments = !(ctx->p.flags & SFK_FLAG_LOS_TAPLOOP) && ctx->sgReady && los_moments_supported(la);
@@ -542,7 +556,8 @@ int stage_analyze(sfk_ctx *ctx, int nb) {
     ctx->timer.end(ST_LOS, st);
 
     FilterArgs fa{};
-    fa.rsp = ctx->dRsp.p; fa.halos = ctx->dHalos.p; fa.batchHalos = ctx->dBatchHalos.p;
+    fa.rsp = la.rsp; fa.halos = ctx->dHalos.p; fa.batchHalos = ctx->dBatchHalos.p;
+    fa.rowBegin = rowBegin; fa.rowCount = rowCount; fa.rspBySlot = la.rspBySlot;
     fa.fR = ctx->dFR.p; fa.fIdx = ctx->dFIdx.p; fa.fCount = ctx->dFCount.p; fa.status = ctx->dStatus.p;
     fa.rings = R; fa.spokes = n; fa.levels = static_cast<int>(ctx->p.levels);
     fa.eta = ctx->p.eta; fa.ringPhi = ctx->dPhi.p;
@@ -550,7 +565,13 @@ int stage_analyze(sfk_ctx *ctx, int nb) {
     CU(launch_filter(fa, nb, st));
     ctx->stats.launches++;
     ctx->timer.end(ST_FILTER, st);
+    return part ? SFK_OK : stage_fit(ctx, nb);
+}
 
+// PennaVolumeFit for the nb halos of the batch from their filtered points.
+int stage_fit(sfk_ctx *ctx, int nb) {
+    cudaStream_t st = ctx->stream;
+    const int R = ctx->rings, n = ctx->spokes;
     FitArgs ft{};
     ft.fR = ctx->dFR.p; ft.fIdx = ctx->dFIdx.p; ft.fCount = ctx->dFCount.p;
     ft.batchHalos = ctx->dBatchHalos.p; ft.irots = ctx->dIrots.p;
@@ -616,6 +637,11 @@ int stage_collect(sfk_ctx *ctx, double *coeffs, int32_t *status) {
 extern "C" {
 
 
+int sfk_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 void sfk_default_params(sfk_params *p) {
     std::memset(p, 0, sizeof *p);
     p->subsample_factor = 1; p->radial_bins = 256; p->spokes = 256; p->rings = 100;
@@ -677,7 +703,12 @@ static int create_impl(sfk_ctx *ctx, const sfk_params *params) try {
 
 void sfk_destroy(sfk_ctx *ctx) {
     if (!ctx) return;
-    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) {
+        if (const NcclApi *api = nccl_api(nullptr)) api->CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -880,6 +911,110 @@ int sfk_split_finish(sfk_ctx *ctx, double *coeffs, int32_t *status) try {
     CU(cudaSetDevice(ctx->p.device));
     CU(cudaDeviceSynchronize());   // the caller's all-reduce of the grid
     int rc = stage_analyze(ctx, static_cast<int>(ctx->order.size()));
+    if (rc) return rc;
+    return stage_collect(ctx, coeffs, status);
+} SFK_CATCH(ctx)
+
+// ---- split-halo mode with the exchange inside the library (NCCL) ------------------------
+
+#define NC(call)                                                                             \
+    do {                                                                                     \
+        ncclResult_t r_ = (call);                                                            \
+        if (r_ != ncclSuccess)                                                               \
+            return fail(ctx, SFK_E_CUDA, std::string(#call) + ": " + api->GetErrorString(r_)); \
+    } while (0)
+
+int sfk_comm_unique_id(void *id128) {
+    std::string err;
+    const NcclApi *api = nccl_api(&err);
+    if (!api || !id128) return SFK_E_UNSUPPORTED;
+    static_assert(sizeof(ncclUniqueId) == SFK_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    if (api->GetUniqueId(&id) != ncclSuccess) return SFK_E_CUDA;
+    std::memcpy(id128, &id, sizeof id);
+    return SFK_OK;
+}
+
+int sfk_comm_init(sfk_ctx *ctx, const void *id128, int32_t rank, int32_t nranks) try {
+    if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks)
+        return fail(ctx, SFK_E_INVALID, "sfk_comm_init: bad arguments");
+    if (ctx->comm) return fail(ctx, SFK_E_INVALID, "sfk_comm_init: communicator already set");
+    std::string err;
+    const NcclApi *api = nccl_api(&err);
+    if (!api) return fail(ctx, SFK_E_UNSUPPORTED, "sfk_comm_init: " + err);
+    CU(cudaSetDevice(ctx->p.device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    NC(api->CommInitRank(&ctx->comm, nranks, id, rank));
+    ctx->commRank = rank; ctx->commSize = nranks;
+    return SFK_OK;
+} SFK_CATCH(ctx)
+
+int sfk_split_finish_comm(sfk_ctx *ctx, double *coeffs, int32_t *status) try {
+    if (!ctx || !ctx->inSnapshot || ctx->splitPhase != 0)
+        return fail(ctx, SFK_E_INVALID, "sfk_split_finish_comm: no snapshot open or a split pass is already open");
+    if (!ctx->comm) return fail(ctx, SFK_E_INVALID, "sfk_split_finish_comm: call sfk_comm_init first");
+    if (ctx->p.percentile_profile)
+        return fail(ctx, SFK_E_UNSUPPORTED, "sfk_split_finish_comm: PercentileProfile is not supported in split-halo mode");
+    const NcclApi *api = nccl_api(nullptr);
+    cudaStream_t st = ctx->stream;
+    const int G = ctx->commSize, g = ctx->commRank;
+    CU(cudaSetDevice(ctx->p.device));
+    // raw hit counts of this rank's particles; the halo-wide counts and rho_max fix the
+    // fixed-point scale, identically on every rank
+    int rc = stage_prepare(ctx);
+    if (rc) return rc;
+    const int64_t nHalo = static_cast<int64_t>(ctx->halos.size());
+    if (nHalo == 0) { ctx->finished = true; return SFK_OK; }
+    const int R = ctx->rings, n = ctx->spokes, B = ctx->bins;
+    const size_t nc = static_cast<size_t>(nHalo) * R;
+    CU(ctx->dHitCountGlobal.ensure(nc));
+    CU(cudaMemcpyAsync(ctx->dHitCountGlobal.p, ctx->dHitCount.p, nc * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    NC(api->GroupStart());
+    NC(api->AllReduce(ctx->dHitCountGlobal.p, ctx->dHitCountGlobal.p, nc, ncclUint32, ncclSum, ctx->comm, st));
+    NC(api->AllReduce(ctx->dRhoMax.p, ctx->dRhoMax.p, nHalo, ncclUint64, ncclMax, ctx->comm, st));
+    NC(api->GroupEnd());
+    rc = stage_scale(ctx, true);
+    if (rc) return rc;
+    const int nb = static_cast<int>(ctx->order.size());
+    if (nb == 0) return stage_collect(ctx, coeffs, status);
+    // (halo, ring) rows, padded so that every rank owns the same number
+    const int rows = nb * R;
+    const int rowsPer = (rows + G - 1) / G, rowsPad = rowsPer * G;
+    const size_t rowCells = static_cast<size_t>(n) * B;
+    if (rowsPad * rowCells * sizeof(unsigned long long) > (size_t(96) << 30))
+        return fail(ctx, SFK_E_NOMEM, "sfk_split_finish_comm: the bin grids of all halos must fit in HBM at once");
+    CU(ctx->dGrid.ensure(rowsPad * rowCells));
+    CU(ctx->dRspRows.ensure(static_cast<size_t>(rowsPad) * n));
+    CU(ctx->dFR.ensure(static_cast<size_t>(rowsPad) * n));
+    CU(ctx->dFIdx.ensure(static_cast<size_t>(rowsPad) * n));
+    CU(ctx->dFCount.ensure(rowsPad));
+    rc = stage_bin(ctx, ctx->order);   // this rank's private grid (Halo.Split's copy)
+    if (rc) return rc;
+    // Halo.Join: sum the private grids; rank g receives rows [g rowsPer, (g + 1) rowsPer) in place
+    NC(api->ReduceScatter(ctx->dGrid.p, ctx->dGrid.p + static_cast<size_t>(g) * rowsPer * rowCells,
+                          rowsPer * rowCells, ncclInt64, ncclSum, ctx->comm, st));
+    const int rowBegin = g * rowsPer, rowCount = std::max(0, std::min(rows, rowBegin + rowsPer) - rowBegin);
+    CU(cudaMemsetAsync(ctx->dFCount.p + rowBegin, 0, rowsPer * sizeof(int32_t), st));
+    rc = stage_analyze(ctx, nb, rowBegin, rowCount);   // RingBuffer.Splashback + FilterPoints of my rings
+    if (rc) return rc;
+    // every rank gets every ring's R_sp and filtered points, then fits all halos itself: the
+    // fit sums in the single-GPU order, so the coefficients are bitwise those of one GPU
+    NC(api->GroupStart());
+    NC(api->AllGather(ctx->dRspRows.p + static_cast<size_t>(rowBegin) * n, ctx->dRspRows.p, static_cast<size_t>(rowsPer) * n,
+                      ncclFloat64, ctx->comm, st));
+    NC(api->AllGather(ctx->dFR.p + static_cast<size_t>(rowBegin) * n, ctx->dFR.p, static_cast<size_t>(rowsPer) * n, ncclFloat64,
+                      ctx->comm, st));
+    NC(api->AllGather(ctx->dFIdx.p + static_cast<size_t>(rowBegin) * n, ctx->dFIdx.p, static_cast<size_t>(rowsPer) * n, ncclInt32,
+                      ctx->comm, st));
+    NC(api->AllGather(ctx->dFCount.p + rowBegin, ctx->dFCount.p, rowsPer, ncclInt32, ctx->comm, st));
+    NC(api->AllReduce(ctx->dStatus.p, ctx->dStatus.p, nHalo, ncclInt32, ncclMax, ctx->comm, st));
+    NC(api->AllReduce(ctx->dNInter.p, ctx->dNInter.p, nHalo, ncclUint64, ncclSum, ctx->comm, st));
+    NC(api->GroupEnd());
+    for (int s = 0; s < nb; s++)
+        CU(cudaMemcpyAsync(ctx->dRsp.p + static_cast<size_t>(ctx->order[s]) * R * n, ctx->dRspRows.p + static_cast<size_t>(s) * R * n,
+                           static_cast<size_t>(R) * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    rc = stage_fit(ctx, nb);
     if (rc) return rc;
     return stage_collect(ctx, coeffs, status);
 } SFK_CATCH(ctx)

@@ -515,9 +515,10 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
     }
     __syncthreads();
     const int lane = lane_id();
-    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kLosWarps + (threadIdx.x >> 5);
+    const int64_t gw0 = static_cast<int64_t>(blockIdx.x) * kLosWarps + (threadIdx.x >> 5);
     const int64_t perHalo = static_cast<int64_t>(a.rings) * a.spokes;
-    if (gw >= perHalo * nb) return;
+    if (gw0 >= a.losCount) return;
+    const int64_t gw = a.losBegin + gw0;
     const int slot = static_cast<int>(gw / perHalo);
     const int64_t rl = gw - slot * perHalo;
     const int haloIdx = a.batchHalos[slot];
@@ -561,7 +562,7 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
     for (int e = B + padL + lane; e < PER * rowLen; e += 32) ys[(e % PER) * rowLen + e / PER] = yLast;
     __syncwarp();
 
-    double *out = a.rsp + static_cast<size_t>(haloIdx) * perHalo + rl;
+    double *out = a.rspBySlot ? a.rsp + gw : a.rsp + static_cast<size_t>(haloIdx) * perHalo + rl;
     if (B <= window) {   // Smooth: ok = false, smooth.go:51-53
         if (lane == 0) *out = nan_f64();
         return;
@@ -686,9 +687,10 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel(LosArgs a, int nb) 
     }
     __syncthreads();
     const int lane = lane_id();
-    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kLosWarps + (threadIdx.x >> 5);
+    const int64_t gw0 = static_cast<int64_t>(blockIdx.x) * kLosWarps + (threadIdx.x >> 5);
     const int64_t perHalo = static_cast<int64_t>(a.rings) * a.spokes;
-    if (gw >= perHalo * nb) return;
+    if (gw0 >= a.losCount) return;
+    const int64_t gw = a.losBegin + gw0;
     const int slot = static_cast<int>(gw / perHalo);
     const int64_t rl = gw - slot * perHalo;   // ring*spokes + los
     const int haloIdx = a.batchHalos[slot];
@@ -717,7 +719,7 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel(LosArgs a, int nb) 
     }
     __syncwarp();
 
-    double *out = a.rsp + static_cast<size_t>(haloIdx) * perHalo + rl;
+    double *out = a.rspBySlot ? a.rsp + gw : a.rsp + static_cast<size_t>(haloIdx) * perHalo + rl;
     if (bins <= window) {  // Smooth: ok = false, smooth.go:51-53
         if (lane == 0) *out = __longlong_as_double(0x7ff8000000000000ll);
         return;
@@ -875,12 +877,13 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(FilterArgs a) {
     unsigned char *keep = reinterpret_cast<unsigned char *>(pHi + a.spokes);
     unsigned char *pNode = keep + a.spokes;                            // [levels][spokes]
 
-    const int ring = blockIdx.x, slot = blockIdx.y;
+    const int row = a.rowBegin + static_cast<int>(blockIdx.x);
+    const int slot = row / a.rings, ring = row - slot * a.rings;
     const int haloIdx = a.batchHalos[slot];
     const HaloDev &h = a.halos[haloIdx];
     const int tid = threadIdx.x;
-    const size_t ringBase = (static_cast<size_t>(slot) * a.rings + ring) * a.spokes;
-    const double *rsp = a.rsp + (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes;
+    const size_t ringBase = static_cast<size_t>(row) * a.spokes;
+    const double *rsp = a.rspBySlot ? a.rsp + ringBase : a.rsp + (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes;
 
     // valid points in LoS order (ring_buffer.go OkPolarCoords): staged through shared memory so
     // that the ordered compaction does not wait on one global load per LoS (n <= i: in place)
@@ -1480,7 +1483,8 @@ bool los_moments_supported(const LosArgs &a) { return a.bins == 256 && a.window 
 
 cudaError_t launch_los(const LosArgs &a, const SgPoly *sg, int nb, cudaStream_t s) {
     if (nb <= 0) return cudaSuccess;
-    const int64_t warps = static_cast<int64_t>(nb) * a.rings * a.spokes;
+    const int64_t warps = a.losCount;
+    if (warps <= 0) return cudaSuccess;
     const unsigned grid = static_cast<unsigned>((warps + kLosWarps - 1) / kLosWarps);
     if (sg && los_moments_supported(a)) {
         const size_t fsmem = sizeof(double) * (4 * (a.window / 2 + 1) + 256 + kLosWarps * 8 * kLosFastRow);
@@ -1507,8 +1511,8 @@ cudaError_t launch_filter(const FilterArgs &a, int nb, cudaStream_t s) {
         cudaError_t e = cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
     }
-    dim3 grid(a.rings, nb);
-    filter_kernel<<<grid, kFilterThreads, smem, s>>>(a);
+    if (a.rowCount <= 0) return cudaSuccess;
+    filter_kernel<<<a.rowCount, kFilterThreads, smem, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -54,6 +54,10 @@ struct LosArgs {
     double *profiles;   // TAPS: [nHalo][rings][spokes][bins], else null
     int rings, spokes, bins, window;
     double dLim;
+    // lines of sight [losBegin, losBegin + losCount) of the batch's flat (slot, ring, LoS) order;
+    // rspBySlot: rsp is indexed by that flat order instead of by halo (ring-partitioned analysis)
+    int64_t losBegin, losCount;
+    int rspBySlot;
 };
 
 struct FilterArgs {
@@ -67,6 +71,8 @@ struct FilterArgs {
     int rings, spokes, levels;
     double eta, dPhiUnused;
     const double *ringPhi;
+    // (slot, ring) rows [rowBegin, rowBegin + rowCount) of the batch; rspBySlot as in LosArgs
+    int rowBegin, rowCount, rspBySlot;
 };
 
 struct FitArgs {

@@ -31,6 +31,18 @@ def cli_path():
     return os.path.join(_HERE, "shellfish_cli")
 
 
+def partition_halos(weights, groups, n_ranks):
+    """PartitionHalos of host/sf_shell.cpp: owner rank of every halo."""
+    w = np.ascontiguousarray(weights, np.float64)
+    g = np.ascontiguousarray(groups, np.int64)
+    own = np.zeros(len(w), np.int32)
+    f = lib().sfh_partition_halos
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    f.restype = None
+    f(w.ctypes.data, g.ctypes.data, len(w), n_ranks, own.ctypes.data)
+    return own
+
+
 def go_g6(v):
     return lib().sfh_go_g6(float(v)).decode()
 

@@ -132,12 +132,30 @@ def gather_table(parts, rank, local_rows, n_total, dist=None, device="cpu"):
     return table
 
 
-def split_halo_finish(ctx, dist):
-    """Split-halo exchange (BASELINE config 3): every rank has pushed its share
-    of the particle blocks into `ctx`; the three all-reduces below replace
-    Halo.Split/Join (los/halo.go:107-140).  Returns (coeffs, status), identical
-    on every rank."""
+def comm_init(ctx, dist, device):
+    """Joins `ctx` to an NCCL communicator owned by libsfk (sfk_comm_init): rank 0 draws
+    the unique id, torch.distributed carries its 128 bytes to the other ranks."""
+    import torch
     from . import api
+    rank, world = dist.get_rank(), dist.get_world_size()
+    raw = api.comm_unique_id() if rank == 0 else bytes(api.COMM_ID_BYTES)
+    t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+    dist.broadcast(t, src=0)
+    ctx.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+
+def split_halo_finish(ctx, dist, in_library=False):
+    """Split-halo exchange (BASELINE config 3): every rank has pushed its share
+    of the particle blocks into `ctx`.  in_library: the whole exchange runs inside
+    libsfk over its own NCCL communicator (comm_init first): reduce-scatter of the
+    grid by ring, ring-partitioned analysis, all-gather of the filtered points.
+    Otherwise the three all-reduces below, issued through torch.distributed on the
+    library's exchange buffers, replace Halo.Split/Join (los/halo.go:107-140) and
+    every rank analyses every ring.  Returns (coeffs, status), identical on every
+    rank."""
+    from . import api
+    if in_library:
+        return ctx.split_finish_comm()
     ctx.split_count()
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(ctx.split_buffer(api.SPLIT_HIT_COUNTS), op=dist.ReduceOp.SUM)

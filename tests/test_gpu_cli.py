@@ -42,10 +42,12 @@ def _setup(tmp_path, seed, n_halos, n_per, n_bg, cells, box=62.5):
     return halos, rb, min_mass, str(cfg)
 
 
-def _run_cli(cfg, halos, flags, seed=1337, snap=100):
+def _run_cli(cfg, halos, flags, seed=1337, snap=100, gpus=None):
     stdin = "# ID Snap X Y Z R200m\n" + "".join(
         "%d %d %.17g %.17g %.17g %.17g\n" % (i, snap, *h[:4]) for i, h in enumerate(halos))
     env = dict(os.environ, SHELLFISH_GLOBAL_CONFIG=cfg, SHELLFISH_SEED=str(seed))
+    if gpus is not None:
+        env["SHELLFISH_GPUS"] = gpus
     r = subprocess.run([H.cli_path(), "shell"] + flags, input=stdin, capture_output=True, text=True, env=env,
                        timeout=600)
     assert r.returncode == 0, r.stderr
@@ -76,6 +78,22 @@ def test_cli_matches_binding_and_oracle(tmp_path):
     for h in range(len(halos)):
         scale = np.max(np.abs(ref["coeffs"][h]))
         assert np.all(np.abs(got[h] - ref["coeffs"][h]) <= (1e-5 + 5e-6) * scale)   # + the %.6g rounding
+
+
+def test_cli_several_contexts_give_the_same_catalog(tmp_path):
+    """SHELLFISH_GPUS: one context per listed device, halos partitioned by estimated particle
+    count with block affinity, every block pushed to the contexts whose halos touch it, rows
+    merged in input order.  Two and three contexts on GPU 0 (and every GPU of the box when there
+    are several) print the catalog of the single-context run, byte for byte."""
+    import torch
+    halos, blocks, min_mass, cfg = _setup(tmp_path, 15, 7, 12000, 20000, 3, box=30.0)
+    one = _run_cli(cfg, halos, ["--Rings", "8"], gpus="0")
+    assert len(one) == 1 + len(halos)
+    assert _run_cli(cfg, halos, ["--Rings", "8"], gpus="0,0") == one
+    assert _run_cli(cfg, halos, ["--Rings", "8"], gpus="0,0,0") == one
+    if torch.cuda.device_count() > 1:
+        assert _run_cli(cfg, halos, ["--Rings", "8"], gpus="all") == one
+        assert _run_cli(cfg, halos, ["--Rings", "8"], gpus="1,0") == one
 
 
 def test_cli_memo_and_skipped_halo(tmp_path):

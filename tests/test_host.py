@@ -528,3 +528,18 @@ def test_truncated_snapshots_are_reported(tmp_path):
     open(f, "wb").write(bytes(hdr))
     with pytest.raises(ValueError, match="unexpected EOF"):
         H.read_block("Gadget-2", f)
+
+
+def test_cli_halo_partition_equals_the_python_one():
+    """PartitionHalos (host/sf_shell.cpp, SHELLFISH_GPUS) == shard.partition_halos."""
+    from shellfish_b200 import shard
+    rng = np.random.default_rng(4)
+    for n, ranks in ((1000, 8), (37, 3), (5, 8), (64, 1)):
+        w = rng.uniform(0.3, 3.0, n)
+        grp = rng.integers(-1, max(2, n // 2), n)
+        own = H.partition_halos(w, grp, ranks)
+        parts = shard.partition_halos(w, ranks, grp)
+        want = np.empty(n, np.int32)
+        for r, p in enumerate(parts):
+            want[p] = r
+        assert np.array_equal(own, want)
