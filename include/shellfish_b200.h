@@ -130,13 +130,18 @@ int sfk_block_halo_mask(sfk_ctx *ctx, const float origin[3], const float width[3
  * touching the block, in halo order, Transform + Intersect
  * (los/halo.go:168-197,147-164) and queueing of the surviving particles with
  * the weight of chanLoadSphereVec (cmd/shell.go:479-500).  xyz is [n][3],
- * mass is [n]; both are host pointers. */
+ * mass is [n]; both are host pointers, consumed when the call returns (the copy runs on
+ * a second stream into one of two staging buffers and overlaps the cull of the previous
+ * block, so page-locked host memory pays). */
 int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
                    const sfk_cosmo *cosmo, double total_width,
                    const float origin[3], const float width[3]);
 
 /* Same with xyz/mass already in device memory of ctx's GPU (used to time the
- * kernels with inputs resident in HBM). */
+ * kernels with inputs resident in HBM).  The buffers must be complete on the device when
+ * they are handed over (work queued before the first device push of a snapshot is waited
+ * for once) and must stay valid and unchanged until sfk_finish_snapshot returns: the cull
+ * of a block is queued on the context's stream, not finished, when the call returns. */
 int sfk_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass,
                           int64_t n, const sfk_cosmo *cosmo, double total_width,
                           const float origin[3], const float width[3]);

@@ -38,6 +38,15 @@ if world > 1:
 box = 60.0
 halos, blocks, mass = synth.make_box(3, box, 1, args.particles, args.particles // 10, args.cells,
                                      centers=[[box / 2] * 3], radii=[2.0])
+# synth writes a block's halo particles in the order it drew them (NFW body first, by radius
+# population, then the envelope, then the background); a snapshot file is not sorted like that,
+# and "contiguous-equal" shares of a sorted list would give one rank the dense core.  Shuffle
+# every block once (same permutation on every rank): sums are exact, the result cannot change.
+_rng = np.random.default_rng(11)
+for _b in blocks:
+    _perm = _rng.permutation(len(_b["ms"]))
+    _b["xs"] = np.ascontiguousarray(_b["xs"][_perm])
+    _b["ms"] = np.ascontiguousarray(_b["ms"][_perm])
 params = api.default_params(seed=1337, rings=args.rings, device=local)
 ctx = api.ShellContext(params)
 if world > 1:
@@ -91,10 +100,12 @@ if world > 1:
     for mode in ("in_library", "allreduce"):
         (coeffs, status), ms_push, ms_fin, st = best(mine, mode)
         line[mode] = {"push_ms": ms_push, "finish_ms": ms_fin, "coeffs": coeffs.tolist(), "status": int(status[0]),
-                      "n_intersections": st["n_intersections"]}
+                      "n_intersections": st["n_intersections"],
+                      "rank0_stage_ms": {k: round(st[k], 3) for k in ("ms_cull", "ms_hits", "ms_bin", "ms_los", "ms_filter", "ms_fit")}}
 if rank == 0:
     (c1, s1), ms_push, ms_fin, st1 = best(blocks, "single")
-    line["single_gpu"] = {"push_ms": ms_push, "finish_ms": ms_fin, "n_intersections": st1["n_intersections"]}
+    line["single_gpu"] = {"push_ms": ms_push, "finish_ms": ms_fin, "n_intersections": st1["n_intersections"],
+                          "stage_ms": {k: round(st1[k], 3) for k in ("ms_cull", "ms_hits", "ms_bin", "ms_los", "ms_filter", "ms_fit")}}
     for mode in ("in_library", "allreduce"):
         if mode in line:
             d = line[mode]

@@ -252,6 +252,7 @@ class ShellContext:
     def comm_init(self, unique_id, rank, nranks):
         """Collective: joins this context to the NCCL communicator named by `unique_id`
         (comm_unique_id() of one rank, handed to the others by the host)."""
+        _preload_nccl()
         buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
         self._ck(lib().sfk_comm_init(self._h, buf, rank, nranks), "sfk_comm_init")
 
@@ -405,8 +406,27 @@ class ShellContext:
 COMM_ID_BYTES = 128   # SFK_COMM_ID_BYTES
 
 
+def _preload_nccl():
+    """libsfk binds NCCL with dlopen, preferring a libnccl.so.2 already in the process.  In a
+    Python process that will also import torch, that copy must be the one torch was built
+    against (its bundled nvidia-nccl wheel): the loader shares libraries by SONAME, so an older
+    system libnccl loaded first would be handed to torch as well.  Load the wheel's copy first."""
+    if os.environ.get("SFK_NCCL_LIB"):
+        return
+    try:
+        import glob
+        import nvidia.nccl
+        for d in list(getattr(nvidia.nccl, "__path__", [])):
+            for f in sorted(glob.glob(os.path.join(d, "lib", "libnccl.so.*"))):
+                C.CDLL(f, mode=C.RTLD_GLOBAL)
+                return
+    except (ImportError, OSError):
+        pass
+
+
 def comm_unique_id():
     """ncclGetUniqueId through the library: bytes to hand to every rank's comm_init."""
+    _preload_nccl()
     buf = C.create_string_buffer(COMM_ID_BYTES)
     if lib().sfk_comm_unique_id(buf) != 0:
         raise ShellfishError("sfk_comm_unique_id: NCCL is not available (set SFK_NCCL_LIB)")

@@ -45,8 +45,6 @@ struct DevBuf {
     }
 };
 
-struct Seg { int64_t start; int32_t count; int32_t halo; };
-
 struct StageTimer {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[6];
     void begin(int stage, cudaStream_t s) {
@@ -92,17 +90,25 @@ struct sfk_ctx {
     std::vector<HaloDev> halos;
     std::vector<double> ox, oy, oz;   // float64 origins for SheetIntersect
     DevBuf<HaloDev> dHalos;
-    DevBuf<Cand> dCands;
-    int64_t candCount = 0;
-    std::vector<Seg> segs;
+    // candidates: appended in arrival order by cull_kernel (dCandsRaw), bucketed by halo at
+    // finish (dCands).  candUpper bounds the device-side count without a round trip.
+    DevBuf<Cand> dCandsRaw, dCands;
+    DevBuf<unsigned long long> dCandTotal;
+    DevBuf<uint32_t> dHaloCandCount, dCandCursor;
+    DevBuf<int64_t> dCandOffset;
+    int64_t candUpper = 0, candCount = 0;
+    bool pushed = false, cullOpen = false;
     std::vector<int64_t> candPerHalo;
     std::vector<int64_t> interPerHalo;   // ProfileRing.Insert calls per halo (after finish)
 
-    // block staging
-    DevBuf<float> dXyz, dMass;
+    // block staging: two buffers, so that the host-to-device copy of a block (copyStream)
+    // overlaps the cull of the previous one (stream)
+    DevBuf<float> dXyz[2], dMass[2];
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evCopied[2] = {nullptr, nullptr}, evCulled[2] = {nullptr, nullptr};
+    bool culledValid[2] = {false, false};
+    int64_t pushIdx = 0;
     DevBuf<int32_t> dHaloList;
-    DevBuf<uint32_t> dCounts;
-    DevBuf<int64_t> dSegStart;
 
     // results (per halo of the snapshot)
     DevBuf<double> dRsp, dCoeffs;
@@ -236,17 +242,29 @@ bool sheet_intersect(const sfk_ctx *c, size_t i, const float origin[3], const fl
            in_range(c->oz[i], r, origin[2], width[2], tw);
 }
 
-int grow_cands(sfk_ctx *ctx, int64_t need) {
-    if (static_cast<size_t>(need) <= ctx->dCands.cap) return SFK_OK;
-    size_t cap = std::max<size_t>({static_cast<size_t>(need), ctx->dCands.cap * 3 / 2, size_t(1) << 20});
-    Cand *np = nullptr;
-    CU(cudaMalloc(&np, cap * sizeof(Cand)));
-    if (ctx->candCount > 0)
-        CU(cudaMemcpyAsync(np, ctx->dCands.p, ctx->candCount * sizeof(Cand), cudaMemcpyDeviceToDevice, ctx->stream));
+// Makes room for `extra` more candidates.  The device-side count is only known to the host
+// as an upper bound (every pushed block could have kept all its particles for every listed
+// halo); when that bound no longer fits, the exact count is fetched (one stream sync) and the
+// list grows geometrically if it must.
+int reserve_cands(sfk_ctx *ctx, int64_t extra) {
+    if (static_cast<size_t>(ctx->candUpper + extra) <= ctx->dCandsRaw.cap) { ctx->candUpper += extra; return SFK_OK; }
+    unsigned long long exact = 0;
+    CU(cudaMemcpyAsync(&exact, ctx->dCandTotal.p, sizeof exact, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->dCands.release();
-    ctx->dCands.p = np;
-    ctx->dCands.cap = cap;
+    ctx->candUpper = static_cast<int64_t>(exact);
+    const size_t need = static_cast<size_t>(ctx->candUpper + extra);
+    if (need > ctx->dCandsRaw.cap) {
+        const size_t cap = std::max<size_t>({need, ctx->dCandsRaw.cap * 3 / 2, size_t(1) << 22});
+        Cand *np = nullptr;
+        CU(cudaMalloc(&np, cap * sizeof(Cand)));
+        if (exact > 0)
+            CU(cudaMemcpyAsync(np, ctx->dCandsRaw.p, exact * sizeof(Cand), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->dCandsRaw.release();
+        ctx->dCandsRaw.p = np;
+        ctx->dCandsRaw.cap = cap;
+    }
+    ctx->candUpper += extra;
     return SFK_OK;
 }
 
@@ -254,49 +272,32 @@ int push_block_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, int64_t
                     const sfk_cosmo *cosmo, double tw, const float origin[3], const float width[3]) {
     // binIntersections for this header, cmd/shell.go:599-611 (halo order kept)
     std::vector<int32_t> list;
+    int64_t nOwned = 0;
     for (size_t i = 0; i < ctx->halos.size(); i++)
-        if (ctx->halos[i].valid && sheet_intersect(ctx, i, origin, width, tw)) list.push_back(static_cast<int32_t>(i));
+        if (ctx->halos[i].valid && sheet_intersect(ctx, i, origin, width, tw)) {
+            list.push_back(static_cast<int32_t>(i));
+            nOwned += ctx->halos[i].owned ? 1 : 0;
+        }
     if (list.empty() || n <= 0) return SFK_OK;
     const int nList = static_cast<int>(list.size());
-    CU(ctx->dHaloList.upload(list, ctx->stream));
-    CU(ctx->dCounts.ensure(nList));
-    CU(ctx->dSegStart.ensure(nList));
-    CU(cudaMemsetAsync(ctx->dCounts.p, 0, nList * sizeof(uint32_t), ctx->stream));
     const int64_t sf = ctx->p.subsample_factor;
+    const int64_t sf3 = sf * sf * sf;
+    int rc = reserve_cands(ctx, (n + sf3 - 1) / sf3 * nOwned);
+    if (rc) return rc;
+    // pageable source: the copy is staged before the call returns, `list` may die
+    CU(ctx->dHaloList.upload(list, ctx->stream));
     CullArgs a{};
-    a.xyz = dxyz; a.mass = dmass; a.n = n; a.sf3 = sf * sf * sf;
+    a.xyz = dxyz; a.mass = dmass; a.n = n; a.sf3 = sf3;
     a.haloList = ctx->dHaloList.p; a.nList = nList; a.halos = ctx->dHalos.p;
     a.tw = static_cast<float>(tw);
     // chanLoadSphereVec uses the block's own header, cmd/shell.go:487-488
     a.rhoM = rho_average(cosmo->h100 * 100, cosmo->omega_m, cosmo->omega_l, cosmo->z);
-    a.counts = ctx->dCounts.p; a.segStart = ctx->dSegStart.p; a.cands = nullptr;
-    ctx->timer.begin(ST_CULL, ctx->stream);
-    CU(launch_cull(a, false, ctx->stream));
+    a.cands = ctx->dCandsRaw.p; a.cap = static_cast<int64_t>(ctx->dCandsRaw.cap);
+    a.total = ctx->dCandTotal.p; a.haloCount = ctx->dHaloCandCount.p;
+    if (!ctx->cullOpen) { ctx->timer.begin(ST_CULL, ctx->stream); ctx->cullOpen = true; }
+    CU(launch_cull(a, ctx->stream));
     ctx->stats.launches++;
-    std::vector<uint32_t> counts(nList);
-    CU(cudaMemcpyAsync(counts.data(), ctx->dCounts.p, nList * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    std::vector<int64_t> segStart(nList);
-    int64_t total = 0;
-    for (int k = 0; k < nList; k++) { segStart[k] = ctx->candCount + total; total += counts[k]; }
-    if (total > 0) {
-        int rc = grow_cands(ctx, ctx->candCount + total);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(ctx->dSegStart.p, segStart.data(), nList * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemsetAsync(ctx->dCounts.p, 0, nList * sizeof(uint32_t), ctx->stream));
-        a.cands = ctx->dCands.p;
-        CU(launch_cull(a, true, ctx->stream));
-        ctx->stats.launches++;
-        // segStart is a stack vector: the copy above must finish before return
-        CU(cudaStreamSynchronize(ctx->stream));
-        for (int k = 0; k < nList; k++)
-            if (counts[k]) {
-                ctx->segs.push_back({segStart[k], static_cast<int32_t>(counts[k]), list[k]});
-                ctx->candPerHalo[list[k]] += counts[k];
-            }
-        ctx->candCount += total;
-    }
-    ctx->timer.end(ST_CULL, ctx->stream);
+    ctx->pushed = true;
     return SFK_OK;
 }
 
@@ -370,10 +371,32 @@ int stage_prepare(sfk_ctx *ctx) {
         CU(cudaStreamSynchronize(st));
     }
 
-    // pieces: <= 256 candidates of one halo each, grouped per halo
-    for (const Seg &s : ctx->segs)
-        for (int32_t off = 0; off < s.count; off += 256)
-            ctx->perHalo[s.halo].push_back({s.start + off, std::min<int32_t>(256, s.count - off), s.halo});
+    // bucket the candidates by halo (counting sort on the device), then cut every halo's run
+    // into pieces of <= 256 candidates
+    {
+        std::vector<uint32_t> cnt(nHalo);
+        unsigned long long total = 0;
+        CU(cudaMemcpyAsync(cnt.data(), ctx->dHaloCandCount.p, nHalo * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&total, ctx->dCandTotal.p, sizeof total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (total > ctx->dCandsRaw.cap) return fail(ctx, SFK_E_NOMEM, "candidate list overflow");
+        ctx->candCount = static_cast<int64_t>(total);
+        std::vector<int64_t> offset(nHalo);
+        int64_t run = 0;
+        for (int64_t i = 0; i < nHalo; i++) { offset[i] = run; run += cnt[i]; ctx->candPerHalo[i] = cnt[i]; }
+        CU(ctx->dCands.ensure(std::max<int64_t>(run, 1)));
+        CU(ctx->dCandOffset.upload(offset, st));
+        CU(ctx->dCandCursor.ensure(nHalo));
+        CU(cudaMemsetAsync(ctx->dCandCursor.p, 0, nHalo * sizeof(uint32_t), st));
+        CU(launch_bucket(ctx->dCandsRaw.p, ctx->candCount, ctx->dCandOffset.p, ctx->dCandCursor.p, ctx->dCands.p, st));
+        ctx->stats.launches++;
+        if (ctx->cullOpen) { ctx->timer.end(ST_CULL, st); ctx->cullOpen = false; }
+        CU(cudaStreamSynchronize(st));   // `offset` is a local vector
+        for (int64_t i = 0; i < nHalo; i++)
+            for (int64_t off = 0; off < static_cast<int64_t>(cnt[i]); off += 256)
+                ctx->perHalo[i].push_back({offset[i] + off, static_cast<int32_t>(std::min<int64_t>(256, cnt[i] - off)),
+                                           static_cast<int32_t>(i)});
+    }
     std::vector<Piece> all;
     for (auto &v : ctx->perHalo) all.insert(all.end(), v.begin(), v.end());
 
@@ -677,6 +700,11 @@ static int create_impl(sfk_ctx *ctx, const sfk_params *params) try {
         return fail(ctx, SFK_E_NODEVICE, "kernels are built for sm_100a only (found sm_" +
                                              std::to_string(prop.major) + std::to_string(prop.minor) + ")");
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CU(cudaEventCreateWithFlags(&ctx->evCopied[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->evCulled[k], cudaEventDisableTiming));
+    }
     ctx->rings = static_cast<int>(params->rings);
     ctx->spokes = static_cast<int>(params->spokes);
     ctx->bins = static_cast<int>(params->radial_bins);
@@ -708,6 +736,11 @@ void sfk_destroy(sfk_ctx *ctx) {
         if (const NcclApi *api = nccl_api(nullptr)) api->CommDestroy(ctx->comm);
         ctx->comm = nullptr;
     }
+    if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
+    for (int k = 0; k < 2; k++) {
+        if (ctx->evCopied[k]) cudaEventDestroy(ctx->evCopied[k]);
+        if (ctx->evCulled[k]) cudaEventDestroy(ctx->evCulled[k]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -720,8 +753,11 @@ int sfk_begin_snapshot(sfk_ctx *ctx, const sfk_cosmo *cosmo, float min_mass) try
     ctx->cosmo0 = *cosmo;
     ctx->minMass = min_mass;
     ctx->halos.clear(); ctx->ox.clear(); ctx->oy.clear(); ctx->oz.clear();
-    ctx->segs.clear(); ctx->candPerHalo.clear();
-    ctx->candCount = 0;
+    ctx->candPerHalo.clear();
+    ctx->candCount = 0; ctx->candUpper = 0; ctx->pushed = false;
+    if (ctx->cullOpen) { ctx->timer.end(ST_CULL, ctx->stream); ctx->cullOpen = false; ctx->timer.collect(ST_CULL); }
+    CU(ctx->dCandTotal.ensure(1));
+    CU(cudaMemsetAsync(ctx->dCandTotal.p, 0, sizeof(unsigned long long), ctx->stream));
     ctx->inSnapshot = true; ctx->finished = false; ctx->splitPhase = 0;
     ctx->stats = sfk_stats{};
     return SFK_OK;
@@ -768,6 +804,8 @@ int sfk_add_halos(sfk_ctx *ctx, int64_t n, const double *x, const double *y, con
     }
     ctx->candPerHalo.assign(n, 0);
     CU(ctx->dHalos.upload(ctx->halos, ctx->stream));
+    CU(ctx->dHaloCandCount.ensure(std::max<int64_t>(n, 1)));
+    CU(cudaMemsetAsync(ctx->dHaloCandCount.p, 0, std::max<int64_t>(n, 1) * sizeof(uint32_t), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stats.n_halos = n;
     return SFK_OK;
@@ -776,7 +814,7 @@ int sfk_add_halos(sfk_ctx *ctx, int64_t n, const double *x, const double *y, con
 int sfk_set_owned(sfk_ctx *ctx, int64_t n, const uint8_t *owned) try {
     if (!ctx || !ctx->inSnapshot || !owned || n != static_cast<int64_t>(ctx->halos.size()))
         return fail(ctx, SFK_E_INVALID, "sfk_set_owned: call after sfk_add_halos with one flag per halo");
-    if (ctx->candCount != 0) return fail(ctx, SFK_E_INVALID, "sfk_set_owned: blocks were already pushed");
+    if (ctx->pushed) return fail(ctx, SFK_E_INVALID, "sfk_set_owned: blocks were already pushed");
     for (int64_t i = 0; i < n; i++) ctx->halos[i].owned = owned[i] ? 1 : 0;
     CU(ctx->dHalos.upload(ctx->halos, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -805,11 +843,27 @@ int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
     int64_t hits = 0;
     sfk_block_halo_mask(ctx, origin, width, total_width, nullptr, &hits);
     if (hits == 0 || n == 0) return SFK_OK;   // sphereLoop skips the read, cmd/shell.go:389-391
-    CU(ctx->dXyz.ensure(3 * n));
-    CU(ctx->dMass.ensure(n));
-    CU(cudaMemcpyAsync(ctx->dXyz.p, xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->dMass.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    return push_block_impl(ctx, ctx->dXyz.p, ctx->dMass.p, n, cosmo, total_width, origin, width);
+    // The copy runs on its own stream into one of two staging buffers, so it overlaps the cull
+    // of the previous block; the call returns once the caller's buffers have been consumed
+    // (cgo may not retain Go pointers; io.VectorBuffer reuses its slices), not once the block
+    // has been culled.
+    const int slot = static_cast<int>(ctx->pushIdx++ & 1);
+    if (ctx->culledValid[slot]) CU(cudaStreamWaitEvent(ctx->copyStream, ctx->evCulled[slot], 0));
+    if (static_cast<size_t>(3 * n) > ctx->dXyz[slot].cap || static_cast<size_t>(n) > ctx->dMass[slot].cap) {
+        if (ctx->culledValid[slot]) CU(cudaEventSynchronize(ctx->evCulled[slot]));   // the old buffer is still being read
+        CU(ctx->dXyz[slot].ensure(3 * n));
+        CU(ctx->dMass[slot].ensure(n));
+    }
+    CU(cudaMemcpyAsync(ctx->dXyz[slot].p, xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->copyStream));
+    CU(cudaMemcpyAsync(ctx->dMass[slot].p, mass, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copyStream));
+    CU(cudaEventRecord(ctx->evCopied[slot], ctx->copyStream));
+    CU(cudaStreamSynchronize(ctx->copyStream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->evCopied[slot], 0));
+    int rc = push_block_impl(ctx, ctx->dXyz[slot].p, ctx->dMass[slot].p, n, cosmo, total_width, origin, width);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->evCulled[slot], ctx->stream));
+    ctx->culledValid[slot] = true;
+    return SFK_OK;
 } SFK_CATCH(ctx)
 
 int sfk_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass, int64_t n,
@@ -818,8 +872,10 @@ int sfk_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass,
     if (!ctx || !ctx->inSnapshot || ctx->finished || !cosmo || n < 0 || (n > 0 && (!d_xyz || !d_mass)))
         return fail(ctx, SFK_E_INVALID, "sfk_push_block_device: bad arguments or no snapshot open");
     CU(cudaSetDevice(ctx->p.device));
-    // the caller's buffers live on other streams: order after everything queued so far
-    CU(cudaDeviceSynchronize());
+    // The caller's buffers were filled on other streams: everything queued on the device before
+    // the FIRST device push of a snapshot is waited for once; later buffers must be complete when
+    // they are handed over.  The cull of the block is queued, not finished, on return.
+    if (!ctx->pushed) CU(cudaDeviceSynchronize());
     return push_block_impl(ctx, d_xyz, d_mass, n, cosmo, total_width, origin, width);
 } SFK_CATCH(ctx)
 
@@ -1074,11 +1130,12 @@ int sfk_mass_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64
         return fail(ctx, SFK_E_INVALID, "sfk_mass_push_block: call sfk_mass_begin first");
     if (n == 0 || ctx->massHalos == 0) return SFK_OK;
     CU(cudaSetDevice(ctx->p.device));
-    CU(ctx->dXyz.ensure(3 * n));
-    CU(ctx->dMass.ensure(n));
-    CU(cudaMemcpyAsync(ctx->dXyz.p, xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->dMass.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = mass_push_impl(ctx, ctx->dXyz.p, ctx->dMass.p, n, total_width);
+    CU(cudaStreamSynchronize(ctx->stream));   // a shell-pass cull may still read the staging buffer
+    CU(ctx->dXyz[0].ensure(3 * n));
+    CU(ctx->dMass[0].ensure(n));
+    CU(cudaMemcpyAsync(ctx->dXyz[0].p, xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->dMass[0].p, mass, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = mass_push_impl(ctx, ctx->dXyz[0].p, ctx->dMass[0].p, n, total_width);
     if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));   // the caller may reuse its buffers (io.VectorBuffer does)
     return SFK_OK;

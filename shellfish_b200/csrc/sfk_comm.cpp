@@ -33,12 +33,12 @@ bool bind(void *h, const char *name, F &fn) {
 const NcclApi *nccl_api(std::string *err) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (!g_loaded && g_err.empty()) {
-        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
         if (!h) {
             const char *env = getenv("SFK_NCCL_LIB");
-            if (env && *env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+            if (env && *env) h = dlopen(env, RTLD_NOW | RTLD_LOCAL);
         }
-        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
         if (!h) {
             g_err = std::string("cannot load libnccl.so.2 (set SFK_NCCL_LIB): ") + dlerror();
         } else if (bind(h, "ncclGetUniqueId", g_api.GetUniqueId) && bind(h, "ncclCommInitRank", g_api.CommInitRank) &&

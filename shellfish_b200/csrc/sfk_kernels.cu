@@ -46,10 +46,12 @@ struct CullHalo {
 // positions in place, halo after halo (Halo.Transform mutates sphBuf.xs,
 // cmd/shell.go:441), so the position a halo sees depends on every earlier
 // halo of the block: the loop over the block's halo list is sequential per
-// particle and carries x, y, z in registers.
-template <bool FILL>
+// particle and carries x, y, z in registers.  Survivors are appended to one
+// list with a warp-aggregated slot claim; the bins are exact integers, so the
+// order of a halo's candidates cannot change a result.
 __global__ void __launch_bounds__(kCullThreads) cull_kernel(CullArgs a) {
     __shared__ CullHalo sh[kCullHaloChunk];
+    __shared__ int shIdx[kCullHaloChunk];
     const int64_t j = static_cast<int64_t>(blockIdx.x) * kCullThreads + threadIdx.x;
     const int64_t i = j * a.sf3;
     const bool live = i < a.n;
@@ -68,8 +70,10 @@ __global__ void __launch_bounds__(kCullThreads) cull_kernel(CullArgs a) {
         const int m = min(kCullHaloChunk, a.nList - base);
         __syncthreads();
         if (threadIdx.x < m) {
-            const HaloDev &h = a.halos[a.haloList[base + threadIdx.x]];
+            const int hi = a.haloList[base + threadIdx.x];
+            const HaloDev &h = a.halos[hi];
             sh[threadIdx.x] = CullHalo{h.x0, h.y0, h.z0, h.owned ? h.lo2 : INFINITY, h.hi2, h.sphVol};
+            shIdx[threadIdx.x] = hi;
         }
         __syncthreads();
         for (int k = 0; k < m; k++) {
@@ -86,21 +90,43 @@ __global__ void __launch_bounds__(kCullThreads) cull_kernel(CullArgs a) {
             const unsigned mask = __ballot_sync(0xffffffffu, keep);
             if (mask == 0) continue;
             const int leader = __ffs(mask) - 1;
-            uint32_t off = 0;
-            if (lane_id() == leader) off = atomicAdd(&a.counts[base + k], __popc(mask));
-            if (FILL) {
-                off = __shfl_sync(0xffffffffu, off, leader);
-                if (keep) {
-                    const int rank = __popc(mask & ((1u << lane_id()) - 1u));
+            const int halo = shIdx[k];
+            unsigned long long off = 0;
+            if (lane_id() == leader) {
+                off = atomicAdd(a.total, static_cast<unsigned long long>(__popc(mask)));
+                atomicAdd(&a.haloCount[halo], static_cast<uint32_t>(__popc(mask)));
+            }
+            off = __shfl_sync(0xffffffffu, off, leader);
+            if (keep) {
+                const long long at = static_cast<long long>(off) + __popc(mask & ((1u << lane_id()) - 1u));
+                if (at < a.cap) {   // the host sizes the list from an upper bound: never false
                     Cand c;
                     c.vx = dx; c.vy = dy; c.vz = dz;   // Insert: vec - float32(origin)
-                    c.halo = a.haloList[base + k];
+                    c.halo = halo;
                     c.rho = (mScaled / h.sphVol) / a.rhoM;
-                    a.cands[a.segStart[base + k] + off + rank] = c;
+                    a.cands[at] = c;
                 }
             }
         }
     }
+}
+
+// Counting sort of the candidate list by halo (offsets from the per-halo counts of cull_kernel).
+__global__ void __launch_bounds__(256) bucket_kernel(const Cand *cands, int64_t n, const int64_t *offset,
+                                                     uint32_t *cursor, Cand *sorted) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    const bool live = i < n;
+    Cand c;
+    c.halo = -1 - static_cast<int>(lane_id());
+    if (live) c = cands[i];
+    // candidates arrive in runs of one halo: one cursor claim per (warp, halo)
+    const unsigned peers = __match_any_sync(0xffffffffu, c.halo);
+    if (!live) return;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (static_cast<int>(lane_id()) == leader) base = atomicAdd(&cursor[c.halo], static_cast<uint32_t>(__popc(peers)));
+    base = __shfl_sync(peers, base, leader);
+    sorted[offset[c.halo] + base + __popc(peers & ((1u << lane_id()) - 1u))] = c;
 }
 
 // ----------------------------------------------------------------- hits --
@@ -1356,12 +1382,18 @@ __global__ void fit_finish_kernel(FitArgs a) {
 
 // --------------------------------------------------------------- launch --
 
-cudaError_t launch_cull(const CullArgs &a, bool fill, cudaStream_t s) {
+cudaError_t launch_cull(const CullArgs &a, cudaStream_t s) {
     const int64_t live = (a.n + a.sf3 - 1) / a.sf3;
     if (live <= 0 || a.nList <= 0) return cudaSuccess;
     const unsigned grid = static_cast<unsigned>((live + kCullThreads - 1) / kCullThreads);
-    if (fill) cull_kernel<true><<<grid, kCullThreads, 0, s>>>(a);
-    else cull_kernel<false><<<grid, kCullThreads, 0, s>>>(a);
+    cull_kernel<<<grid, kCullThreads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bucket(const Cand *cands, int64_t n, const int64_t *offset, uint32_t *cursor, Cand *sorted,
+                          cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    bucket_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(cands, n, offset, cursor, sorted);
     return cudaGetLastError();
 }
 

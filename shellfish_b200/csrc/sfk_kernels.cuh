@@ -17,10 +17,17 @@ struct CullArgs {
     const HaloDev *halos;
     float tw;                // float32(TotalWidth), los/halo.go:172
     double rhoM;             // mean density of this block's cosmology
-    uint32_t *counts;        // [nList] candidates per listed halo
-    const int64_t *segStart; // [nList] first slot of each segment (fill pass)
+    // one pass: survivors are appended to one list (they carry their halo index) and
+    // bucketed by halo at sfk_finish_snapshot
     Cand *cands;
+    int64_t cap;                  // slots of cands
+    unsigned long long *total;    // [1] candidates appended so far
+    uint32_t *haloCount;          // [nHalo] candidates per halo
 };
+
+// Buckets the appended candidates by halo: sorted[offset[halo] + k] for the k-th arrival.
+cudaError_t launch_bucket(const Cand *cands, int64_t n, const int64_t *offset, uint32_t *cursor, Cand *sorted,
+                          cudaStream_t s);
 
 struct BinArgs {
     const HitRec *recs;
@@ -135,7 +142,7 @@ struct ShellFractionArgs {
     int nHalo, order, bins, nTheta, nPhi;
 };
 cudaError_t launch_shell_fraction(const ShellFractionArgs &a, cudaStream_t s);
-cudaError_t launch_cull(const CullArgs &a, bool fill, cudaStream_t s);
+cudaError_t launch_cull(const CullArgs &a, cudaStream_t s);
 cudaError_t launch_hit_count(const Piece *pieces, int nPieces, const Cand *cands, const HaloDev *halos,
                              const float *norms, int rings, uint32_t *hitCount,
                              unsigned long long *rhoMaxBits, cudaStream_t s);

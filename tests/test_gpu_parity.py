@@ -202,8 +202,10 @@ def test_device_and_host_push_agree():
     ctx = api.ShellContext(params)
     ctx.begin_snapshot(blocks[0], mass)
     ctx.add_halos(halos)
+    keep = []   # device buffers stay valid until finish_snapshot: the cull of a block is queued, not finished
     for b in blocks:
-        ctx.push_block_device(b, torch.from_numpy(b["xs"]).cuda(), torch.from_numpy(b["ms"]).cuda())
+        keep.append((torch.from_numpy(b["xs"]).cuda(), torch.from_numpy(b["ms"]).cuda()))
+        ctx.push_block_device(b, *keep[-1])
     c_dev, s_dev = ctx.finish_snapshot()
     assert np.array_equal(c_host, c_dev) and np.array_equal(s_host, s_dev)
 
