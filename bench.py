@@ -12,7 +12,7 @@ Workload: BASELINE.json configs[1] -- 1000 halos (>= 5e4 particles each) in a
 synthetic 512^3-particle LGadget-2-like box of 8^3 blocks, default shell.config
 (100 rings x 256 LoS x 256 bins).  Under torchrun every rank sees the SAME
 snapshot; the halo list is partitioned across the ranks by estimated particle
-count (north_star; shard.partition_halos, LPT with block affinity), a rank pushes
+count (north_star; shard.partition_spatial: equal-weight runs along a Z-curve), a rank pushes
 only the blocks its halos touch, and there is no data-path collective: strong
 scaling of one job.
 """
@@ -215,7 +215,7 @@ def main():
     # analysis stages, halos of one block kept together; every rank computes the same partition
     r3 = np.maximum(halos[:, 3], 0.0) ** 3
     weights = r3 / max(r3.mean(), 1e-300) + 0.25
-    parts = shard.partition_halos(weights, world, shard.block_of(halos, blocks))
+    parts = shard.partition_spatial(weights, halos[:, :3], blocks[0]["TotalWidth"], world)
     mine = parts[rank]
     owned = np.zeros(nH, bool)
     owned[mine] = True
@@ -357,7 +357,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config,
             "meta": dict(meta, parallelism="halo list partitioned over %d GPU(s) by estimated particle count "
-                                          "(LPT, block affinity); no data-path collective; catalog rows gathered by "
+                                          "(equal-weight runs along a Z-curve); no data-path collective; catalog rows gathered by "
                                           "halo index" % world),
             "halos_ok": nok // max(1, args.steps),
             "intersections_per_s": tot["n_intersections"] / (ms * 1e-3),

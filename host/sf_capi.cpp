@@ -57,7 +57,15 @@ int sfh_parse_catalog(const char *data, const int *icols, int nI, const int *fco
 }
 const char *sfh_last_text() { return g_text.c_str(); }
 
-// PartitionHalos of sf_shell.cpp (the multi-GPU CLI's halo partition)
+void sfh_partition_spatial(const double *weights, const double *xyz, int n, double totalWidth, int nRanks, int *owner) {
+    std::vector<double> w(weights, weights + n), x(n), y(n), z(n);
+    for (int i = 0; i < n; i++) { x[i] = xyz[3 * i]; y[i] = xyz[3 * i + 1]; z[i] = xyz[3 * i + 2]; }
+    std::vector<int> own;
+    PartitionHalosSpatial(w, x, y, z, totalWidth, nRanks, own);
+    for (int i = 0; i < n; i++) owner[i] = own[i];
+}
+
+// PartitionHalos of sf_shell.cpp (LPT with affinity groups)
 void sfh_partition_halos(const double *weights, const int64_t *groups, int n, int nRanks, int *owner) {
     std::vector<int> own;
     PartitionHalos(std::vector<double>(weights, weights + n), std::vector<int64_t>(groups, groups + n), nRanks, own);

@@ -3,9 +3,12 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <thread>
 #include <sys/stat.h>
 
@@ -259,6 +262,38 @@ void PartitionHalos(const std::vector<double> &weights, const std::vector<int64_
     for (size_t i = 0; i < weights.size(); i++) owner[i] = gOwner[groups[i]];
 }
 
+void PartitionHalosSpatial(const std::vector<double> &weights, const std::vector<double> &x, const std::vector<double> &y,
+                           const std::vector<double> &z, double totalWidth, int nRanks, std::vector<int> &owner) {
+    const size_t n = weights.size();
+    owner.assign(n, 0);
+    if (n == 0 || nRanks <= 1) return;
+    const int bits = 10;
+    std::vector<int64_t> key(n);
+    for (size_t i = 0; i < n; i++) {
+        const double c[3] = {x[i], y[i], z[i]};
+        int64_t q[3], k = 0;
+        for (int ax = 0; ax < 3; ax++) {
+            const double v = std::floor(c[ax] / totalWidth * static_cast<double>(1 << bits));
+            q[ax] = static_cast<int64_t>(std::min(std::max(v, 0.0), static_cast<double>((1 << bits) - 1)));
+        }
+        for (int b = 0; b < bits; b++)
+            for (int ax = 0; ax < 3; ax++) k |= ((q[ax] >> b) & 1) << (3 * b + (2 - ax));
+        key[i] = k;
+    }
+    std::vector<size_t> order(n);
+    for (size_t i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return key[a] < key[b]; });
+    std::vector<double> cum(n);
+    double run = 0;
+    for (size_t k = 0; k < n; k++) { run += weights[order[k]]; cum[k] = run; }   // numpy.cumsum: sequential
+    const double total = run > 0 ? run : 1.0;
+    for (size_t k = 0; k < n; k++) {
+        const double wv = weights[order[k]];
+        const int64_t r = static_cast<int64_t>((cum[k] - wv / 2) / total * static_cast<double>(nRanks));
+        owner[order[k]] = static_cast<int>(std::min<int64_t>(r, nRanks - 1));
+    }
+}
+
 std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::string &stdinData, uint64_t seed,
                      const std::vector<int> &devices, std::vector<std::string> &outLines) {
     if (devices.empty()) return "No GPU selected.";
@@ -296,7 +331,7 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
     if (firstSnap < g.particle.SnapMin || firstSnap > g.particle.SnapMax)
         return "Snapshot " + std::to_string(firstSnap) + " is outside [SnapMin, SnapMax] = [" +
                std::to_string(g.particle.SnapMin) + ", " + std::to_string(g.particle.SnapMax) + "].";
-    std::unique_ptr<VectorBuffer> buf;
+    std::unique_ptr<VectorBuffer> buf, buf2;
     if (!(err = NewVectorBuffer(g.SnapshotType, cat.ParticleCatalog(static_cast<int>(firstSnap), 0), g.Endianness, ctx, buf)).empty())
         return err;
     std::vector<Header> hds0;
@@ -352,53 +387,90 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
         std::vector<Header> hds;
         if (!(err = ReadHeaders(static_cast<int>(snap), *buf, cat, g.MemoDir, hds, files)).empty()) return err;
         // several GPUs: halos partitioned by estimated particle count (R200m^3 plus a constant
-        // for the per-halo analysis), the halos of one block kept on one GPU
+        // for the per-halo analysis) into equal-weight runs along a Z-curve, so that a GPU's
+        // halos are spatially compact and touch few blocks
         std::vector<int> owner(idxs.size(), 0);
         if (G > 1) {
             std::vector<double> w(idxs.size());
-            std::vector<int64_t> grp(idxs.size(), -1);
             double mean = 0;
             for (size_t i = 0; i < idxs.size(); i++) { w[i] = r[i] > 0 ? r[i] * r[i] * r[i] : 0.0; mean += w[i]; }
             mean = idxs.empty() ? 1.0 : std::max(mean / static_cast<double>(idxs.size()), 1e-300);
-            for (size_t i = 0; i < idxs.size(); i++) {
-                w[i] = w[i] / mean + 0.25;
-                for (size_t b = 0; b < hds.size() && grp[i] < 0; b++) {
-                    const Header &h = hds[b];
-                    if (x[i] >= h.Origin[0] && x[i] < static_cast<double>(h.Origin[0]) + h.Width[0] &&
-                        y[i] >= h.Origin[1] && y[i] < static_cast<double>(h.Origin[1]) + h.Width[1] &&
-                        z[i] >= h.Origin[2] && z[i] < static_cast<double>(h.Origin[2]) + h.Width[2])
-                        grp[i] = static_cast<int64_t>(b);
-                }
-            }
-            PartitionHalos(w, grp, G, owner);
+            for (size_t i = 0; i < idxs.size(); i++) w[i] = w[i] / mean + 0.25;
+            PartitionHalosSpatial(w, x, y, z, hds.empty() ? 1.0 : hds[0].TotalWidth, G, owner);
             std::vector<uint8_t> mine(idxs.size());
             for (int d = 0; d < G; d++) {
                 for (size_t i = 0; i < idxs.size(); i++) mine[i] = owner[i] == d;
                 if (sfk_set_owned(ctxs[d], static_cast<int64_t>(mine.size()), mine.data()) != 0) return sfk_last_error(ctxs[d]);
             }
         }
+        // binIntersections first (cmd/shell.go:599-611): the blocks some halo touches, and for each
+        // the GPUs that own such a halo
         std::vector<uint8_t> hit(idxs.size());
+        std::vector<size_t> needed;
+        std::vector<std::vector<char>> wantsOf;
         for (size_t i = 0; i < hds.size(); i++) {
             int64_t nHit = 0;
             if (sfk_block_halo_mask(sfk, hds[i].Origin, hds[i].Width, hds[i].TotalWidth, hit.data(), &nHit) != 0)
                 return sfk_last_error(sfk);
             if (nHit == 0) continue;
-            // the block is read once and pushed to every GPU that owns a halo touching it
             std::vector<char> wants(G, 0);
             for (size_t k = 0; k < hit.size(); k++) if (hit[k]) wants[owner[k]] = 1;
-            const float *xs, *ms;
-            int64_t n;
-            const auto tRead = std::chrono::steady_clock::now();
-            if (!(err = buf->Read(files[i], &xs, &ms, &n)).empty()) return err;
-            readSeconds += since(tRead); blocksRead++; particlesRead += n;
-            const sfk_cosmo hc{hds[i].Cosmo.Z, hds[i].Cosmo.OmegaM, hds[i].Cosmo.OmegaL, hds[i].Cosmo.H100};
+            needed.push_back(i);
+            wantsOf.push_back(wants);
+        }
+        // Every needed block is read once, by a reader thread that runs one block ahead of the
+        // pushes through two VectorBuffers (a buffer's arrays are reused by its next Read,
+        // io/io.go:57-67), and is pushed to every GPU that wants it.
+        if (!buf2 && !(err = NewVectorBuffer(g.SnapshotType, cat.ParticleCatalog(static_cast<int>(firstSnap), 0),
+                                             g.Endianness, ctx, buf2)).empty())
+            return err;
+        struct Slot { const float *xs = nullptr, *ms = nullptr; int64_t n = 0; std::string err; double seconds = 0; };
+        Slot slots[2];
+        std::mutex mu;
+        std::condition_variable cv;
+        size_t produced = 0, consumed = 0;   // blocks read / blocks pushed
+        bool stop = false;
+        VectorBuffer *bufs[2] = {buf.get(), buf2.get()};
+        std::thread reader([&] {
+            for (size_t k = 0; k < needed.size(); k++) {
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return stop || k < consumed + 2; });
+                    if (stop) return;
+                }
+                Slot &s = slots[k & 1];
+                const auto t0 = std::chrono::steady_clock::now();
+                s.err = bufs[k & 1]->Read(files[needed[k]], &s.xs, &s.ms, &s.n);
+                s.seconds = since(t0);
+                std::lock_guard<std::mutex> lk(mu);
+                produced = k + 1;
+                cv.notify_all();
+                if (!s.err.empty()) return;
+            }
+        });
+        struct Joiner { std::thread &t; std::mutex &m; std::condition_variable &c; bool &stop;
+                        ~Joiner() { { std::lock_guard<std::mutex> lk(m); stop = true; } c.notify_all(); if (t.joinable()) t.join(); } }
+            joiner{reader, mu, cv, stop};
+        for (size_t k = 0; k < needed.size(); k++) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return produced > k; });
+            }
+            Slot &s = slots[k & 1];
+            if (!s.err.empty()) return s.err;
+            readSeconds += s.seconds; blocksRead++; particlesRead += s.n;
+            const Header &h = hds[needed[k]];
+            const sfk_cosmo hc{h.Cosmo.Z, h.Cosmo.OmegaM, h.Cosmo.OmegaL, h.Cosmo.H100};
             for (int d = 0; d < G; d++)
-                if (wants[d] && sfk_push_block(ctxs[d], xs, ms, n, &hc, hds[i].TotalWidth, hds[i].Origin, hds[i].Width) != 0)
+                if (wantsOf[k][d] && sfk_push_block(ctxs[d], s.xs, s.ms, s.n, &hc, h.TotalWidth, h.Origin, h.Width) != 0)
                     return sfk_last_error(ctxs[d]);
+            std::lock_guard<std::mutex> lk(mu);
+            consumed = k + 1;
+            cv.notify_all();
         }
         if (perf) {
             std::fprintf(stderr, "Snap %lld, sphereLoop ended\nTime: %.6gs\n", static_cast<long long>(snap), since(tStart));
-            std::fprintf(stderr, "Read: %.6gs in buf.Read (%lld blocks, %lld particles)\n", readSeconds,
+            std::fprintf(stderr, "Read: %.6gs in buf.Read, overlapped with the pushes (%lld blocks, %lld particles)\n", readSeconds,
                          static_cast<long long>(blocksRead), static_cast<long long>(particlesRead));
         }
         // haloAnalysis, cmd/shell.go:502-528: a failed fit leaves the zero row

@@ -62,5 +62,10 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
 // to one rank.  Same result as shellfish_b200/shard.py partition_halos.  owner[i] in [0, nRanks).
 void PartitionHalos(const std::vector<double> &weights, const std::vector<int64_t> &groups, int nRanks,
                     std::vector<int> &owner);
+// Partition along a space-filling curve (what RunShell uses): halos sorted by the Z-curve key
+// of their centre (10 bits per axis over totalWidth), cut into nRanks contiguous runs of equal
+// weight.  Same result as shellfish_b200/shard.py partition_spatial.
+void PartitionHalosSpatial(const std::vector<double> &weights, const std::vector<double> &x, const std::vector<double> &y,
+                           const std::vector<double> &z, double totalWidth, int nRanks, std::vector<int> &owner);
 
 }  // namespace sfhost

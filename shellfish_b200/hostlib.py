@@ -43,6 +43,18 @@ def partition_halos(weights, groups, n_ranks):
     return own
 
 
+def partition_spatial(weights, xyz, total_width, n_ranks):
+    """PartitionHalosSpatial of host/sf_shell.cpp (what the CLI uses with SHELLFISH_GPUS)."""
+    w = np.ascontiguousarray(weights, np.float64)
+    x = np.ascontiguousarray(xyz, np.float64)
+    own = np.zeros(len(w), np.int32)
+    f = lib().sfh_partition_spatial
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
+    f.restype = None
+    f(w.ctypes.data, x.ctypes.data, len(w), float(total_width), n_ranks, own.ctypes.data)
+    return own
+
+
 def go_g6(v):
     return lib().sfh_go_g6(float(v)).decode()
 

@@ -543,3 +543,21 @@ def test_cli_halo_partition_equals_the_python_one():
         for r, p in enumerate(parts):
             want[p] = r
         assert np.array_equal(own, want)
+
+
+def test_cli_spatial_partition_equals_the_python_one():
+    """PartitionHalosSpatial (what SHELLFISH_GPUS uses) == shard.partition_spatial (what bench.py uses)."""
+    from shellfish_b200 import shard
+    rng = np.random.default_rng(6)
+    for n, ranks in ((1000, 8), (37, 3), (5, 8), (64, 1), (0, 4)):
+        w = rng.uniform(0.3, 3.0, n)
+        xyz = rng.random((n, 3)) * 250.0
+        own = H.partition_spatial(w, xyz, 250.0, ranks)
+        parts = shard.partition_spatial(w, xyz, 250.0, ranks)
+        want = np.zeros(n, np.int32)
+        for r, p in enumerate(parts):
+            want[p] = r
+        assert np.array_equal(own, want)
+        if n >= 100:
+            loads = np.array([w[p].sum() for p in parts])
+            assert loads.max() / loads.mean() < 1.03
