@@ -350,9 +350,18 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
     p.percentile = c.percentile; p.seed = seed;
     std::vector<sfk_ctx *> ctxs(G, nullptr);
     struct Guard { std::vector<sfk_ctx *> &c; ~Guard() { for (sfk_ctx *x : c) if (x) sfk_destroy(x); } } guard{ctxs};
-    for (int d = 0; d < G; d++) {
-        p.device = devices[d];
-        if (sfk_create(&ctxs[d], &p) != 0) return sfk_last_error(ctxs[d]);
+    {   // CUDA context creation takes a second per device: one thread each
+        std::vector<int> rcs(G, 0);
+        std::vector<std::thread> th;
+        for (int d = 0; d < G; d++)
+            th.emplace_back([&, d] {
+                sfk_params q = p;
+                q.device = devices[d];
+                rcs[d] = sfk_create(&ctxs[d], &q);
+            });
+        for (std::thread &t : th) t.join();
+        for (int d = 0; d < G; d++)
+            if (rcs[d] != 0) return ctxs[d] ? sfk_last_error(ctxs[d]) : "sfk_create failed";
     }
     sfk_ctx *sfk = ctxs[0];
     const sfk_cosmo cosmo0{hds0[0].Cosmo.Z, hds0[0].Cosmo.OmegaM, hds0[0].Cosmo.OmegaL, hds0[0].Cosmo.H100};
