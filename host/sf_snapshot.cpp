@@ -372,6 +372,16 @@ public:
         std::vector<unsigned char> img;
         std::string err = load(fname, hd, img, nullptr);
         if (!err.empty()) return err;
+        // the reference indexes sheet[x + y*GridWidth + z*GridWidth^2] for x, y, z < SegmentWidth
+        // (io/gotetra.go:73-85) and panics on a header that does not fit; refuse it here
+        if (!(hd.SegmentWidth > 0 && hd.SegmentWidth <= hd.GridWidth && hd.GridWidth <= 4096 &&
+              hd.GridWidth * hd.GridWidth * hd.GridWidth == hd.GridCount)) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "Corruption detected in %s: SegmentWidth = %lld, GridWidth = %lld, GridCount = %lld.",
+                     fname.c_str(), static_cast<long long>(hd.SegmentWidth), static_cast<long long>(hd.GridWidth),
+                     static_cast<long long>(hd.GridCount));
+            return buf;
+        }
         sw_ = hd.SegmentWidth; gw_ = hd.GridWidth;
         mass_ = calcUniformMass(hd.Count, hd.TotalWidth, hd.Cosmo);
         return "";
@@ -389,19 +399,20 @@ public:
             return buf;
         }
         if (hd.GridCount < 0 || 12 * hd.GridCount > static_cast<int64_t>(img.size())) return "read " + fname + ": unexpected EOF";
-        std::vector<float> sheet(3 * hd.GridCount);
-        c.array(sheet.data(), sheet.size());
-        if (!c.ok) return "read " + fname + ": unexpected EOF";
+        if (c.p + 12 * hd.GridCount > c.end) return "read " + fname + ": unexpected EOF";
         xs_.resize(3 * sw_ * sw_ * sw_);
-        ms_.assign(sw_ * sw_ * sw_, mass_);
-        int64_t si = 0;   // the SegmentWidth^3 corner of the GridWidth^3 sheet, :73-85
+        if (static_cast<int64_t>(ms_.size()) != sw_ * sw_ * sw_) ms_.assign(sw_ * sw_ * sw_, mass_);
+        // the SegmentWidth^3 corner of the GridWidth^3 sheet (:73-85), one x-row at a time
+        // straight out of the file image
+        const unsigned char *sheet = c.p;
         for (int64_t z = 0; z < sw_; z++)
             for (int64_t y = 0; y < sw_; y++)
-                for (int64_t x = 0; x < sw_; x++) {
-                    const int64_t gi = x + y * gw_ + z * gw_ * gw_;
-                    std::memcpy(&xs_[3 * si], &sheet[3 * gi], 3 * sizeof(float));
-                    si++;
-                }
+                std::memcpy(&xs_[3 * (y + z * sw_) * sw_], sheet + 12 * (y * gw_ + z * gw_ * gw_), 12 * sw_);
+        if (c.swap)
+            for (float &v : xs_) {
+                unsigned char *b = reinterpret_cast<unsigned char *>(&v);
+                std::swap(b[0], b[3]); std::swap(b[1], b[2]);
+            }
         *xs = xs_.data(); *ms = ms_.data(); *n = sw_ * sw_ * sw_;
         return "";
     }

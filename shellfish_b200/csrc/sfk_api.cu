@@ -217,8 +217,13 @@ int validate(sfk_ctx *ctx, const sfk_params &p) {
     if (p.levels > kMaxLevels) return fail(ctx, SFK_E_UNSUPPORTED, "Levels above 6 is not supported.");
     if (p.rings > kMaxRings) return fail(ctx, SFK_E_UNSUPPORTED, "Rings above 1024 is not supported.");
     if (p.spokes > 16384) return fail(ctx, SFK_E_UNSUPPORTED, "Spokes above 16384 is not supported.");
-    if (p.smoothing_window % 2 != 1) return fail(ctx, SFK_E_INVALID, "Kernel width must be odd.");
-    if (p.smoothing_window <= 4) return fail(ctx, SFK_E_INVALID, "Kernel width cannot be smaller than pOrder.");
+    // NewSavGolKernel's panics (filter.go:218-262) are only reachable where the reference builds
+    // the kernels: Smooth returns ok = false before that when RadialBins <= SmoothingWindow
+    // (smooth.go:51-53), and PercentileProfile never smooths
+    if (!p.percentile_profile && p.radial_bins > p.smoothing_window) {
+        if (p.smoothing_window % 2 != 1) return fail(ctx, SFK_E_INVALID, "Kernel width must be odd.");
+        if (p.smoothing_window <= 4) return fail(ctx, SFK_E_INVALID, "Kernel width cannot be smaller than pOrder.");
+    }
     if (bin_smem_bytes(static_cast<int>(p.radial_bins)) > 227 * 1024)
         return fail(ctx, SFK_E_UNSUPPORTED, "RadialBins too large for one shared-memory tile.");
     return SFK_OK;
@@ -292,6 +297,7 @@ int push_block_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, int64_t
     a.tw = static_cast<float>(tw);
     // chanLoadSphereVec uses the block's own header, cmd/shell.go:487-488
     a.rhoM = rho_average(cosmo->h100 * 100, cosmo->omega_m, cosmo->omega_l, cosmo->z);
+    a.tma = sf3 == 1 && reinterpret_cast<uintptr_t>(dxyz) % 16 == 0 && reinterpret_cast<uintptr_t>(dmass) % 16 == 0;
     a.cands = ctx->dCandsRaw.p; a.cap = static_cast<int64_t>(ctx->dCandsRaw.cap);
     a.total = ctx->dCandTotal.p; a.haloCount = ctx->dHaloCandCount.p;
     if (!ctx->cullOpen) { ctx->timer.begin(ST_CULL, ctx->stream); ctx->cullOpen = true; }

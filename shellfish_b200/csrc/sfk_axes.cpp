@@ -15,7 +15,11 @@ namespace sfk {
 
 namespace {
 
-#include "sfk_axis_tables.inc"   // kAxisN, kAxisRatios, kACGrid, kBCGrid, kCGrid (scripts/make_axis_tables.py)
+// The correction tables Shell.Axes interpolates are data of the reference
+// (los/analyze/ellipse_grid/grid.go); the product uses those very numbers
+// (scripts/import_axis_tables.py).  sfk_axis_tables.inc holds the same grids recomputed from
+// first principles (scripts/make_axis_tables.py): a cross-check kept by tests/test_shellprops.py.
+#include "sfk_axis_tables_ref.inc"   // kRefAxisN, kRefAxisRatios, kRefACGrid, kRefBCGrid, kRefCGrid
 
 const double kPi = 3.14159265358979323846264338327950288419716939937510582097494459;
 // Go folds constant expressions exactly before rounding once.
@@ -202,8 +206,8 @@ void axes_from_moments(const double m[9], double out[6]) {
     (void)aIdx;
     const double ac = a / c, bc = b / c;
     // axisInterpolators, shell.go:356-374: built once per process
-    static const BiCubic acTable(kAxisRatios, kACGrid, kAxisN), bcTable(kAxisRatios, kBCGrid, kAxisN),
-        cTable(kAxisRatios, kCGrid, kAxisN);
+    static const BiCubic acTable(kRefAxisRatios, kRefACGrid, kRefAxisN), bcTable(kRefAxisRatios, kRefBCGrid, kRefAxisN),
+        cTable(kRefAxisRatios, kRefCGrid, kRefAxisN);
     const double acRatio = acTable.eval(ac, bc);
     const double bcRatio = bcTable.eval(ac, bc);
     const double cRatio = cTable.eval(ac, bc);

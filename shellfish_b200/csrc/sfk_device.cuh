@@ -20,6 +20,43 @@ __device__ __forceinline__ double sqrt_pos(double x) {
     return fma(r, 0.5 * y, s);
 }
 
+// ---- TMA: 1-D bulk copies global -> shared, completion on an mbarrier -------------------
+__device__ __forceinline__ uint32_t smem_addr_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_addr_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep, do not spin
+            : "memory");
+    } while (!done);
+}
+// src and dst 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_addr_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_addr_u32(bar))
+        : "memory");
+}
+
 // Go's math.Pow for small non-negative integer exponents (src/math/pow.go):
 // repeated squaring on frexp mantissas.
 __device__ inline double go_pow_int(double x, int yi) {

@@ -49,15 +49,38 @@ struct CullHalo {
 // particle and carries x, y, z in registers.  Survivors are appended to one
 // list with a warp-aggregated slot claim; the bins are exact integers, so the
 // order of a halo's candidates cannot change a result.
+//
+// A full tile of 256 particles (3 KB of positions + 1 KB of masses, contiguous in the block's
+// arrays) is staged in shared memory by two TMA bulk copies (cp.async.bulk, completion on an
+// mbarrier) issued by one thread: the [n][3] layout would otherwise cost three stride-3 scalar
+// loads per thread.  The last, partial tile of a block and subsampled passes load directly.
 __global__ void __launch_bounds__(kCullThreads) cull_kernel(CullArgs a) {
     __shared__ CullHalo sh[kCullHaloChunk];
     __shared__ int shIdx[kCullHaloChunk];
-    const int64_t j = static_cast<int64_t>(blockIdx.x) * kCullThreads + threadIdx.x;
+    __shared__ __align__(16) float sXyz[3 * kCullThreads];
+    __shared__ __align__(16) float sMass[kCullThreads];
+    __shared__ __align__(8) uint64_t bar;
+    const int64_t tile0 = static_cast<int64_t>(blockIdx.x) * kCullThreads;
+    const int64_t j = tile0 + threadIdx.x;
     const int64_t i = j * a.sf3;
     const bool live = i < a.n;
     float x = 0.f, y = 0.f, z = 0.f;
     double mScaled = 0.0;
-    if (live) {
+    if (a.tma && tile0 + kCullThreads <= a.n) {   // uniform over the CTA
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            fence_barrier_init();
+            mbar_expect_tx(&bar, 16 * kCullThreads);
+            tma_load_1d(sXyz, a.xyz + 3 * tile0, 12 * kCullThreads, &bar);
+            tma_load_1d(sMass, a.mass + tile0, 4 * kCullThreads, &bar);
+        }
+        __syncthreads();   // the barrier is initialised before anybody polls it
+        mbar_wait(&bar, 0);
+        x = sXyz[3 * threadIdx.x];       // stride 3 is coprime to the 32 banks: conflict-free
+        y = sXyz[3 * threadIdx.x + 1];
+        z = sXyz[3 * threadIdx.x + 2];
+        mScaled = static_cast<double>(sMass[threadIdx.x]);   // sf3 == 1
+    } else if (live) {
         x = a.xyz[3 * i];
         y = a.xyz[3 * i + 1];
         z = a.xyz[3 * i + 2];

@@ -19,6 +19,7 @@ struct CullArgs {
     double rhoM;             // mean density of this block's cosmology
     // one pass: survivors are appended to one list (they carry their halo index) and
     // bucketed by halo at sfk_finish_snapshot
+    int tma;                      // sf3 == 1 and both arrays 16-byte aligned: full tiles are staged by TMA
     Cand *cands;
     int64_t cap;                  // slots of cands
     unsigned long long *total;    // [1] candidates appended so far

@@ -23,11 +23,21 @@ def random_shell(rng, order, radius=1.0, amp=0.25):
     return cs
 
 
-def axis_tables():
-    """The generated correction tables of the product (sfk_axis_tables.inc)."""
-    txt = open(os.path.join(ROOT, "shellfish_b200", "csrc", "sfk_axis_tables.inc")).read()
+def _tables(fname, prefix):
+    txt = open(os.path.join(ROOT, "shellfish_b200", "csrc", fname)).read()
 
     def arr(name):
         body = re.search(name + r"\[\] = \{([^}]*)\}", txt).group(1)
         return np.array([float(v) for v in body.replace("\n", " ").split(",") if v.strip()])
-    return arr("kAxisRatios"), arr("kACGrid"), arr("kBCGrid"), arr("kCGrid")
+    return arr(prefix + "AxisRatios"), arr(prefix + "ACGrid"), arr(prefix + "BCGrid"), arr(prefix + "CGrid")
+
+
+def axis_tables():
+    """The correction tables of the product: the reference's own data
+    (los/analyze/ellipse_grid/grid.go through scripts/import_axis_tables.py)."""
+    return _tables("sfk_axis_tables_ref.inc", "kRef")
+
+
+def regenerated_axis_tables():
+    """The same grids recomputed from first principles (scripts/make_axis_tables.py)."""
+    return _tables("sfk_axis_tables.inc", "k")

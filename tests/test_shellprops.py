@@ -9,6 +9,8 @@ Three implementations meet here:
   * closed forms / numpy / scipy.
 The GPU tier (tests/test_gpu_shellprops.py) then only has to show that the kernel
 returns what its host-compiled source returns."""
+import os
+
 import numpy as np
 import pytest
 
@@ -199,6 +201,25 @@ def test_reference_test_case_ellipsoid_2_4_3():
     # grid.go holds 1.1153 there, and so does the regenerated table
     sph = api.axes_from_moments(_ellipsoid_moments(1, 1, 1))
     assert abs(sph[0] - 1.1153) < 2e-4, sph
+
+
+def test_reference_tables_are_imported_verbatim_and_match_the_recomputed_ones():
+    """The product interpolates the reference's own data (ellipse_grid/grid.go, imported by
+    scripts/import_axis_tables.py); the grids recomputed from first principles
+    (scripts/make_axis_tables.py) agree with them within the Monte-Carlo noise of the reference's
+    entries (1e6 samples each): median 5e-4, max 3e-3 relative."""
+    ref, gen = shells.axis_tables(), shells.regenerated_axis_tables()
+    assert np.array_equal(ref[0], gen[0]) and len(ref[0]) == 24
+    for a, b in zip(ref[1:], gen[1:]):
+        assert a.shape == b.shape == (576,)
+        rel = np.abs(a - b) / np.abs(a)
+        assert np.median(rel) < 8e-4 and rel.max() < 3.5e-3
+    assert ref[3].reshape(24, 24)[23, 23] == 1.1153          # the entry a sphere reads (flipped c grid)
+    src = "/root/reference/los/analyze/ellipse_grid/grid.go"  # only in the build container
+    if os.path.exists(src):
+        import re
+        nums = [float(v) for v in re.findall(r"-?\d+\.?\d*(?:e-?\d+)?", open(src).read().split("ACCorrectionGrid")[1].split("{")[1])]
+        assert np.array_equal(np.array(nums[:576]), ref[1])
 
 
 def test_committed_tables_are_what_the_generator_writes(tmp_path):
