@@ -212,6 +212,33 @@ int64_t sfh_read_block(const char *type, const char *fname, const char *endianne
     return n;
 }
 
+// Particle IDs of a block (VectorBuffer::ReadIDs); returns the count or -1
+int64_t sfh_read_ids(const char *type, const char *fname, const char *endianness, int64_t npartNum, int64_t *ids, int64_t cap,
+                     int dmTypes) {
+    Context ctx;
+    ctx.LGadgetNPartNum = npartNum;
+    if (dmTypes) { ctx.GadgetDMTypeIndices.clear(); for (int i = 0; i < 6; i++) if (dmTypes >> i & 1) ctx.GadgetDMTypeIndices.push_back(i); }
+    std::unique_ptr<VectorBuffer> buf;
+    std::string err = NewVectorBuffer(type, fname, endianness, ctx, buf);
+    if (!err.empty()) { keep(err); return -1; }
+    const int64_t *p;
+    int64_t n;
+    if (!(err = buf->ReadIDs(fname, &p, &n)).empty()) { keep(err); return -1; }
+    for (int64_t i = 0; i < n && i < cap; i++) ids[i] = p[i];
+    return n;
+}
+
+// io.WriteFilter; particles are concatenated, lens[i] per halo.  Returns 0 or -1
+int sfh_write_filter(const char *path, const char *endianness, int n, const int64_t *snaps, const int64_t *ids,
+                     const int64_t *lens, const int64_t *particles) {
+    std::vector<std::vector<int64_t>> ps(n);
+    int64_t at = 0;
+    for (int i = 0; i < n; i++) { ps[i].assign(particles + at, particles + at + lens[i]); at += lens[i]; }
+    std::string err = WriteFilter(path, endianness, std::vector<int64_t>(snaps, snaps + n), std::vector<int64_t>(ids, ids + n), ps);
+    if (!err.empty()) { keep(err); return -1; }
+    return 0;
+}
+
 void sfh_bounding_box(const float *xs, int64_t n, double tw, float *origin, float *width) { boundingBox(xs, n, tw, origin, width); }
 
 }  // extern "C"

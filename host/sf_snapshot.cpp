@@ -199,6 +199,27 @@ public:
         *xs = xs_.data(); *ms = ms_.data(); *n = count;
         return "";
     }
+    std::string ReadIDs(const std::string &fname, const int64_t **ids, int64_t *n) override {
+        // [hdr] [pos 12 N] [vel 12 N] [ids 8 N], io/lgadget2.go:107-116
+        FileReader fr;
+        std::string err;
+        if (!fr.open(fname, err)) return err;
+        unsigned char head[kGadgetPosOffset];
+        if (!fr.read_at(0, head, sizeof head)) return "read " + fname + ": unexpected EOF";
+        Cursor c{head, head + sizeof head, swap_};
+        c.get<int32_t>();
+        LGadget2Header gh = parse_lgadget(c, true);
+        int64_t count = 0;
+        err = particle_num(gh.NPart, count);
+        if (!err.empty()) return err;
+        const int64_t at = kGadgetPosOffset + 12 * count + 4 + (4 + 12 * count + 4) + 4;
+        if (count < 0 || at + 8 * count > fr.size) return "read " + fname + ": unexpected EOF";
+        ids_.resize(count);
+        if (!fr.read_at(at, ids_.data(), 8 * static_cast<size_t>(count))) return "read " + fname + ": unexpected EOF";
+        if (swap_) swap_array(ids_.data(), ids_.size());
+        *ids = ids_.data(); *n = count;
+        return "";
+    }
     std::string ReadHeader(const std::string &fname, Header &out) override {   // :259-273 + postprocess :25-40
         LGadget2Header hd{};
         std::string err = header(fname, hd);
@@ -246,6 +267,7 @@ private:
     Context ctx_;
     float mass_ = 0;
     std::vector<float> xs_, ms_;
+    std::vector<int64_t> ids_;
 };
 
 // -------------------------------------------------------------- Gadget-2
@@ -314,6 +336,45 @@ public:
         *xs = xs_.data(); *ms = ms_.data(); *n = dmN;
         return "";
     }
+    std::string ReadIDs(const std::string &fname, const int64_t **ids, int64_t *n) override {
+        // ids of every species, 8 or 4 bytes each (io/gadget2.go:109-120), then packInt64 keeps the DM species (:133)
+        FileReader fr;
+        std::string err;
+        if (!fr.open(fname, err)) return err;
+        unsigned char head[kGadgetPosOffset];
+        if (!fr.read_at(0, head, sizeof head)) return "read " + fname + ": unexpected EOF";
+        Cursor c{head, head + sizeof head, swap_};
+        c.get<int32_t>();
+        Gadget2Header gh = parse_gadget(c, false);
+        int64_t totalN = 0;
+        for (int i = 0; i < 6; i++) totalN += gh.NPart[i];
+        int64_t at = kGadgetPosOffset + 12 * totalN + 4 + (4 + 12 * totalN + 4);
+        int32_t idBytes = 0;
+        if (totalN < 0 || !fr.read_at(at, &idBytes, 4)) return "read " + fname + ": unexpected EOF";
+        if (swap_) swap_array(&idBytes, 1);
+        at += 4;
+        std::vector<int64_t> all(totalN);
+        const int64_t each = totalN > 0 ? idBytes / totalN : 8;
+        if (each == 8) {
+            if (!fr.read_at(at, all.data(), 8 * static_cast<size_t>(totalN))) return "read " + fname + ": unexpected EOF";
+            if (swap_) swap_array(all.data(), all.size());
+        } else if (each == 4) {
+            std::vector<int32_t> i32(totalN);
+            if (!fr.read_at(at, i32.data(), 4 * static_cast<size_t>(totalN))) return "read " + fname + ": unexpected EOF";
+            if (swap_) swap_array(i32.data(), i32.size());
+            for (int64_t k = 0; k < totalN; k++) all[k] = i32[k];
+        } else {
+            return "Cannot read particle IDs of " + fname + ": " + std::to_string(each) + " bytes per ID.";
+        }
+        ids_.clear();
+        int64_t off = 0;
+        for (int i = 0; i < 6; i++) {
+            if (isDM(i)) ids_.insert(ids_.end(), all.begin() + off, all.begin() + off + gh.NPart[i]);
+            off += gh.NPart[i];
+        }
+        *ids = ids_.data(); *n = static_cast<int64_t>(ids_.size());
+        return "";
+    }
     std::string ReadHeader(const std::string &fname, Header &out) override {   // :386-400 + postprocess :29-48
         Gadget2Header hd{};
         std::string err = header(fname, hd);
@@ -354,6 +415,7 @@ private:
     bool swap_;
     Context ctx_;
     std::vector<float> xs_, ms_;
+    std::vector<int64_t> ids_;
 };
 
 // --------------------------------------------------------------- gotetra
@@ -416,6 +478,12 @@ public:
         *xs = xs_.data(); *ms = ms_.data(); *n = sw_ * sw_ * sw_;
         return "";
     }
+    std::string ReadIDs(const std::string &, const int64_t **ids, int64_t *n) override {
+        // the gotetra reader allocates its ID slice and never fills it (io/gotetra.go:40,87): zeros
+        ids_.assign(sw_ * sw_ * sw_, 0);
+        *ids = ids_.data(); *n = sw_ * sw_ * sw_;
+        return "";
+    }
     std::string ReadHeader(const std::string &fname, Header &out) override {   // :213-226 + postprocess :122-128
         RawGotetraHeader hd;
         std::vector<unsigned char> img;
@@ -462,9 +530,34 @@ private:
     int64_t sw_ = 0, gw_ = 0;
     float mass_ = 0;
     std::vector<float> xs_, ms_;
+    std::vector<int64_t> ids_;
 };
 
 }  // namespace
+
+std::string WriteFilter(const std::string &path, const std::string &endianness, const std::vector<int64_t> &snaps,
+                        const std::vector<int64_t> &ids, const std::vector<std::vector<int64_t>> &particles) {
+    const bool big = needs_swap(endianness);   // flagToOrder, io/filter_data.go:20-34 (the host is little endian)
+    FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) return "open " + path + ": " + std::strerror(errno);
+    auto put32 = [&](int32_t v) { if (big) swap_array(&v, 1); std::fwrite(&v, 4, 1, f); };
+    auto put64 = [&](int64_t v) { if (big) swap_array(&v, 1); std::fwrite(&v, 8, 1, f); };
+    put32(big ? -1 : 0);
+    put32(static_cast<int32_t>(snaps.size()));
+    const int64_t baseOffset = 4 + 4 + static_cast<int64_t>(snaps.size()) * 32;
+    for (size_t i = 0; i < snaps.size(); i++) {   // haloInfo{ID, Snap, StartByte, Len}
+        put64(ids[i]); put64(snaps[i]);
+        put64(baseOffset);                        // totLen stays 0 in the reference, :52
+        put64(static_cast<int64_t>(particles[i].size()));
+    }
+    for (const std::vector<int64_t> &p : particles) {
+        if (!big) { if (!p.empty()) std::fwrite(p.data(), 8, p.size(), f); }
+        else for (int64_t v : p) put64(v);
+    }
+    const bool ok = std::ferror(f) == 0;
+    std::fclose(f);
+    return ok ? "" : "write " + path + ": " + std::strerror(errno);
+}
 
 float calcUniformMass(int64_t count, double tw, const Cosmology &c) {
     const double rhoM0 = sfk::rho_average(c.H100 * 100, c.OmegaM, c.OmegaL, 0);

@@ -37,6 +37,9 @@ public:
     // xs: [N][3] Mpc/h, ms: [N] Msun/h.  The arrays are owned by the buffer
     // and reused by the next Read, like the reference's slices.
     virtual std::string Read(const std::string &fname, const float **xs, const float **ms, int64_t *n) = 0;
+    // The particle IDs Read's fourth return value holds (only `stats` with ShellParticleFile
+    // asks for them): ids[i] belongs to xs[i] of the same file.  Owned by the buffer.
+    virtual std::string ReadIDs(const std::string &fname, const int64_t **ids, int64_t *n) = 0;
     virtual std::string ReadHeader(const std::string &fname, Header &out) = 0;
     virtual float MinMass() const = 0;
     virtual std::string TotalParticles(const std::string &fname, int64_t &n) = 0;
@@ -46,6 +49,13 @@ public:
 std::string NewVectorBuffer(const std::string &snapshotType, const std::string &fname,
                             const std::string &endianness, const Context &ctx,
                             std::unique_ptr<VectorBuffer> &out);
+
+// io.WriteFilter, io/filter_data.go:36-63: the ShellParticleFile of `shellfish stats`.  Layout:
+// int32 endianness flag (0 little, -1 big), int32 halo count, per halo {ID, Snap, StartByte, Len}
+// int64, then every halo's particle IDs.  StartByte is the same for every halo -- the reference
+// never advances totLen -- and ReadFilter ignores it; kept, so that the bytes are the reference's.
+std::string WriteFilter(const std::string &path, const std::string &endianness, const std::vector<int64_t> &snaps,
+                        const std::vector<int64_t> &ids, const std::vector<std::vector<int64_t>> &particles);
 
 // io/io.go:263-304
 void boundingBox(const float *xs, int64_t n, double totalWidth, float origin[3], float width[3]);

@@ -74,8 +74,6 @@ int find_order(size_t len) {   // findOrder, cmd/stats.go:423-434 (panics on "Im
 
 std::string RunStats(const GlobalConfig &g, const StatsConfig &c, const std::string &stdinData, int device,
                      std::vector<std::string> &outLines) {
-    if (c.shellFilter)
-        return "ShellParticleFile / ShellWidth are not supported by this build (particle IDs are not read).";
     // cmd/stats.go:191-207
     const size_t P2 = static_cast<size_t>(2 * c.order * c.order);
     std::vector<int> floatIdx(4 + P2);
@@ -93,6 +91,7 @@ std::string RunStats(const GlobalConfig &g, const StatsConfig &c, const std::str
     // output columns, cmd/stats.go:209-219
     std::vector<std::vector<double>> cols(12, std::vector<double>(n, 0.0));   // masses rads vols sas as bs cs ax ay az rmins rmaxes
 
+    std::vector<std::vector<int64_t>> shellParticles(n);   // per input row, :221
     std::map<int64_t, std::vector<size_t>> idxBins;   // binCoeffsBySnap + sort.Ints
     for (size_t i = 0; i < n; i++) idxBins[snaps[i]].push_back(i);
     int64_t firstSnap = -1;   // the reference opens snaps[0] (:232); a -1 there indexes out of range
@@ -159,6 +158,9 @@ std::string RunStats(const GlobalConfig &g, const StatsConfig &c, const std::str
         if (!(err = ReadHeaders(static_cast<int>(snap), *buf, cat, g.MemoDir, hds, files)).empty()) return err;
         if (sfk_mass_begin(sfk, static_cast<int64_t>(nh), order, centers.data(), coeffs.data(), rLow.data(), rHigh.data()) != 0)
             return sfk_last_error(sfk);
+        // ShellParticleFile: IDs of the particles within ShellWidth * R200m of each surface, :326-341
+        if (c.shellFilter && sfk_mass_set_band(sfk, c.shellWidth, radii.data(), rLow.data(), rHigh.data()) != 0)
+            return sfk_last_error(sfk);
         for (size_t i = 0; i < hds.size(); i++) {
             // binSphereIntersections, :694-708: a block no R200m sphere touches is not read
             bool any = false;
@@ -169,10 +171,27 @@ std::string RunStats(const GlobalConfig &g, const StatsConfig &c, const std::str
             int64_t np;
             if (!(err = buf->Read(files[i], &xs, &ms, &np)).empty()) return err;
             if (sfk_mass_push_block(sfk, xs, ms, np, hds[i].TotalWidth) != 0) return sfk_last_error(sfk);
+            if (c.shellFilter) {
+                int64_t nPairs = 0, nIds = 0;
+                const int64_t *pairs = nullptr, *pids = nullptr;
+                if (sfk_mass_take_band(sfk, &nPairs, &pairs) != 0) return sfk_last_error(sfk);
+                if (nPairs > 0) {
+                    if (!(err = buf->ReadIDs(files[i], &pids, &nIds)).empty()) return err;
+                    for (int64_t k = 0; k < nPairs; k++) {
+                        const int64_t halo = pairs[k] >> 32, idx = pairs[k] & 0xffffffffll;
+                        if (idx >= nIds) return "read " + files[i] + ": fewer particle IDs than positions";
+                        shellParticles[idxs[halo]].push_back(pids[idx]);
+                    }
+                }
+            }
         }
         std::vector<double> masses(nh);
         if (sfk_mass_finish(sfk, masses.data()) != 0) return sfk_last_error(sfk);
         for (size_t j = 0; j < nh; j++) cols[0][idxs[j]] = masses[j];
+    }
+
+    if (c.shellFilter && !c.skipMass) {   // writeShellParticles, :344-346, 599-640
+        if (!(err = WriteFilter(c.shellParticleFile, g.Endianness, snaps, ids, shellParticles)).empty()) return err;
     }
 
     // cmd/stats.go:342-358

@@ -218,6 +218,16 @@ int sfk_mass_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64
 int sfk_mass_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass,
                                int64_t n, double total_width);
 int sfk_mass_finish(sfk_ctx *ctx, double *masses);
+/* ShellParticleFile (cmd/stats.go:326-341, appendShellParticlesChan :545-597): after
+ * sfk_mass_begin, sfk_mass_set_band switches the collection on -- shell_width is ShellWidth
+ * (!= 0; negative: every particle inside the surface), radii[i] = float32(R200m) of halo i
+ * (geom.Sphere.R), r_low / r_high as in sfk_mass_begin.  After every sfk_mass_push_block[_device]
+ * sfk_mass_take_band returns the block's selected (halo, particle) pairs as halo << 32 |
+ * index-in-block, sorted (the reference's order with one worker); the array belongs to the
+ * context and lasts until the next push. */
+int sfk_mass_set_band(sfk_ctx *ctx, double shell_width, const float *radii, const double *r_low,
+                      const double *r_high);
+int sfk_mass_take_band(sfk_ctx *ctx, int64_t *n, const int64_t **pairs);
 /* sphereSheetIntersect, cmd/stats.go:685-692 (radius = float32(R200m)); returns 0 or 1. */
 int sfk_sphere_block_hit(const float center[3], float radius, const float origin[3],
                          const float width[3], double total_width);

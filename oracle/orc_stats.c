@@ -50,6 +50,43 @@ double orc_mass_contained(double totalWidth, const float *xs, const float *ms, i
     return total;
 }
 
+/* appendShellParticles + appendShellParticlesChan, cmd/stats.go:482-520, 545-597, with one
+ * worker: indices (into the block) of the particles within shellWidth * sphereR of the surface,
+ * or inside it when shellWidth < 0.  out has room for n entries; returns the count. */
+int64_t orc_shell_particles(double totalWidth, const float *xs, int64_t n, const double *cs, int order,
+                            const float c[3], float sphereR, double rLow, double rHigh, double shellWidth,
+                            int64_t *out) {
+    float tw2 = (float)totalWidth / 2;
+    double delta = (double)sphereR * shellWidth;
+    if (shellWidth < 0) delta = 0;
+    rLow -= delta;
+    rHigh += delta;
+    float low2 = (float)(rLow * rLow), high2 = (float)(rHigh * rHigh);
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; i++) {
+        float x = xs[3 * i], y = xs[3 * i + 1], z = xs[3 * i + 2];
+        x = x - c[0]; y = y - c[1]; z = z - c[2];
+        x = wrap_half(x, tw2); y = wrap_half(y, tw2); z = wrap_half(z, tw2);
+        float r2 = x * x + y * y + z * z;
+        if (shellWidth < 0) {
+            if (r2 < high2) {
+                double r = sqrt((double)r2);
+                double phi = atan2((double)y, (double)x);
+                double theta = acos((double)z / r);
+                double rs = orc_penna_func(cs, order, order, 2, phi, theta);
+                if (rs > r) out[m++] = i;
+            }
+        } else if (r2 > low2 && r2 < high2) {
+            double r = sqrt((double)r2);
+            double phi = atan2((double)y, (double)x);
+            double theta = acos((double)z / r);
+            double rs = orc_penna_func(cs, order, order, 2, phi, theta);
+            if (rs + delta > r && rs - delta < r) out[m++] = i;
+        }
+    }
+    return m;
+}
+
 static double wrap_dist(double x1, double x2, double width) {
     double dist = x1 - x2;
     if (dist > width / 2) return dist - width;

@@ -100,6 +100,9 @@ def lib():
         L.orc_mass_contained.restype = C.c_double
         L.orc_mass_contained.argtypes = [C.c_double, c_float_p, c_float_p, C.c_int64, c_double_p, C.c_int,
                                          c_float_p, C.c_double, C.c_double, C.c_int]
+        L.orc_shell_particles.restype = C.c_int64
+        L.orc_shell_particles.argtypes = [C.c_double, c_float_p, C.c_int64, c_double_p, C.c_int, c_float_p, C.c_float,
+                                          C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int64)]
         L.orc_sphere_sheet_intersect.restype = C.c_int
         L.orc_sphere_sheet_intersect.argtypes = [c_float_p, C.c_float, c_float_p, c_float_p, C.c_double]
         L.orc_nth_largest.restype = C.c_double
@@ -329,6 +332,19 @@ def mass_contained(total_width, xs, ms, cs, center, r_low, r_high, workers=1):
     order = int(round((len(cs) / 2) ** 0.5))
     return lib().orc_mass_contained(total_width, fp(xs), fp(ms), len(ms), dp(cs), order, fp(c), r_low, r_high,
                                     workers)
+
+
+def shell_particles(total_width, xs, cs, center, sphere_r, r_low, r_high, shell_width):
+    """appendShellParticles (cmd/stats.go:482-597) for one halo over one block, one worker:
+    indices of the selected particles in block order."""
+    xs = np.ascontiguousarray(xs, np.float32)
+    cs = np.ascontiguousarray(cs, np.float64)
+    c = np.ascontiguousarray(center, np.float32)
+    order = int(round((len(cs) / 2) ** 0.5))
+    out = np.zeros(len(xs), np.int64)
+    m = lib().orc_shell_particles(total_width, fp(xs), len(xs), dp(cs), order, fp(c), float(np.float32(sphere_r)),
+                                  r_low, r_high, shell_width, out.ctypes.data_as(C.POINTER(C.c_int64)))
+    return out[:m]
 
 
 def sphere_sheet_intersect(center, r, origin, width, total_width):

@@ -199,6 +199,9 @@ int orc_shell_contains(const double *cs, int order, double x, double y, double z
 double orc_mass_contained(double totalWidth, const float *xs, const float *ms, int64_t n,
                           const double *cs, int order, const float c[3],
                           double rLow, double rHigh, int workers);
+int64_t orc_shell_particles(double totalWidth, const float *xs, int64_t n, const double *cs, int order,
+                            const float c[3], float sphereR, double rLow, double rHigh, double shellWidth,
+                            int64_t *out);
 int orc_sphere_sheet_intersect(const float c[3], float r, const float origin[3],
                                const float width[3], double tw);
 

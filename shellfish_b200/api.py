@@ -54,7 +54,7 @@ EXPORTS = ["sfk_device_count", "sfk_default_params", "sfk_create", "sfk_destroy"
            "sfk_add_halos", "sfk_set_owned", "sfk_block_halo_mask", "sfk_push_block", "sfk_push_block_device",
            "sfk_finish_snapshot", "sfk_row_length", "sfk_split_count", "sfk_split_bin", "sfk_split_buffer", "sfk_split_finish",
            "sfk_comm_unique_id", "sfk_comm_init", "sfk_split_finish_comm",
-           "sfk_mass_begin", "sfk_mass_push_block", "sfk_mass_push_block_device", "sfk_mass_finish",
+           "sfk_mass_begin", "sfk_mass_push_block", "sfk_mass_push_block_device", "sfk_mass_finish", "sfk_mass_set_band", "sfk_mass_take_band",
            "sfk_sphere_block_hit", "sfk_shell_props", "sfk_shell_sums", "sfk_angular_fraction", "sfk_axes_from_moments", "sfk_get_stats", "sfk_stream", "sfk_get_rsp", "sfk_get_candidate_count", "sfk_get_intersection_count",
            "sfk_get_profiles", "sfk_get_counts", "sfk_get_grid", "sfk_get_ring_tables"]
 
@@ -266,6 +266,38 @@ class ShellContext:
         return coeffs, status
 
     # ---- stats mode: M_sp ----------------------------------------------------------
+    def shell_particles(self, centers, coeffs, r_low, r_high, radii, shell_width, blocks):
+        """The ShellParticleFile selection (sfk_mass_set_band / sfk_mass_take_band): per block, an
+        int64 array of halo << 32 | particle index, sorted.  Returns (masses, [pairs per block])."""
+        centers = np.ascontiguousarray(centers, np.float32)
+        coeffs = np.ascontiguousarray(coeffs, np.float64)
+        r_low = np.ascontiguousarray(r_low, np.float64)
+        r_high = np.ascontiguousarray(r_high, np.float64)
+        radii = np.ascontiguousarray(radii, np.float32)
+        n = len(centers)
+        order = int(round((coeffs.shape[1] / 2) ** 0.5))
+        dp_, fp_ = C.POINTER(C.c_double), C.POINTER(C.c_float)
+        L = lib()
+        L.sfk_mass_set_band.argtypes = [C.c_void_p, C.c_double, fp_, dp_, dp_]
+        L.sfk_mass_take_band.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.POINTER(C.c_int64))]
+        self._ck(L.sfk_mass_begin(self._h, C.c_int64(n), C.c_int32(order), centers.ctypes.data_as(fp_),
+                                  coeffs.ctypes.data_as(dp_), r_low.ctypes.data_as(dp_), r_high.ctypes.data_as(dp_)),
+                 "sfk_mass_begin")
+        self._ck(L.sfk_mass_set_band(self._h, float(shell_width), radii.ctypes.data_as(fp_), r_low.ctypes.data_as(dp_),
+                                     r_high.ctypes.data_as(dp_)), "sfk_mass_set_band")
+        per_block = []
+        for b in blocks:
+            xs = np.ascontiguousarray(b["xs"], np.float32)
+            ms = np.ascontiguousarray(b["ms"], np.float32)
+            self._ck(L.sfk_mass_push_block(self._h, xs.ctypes.data_as(fp_), ms.ctypes.data_as(fp_), C.c_int64(len(ms)),
+                                           C.c_double(b["TotalWidth"])), "sfk_mass_push_block")
+            cnt, ptr = C.c_int64(), C.POINTER(C.c_int64)()
+            self._ck(L.sfk_mass_take_band(self._h, C.byref(cnt), C.byref(ptr)), "sfk_mass_take_band")
+            per_block.append(np.ctypeslib.as_array(ptr, shape=(cnt.value,)).copy() if cnt.value else np.zeros(0, np.int64))
+        out = np.zeros(n)
+        self._ck(L.sfk_mass_finish(self._h, out.ctypes.data_as(dp_)), "sfk_mass_finish")
+        return out, per_block
+
     def mass_contained(self, centers, coeffs, r_low, r_high, blocks, radii=None, device_blocks=None):
         """massContained (cmd/stats.go:451-543) for every halo over `blocks`
         (dicts with xs, ms, TotalWidth, Origin, Width).  With `radii` given, blocks

@@ -125,6 +125,14 @@ struct sfk_ctx {
     int64_t massHalos = 0;
     int massOrder = 0;
     bool massOpen = false;
+    // ShellParticleFile pass
+    bool bandOn = false;
+    int bandInside = 0;
+    DevBuf<float> dBandLow2, dBandHigh2;
+    DevBuf<double> dBandDelta;
+    DevBuf<long long> dBandList;
+    DevBuf<unsigned long long> dBandCount;
+    std::vector<long long> hBand;
     // `stats` shell properties
     DevBuf<double> dPropCoeffs, dPropSums, dGlX, dGlW;
     int glTheta = 0;
@@ -1114,8 +1122,11 @@ int sfk_mass_begin(sfk_ctx *ctx, int64_t n_halo, int32_t order, const float *cen
     if (n_halo) CU(cudaMemsetAsync(ctx->dMassSums.p, 0, n_halo * sizeof(double), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));   // the host vectors die here
     ctx->massHalos = n_halo; ctx->massOrder = order; ctx->massOpen = true;
+    ctx->bandOn = false;
     return SFK_OK;
 } SFK_CATCH(ctx)
+
+static int band_pass(sfk_ctx *ctx, const float *dxyz, int64_t n, double total_width);
 
 static int mass_push_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, int64_t n, double total_width) try {
     MassArgs a{};
@@ -1134,6 +1145,7 @@ static int mass_push_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, i
 int sfk_mass_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n, double total_width) try {
     if (!ctx || !ctx->massOpen || n < 0 || (n > 0 && (!xyz || !mass)))
         return fail(ctx, SFK_E_INVALID, "sfk_mass_push_block: call sfk_mass_begin first");
+    ctx->hBand.clear();
     if (n == 0 || ctx->massHalos == 0) return SFK_OK;
     CU(cudaSetDevice(ctx->p.device));
     CU(cudaStreamSynchronize(ctx->stream));   // a shell-pass cull may still read the staging buffer
@@ -1143,6 +1155,7 @@ int sfk_mass_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64
     CU(cudaMemcpyAsync(ctx->dMass[0].p, mass, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     int rc = mass_push_impl(ctx, ctx->dXyz[0].p, ctx->dMass[0].p, n, total_width);
     if (rc) return rc;
+    if (ctx->bandOn && (rc = band_pass(ctx, ctx->dXyz[0].p, n, total_width)) != 0) return rc;
     CU(cudaStreamSynchronize(ctx->stream));   // the caller may reuse its buffers (io.VectorBuffer does)
     return SFK_OK;
 } SFK_CATCH(ctx)
@@ -1151,10 +1164,81 @@ int sfk_mass_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_
                                double total_width) try {
     if (!ctx || !ctx->massOpen || n < 0 || (n > 0 && (!d_xyz || !d_mass)))
         return fail(ctx, SFK_E_INVALID, "sfk_mass_push_block_device: call sfk_mass_begin first");
+    ctx->hBand.clear();
     if (n == 0 || ctx->massHalos == 0) return SFK_OK;
     CU(cudaSetDevice(ctx->p.device));
     CU(cudaDeviceSynchronize());   // the caller's buffers live on other streams
-    return mass_push_impl(ctx, d_xyz, d_mass, n, total_width);
+    int rc = mass_push_impl(ctx, d_xyz, d_mass, n, total_width);
+    if (rc) return rc;
+    if (ctx->bandOn) return band_pass(ctx, d_xyz, n, total_width);
+    return SFK_OK;
+} SFK_CATCH(ctx)
+
+int sfk_mass_set_band(sfk_ctx *ctx, double shell_width, const float *radii, const double *r_low,
+                      const double *r_high) try {
+    if (!ctx || !ctx->massOpen || shell_width == 0 || (ctx->massHalos > 0 && (!radii || !r_low || !r_high)))
+        return fail(ctx, SFK_E_INVALID, "sfk_mass_set_band: call sfk_mass_begin first; ShellWidth must not be 0");
+    CU(cudaSetDevice(ctx->p.device));
+    const int64_t n = ctx->massHalos;
+    std::vector<float> lo(n), hi(n);
+    std::vector<double> delta(n);
+    for (int64_t i = 0; i < n; i++) {
+        // appendShellParticlesChan, cmd/stats.go:554-560 (a negative rLow - delta is squared too)
+        double d = static_cast<double>(radii[i]) * shell_width;
+        if (shell_width < 0) d = 0;
+        const double rl = r_low[i] - d, rh = r_high[i] + d;
+        lo[i] = static_cast<float>(rl * rl); hi[i] = static_cast<float>(rh * rh);
+        delta[i] = d;
+    }
+    CU(ctx->dBandLow2.upload(lo, ctx->stream));
+    CU(ctx->dBandHigh2.upload(hi, ctx->stream));
+    CU(ctx->dBandDelta.upload(delta, ctx->stream));
+    CU(ctx->dBandCount.ensure(1));
+    CU(ctx->dBandList.ensure(size_t(1) << 20));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->bandInside = shell_width < 0 ? 1 : 0;
+    ctx->bandOn = true;
+    ctx->hBand.clear();
+    return SFK_OK;
+} SFK_CATCH(ctx)
+
+// The band pass over the block that sits in dXyz[0] (sfk_mass_push_block just put it there).
+static int band_pass(sfk_ctx *ctx, const float *dxyz, int64_t n, double total_width) {
+    for (;;) {
+        CU(cudaMemsetAsync(ctx->dBandCount.p, 0, sizeof(unsigned long long), ctx->stream));
+        MassArgs a{};
+        a.xyz = dxyz; a.mass = nullptr; a.n = n;
+        a.tw2 = static_cast<float>(total_width) / 2;
+        a.centers = ctx->dMassCenters.p; a.low2 = ctx->dBandLow2.p; a.high2 = ctx->dBandHigh2.p;
+        a.coeffs = ctx->dMassCoeffs.p; a.masses = nullptr;
+        a.list = ctx->dMassList.p; a.listCount = ctx->dMassList.p + ctx->massHalos;
+        a.bboxKeys = reinterpret_cast<unsigned *>(ctx->dMassList.p + ctx->massHalos + 1);
+        a.nHalo = static_cast<int>(ctx->massHalos); a.order = ctx->massOrder; a.P2 = 2 * ctx->massOrder * ctx->massOrder;
+        a.bandDelta = ctx->dBandDelta.p; a.bandInside = ctx->bandInside;
+        a.bandList = ctx->dBandList.p; a.bandCount = ctx->dBandCount.p; a.bandCap = ctx->dBandList.cap;
+        CU(launch_band(a, ctx->stream));
+        ctx->stats.launches += 3;
+        unsigned long long cnt = 0;
+        CU(cudaMemcpyAsync(&cnt, ctx->dBandCount.p, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (cnt > ctx->dBandList.cap) {   // grow and run the block again
+            CU(ctx->dBandList.ensure(static_cast<size_t>(cnt) * 5 / 4));
+            continue;
+        }
+        ctx->hBand.resize(cnt);
+        if (cnt) CU(cudaMemcpy(ctx->hBand.data(), ctx->dBandList.p, cnt * sizeof(long long), cudaMemcpyDeviceToHost));
+        std::sort(ctx->hBand.begin(), ctx->hBand.end());   // by halo, then by particle index: the reference's order at Threads = 1
+        return SFK_OK;
+    }
+}
+
+int sfk_mass_take_band(sfk_ctx *ctx, int64_t *n, const int64_t **pairs) try {
+    if (!ctx || !ctx->massOpen || !ctx->bandOn || !n || !pairs)
+        return fail(ctx, SFK_E_INVALID, "sfk_mass_take_band: call sfk_mass_set_band and push a block first");
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+    *n = static_cast<int64_t>(ctx->hBand.size());
+    *pairs = reinterpret_cast<const int64_t *>(ctx->hBand.data());
+    return SFK_OK;
 } SFK_CATCH(ctx)
 
 int sfk_mass_finish(sfk_ctx *ctx, double *masses) try {

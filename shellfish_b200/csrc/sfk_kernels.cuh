@@ -123,8 +123,14 @@ struct MassArgs {
     unsigned *bboxKeys;          // [6] scratch: the block's coordinate range
     int *list, *listCount;       // [nHalo] + [1] scratch: halos this block can reach
     int nHalo, order, P2;
+    // ShellParticleFile pass (launch_band): low2 / high2 are the widened band, cmd/stats.go:556-560
+    const double *bandDelta;     // [nHalo] float64(sphere.R) * ShellWidth (0 when ShellWidth < 0)
+    int bandInside;              // ShellWidth < 0: everything inside the surface
+    long long *bandList;         // [bandCap] halo << 32 | particle index
+    unsigned long long *bandCount, bandCap;
 };
 cudaError_t launch_mass(const MassArgs &a, cudaStream_t s);
+cudaError_t launch_band(const MassArgs &a, cudaStream_t s);
 
 // `stats` shell property integrals, los/analyze/shell.go:58-283
 struct ShellPropArgs {

@@ -49,6 +49,34 @@ __device__ bool shell_contains(const double *cs, int order, double x, double y, 
     return sum > r;
 }
 
+// appendShellParticlesChan, cmd/stats.go:545-597: is the particle within `delta` of the
+// surface (delta >= 0), or anywhere inside it (inside != 0, ShellWidth < 0)?
+__device__ bool shell_band(const double *cs, int order, float xf, float yf, float zf, float r2, double delta, int inside) {
+    const double x = xf, y = yf, z = zf;
+    const double r = sqrt(static_cast<double>(r2));
+    const double phi = atan2(y, x);
+    const double theta = acos(z / r);
+    double sinPhi, cosPhi, sinTh, cosTh;
+    sincos(phi, &sinPhi, &cosPhi);
+    sincos(theta, &sinTh, &cosTh);
+    int idx = 0;
+    double rs = 0.0;
+    for (int k = 0; k < 2; k++) {
+        const double cosK = go_pow_int(cosTh, k);
+        for (int j = 0; j < order; j++) {
+            const double sinJ = go_pow_int(sinPhi, j);
+            for (int i = 0; i < order; i++) {
+                const double cosI = go_pow_int(cosPhi, i);
+                const double sinIJ = go_pow_int(sinTh, i + j);
+                rs += cs[idx] * sinIJ * cosK * sinJ * cosI;
+                idx++;
+            }
+        }
+    }
+    if (inside) return rs > r;
+    return rs + delta > r && rs - delta < r;
+}
+
 __device__ __forceinline__ float wrap_half(float x, float tw2) {   // cmd/stats.go:429-436
     if (x > tw2) return x - tw2;
     if (x < -tw2) return x + tw2;
@@ -184,7 +212,52 @@ __global__ void __launch_bounds__(kMassThreads) mass_kernel(MassArgs a) {
     }
 }
 
+// The ShellParticleFile pass: the (halo, particle) pairs of one block that appendShellParticlesChan
+// keeps, appended as halo << 32 | particle index.  a.low2 / a.high2 hold the widened band here.
+__global__ void __launch_bounds__(kMassThreads) band_kernel(MassArgs a) {
+    __shared__ float4 sC[kMassHaloChunk];
+    __shared__ float sHigh2[kMassHaloChunk];
+    __shared__ int sIdx[kMassHaloChunk];
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * kMassThreads + threadIdx.x;
+    const bool live = i < a.n;
+    const float px = live ? a.xyz[3 * i] : 0.f, py = live ? a.xyz[3 * i + 1] : 0.f, pz = live ? a.xyz[3 * i + 2] : 0.f;
+    const float tw2 = a.tw2;
+    const int nList = *a.listCount;
+    for (int h0 = 0; h0 < nList; h0 += kMassHaloChunk) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < kMassHaloChunk && h0 + k < nList; k += kMassThreads) {
+            const int h = a.list[h0 + k];
+            sIdx[k] = h;
+            sC[k] = make_float4(a.centers[3 * h], a.centers[3 * h + 1], a.centers[3 * h + 2], a.low2[h]);
+            sHigh2[k] = a.high2[h];
+        }
+        __syncthreads();
+        const int cnt = min(kMassHaloChunk, nList - h0);
+        for (int k = 0; k < cnt; k++) {
+            const float4 c = sC[k];
+            const float x = wrap_half(px - c.x, tw2), y = wrap_half(py - c.y, tw2), z = wrap_half(pz - c.z, tw2);
+            const float r2 = x * x + y * y + z * z;
+            if (!live || !(r2 < sHigh2[k]) || (!a.bandInside && !(r2 > c.w))) continue;
+            const int h = sIdx[k];
+            if (!shell_band(a.coeffs + static_cast<size_t>(h) * a.P2, a.order, x, y, z, r2, a.bandDelta[h], a.bandInside)) continue;
+            const unsigned long long at = atomicAdd(a.bandCount, 1ull);
+            if (at < a.bandCap) a.bandList[at] = static_cast<long long>(h) << 32 | static_cast<long long>(i);
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_band(const MassArgs &a, cudaStream_t s) {
+    if (a.n <= 0 || a.nHalo <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(a.bboxKeys, 0xff, 3 * sizeof(unsigned), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a.bboxKeys + 3, 0, 3 * sizeof(unsigned), s);
+    if (e != cudaSuccess) return e;
+    bbox_kernel<<<static_cast<unsigned>(std::min<int64_t>(148 * 8, (a.n + 255) / 256)), 256, 0, s>>>(a.xyz, a.n, a.bboxKeys);
+    list_kernel<<<1, 1024, 0, s>>>(a);
+    band_kernel<<<static_cast<unsigned>((a.n + kMassThreads - 1) / kMassThreads), kMassThreads, 0, s>>>(a);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_mass(const MassArgs &a, cudaStream_t s) {
     if (a.n <= 0 || a.nHalo <= 0) return cudaSuccess;

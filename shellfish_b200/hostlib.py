@@ -176,6 +176,31 @@ def read_block(kind, fname, endianness="SystemOrder", npart_num=2, pos_units=1.0
     return xs[:n], ms[:n], h, mm.value, tot.value
 
 
+def read_ids(kind, fname, endianness="SystemOrder", npart_num=2, cap=1 << 22, dm_types=()):
+    """Particle IDs of a block file (the reader's ReadIDs), aligned with read_block's positions."""
+    ids = np.zeros(cap, np.int64)
+    f = lib().sfh_read_ids
+    f.restype = C.c_int64
+    n = f(kind.encode(), fname.encode(), endianness.encode(), C.c_int64(npart_num), ids.ctypes.data_as(C.c_void_p),
+          C.c_int64(cap), C.c_int(sum(1 << i for i in dm_types)))
+    if n < 0:
+        raise ValueError(lib().sfh_last_text().decode())
+    return ids[:n]
+
+
+def write_filter(path, endianness, snaps, ids, particles):
+    """io.WriteFilter (io/filter_data.go:36-63): the ShellParticleFile."""
+    snaps = np.ascontiguousarray(snaps, np.int64)
+    ids = np.ascontiguousarray(ids, np.int64)
+    lens = np.array([len(p) for p in particles], np.int64)
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(p, np.int64) for p in particles]) if len(particles) else [], np.int64)
+    rc = lib().sfh_write_filter(path.encode(), endianness.encode(), C.c_int(len(snaps)), snaps.ctypes.data_as(C.c_void_p),
+                                ids.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p),
+                                flat.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise ValueError(lib().sfh_last_text().decode())
+
+
 def bounding_box(xyz, total_width):
     xyz = np.ascontiguousarray(xyz, np.float32)
     o, w = np.zeros(3, np.float32), np.zeros(3, np.float32)

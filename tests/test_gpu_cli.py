@@ -287,6 +287,26 @@ def test_shell_stats_pipeline(tmp_path):
     rows = [l.split() for l in r2.stdout.split("\n")[1:-1]]
     assert all(float(row[2]) == 0.0 for row in rows)
     assert [row[3:] for row in rows] == [l.split()[3:] for l in lines[1:]]
+    # ShellParticleFile (cmd/stats.go:326-346): IDs of the particles within ShellWidth * R200m of the
+    # surfaces, written as io.WriteFilter does; LGadget-2 IDs of the synthetic files are 0 .. N-1 per file
+    sp = os.path.join(os.path.dirname(cfg), "shell-particles.dat")
+    r4 = subprocess.run([H.cli_path(), "stats", "--ShellParticleFile", sp, "--ShellWidth", "0.05"],
+                        input="\n".join(shell_lines) + "\n", capture_output=True, text=True, env=env, timeout=600)
+    assert r4.returncode == 0, r4.stderr
+    assert r4.stdout.split("\n")[:-1] == lines            # the catalog itself is unchanged
+    raw = open(sp, "rb").read()
+    flag, nh = np.frombuffer(raw[:8], np.int32)
+    assert flag == 0 and nh == len(halos)
+    info = np.frombuffer(raw[8:8 + 32 * nh], np.int64).reshape(nh, 4)
+    assert info[:, 0].tolist() == ic[0].tolist() and np.all(info[:, 1] == 100) and np.all(info[:, 2] == 8 + 32 * nh)
+    got_ids = np.frombuffer(raw[8 + 32 * nh:], np.int64)
+    assert len(got_ids) == info[:, 3].sum()
+    want_ids = []
+    for h in range(len(halos)):
+        for b in kept:
+            want_ids += po.shell_particles(b["TotalWidth"], b["xs"], coeffs[h], centers[h], np.float32(r200[h]),
+                                           props[h, 9], props[h, 10], 0.05).tolist()
+    assert got_ids.tolist() == want_ids and len(want_ids) > 100
     # the pipe sentinel of a failed upstream stage is passed on (shellfish.go:366-373)
     r3 = subprocess.run([H.cli_path(), "stats"], input="Shellfish terminating.\n", capture_output=True, text=True, env=env)
     assert r3.returncode == 1 and r3.stdout == "Shellfish terminating.\n"

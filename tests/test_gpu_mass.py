@@ -88,3 +88,26 @@ def test_mass_call_order():
     ctx = api.ShellContext(api.default_params(rings=3))
     with pytest.raises(api.ShellfishError, match="sfk_mass_begin first"):
         ctx._ck(api.lib().sfk_mass_finish(ctx._h, None), "sfk_mass_finish")
+
+
+@pytest.mark.parametrize("width", [0.05, -1.0])
+def test_shell_particle_selection_matches_the_oracle(width):
+    """ShellParticleFile (cmd/stats.go:326-341, appendShellParticlesChan :545-597): the particles
+    within ShellWidth * R200m of each fitted surface (or inside it for ShellWidth < 0), per block,
+    in the reference's one-worker order.  Index lists must be identical."""
+    halos, blocks, mass = synth.make_box(43, 30.0, 3, 25000, 20000, 2, margin=5.0)
+    ctx, coeffs, status = api.run_shell(api.default_params(seed=1337, rings=10), mass, halos, blocks)
+    assert np.all(status == 0)
+    lo, hi = np.array([radial_range(c, 3) for c in coeffs]).T
+    radii = halos[:, 3].astype(np.float32)
+    masses, per_block = ctx.shell_particles(halos[:, :3], coeffs, lo, hi, radii, width, blocks)
+    np.testing.assert_allclose(masses, oracle_masses(halos, coeffs, lo, hi, blocks), rtol=1e-12)
+    total = 0
+    for b, pairs in zip(blocks, per_block):
+        want = []
+        for h in range(len(halos)):
+            idx = po.shell_particles(b["TotalWidth"], b["xs"], coeffs[h], halos[h, :3], radii[h], lo[h], hi[h], width)
+            want += [(h << 32) | int(i) for i in idx]
+        assert pairs.tolist() == want
+        total += len(want)
+    assert total > 1000

@@ -561,3 +561,37 @@ def test_cli_spatial_partition_equals_the_python_one():
         if n >= 100:
             loads = np.array([w[p].sum() for p in parts])
             assert loads.max() / loads.mean() < 1.03
+
+
+def test_filter_file_is_the_references_bytes(tmp_path):
+    """io.WriteFilter, io/filter_data.go:36-63: flag, count, {ID, Snap, StartByte, Len} per halo,
+    then the ID lists.  StartByte is the same for every halo (the reference never advances totLen)."""
+    import struct
+    parts = [[5, 7, 9], [], [11]]
+    for endian, fmt in (("LittleEndian", "<"), ("BigEndian", ">"), ("SystemOrder", "<")):
+        path = str(tmp_path / ("f_%s.dat" % endian))
+        H.write_filter(path, endian, [100, 100, 99], [3, 4, 8], parts)
+        raw = open(path, "rb").read()
+        flag, n = struct.unpack(fmt + "ii", raw[:8])
+        assert struct.unpack("<i", raw[:4])[0] == (-1 if fmt == ">" else 0) or fmt == ">"   # ReadFilter reads the flag little endian
+        assert flag == (-1 if fmt == ">" else 0) and n == 3
+        info = struct.unpack(fmt + "12q", raw[8:8 + 96])
+        base = 4 + 4 + 3 * 32
+        assert info == (3, 100, base, 3, 4, 100, base, 0, 8, 99, base, 1)
+        assert struct.unpack(fmt + "4q", raw[8 + 96:]) == (5, 7, 9, 11) and len(raw) == 8 + 96 + 32
+
+
+def test_readers_return_particle_ids(tmp_path):
+    """ReadIDs: LGadget-2 int64 block (io/lgadget2.go:107-116), Gadget-2 4- or 8-byte IDs packed to
+    the DM species (io/gadget2.go:109-133), gotetra zeros (io/gotetra.go:40,87)."""
+    from shellfish_b200 import snapio
+    rng = np.random.default_rng(0)
+    xs = (rng.random((50, 3)) * 10).astype(np.float32)
+    cosmo = dict(z=0.0, omega_m=0.27, omega_l=0.73, h100=0.7)
+    p = str(tmp_path / "l.0")
+    snapio.write_lgadget2(p, xs, 10.0, cosmo)
+    assert np.array_equal(H.read_ids("LGadget-2", p), np.arange(50))
+    g = str(tmp_path / "g.0")
+    snapio.write_gadget2(g, [xs[:10], xs[10:40], None, None, None, None], 10.0, cosmo, [0.5, 1.0, 0, 0, 0, 0])
+    assert np.array_equal(H.read_ids("Gadget-2", g), np.arange(10, 40))          # type 1 only, file order
+    assert np.array_equal(H.read_ids("Gadget-2", g, dm_types=(0, 1)), np.arange(40))

@@ -118,3 +118,20 @@ def test_mass_contained_general_shell_against_numpy():
     want = ms[(r < lo) | ((r < hi) & (surf > r))].astype(np.float64).sum()
     got = po.mass_contained(box, xs, ms, cs, c, lo, hi)
     assert abs(got - want) <= 1e-6 * want               # a particle within 1e-9 of the surface may flip
+
+
+def test_shell_particles_closed_form_for_a_sphere():
+    """appendShellParticlesChan (cmd/stats.go:545-597) on a spherical shell R = 1: the band keeps
+    |r - 1| < ShellWidth * R200m, a negative ShellWidth keeps r < 1; the half-box wrap applies."""
+    rng = np.random.default_rng(8)
+    xs = (rng.random((20000, 3)) * 6 - 3 + 10).astype(np.float32)
+    c = np.array([10.0, 10.0, 10.0], np.float32)
+    cs = np.zeros(18)
+    cs[0] = 1.0
+    d = (xs - c).astype(np.float64)
+    r = np.sqrt((d.astype(np.float32) ** 2).sum(1).astype(np.float32).astype(np.float64))
+    band = po.shell_particles(100.0, xs, cs, c, 0.8, 0.9, 1.1, 0.25)     # delta = 0.8 * 0.25 = 0.2
+    want = np.flatnonzero((r > 0.8) & (r < 1.2) & (r > 0.9 - 0.2) & (r < 1.1 + 0.2))
+    assert np.array_equal(band, want) and len(band) > 100
+    inside = po.shell_particles(100.0, xs, cs, c, 0.8, 0.9, 1.1, -1.0)
+    assert np.array_equal(inside, np.flatnonzero(r < 1.0))
