@@ -526,8 +526,8 @@ __device__ __forceinline__ double fast_log(double x, const double2 *tab) {
 //
 // MOMENTS == true (default whenever every ln rho is finite, i.e. rho_bg > 0): the two
 // Savitzky-Golay FIRs are evaluated through the five sliding polynomial moments of
-// sfk_sgmath.cuh -- one direct pass over the window for the lane's first output (taps +-k
-// paired: 7 operations per two taps), PER - 1 binomial shifts for the rest -- and ln() is
+// sfk_sgmath.cuh -- one direct pass over the window for the lane's first output, PER - 1
+// binomial shifts for the rest -- and ln() is
 // fast_log.  Same values as the tap loop to ~1e-13 (tests/test_sgmoments.py), same R_sp.
 // MOMENTS == false: ConvolveAt verbatim (filter.go:104-161) as a register sliding window:
 // per tap one shared-memory read of ln(rho) per lane (conflict-free permuted layout) and one
@@ -549,13 +549,13 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
     const int padL = center + 1;
     constexpr int rowLen = kLosFastRow;
     double2 *taps = reinterpret_cast<double2 *>(sm);                       // tap loop: [window] (value, deriv)
-    double *upow = sm;                                                     // moments: [center + 1][4] u, u^2, u^3, u^4
-    const int tabOff = MOMENTS ? 4 * (center + 1) : 2 * window;
+    double *upow = sm;                                                     // moments: [window][4] u, u^2, u^3, u^4 of every tap
+    const int tabOff = MOMENTS ? 4 * window : 2 * window;
     const double2 *logTab = reinterpret_cast<const double2 *>(sm + tabOff);   // moments: [128]
     double *ys = sm + tabOff + (MOMENTS ? 256 : 0) + (threadIdx.x >> 5) * (PER * rowLen);
     if (MOMENTS) {
-        for (int k = threadIdx.x; k <= center; k += blockDim.x) {
-            const double u = static_cast<double>(k) / static_cast<double>(center);
+        for (int k = threadIdx.x; k < window; k += blockDim.x) {
+            const double u = static_cast<double>(k - center) / static_cast<double>(center);
             upow[4 * k] = u; upow[4 * k + 1] = u * u; upow[4 * k + 2] = u * u * u; upow[4 * k + 3] = (u * u) * (u * u);
         }
         for (int k = threadIdx.x; k < 256; k += blockDim.x) sm[tabOff + k] = a.logTab[k];
@@ -621,10 +621,23 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
     const double *yl = ys + lane;
     double s0[PER], s1[PER];
     if (MOMENTS) {
-        double M[5] = {yl[((1 + center) % PER) * rowLen + (1 + center) / PER], 0.0, 0.0, 0.0, 0.0};
-        for (int k = 1; k <= center; k++) {
-            const int qp = 1 + center + k, qm = 1 + center - k;
-            sg_accumulate_pair(M, yl[(qp % PER) * rowLen + qp / PER], yl[(qm % PER) * rowLen + qm / PER], upow + 4 * k);
+        // Anchor: the five moments of output c = 0 over taps 0 .. window-1, i.e. positions q = 1 ..
+        // window, walked in aligned blocks of PER positions so that the row of every read is a
+        // compile-time offset and only the column advances (no index arithmetic per tap).
+        double M[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 1; j < PER; j++) sg_accumulate(M, yl[j * rowLen], upow + 4 * (j - 1));   // q = 1 .. PER-1
+        const int bLast = window / PER;                   // the block holding q = window
+        for (int b = 1; b < bLast; b++) {
+            const double *yb = yl + b;
+            const double *ub = upow + 4 * (b * PER - 1);
+#pragma unroll
+            for (int j = 0; j < PER; j++) sg_accumulate(M, yb[j * rowLen], ub + 4 * j);
+        }
+        if (bLast >= 1) {
+#pragma unroll
+            for (int j = 0; j < PER; j++)
+                if (bLast * PER + j <= window) sg_accumulate(M, yl[j * rowLen + bLast], upow + 4 * (bLast * PER + j - 1));
         }
 #pragma unroll
         for (int c = 0; c < PER; c++) {
@@ -990,39 +1003,36 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(FilterArgs a) {
         // so each KDE still sums its own points in the reference's order.
         for (int t = tid; t < nKde * kKdeKnots; t += kFilterThreads) Y[t] = 0.0;
         __syncthreads();
-        // The points are in LoS order, so a point's node index is non-decreasing at every level:
-        // each node's sum is one contiguous run of points and lives in a register until the node
-        // changes (the change depends on p only: no divergence).
+        // The points are in LoS order, so a point's wedge at the finest level is non-decreasing:
+        // every finest-level KDE is the sum over one contiguous run of points and lives in a
+        // register until the wedge changes (which depends on p only: no divergence).  A coarser
+        // KDE is the sum of its two children -- the reference sums each KDE over its own points in
+        // order (binByTheta, kde.go:156-174); regrouping moves a sum by an ulp, like the choice of
+        // exp() does, and decides nothing beyond tie level.
+        const double invHk = 1.0 / hk;
+        const unsigned char *fine = pNode + (a.levels - 1) * a.spokes;
         for (int i = tid; i < kKdeKnots; i += kFilterThreads) {
             const double xi = sm.X[i];
-            double acc0 = 0.0;
-            double accL[kMaxLevels];
-            int nodeL[kMaxLevels];
-#pragma unroll
-            for (int l = 0; l < kMaxLevels; l++) { accL[l] = 0.0; nodeL[l] = 0; }
+            double acc = 0.0;
+            int node = 0;
+            double *yFine = Y + ((1 << a.levels) - 1) * kKdeKnots + i;
             for (int p = 0; p < nv; p++) {
-#pragma unroll
-                for (int l = 0; l < kMaxLevels; l++) {
-                    if (l < a.levels) {
-                        const int node = pNode[l * a.spokes + p];
-                        if (node != nodeL[l]) {
-                            Y[((2 << l) - 1 + nodeL[l]) * kKdeKnots + i] = accL[l];
-                            accL[l] = 0.0;
-                            nodeL[l] = node;
-                        }
-                    }
+                const int nd = fine[p];
+                if (nd != node) {
+                    yFine[node * kKdeKnots] = acc;
+                    acc = 0.0;
+                    node = nd;
                 }
                 if (i < pLo[p] || i > pHi[p]) continue;
-                const double udx = (xi - pR[p]) / hk;
-                const double e = exp(-udx * udx);
-                acc0 += e;
-#pragma unroll
-                for (int l = 0; l < kMaxLevels; l++) accL[l] += e;
+                const double udx = (xi - pR[p]) * invHk;
+                acc += exp(-udx * udx);
             }
-#pragma unroll
-            for (int l = 0; l < kMaxLevels; l++)
-                if (l < a.levels) Y[((2 << l) - 1 + nodeL[l]) * kKdeKnots + i] = accL[l];
-            Y[i] = acc0;
+            yFine[node * kKdeKnots] = acc;
+            for (int l = a.levels - 1; l >= 0; l--) {
+                double *par = Y + ((1 << l) - 1) * kKdeKnots + i;
+                const double *ch = Y + ((2 << l) - 1) * kKdeKnots + i;
+                for (int n = 0; n < (1 << l); n++) par[n * kKdeKnots] = ch[2 * n * kKdeKnots] + ch[(2 * n + 1) * kKdeKnots];
+            }
         }
         __syncthreads();
         for (int k = tid; k < nKde; k += kFilterThreads)
@@ -1542,7 +1552,7 @@ cudaError_t launch_los(const LosArgs &a, const SgPoly *sg, int nb, cudaStream_t 
     if (warps <= 0) return cudaSuccess;
     const unsigned grid = static_cast<unsigned>((warps + kLosWarps - 1) / kLosWarps);
     if (sg && los_moments_supported(a)) {
-        const size_t fsmem = sizeof(double) * (4 * (a.window / 2 + 1) + 256 + kLosWarps * 8 * kLosFastRow);
+        const size_t fsmem = sizeof(double) * (4 * a.window + 256 + kLosWarps * 8 * kLosFastRow);
         los_kernel_fast<8, true><<<grid, kLosWarps * 32, fsmem, s>>>(a, nb, *sg);
     } else if (a.bins == 256 && a.window <= kLosFastMaxWindow) {
         const size_t fsmem = sizeof(double) * (2 * a.window + kLosWarps * 8 * kLosFastRow);
