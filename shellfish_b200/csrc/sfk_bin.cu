@@ -103,7 +103,7 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
         st1 = max(static_cast<int>(r01 & 0xffffu), t0);
         len1 = max(min(static_cast<int>(r01 >> 16), t1) - st1, 0);
         st2 = max(static_cast<int>(r23 & 0xffffu), t0);
-        len2 = max(min(static_cast<int>(r23 >> 16), t1) - st2, 0);
+        len2 = max(min(static_cast<int>((r23 >> 16) & 0x7fffu), t1) - st2, 0);
         if (len1 == 0) st1 = t0;   // keep the packed start offsets within 0..31
         if (len2 == 0) st2 = t0;
     }
@@ -136,12 +136,11 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
                                 : static_cast<int>(rmeta >> 16) + (off - l1);   // LoS within the tile
         const HitRec rec = grp[r];
         const double2 cs = sTrig[ll];
-        const bool isA = rec.caseA != 0;
+        const bool isA = (rec.r23 & kHitCaseA) != 0;
         // literal geometry of insertToRing, los/halo.go:233-262
-        const double cx = rec.cx, cy = rec.cy, cz = rec.cz;
+        const double cx = rec.cx, cy = rec.cy;
         const double projDist2 = cx * cx + cy * cy;
-        double projRad2 = rad2 - cz * cz;
-        if (projRad2 < 0) projRad2 = 0;
+        const double projRad2 = rec.projRad2;   // max(rad2 - cz*cz, 0), formed once per record by hits_kernel
         const double b = cy * cs.x - cx * cs.y;
         const double b2 = b * b;
         const double m2 = projDist2 - b2;   // radicand of midDist / cMidDist
@@ -268,7 +267,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
                 for (int sub = 0; sub < kChunkRecs / 32; sub++) {
                     // a kept record has at least one LoS in the tile (bin_round relies on it)
                     const bool ov = min(static_cast<int>(rr[sub].x >> 16), t1) > max(static_cast<int>(rr[sub].x & 0xffffu), t0) ||
-                                    min(static_cast<int>(rr[sub].y >> 16), t1) > max(static_cast<int>(rr[sub].y & 0xffffu), t0);
+                                    min(static_cast<int>((rr[sub].y >> 16) & 0x7fffu), t1) > max(static_cast<int>(rr[sub].y & 0xffffu), t0);
                     const unsigned m = __ballot_sync(0xffffffffu, ov);
                     if (ov) {
                         const int at = (head + count + __popc(m & ((1u << lane) - 1u))) & (kRingSlots - 1);

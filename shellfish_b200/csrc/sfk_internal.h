@@ -47,11 +47,13 @@ static_assert(sizeof(Cand) == 24, "Cand layout");
 
 // One (particle, ring) pair that passed sphereIntersectRing, in ring frame.
 struct alignas(16) HitRec {
-    float cx, cy, cz;   // RotateVec output (float32), los/halo.go:231
-    uint32_t caseA;     // projected circle contains the centre, :241
-    uint32_t r01, r23;  // idxRange result packed lo | hi << 16: [iLo1,iHi1), [iLo2,iHi2), :284-310
+    float cx, cy;       // RotateVec output (float32) in the ring plane, los/halo.go:231
+    uint32_t r01, r23;  // idxRange result packed lo | hi << 16: [iLo1,iHi1), [iLo2,iHi2), :284-310;
+                        // bit 31 of r23: the projected circle contains the centre, :241
     double rhoS;        // rho * scale
+    double projRad2;    // max(radius^2 - cz^2, 0), :235-238 (cz itself is needed nowhere else)
 };
+constexpr uint32_t kHitCaseA = 0x80000000u;
 static_assert(sizeof(HitRec) == 32, "HitRec layout");
 
 // Work item of the hit kernels: <= 256 candidates of one halo.

@@ -211,9 +211,15 @@ __device__ bool has_nan_los(double cx, double cy, double projDist2, double phiC,
 // PRUNE == false (SFK_FLAG_NO_PRUNE, tests only) is the reference verbatim: all n LoS for a
 // centre-containing hit, float64 asin / atan2 and idxRange as written for the others, nothing
 // dropped.  tests/test_gpu_parity.py shows that both instantiations give identical integer bins.
+struct HitTmp {   // make_hit_impl's working record
+    float cx, cy, cz;
+    uint32_t caseA, r01, r23;
+    double rhoS;
+};
+
 template <bool PRUNE>
-__device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, double dPhi, double invDPhi, int n,
-                         const double *ringCos, const double *ringSin, HitRec &r) {
+__device__ bool make_hit_impl(const float *rot, const Cand &c, const HaloDev &h, double dPhi, double invDPhi, int n,
+                              const double *ringCos, const double *ringSin, HitTmp &r) {
     rotate_vec(rot, c.vx, c.vy, c.vz, r.cx, r.cy, r.cz);
     const double cx = r.cx, cy = r.cy, cz = r.cz;
     const double projDist2 = cx * cx + cy * cy;
@@ -362,6 +368,22 @@ __device__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, doub
     return true;
 }
 
+template <bool PRUNE>
+__device__ __forceinline__ bool make_hit(const float *rot, const Cand &c, const HaloDev &h, double dPhi, double invDPhi,
+                                         int n, const double *ringCos, const double *ringSin, HitRec &out) {
+    HitTmp r;
+    if (!make_hit_impl<PRUNE>(rot, c, h, dPhi, invDPhi, n, ringCos, ringSin, r)) return false;
+    out.cx = r.cx; out.cy = r.cy;
+    out.r01 = r.r01;
+    out.r23 = r.r23 | (r.caseA ? kHitCaseA : 0u);
+    out.rhoS = r.rhoS;
+    const double cz = r.cz;
+    double projRad2 = h.rad2 - cz * cz;   // as in make_hit_impl and insertToRing, halo.go:235-238
+    if (projRad2 < 0) projRad2 = 0;
+    out.projRad2 = projRad2;
+    return true;
+}
+
 // Raw hit counts: one CTA per Piece (<= 256 candidates of one halo).  Counts
 // sphereIntersectRing successes per (halo, ring) -- an upper bound of the
 // records hits_kernel will write -- and the halo's largest rho.
@@ -491,9 +513,9 @@ hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const 
 
 constexpr int kLosWarps = 8;
 // columns of the padded ln(rho) rows of los_kernel_fast<8> (256 bins): positions
-// 0 .. B + window + 8 must fit in 8 rows, so the fast path serves windows up to 231
+// 0 .. B + window + 8 must fit in 8 rows, so the fast path serves windows up to 224 (the moments path shifts by up to 7)
 constexpr int kLosFastRow = 64;
-constexpr int kLosFastMaxWindow = 8 * kLosFastRow - 256 - 24;
+constexpr int kLosFastMaxWindow = 8 * kLosFastRow - 256 - 32;
 
 __device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8000000000000ll); }
 
@@ -526,8 +548,8 @@ __device__ __forceinline__ double fast_log(double x, const double2 *tab) {
 //
 // MOMENTS == true (default whenever every ln rho is finite, i.e. rho_bg > 0): the two
 // Savitzky-Golay FIRs are evaluated through the five sliding polynomial moments of
-// sfk_sgmath.cuh -- one direct pass over the window for the lane's first output, PER - 1
-// binomial shifts for the rest -- and ln() is
+// sfk_sgmath.cuh -- one direct pass over the window for the lane's first output (taps +-k
+// paired: 7 operations per two taps), PER - 1 binomial shifts for the rest -- and ln() is
 // fast_log.  Same values as the tap loop to ~1e-13 (tests/test_sgmoments.py), same R_sp.
 // MOMENTS == false: ConvolveAt verbatim (filter.go:104-161) as a register sliding window:
 // per tap one shared-memory read of ln(rho) per lane (conflict-free permuted layout) and one
@@ -546,16 +568,19 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
     // position p = i + padL, padL = center + 1, the positions below / above hold sample 0 / B-1.
     // Position p is stored at row p % PER, column p / PER, so the FIR below reads row jj at
     // column (lane + const): conflict-free and with no index arithmetic.
-    const int padL = center + 1;
+    // The moments path shifts everything by `shift` positions so that the window centre of a
+    // lane's first output sits on row 0 (see the anchor below).
+    const int shift = MOMENTS ? (PER - ((1 + center) % PER)) % PER : 0;
+    const int padL = center + 1 + shift;
     constexpr int rowLen = kLosFastRow;
     double2 *taps = reinterpret_cast<double2 *>(sm);                       // tap loop: [window] (value, deriv)
-    double *upow = sm;                                                     // moments: [window][4] u, u^2, u^3, u^4 of every tap
-    const int tabOff = MOMENTS ? 4 * window : 2 * window;
+    double *upow = sm;                                                     // moments: [center + 1][4] u, u^2, u^3, u^4 of tap pair k
+    const int tabOff = MOMENTS ? 4 * (center + 1) : 2 * window;
     const double2 *logTab = reinterpret_cast<const double2 *>(sm + tabOff);   // moments: [128]
     double *ys = sm + tabOff + (MOMENTS ? 256 : 0) + (threadIdx.x >> 5) * (PER * rowLen);
     if (MOMENTS) {
-        for (int k = threadIdx.x; k < window; k += blockDim.x) {
-            const double u = static_cast<double>(k - center) / static_cast<double>(center);
+        for (int k = threadIdx.x; k <= center; k += blockDim.x) {
+            const double u = static_cast<double>(k) / static_cast<double>(center);
             upow[4 * k] = u; upow[4 * k + 1] = u * u; upow[4 * k + 2] = u * u * u; upow[4 * k + 3] = (u * u) * (u * u);
         }
         for (int k = threadIdx.x; k < 256; k += blockDim.x) sm[tabOff + k] = a.logTab[k];
@@ -616,34 +641,33 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
         if (lane == 0) *out = nan_f64();
         return;
     }
-    // Output i0 + c reads positions lane*PER + c + 1 + j, j = 0 .. window-1 (tap j, sample
+    // Output i0 + c reads positions lane*PER + shift + c + 1 + j, j = 0 .. window-1 (tap j, sample
     // i0 + c - center + j); position lane*PER + q sits at row q % PER, column lane + q / PER.
     const double *yl = ys + lane;
     double s0[PER], s1[PER];
     if (MOMENTS) {
-        // Anchor: the five moments of output c = 0 over taps 0 .. window-1, i.e. positions q = 1 ..
-        // window, walked in aligned blocks of PER positions so that the row of every read is a
-        // compile-time offset and only the column advances (no index arithmetic per tap).
-        double M[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        // Anchor: the five moments of output c = 0.  Its window centre is position qc = shift + 1 +
+        // center, a multiple of PER by the choice of `shift`, i.e. row 0 of column c0.  Taps +-k are
+        // paired (7 operations per two taps); with k = PER*m + j the sample at qc + k sits at row j,
+        // column c0 + m, and the one at qc - k at row (PER - j) % PER, column c0 - m - (j > 0): the
+        // rows are compile-time offsets and only the columns move (no index arithmetic per tap).
+        const int c0 = (shift + 1 + center) / PER;
+        double M[5] = {yl[c0], 0.0, 0.0, 0.0, 0.0};
+        for (int m = 0; m * PER <= center; m++) {
+            const double *yp = yl + c0 + m, *ym = yl + c0 - m;
+            const double *ub = upow + 4 * PER * m;
 #pragma unroll
-        for (int j = 1; j < PER; j++) sg_accumulate(M, yl[j * rowLen], upow + 4 * (j - 1));   // q = 1 .. PER-1
-        const int bLast = window / PER;                   // the block holding q = window
-        for (int b = 1; b < bLast; b++) {
-            const double *yb = yl + b;
-            const double *ub = upow + 4 * (b * PER - 1);
-#pragma unroll
-            for (int j = 0; j < PER; j++) sg_accumulate(M, yb[j * rowLen], ub + 4 * j);
-        }
-        if (bLast >= 1) {
-#pragma unroll
-            for (int j = 0; j < PER; j++)
-                if (bLast * PER + j <= window) sg_accumulate(M, yl[j * rowLen + bLast], upow + 4 * (bLast * PER + j - 1));
+            for (int j = 0; j < PER; j++) {
+                const int k = m * PER + j;
+                if ((j > 0 || m > 0) && k <= center)
+                    sg_accumulate_pair(M, yp[j * rowLen], ym[((PER - j) % PER) * rowLen - (j > 0 ? 1 : 0)], ub + 4 * j);
+            }
         }
 #pragma unroll
         for (int c = 0; c < PER; c++) {
             sg_outputs(M, sg, s0[c], s1[c]);
             if (c < PER - 1) {
-                const int qo = c + 1, qi = c + 1 + window;
+                const int qo = shift + c + 1, qi = shift + c + 1 + window;
                 sg_advance(M, sg, yl[(qo % PER) * rowLen + qo / PER], yl[(qi % PER) * rowLen + qi / PER]);
             }
         }
@@ -1552,7 +1576,7 @@ cudaError_t launch_los(const LosArgs &a, const SgPoly *sg, int nb, cudaStream_t 
     if (warps <= 0) return cudaSuccess;
     const unsigned grid = static_cast<unsigned>((warps + kLosWarps - 1) / kLosWarps);
     if (sg && los_moments_supported(a)) {
-        const size_t fsmem = sizeof(double) * (4 * a.window + 256 + kLosWarps * 8 * kLosFastRow);
+        const size_t fsmem = sizeof(double) * (4 * (a.window / 2 + 1) + 256 + kLosWarps * 8 * kLosFastRow);
         los_kernel_fast<8, true><<<grid, kLosWarps * 32, fsmem, s>>>(a, nb, *sg);
     } else if (a.bins == 256 && a.window <= kLosFastMaxWindow) {
         const size_t fsmem = sizeof(double) * (2 * a.window + kLosWarps * 8 * kLosFastRow);
