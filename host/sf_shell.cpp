@@ -348,6 +348,7 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
     p.subsample_factor = c.subsampleFactor; p.los_slope_cutoff = c.losSlopeCutoff;
     p.background_rho_mult = c.backgroundRhoMult; p.percentile_profile = c.percentileProfile;
     p.percentile = c.percentile; p.seed = seed;
+    const auto tCreate = std::chrono::steady_clock::now();
     std::vector<sfk_ctx *> ctxs(G, nullptr);
     struct Guard { std::vector<sfk_ctx *> &c; ~Guard() { for (sfk_ctx *x : c) if (x) sfk_destroy(x); } } guard{ctxs};
     {   // CUDA context creation takes a second per device: one thread each
@@ -374,6 +375,7 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
     auto since = [&](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     };
+    if (perf) std::fprintf(stderr, "Setup: %.6gs creating %d GPU context(s)\n", since(tCreate), G);
     for (const auto &kv : idxBins) {
         const int64_t snap = kv.first;
         if (snap == -1) continue;
