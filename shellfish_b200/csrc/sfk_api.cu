@@ -905,8 +905,10 @@ int sfk_finish_snapshot(sfk_ctx *ctx, double *coeffs, int32_t *status) try {
     rc = stage_scale(ctx, false);
     if (rc) return rc;
     // batches of halos in input order, bounded by hit-record and grid memory
-    const int64_t maxBatch = 64;
-    const int64_t hitBudget = (int64_t(6) << 30) / static_cast<int64_t>(sizeof(HitRec));
+    // 256 halos in flight: 13 GB of bin grid + up to 24 GB of hit records out of 180 GB; fewer,
+    // larger batches mean fewer kernel tails and fewer latency-bound fit launches per snapshot
+    const int64_t maxBatch = 256;
+    const int64_t hitBudget = (int64_t(24) << 30) / static_cast<int64_t>(sizeof(HitRec));
     size_t pos = 0;
     while (pos < ctx->order.size()) {
         std::vector<int32_t> batch;
