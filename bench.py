@@ -158,7 +158,12 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     halos, blocks, mass, config, meta = workload(args)
-    n = max(1, min(args.cpu_halos, len(halos)))
+    # bounded sample: the first n halos per step, n chosen so that warm-up + timed steps take about
+    # three minutes (one halo of this workload costs the port ~3.6 s on 16 cores); halos are
+    # independent, so halos/s does not depend on n
+    est = 3.6 * 16.0 / max(cores, 1)
+    n = int(180.0 / (max(1, args.steps + args.warmup) * est))
+    n = max(1, min(n, args.cpu_halos, len(halos)))
     for _ in range(args.warmup):
         cpu_sample(args, halos, blocks, mass, n, cores)
     tot, inter = 0.0, 0
@@ -179,12 +184,13 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-# ncu --set full capture of one bin_kernel launch (profiles/, see the note in the line):
-# dram__bytes_read.sum + dram__bytes_write.sum over the launch's algorithmic bytes, and warp
-# instructions executed per ProfileRing.Insert
-NCU_CAPTURE = "profiles/r01g_bin_kernel_v6_by_line.txt"
-NCU_TRAFFIC_RATIO = (2.206682 + 0.804353) / 1.704478
-NCU_WARP_INST_PER_INTERSECTION = 10.08e9 / 1.26e9 / 1.0   # 10.08e9 warp instructions, 1.26e9 inserts (16 halos)
+# ncu --set full capture of one bin_kernel launch (profiles/ncu_bin_constants.json, written by
+# profiles/make_ncu_constants.py): dram__bytes_read.sum + dram__bytes_write.sum over the launch's
+# algorithmic bytes, and warp instructions executed per ProfileRing.Insert
+_NCU = json.load(open(os.path.join(ROOT, "profiles", "ncu_bin_constants.json")))
+NCU_CAPTURE = _NCU["capture"]
+NCU_TRAFFIC_RATIO = _NCU["traffic_ratio"]
+NCU_WARP_INST_PER_INTERSECTION = _NCU["warp_inst_per_intersection"]
 
 
 def main():

@@ -30,7 +30,11 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:bin_
     -o $OUT/${TAG}_bin $B64 --no-e2e > $OUT/${TAG}_ncu_bin.log 2>&1
 echo "ncu full (bin) rc=$?"
 if [ -f $OUT/${TAG}_bin.ncu-rep ]; then
-    python profiles/ncu_by_line.py $OUT/${TAG}_bin.ncu-rep sfk_bin bin_kernel > $OUT/${TAG}_bin_kernel_by_line.txt 2>&1 || true
+    python profiles/ncu_by_line.py $OUT/${TAG}_bin.ncu-rep sfk_bin bin_kernelILb0 > $OUT/${TAG}_bin_kernel_by_line.txt 2>&1 || true
+    cp profiles/ncu_bin_constants.json $OUT/${TAG}_ncu_bin_constants_before.json
+    cp $OUT/${TAG}_bin_kernel_by_line.txt profiles/${TAG}_bin_kernel_by_line.txt
+    python profiles/make_ncu_constants.py profiles/${TAG}_bin_kernel_by_line.txt $OUT/${TAG}_bench64.json > $OUT/${TAG}_ncu_constants.log 2>&1 \
+        && cp profiles/ncu_bin_constants.json $OUT/${TAG}_ncu_bin_constants.json || true
 fi
 
 # the other kernels of one batch: hits, los, filter, the four fit kernels
