@@ -528,6 +528,13 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
     outLines.push_back(CommentString({"ID", "Snapshot"}, {"X [cMpc/h]", "Y [cMpc/h]", "Z [cMpc/h]", "R200m [cMpc/h]", "P_ijk"},
                                      {0, 1, 2, 3, 4, 5, 6}, {1, 1, 1, 1, 1, 1, static_cast<int>(rowLen)}));
     outLines.insert(outLines.end(), lines.begin(), lines.end());
+    if (perf) std::fprintf(stderr, "Catalog formatted\nTime: %.6gs\n", since(tStart));
+    {   // freeing tens of GB per device takes a while: one thread per context
+        std::vector<std::thread> th;
+        for (int d = 0; d < G; d++) th.emplace_back([&, d] { sfk_destroy(ctxs[d]); ctxs[d] = nullptr; });
+        for (std::thread &t : th) t.join();
+    }
+    if (perf) std::fprintf(stderr, "Contexts released\nTime: %.6gs\n", since(tStart));
     return "";
 }
 
