@@ -422,7 +422,7 @@ hit_count_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, c
     if (lane_id() == 0 && bits) atomicMax(&rhoMaxBits[pc.halo], bits);
 }
 
-constexpr int kHitRingChunk = 64;   // rings per queue pass: 256 x 64 entries of 4 B = 64 KB
+constexpr int kHitRingChunk = 32;   // rings per queue pass: 256 x 32 entries of 4 B = 32 KB
 
 // Ring-frame records: one CTA per Piece.  Phase 1 tests every (candidate,
 // ring) pair of a ring chunk and queues the hits in shared memory; phase 2
@@ -436,7 +436,7 @@ constexpr int kHitRingChunk = 64;   // rings per queue pass: 256 x 64 entries of
 // the bottom of the queue and all others from the top, and a warp of phase 2
 // runs one branch (the few misfiled entries at |v| ~ rad only cost divergence).
 template <bool PRUNE>
-__global__ void __launch_bounds__(kHitThreads)
+__global__ void __launch_bounds__(kHitThreads, 4)
 hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const float *norms,
             const float *rots, const double *ringCos, const double *ringSin, int rings, int spokes,
             double dPhi, const int64_t *hitOffset, uint32_t *hitCursor, const int32_t *haloSlot,
@@ -659,8 +659,13 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
 #pragma unroll
             for (int j = 0; j < PER; j++) {
                 const int k = m * PER + j;
-                if ((j > 0 || m > 0) && k <= center)
-                    sg_accumulate_pair(M, yp[j * rowLen], ym[((PER - j) % PER) * rowLen - (j > 0 ? 1 : 0)], ub + 4 * j);
+                if ((j > 0 || m > 0) && k <= center) {
+                    // (u, u^2) from the table, u^3 and u^4 formed here: the pass is bound by the
+                    // shared-memory pipe, the FP64 pipe has room
+                    const double2 u12 = *reinterpret_cast<const double2 *>(ub + 4 * j);
+                    const double up[4] = {u12.x, u12.y, u12.x * u12.y, u12.y * u12.y};
+                    sg_accumulate_pair(M, yp[j * rowLen], ym[((PER - j) % PER) * rowLen - (j > 0 ? 1 : 0)], up);
+                }
             }
         }
 #pragma unroll
