@@ -12,9 +12,11 @@
 // about one in four -- into its private 64-slot ring in shared memory with
 // cp.async.  Whenever 32 records are waiting, their ranges are clipped to the
 // tile, a warp scan turns the clipped lengths into a list of (record, LoS)
-// pairs, and the pairs are processed 32 at a time with one pair per lane (each
-// lane finds its record by a shuffle binary search over the scan), so every
-// lane does useful work whatever the range widths.
+// pairs, and the pairs are processed 32 at a time with one pair per lane (a
+// lane finds its record from one REDUX.OR over the records' first-pair indices
+// and two POPCs), so every lane does useful work whatever the range widths.
+// A CTA that owns its 32 rows alone stores the finished tile into the grid
+// (no memset, no read-modify-write); otherwise it adds it with RED.64.
 //
 // Arithmetic.  Everything that DECIDES something is evaluated literally, in
 // the reference's operation order with no FMA contraction (-fmad=false): the
@@ -91,7 +93,7 @@ constexpr int kRingSlots = 64;    // per-warp ring of records that touch the til
 // tile, expand to (record, LoS) pairs, evaluate the chords and add them to the tile.
 template <bool TAPS>
 __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring, int head, int cnt, int lane, int t0,
-                                          int t1, int bins, double rMin, double rMax, double invRMin, double rad2,
+                                          int t1, int bins, double rMin, double rMax, double invRMin,
                                           double invDr, float cK, const double2 *sTrig, const double *sInvG,
                                           uint32_t *lo, uint32_t *hi, size_t tapRing, unsigned &nIns) {
     // rounds take 32 records at a time, so head is 0 or 32 and the round never wraps
@@ -185,10 +187,13 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
     }
 }
 
-template <bool TAPS>
+// BINS: RadialBins as a compile-time constant (256, the default), or 0 for any other value; with
+// it the high words sit at a constant offset from the low ones and the row stride folds into
+// the atomics' addresses.
+template <bool TAPS, int BINS>
 __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
-    const int bins = a.bins;
+    const int bins = BINS ? BINS : a.bins;
     const int stride = bins + 1;   // +1: slot for a start/end edge that lands exactly on rMax
     // byte offsets from the one dynamic array: the compiler must keep seeing shared addresses
     HitRec *rings = reinterpret_cast<HitRec *>(smemRaw);                          // [warps][kRingSlots]
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     unsigned nIns = 0;
 
     {
-        const double rMin = h.rMin, rMax = h.rMax, invRMin = h.invRMin, rad2 = h.rad2;
+        const double rMin = h.rMin, rMax = h.rMax, invRMin = h.invRMin;
         const double invDr = a.invDr;
         const float cK = a.cK;
         const size_t tapRing = (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes;
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
                     if (count >= 32) {
                         cp_async_wait_all();
                         __syncwarp();
-                        bin_round<TAPS>(a, wring, head, 32, lane, t0, t1, bins, rMin, rMax, invRMin, rad2, invDr, cK,
+                        bin_round<TAPS>(a, wring, head, 32, lane, t0, t1, bins, rMin, rMax, invRMin, invDr, cK,
                                         sTrig, sInvG, lo, hi, tapRing, nIns);
                         __syncwarp();   // the slots may be overwritten from here on
                         head = (head + 32) & (kRingSlots - 1);
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
             } else {
                 cp_async_wait_all();
                 __syncwarp();
-                bin_round<TAPS>(a, wring, head, count, lane, t0, t1, bins, rMin, rMax, invRMin, rad2, invDr, cK,
+                bin_round<TAPS>(a, wring, head, count, lane, t0, t1, bins, rMin, rMax, invRMin, invDr, cK,
                                 sTrig, sInvG, lo, hi, tapRing, nIns);
                 count = 0;
             }
@@ -378,14 +383,16 @@ cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s) {
     if (nb <= 0) return cudaSuccess;
     const size_t smem = bin_smem_bytes(a.bins);
     {   // per device, so set it on every launch
-        cudaError_t e = taps ? cudaFuncSetAttribute(bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                             : cudaFuncSetAttribute(bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(bin_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bin_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bin_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
     }
     const int nTiles = (a.spokes + kTileLos - 1) / kTileLos;
     dim3 grid(nTiles * a.chunks, a.rings, nb);
-    if (taps) bin_kernel<true><<<grid, kBinThreads, smem, s>>>(a);
-    else bin_kernel<false><<<grid, kBinThreads, smem, s>>>(a);
+    if (taps) bin_kernel<true, 0><<<grid, kBinThreads, smem, s>>>(a);
+    else if (a.bins == 256) bin_kernel<false, 256><<<grid, kBinThreads, smem, s>>>(a);
+    else bin_kernel<false, 0><<<grid, kBinThreads, smem, s>>>(a);
     if (bin_stores_whole_grid(a)) bin_overflow_kernel<<<1, 256, 0, s>>>(a.grid, a.ovfList, a.ovfCount, a.ovfCap);
     return cudaGetLastError();
 }
