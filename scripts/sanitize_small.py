@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""A tiny end-to-end pass for compute-sanitizer (memcheck / racecheck / initcheck):
+"""A tiny end-to-end pass over every kernel path; also the driver for compute-sanitizer where the
+tool is available (it is closed on the build pool):
    compute-sanitizer --tool memcheck python scripts/sanitize_small.py
 Covers the default path (TMA cull, two-ended hit queue, plain-store bin flush, moments los,
 filter, fit), the tap instantiation, a ragged configuration (generic los kernel, RED flush) and
