@@ -163,6 +163,8 @@ struct sfk_ctx {
     ncclComm_t comm = nullptr;
     int commRank = 0, commSize = 1;
     DevBuf<double> dRspRows;
+    DevBuf<long long> dFlatList;
+    DevBuf<unsigned long long> dFlatCount;
 
     sfk_stats stats{};
     StageTimer timer;
@@ -582,6 +584,9 @@ int stage_analyze(sfk_ctx *ctx, int nb, int rowBegin = 0, int rowCount = -1) {
     la.dLim = ctx->p.los_slope_cutoff;
     la.losBegin = static_cast<int64_t>(rowBegin) * n; la.losCount = static_cast<int64_t>(rowCount) * n;
     la.rspBySlot = part ? 1 : 0;
+    CU(ctx->dFlatList.ensure(static_cast<size_t>(std::max<int64_t>(la.losCount, 1))));
+    CU(ctx->dFlatCount.ensure(1));
+    la.flatList = ctx->dFlatList.p; la.flatCount = ctx->dFlatCount.p; la.listMode = 0;
     // Sliding-moment smoothing only when every ln(rho) is finite and normal (rho_bg > 0; with
     // Gadget-2's MinMass() == 0 the reference's -Inf / NaN propagation must stay sample-exact).
     bool moments = !(ctx->p.flags & SFK_FLAG_LOS_TAPLOOP) && ctx->sgReady && los_moments_supported(la);
@@ -589,7 +594,7 @@ int stage_analyze(sfk_ctx *ctx, int nb, int rowBegin = 0, int rowCount = -1) {
         if (h.valid && !(h.defaultRho >= 1e-290 && h.defaultRho <= 1e290 && h.quantum >= 1e-290)) moments = false;
     ctx->timer.begin(ST_LOS, st);
     CU(launch_los(la, moments ? &ctx->sg : nullptr, nb, st));
-    ctx->stats.launches++;
+    ctx->stats.launches += moments ? 2 : 1;
     ctx->timer.end(ST_LOS, st);
 
     FilterArgs fa{};

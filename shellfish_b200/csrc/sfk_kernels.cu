@@ -591,8 +591,14 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
     const int lane = lane_id();
     const int64_t gw0 = static_cast<int64_t>(blockIdx.x) * kLosWarps + (threadIdx.x >> 5);
     const int64_t perHalo = static_cast<int64_t>(a.rings) * a.spokes;
-    if (gw0 >= a.losCount) return;
-    const int64_t gw = a.losBegin + gw0;
+    int64_t gw;
+    if (!MOMENTS && a.listMode) {   // second pass: the lines the moments kernel handed over
+        if (gw0 >= static_cast<int64_t>(*a.flatCount)) return;
+        gw = a.flatList[gw0];
+    } else {
+        if (gw0 >= a.losCount) return;
+        gw = a.losBegin + gw0;
+    }
     const int slot = static_cast<int>(gw / perHalo);
     const int64_t rl = gw - slot * perHalo;
     const int haloIdx = a.batchHalos[slot];
@@ -617,6 +623,7 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
     long long acc = incl - run;
     const double q = h.quantum, bg = h.defaultRho;
     double yFirst = 0.0, yLast = 0.0;
+    bool flatLane = true;   // my PER values are all equal
 #pragma unroll
     for (int c = 0; c < PER; c++) {
         acc += d[c];
@@ -627,7 +634,16 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
         const int p = lane * PER + c + padL;
         ys[(p % PER) * rowLen + p / PER] = y;
         if (c == 0) yFirst = y;
-        if (c == PER - 1) yLast = y;
+        if (MOMENTS && c > 0) flatLane = flatLane && y == yLast;
+        yLast = y;
+    }
+    if (MOMENTS) {
+        // A run of >= 61 equal values (with the 61 repeated samples of the Extension boundary: a
+        // whole window) covers >= 6 whole lanes, each flat and equal to the next lane's first value.
+        const double nextFirst = __shfl_down_sync(0xffffffffu, yFirst, 1);
+        const unsigned fm = __ballot_sync(0xffffffffu, flatLane && (lane == 31 || yLast == nextFirst));
+        const unsigned run6 = fm & (fm >> 1) & (fm >> 2) & (fm >> 3) & (fm >> 4) & (fm >> 5);
+        if (run6 != 0 && lane == 0) a.flatList[atomicAdd(a.flatCount, 1ull)] = gw;
     }
     // Extension: repeat the end samples
     yFirst = __shfl_sync(0xffffffffu, yFirst, 0);
@@ -1582,7 +1598,14 @@ cudaError_t launch_los(const LosArgs &a, const SgPoly *sg, int nb, cudaStream_t 
     const unsigned grid = static_cast<unsigned>((warps + kLosWarps - 1) / kLosWarps);
     if (sg && los_moments_supported(a)) {
         const size_t fsmem = sizeof(double) * (4 * (a.window / 2 + 1) + 256 + kLosWarps * 8 * kLosFastRow);
+        cudaError_t e = cudaMemsetAsync(a.flatCount, 0, sizeof(unsigned long long), s);
+        if (e != cudaSuccess) return e;
         los_kernel_fast<8, true><<<grid, kLosWarps * 32, fsmem, s>>>(a, nb, *sg);
+        // the lines with exact-tie hazards again, literally; warps beyond the list's length exit at once
+        LosArgs b = a;
+        b.listMode = 1;
+        const size_t tsmem = sizeof(double) * (2 * a.window + kLosWarps * 8 * kLosFastRow);
+        los_kernel_fast<8, false><<<grid, kLosWarps * 32, tsmem, s>>>(b, nb, SgPoly{});
     } else if (a.bins == 256 && a.window <= kLosFastMaxWindow) {
         const size_t fsmem = sizeof(double) * (2 * a.window + kLosWarps * 8 * kLosFastRow);
         los_kernel_fast<8, false><<<grid, kLosWarps * 32, fsmem, s>>>(a, nb, SgPoly{});

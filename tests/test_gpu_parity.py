@@ -460,3 +460,17 @@ def test_product_bin_kernel_writes_the_grid_whose_taps_are_checked(rings, n):
     bg = rp.min()
     rho = np.maximum(rho, bg)
     assert np.max(np.abs(rho - rp) / np.maximum(np.abs(rp), bg)) <= RTOL
+
+
+def test_sparse_halos_with_flat_profile_windows():
+    """Halos of 1500 particles: many lines of sight are clamped to the background, or see no kernel
+    edge, over more than a smoothing window.  There the reference's smoothed values at consecutive
+    bins are bit-identical (identical window contents) and SplashbackRadius' strict comparisons see
+    exact ties; sliding moments would break them (129 of 4608 lines of sight differed before such
+    lines were handed to the literal tap loop, scripts/experiments/flat_profile_ties.py)."""
+    halos, blocks, mass = synth.make_box(5, 20.0, 6, 1500, 3000, 2, r200m_range=(0.6, 0.9))
+    ctx, c, s, ref = run_both(halos, blocks, mass, rings=3)
+    assert_parity(ctx, c, s, ref, len(halos))
+    # the product instantiation (no taps) takes the same decisions
+    _, c2, s2 = api.run_shell(api.default_params(seed=1337, rings=3), mass, halos, blocks)
+    assert np.array_equal(c2, c) and np.array_equal(s2, s)
