@@ -45,7 +45,7 @@ extern "C" {
 /* A/B and tests: evaluate the two Savitzky-Golay filters of Smooth (smooth.go:46-81) with
  * the literal 2 x SmoothingWindow tap loop of ConvolveAt (filter.go:104-161) and libm's log.
  * The default evaluates them through five sliding polynomial moments (same values to
- * ~1e-13, same R_sp) whenever RadialBins = 256, SmoothingWindow <= 224 and the background
+ * ~1e-13, same R_sp) whenever RadialBins = 256, 29 <= SmoothingWindow <= 224 and the background
  * density is positive; every other configuration always takes the tap loop. */
 #define SFK_FLAG_LOS_TAPLOOP 2u
 /* Tests only: build the ring-frame hit records exactly as insertToRing / idxRange do

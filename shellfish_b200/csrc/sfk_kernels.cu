@@ -638,12 +638,15 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
         yLast = y;
     }
     if (MOMENTS) {
-        // A run of >= 61 equal values (with the 61 repeated samples of the Extension boundary: a
-        // whole window) covers >= 6 whole lanes, each flat and equal to the next lane's first value.
+        // Two neighbouring outputs see identical window contents once center + 2 consecutive values
+        // are equal (at an array end the Extension boundary repeats the end sample).  Such a run
+        // covers >= flatLanes = (center - 6) / PER whole lanes, each flat and equal to the next
+        // lane's first value (121 taps: 6 lanes; 31 taps: 1 lane).
         const double nextFirst = __shfl_down_sync(0xffffffffu, yFirst, 1);
         const unsigned fm = __ballot_sync(0xffffffffu, flatLane && (lane == 31 || yLast == nextFirst));
-        const unsigned run6 = fm & (fm >> 1) & (fm >> 2) & (fm >> 3) & (fm >> 4) & (fm >> 5);
-        if (run6 != 0 && lane == 0) a.flatList[atomicAdd(a.flatCount, 1ull)] = gw;
+        unsigned run = fm;
+        for (int k = 1; k < a.flatLanes; k++) run &= fm >> k;
+        if (run != 0 && lane == 0) a.flatList[atomicAdd(a.flatCount, 1ull)] = gw;
     }
     // Extension: repeat the end samples
     yFirst = __shfl_sync(0xffffffffu, yFirst, 0);
@@ -1589,7 +1592,8 @@ cudaError_t launch_percentile(const PercentileArgs &a, int nb, cudaStream_t s) {
 }
 
 // Sliding-moment form of the fast path; false when the shape is not served.
-bool los_moments_supported(const LosArgs &a) { return a.bins == 256 && a.window <= kLosFastMaxWindow && a.window >= 7; }
+// (windows below 29 taps would need runs shorter than a lane to be recognised: tap loop)
+bool los_moments_supported(const LosArgs &a) { return a.bins == 256 && a.window <= kLosFastMaxWindow && a.window >= 29; }
 
 cudaError_t launch_los(const LosArgs &a, const SgPoly *sg, int nb, cudaStream_t s) {
     if (nb <= 0) return cudaSuccess;
@@ -1600,7 +1604,9 @@ cudaError_t launch_los(const LosArgs &a, const SgPoly *sg, int nb, cudaStream_t 
         const size_t fsmem = sizeof(double) * (4 * (a.window / 2 + 1) + 256 + kLosWarps * 8 * kLosFastRow);
         cudaError_t e = cudaMemsetAsync(a.flatCount, 0, sizeof(unsigned long long), s);
         if (e != cudaSuccess) return e;
-        los_kernel_fast<8, true><<<grid, kLosWarps * 32, fsmem, s>>>(a, nb, *sg);
+        LosArgs m = a;
+        m.flatLanes = (a.window / 2 - 6) / 8;
+        los_kernel_fast<8, true><<<grid, kLosWarps * 32, fsmem, s>>>(m, nb, *sg);
         // the lines with exact-tie hazards again, literally; warps beyond the list's length exit at once
         LosArgs b = a;
         b.listMode = 1;

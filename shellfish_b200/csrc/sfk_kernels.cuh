@@ -66,8 +66,8 @@ struct LosArgs {
     // rspBySlot: rsp is indexed by that flat order instead of by halo (ring-partitioned analysis)
     int64_t losBegin, losCount;
     int rspBySlot;
-    // Lines of sight whose ln(rho) holds a long run of identical values (>= 6 whole lanes, i.e. at
-    // least 48 bins: a profile clamped to the background, or without any kernel edge, over half a
+    // Lines of sight whose ln(rho) holds a long run of identical values (>= flatLanes whole lanes of
+    // 8 bins: a profile clamped to the background, or without any kernel edge, over half a
     // smoothing window).  There the reference's outputs at consecutive bins are bit-identical --
     // identical window contents -- and its strict comparisons see exact ties, which the sliding
     // moments cannot reproduce; the moments kernel lists such lines and the literal tap loop
@@ -75,6 +75,7 @@ struct LosArgs {
     long long *flatList;         // [nb * rings * spokes]
     unsigned long long *flatCount;   // [1]
     int listMode;                // tap-loop pass over flatList instead of [losBegin, losBegin + losCount)
+    int flatLanes;               // run length, in whole lanes, that marks a line for the tap loop
 };
 
 struct FilterArgs {

@@ -474,3 +474,24 @@ def test_sparse_halos_with_flat_profile_windows():
     # the product instantiation (no taps) takes the same decisions
     _, c2, s2 = api.run_shell(api.default_params(seed=1337, rings=3), mass, halos, blocks)
     assert np.array_equal(c2, c) and np.array_equal(s2, s)
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_randomized_small_configurations(case):
+    """Seeded random shapes and sizes against the oracle: sparse and dense halos, ragged ring /
+    spoke / bin counts (fast and generic los kernels, stored and RED-added bin tiles), windows,
+    KDE levels, orders, subsampling, several blocks with periodic wrap."""
+    rng = np.random.default_rng(1000 + case)
+    n_halos = int(rng.integers(1, 5))
+    n_per = int(rng.choice([400, 1500, 6000, 20000]))
+    box = float(rng.choice([6.0, 12.0, 25.0]))
+    cells = int(rng.integers(1, 4))
+    halos, blocks, mass = synth.make_box(2000 + case, box, n_halos, n_per, int(rng.integers(0, 4000)), cells,
+                                         r200m_range=(0.5, 0.9))
+    bins = int(rng.choice([256, 256, 128, 200]))
+    kw = dict(rings=int(rng.integers(3, 9)), spokes=int(rng.choice([256, 64, 100, 160])), radial_bins=bins,
+              smoothing_window=int(rng.choice([w for w in (31, 61, 121) if w < bins - 8])),
+              levels=int(rng.integers(1, 4)), order=int(rng.integers(1, 5)),
+              subsample_factor=int(rng.choice([1, 1, 2])), eta=float(rng.choice([10.0, 6.0, 14.0])))
+    ctx, c, s, ref = run_both(halos, blocks, mass, **kw)
+    assert_parity(ctx, c, s, ref, n_halos)
