@@ -88,6 +88,8 @@ typedef struct {
     double ms_cull, ms_hits, ms_bin, ms_los, ms_filter, ms_fit; /* CUDA-event time per stage */
     int64_t bin_launches;    /* launches of the binning kernel */
     int64_t launches;        /* kernel launches of this library since begin_snapshot */
+    int64_t n_los_literal;   /* lines of sight with long plateaus, smoothed by the literal tap loop
+                                instead of sliding moments (exact ties; 0 for well-sampled halos) */
 } sfk_stats;
 
 /* Number of CUDA devices visible to the process (0 when there is none). */

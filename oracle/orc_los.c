@@ -11,8 +11,19 @@
 
 /* ---------------------------------------------------------- ProfileRing */
 
+/* "Exact bins" variant (orc_set_exact_bins), NOT the reference's arithmetic: the same algorithm
+ * with the bin sums carried exactly.  The reference adds rho*(1-rem) and rho*rem, two rounded
+ * products whose sum is rho only up to an ulp, so two stretches of a profile with the same true
+ * density (the plateau inside one particle's kernel, twice along a sparse line of sight) differ
+ * by rounding noise, and SplashbackRadius' strict comparisons then decide on that noise.  The
+ * CUDA path accumulates exact integers (rho - q, q).  This variant lets the tests separate the
+ * two effects: it adds (rho - a, a) with a = rho*rem and keeps every bin as a double-double. */
+static int g_exact_bins = 0;
+void orc_set_exact_bins(int on) { g_exact_bins = on; }
+
 struct orc_ring {
     double *derivs; /* [n][bins], LoS-major (profile_ring.go:35) */
+    double *comp;   /* exact-bins variant: low words of the double-double sums, else NULL */
     int bins, n;
     double lowR, highR, dr;
     /* parity taps, owned by the halo (NULL when disabled) */
@@ -24,6 +35,7 @@ struct orc_ring {
 static void ring_init(orc_ring *p, double lowR, double highR, int bins, int n) {
     memset(p, 0, sizeof *p);
     p->derivs = (double *)calloc((size_t)bins * (size_t)n, sizeof(double));
+    p->comp = g_exact_bins ? (double *)calloc((size_t)bins * (size_t)n, sizeof(double)) : NULL;
     p->bins = bins;
     p->n = n;
     p->lowR = lowR;
@@ -40,6 +52,7 @@ orc_ring *orc_ring_new(double lowR, double highR, int bins, int n) {
 void orc_ring_free(orc_ring *p) {
     if (!p) return;
     free(p->derivs);
+    free(p->comp);
     free(p);
 }
 
@@ -48,9 +61,29 @@ const double *orc_ring_derivs(const orc_ring *p) { return p->derivs; }
 /* One `p.derivs[k] += v` where k may be one past this LoS's row when modf
  * returns idx == bins (profile_ring.go:102-106 has no upper check).  Go only
  * panics when k runs off the whole slice. */
+static inline void dd_add(double *hi, double *lo, double v) {   /* Knuth two-sum */
+    double s = *hi + v;
+    double bb = s - *hi;
+    double e = (*hi - (s - bb)) + (v - bb);
+    *hi = s;
+    *lo += e;
+}
+
 static inline void ring_add(orc_ring *p, int64_t k, double v) {
     if (k < 0 || k >= (int64_t)p->bins * p->n) { p->oob++; return; }
-    p->derivs[k] += v;
+    if (p->comp) dd_add(&p->derivs[k], &p->comp[k], v);
+    else p->derivs[k] += v;
+}
+
+/* exact-bins variant of `derivs[idx] += sign*rho*(1-rem); derivs[idx+1] += sign*rho*rem` */
+static inline void ring_add_split_exact(orc_ring *p, int64_t row, int idx, double rho, double rem, double sign) {
+    double a = rho * rem;
+    double s = rho - a;
+    double bb = s - rho;
+    double e = (rho - (s - bb)) + (-a - bb);   /* rho - a == s + e exactly */
+    ring_add(p, row + idx, sign * s);
+    ring_add(p, row + idx, sign * e);
+    if (idx < p->bins - 1) ring_add(p, row + idx + 1, sign * a);
 }
 
 /* los/profile_ring.go:92-120 */
@@ -63,8 +96,11 @@ void orc_ring_insert(orc_ring *p, double start, double end, double rho, int i) {
         double fidx;
         double rem = modf((start - p->lowR) / p->dr, &fidx);
         int idx = (int)fidx;
+        if (p->comp) ring_add_split_exact(p, row, idx, rho, rem, 1.0);
+        else {
         ring_add(p, row + idx, rho * (1 - rem));
         if (idx < p->bins - 1) ring_add(p, row + idx + 1, rho * rem);
+        }
         if (p->tapStart && idx < p->bins) p->tapStart[row + idx]++;
     } else {
         ring_add(p, row, rho);
@@ -75,18 +111,27 @@ void orc_ring_insert(orc_ring *p, double start, double end, double rho, int i) {
         double fidx;
         double rem = modf((end - p->lowR) / p->dr, &fidx);
         int idx = (int)fidx;
+        if (p->comp) ring_add_split_exact(p, row, idx, rho, rem, -1.0);
+        else {
         ring_add(p, row + idx, -(rho * (1 - rem)));
         if (idx < p->bins - 1) ring_add(p, row + idx + 1, -(rho * rem));
+        }
         if (p->tapEnd && idx < p->bins) p->tapEnd[row + idx]++;
     }
 }
 
 /* los/profile_ring.go:124-130 */
 void orc_ring_retrieve(const orc_ring *p, int i, double *out) {
-    double sum = 0;
+    double sum = 0, lo = 0;
     for (int j = 0; j < p->bins; j++) {
-        sum += p->derivs[j + p->bins * i];
-        out[j] = sum;
+        if (p->comp) {
+            dd_add(&sum, &lo, p->derivs[j + p->bins * i]);
+            lo += p->comp[j + p->bins * i];
+            out[j] = sum + lo;
+        } else {
+            sum += p->derivs[j + p->bins * i];
+            out[j] = sum;
+        }
     }
 }
 
@@ -140,7 +185,7 @@ orc_halo *orc_halo_new(const float *norms, int rings, const double origin[3],
 
 void orc_halo_free(orc_halo *h) {
     if (!h) return;
-    for (int i = 0; i < h->rings; i++) free(h->profs[i].derivs);
+    for (int i = 0; i < h->rings; i++) { free(h->profs[i].derivs); free(h->profs[i].comp); }
     free(h->profs); free(h->rots); free(h->irots); free(h->norms);
     free(h->ringPhis); free(h->ringVecs);
     free(h->tapInserts); free(h->tapStart); free(h->tapEnd);
@@ -173,6 +218,12 @@ void orc_halo_join(orc_halo *dst, const orc_halo *src) {
     for (int r = 0; r < dst->rings; r++) {
         double *a = dst->profs[r].derivs;
         const double *b = src->profs[r].derivs;
+        if (dst->profs[r].comp && src->profs[r].comp) {
+            for (size_t i = 0; i < m; i++) {
+                dd_add(&a[i], &dst->profs[r].comp[i], b[i]);
+                dst->profs[r].comp[i] += src->profs[r].comp[i];
+            }
+        } else
         for (size_t i = 0; i < m; i++) a[i] += b[i];
     }
     if (dst->tapInserts && src->tapInserts) {
@@ -188,7 +239,10 @@ void orc_halo_join(orc_halo *dst, const orc_halo *src) {
 /* los/halo.go:107-123 on an equally sized worker: zero its grid */
 void orc_halo_clear(orc_halo *h) {
     size_t m = (size_t)h->n * (size_t)h->bins;
-    for (int r = 0; r < h->rings; r++) memset(h->profs[r].derivs, 0, m * sizeof(double));
+    for (int r = 0; r < h->rings; r++) {
+        memset(h->profs[r].derivs, 0, m * sizeof(double));
+        if (h->profs[r].comp) memset(h->profs[r].comp, 0, m * sizeof(double));
+    }
     if (h->tapInserts) {
         size_t rn = (size_t)h->rings * (size_t)h->n;
         memset(h->tapInserts, 0, rn * sizeof(uint32_t));

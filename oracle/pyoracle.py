@@ -159,6 +159,12 @@ class Taps(C.Structure):
                 ("nCandidates", C.POINTER(C.c_int64)), ("nIntersections", C.POINTER(C.c_int64))]
 
 
+def set_exact_bins(on):
+    """orc_set_exact_bins: float64 bins like the reference (False, default) or the exact-sum
+    variant used to tell rounding-decided lines of sight apart (see orc_los.c)."""
+    lib().orc_set_exact_bins(C.c_int(1 if on else 0))
+
+
 def norm_vecs(seed, rings):
     out = np.zeros((rings, 3), np.float32)
     lib().orc_norm_vecs(C.c_uint64(seed), C.c_int(rings), fp(out))

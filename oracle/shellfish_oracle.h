@@ -73,6 +73,9 @@ int orc_spline_eval(const orc_spline *sp, double x, double *y);
 
 /* ---- los/profile_ring.go */
 typedef struct orc_ring orc_ring;
+/* Process-wide switch, read when a ring is created: 0 = the reference's float64 bins (default),
+ * 1 = the "exact bins" variant documented in orc_los.c (test infrastructure for tie analysis). */
+void orc_set_exact_bins(int on);
 orc_ring *orc_ring_new(double lowR, double highR, int bins, int n);
 void orc_ring_free(orc_ring *p);
 void orc_ring_insert(orc_ring *p, double start, double end, double rho, int i);

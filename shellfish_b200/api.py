@@ -43,7 +43,7 @@ class Stats(C.Structure):
                 ("n_intersections", C.c_int64), ("n_points", C.c_int64),
                 ("ms_cull", C.c_double), ("ms_hits", C.c_double), ("ms_bin", C.c_double),
                 ("ms_los", C.c_double), ("ms_filter", C.c_double), ("ms_fit", C.c_double),
-                ("bin_launches", C.c_int64), ("launches", C.c_int64)]
+                ("bin_launches", C.c_int64), ("launches", C.c_int64), ("n_los_literal", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

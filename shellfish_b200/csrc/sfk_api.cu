@@ -165,6 +165,7 @@ struct sfk_ctx {
     DevBuf<double> dRspRows;
     DevBuf<long long> dFlatList;
     DevBuf<unsigned long long> dFlatCount;
+    bool flatTotalArmed = false;
 
     sfk_stats stats{};
     StageTimer timer;
@@ -585,8 +586,12 @@ int stage_analyze(sfk_ctx *ctx, int nb, int rowBegin = 0, int rowCount = -1) {
     la.losBegin = static_cast<int64_t>(rowBegin) * n; la.losCount = static_cast<int64_t>(rowCount) * n;
     la.rspBySlot = part ? 1 : 0;
     CU(ctx->dFlatList.ensure(static_cast<size_t>(std::max<int64_t>(la.losCount, 1))));
-    CU(ctx->dFlatCount.ensure(1));
-    la.flatList = ctx->dFlatList.p; la.flatCount = ctx->dFlatCount.p; la.listMode = 0;
+    CU(ctx->dFlatCount.ensure(2));
+    la.flatList = ctx->dFlatList.p; la.flatCount = ctx->dFlatCount.p; la.flatTotal = ctx->dFlatCount.p + 1; la.listMode = 0;
+    if (!ctx->flatTotalArmed) {
+        CU(cudaMemsetAsync(ctx->dFlatCount.p + 1, 0, sizeof(unsigned long long), st));
+        ctx->flatTotalArmed = true;
+    }
     // Sliding-moment smoothing only when every ln(rho) is finite and normal (rho_bg > 0; with
     // Gadget-2's MinMass() == 0 the reference's -Inf / NaN propagation must stay sample-exact).
     bool moments = !(ctx->p.flags & SFK_FLAG_LOS_TAPLOOP) && ctx->sgReady && los_moments_supported(la);
@@ -638,6 +643,9 @@ int stage_collect(sfk_ctx *ctx, double *coeffs, int32_t *status) {
     std::vector<int32_t> dstat(nHalo);
     std::vector<unsigned long long> nInter(nHalo);
     std::vector<long long> nPts(nHalo);
+    unsigned long long flatTotal = 0;
+    if (ctx->flatTotalArmed)
+        CU(cudaMemcpyAsync(&flatTotal, ctx->dFlatCount.p + 1, sizeof flatTotal, cudaMemcpyDeviceToHost, st));
     unsigned ovf[2] = {0, 0};
     if (ctx->dOvfCount.p) CU(cudaMemcpyAsync(ovf, ctx->dOvfCount.p, sizeof ovf, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ctx->hCoeffs.data(), ctx->dCoeffs.p, ctx->hCoeffs.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -661,6 +669,8 @@ int stage_collect(sfk_ctx *ctx, double *coeffs, int32_t *status) {
         ctx->stats.n_points += nPts[i];
     }
     ctx->stats.n_candidates = ctx->candCount;
+    ctx->stats.n_los_literal = static_cast<int64_t>(flatTotal);
+    ctx->flatTotalArmed = false;
     ctx->stats.ms_cull = ctx->timer.collect(ST_CULL);
     ctx->stats.ms_hits = ctx->timer.collect(ST_HITS);
     ctx->stats.ms_bin = ctx->timer.collect(ST_BIN);

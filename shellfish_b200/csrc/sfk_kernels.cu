@@ -543,8 +543,9 @@ __device__ __forceinline__ double fast_log(double x, const double2 *tab) {
 //
 // Smooth (smooth.go:46-81) returns vals = exp(K0 * ln rho) and derivs = K1 * ln rho, and
 // SplashbackRadius (splashback_radius.go:30-58) only COMPARES vals with each other, so the
-// running minimum is taken on K0 * ln rho itself: exp is monotone, NaN and +-Inf order the
-// same way, and the 256 exp() per line of sight are gone.
+// moments path takes the running minimum on K0 * ln rho itself: exp is monotone, NaN and +-Inf
+// order the same way, and the 256 exp() per line of sight are gone.  (Lines where smoothed
+// values can differ by rounding noise only are not decided there, see the flat-run hand-over.)
 //
 // MOMENTS == true (default whenever every ln rho is finite, i.e. rho_bg > 0): the two
 // Savitzky-Golay FIRs are evaluated through the five sliding polynomial moments of
@@ -595,6 +596,7 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
     if (!MOMENTS && a.listMode) {   // second pass: the lines the moments kernel handed over
         if (gw0 >= static_cast<int64_t>(*a.flatCount)) return;
         gw = a.flatList[gw0];
+        if (gw0 == 0 && lane_id() == 0) atomicAdd(a.flatTotal, *a.flatCount);
     } else {
         if (gw0 >= a.losCount) return;
         gw = a.losBegin + gw0;
@@ -638,10 +640,14 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
         yLast = y;
     }
     if (MOMENTS) {
-        // Two neighbouring outputs see identical window contents once center + 2 consecutive values
-        // are equal (at an array end the Extension boundary repeats the end sample).  Such a run
-        // covers >= flatLanes = (center - 6) / PER whole lanes, each flat and equal to the next
-        // lane's first value (121 taps: 6 lanes; 31 taps: 1 lane).
+        // Exact ties.  Two outputs see identical window contents once center + 2 consecutive values
+        // are equal (at an array end the Extension boundary repeats the end sample); such a run
+        // covers >= (center - 6) / PER whole lanes, each flat and equal to the next lane's first
+        // value.  Sparse lines of sight also repeat whole step patterns -- the same two plateau
+        // levels around an edge at the same fraction of a bin -- whose smoothed derivatives are
+        // equal in exact arithmetic and ordered by rounding alone.  Both need long plateaus, so a
+        // line is handed to the literal instantiation as soon as it holds flatLanes <= 2 whole
+        // flat lanes in a row (>= 16 equal bins); profiles of >= 1e4-particle halos have none.
         const double nextFirst = __shfl_down_sync(0xffffffffu, yFirst, 1);
         const unsigned fm = __ballot_sync(0xffffffffu, flatLane && (lane == 31 || yLast == nextFirst));
         unsigned run = fm;
@@ -713,8 +719,8 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
 #pragma unroll
                 for (int c = 0; c < PER; c++) {
                     const double x = w[(c + jj) % PER];
-                    s0[c] = fma(x, tp.x, s0[c]);
-                    s1[c] = fma(x, tp.y, s1[c]);
+                    s0[c] = s0[c] + x * tp.x;   // multiply, round, add: Go on amd64 does not fuse,
+                    s1[c] = s1[c] + x * tp.y;   // and equal-step ties are decided by these roundings
                 }
             }
         }
@@ -728,14 +734,22 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel_fast(LosArgs a, int
 #pragma unroll
                     for (int c = 0; c < PER; c++) {
                         const double x = w[(c + jj) % PER];
-                        s0[c] = fma(x, tp.x, s0[c]);
-                        s1[c] = fma(x, tp.y, s1[c]);
+                        s0[c] = s0[c] + x * tp.x;
+                        s1[c] = s1[c] + x * tp.y;
                     }
                 }
             }
         }
     }
-    // s0 = ln vals, s1 = d ln rho / d ln r.
+    // s0 = ln vals, s1 = d ln rho / d ln r.  The literal instantiation forms vals = exp(s0) as Smooth
+    // does: exp is monotone but not injective in floating point -- for |s0| < 1 several neighbouring
+    // doubles share one exp -- so where smoothed values differ by rounding noise only (the flat
+    // windows this instantiation is handed) the reference sees exact ties that a comparison of the
+    // logarithms would break.
+    if (!MOMENTS) {
+#pragma unroll
+        for (int c = 0; c < PER; c++) s0[c] = exp(s0[c]);
+    }
 
     // SplashbackRadius: rhoMin starts at vals[0]; i = 1 .. B-2 is a candidate when
     // vals[i] < min(vals[0..i-1]) and derivs[i] is a strict local minimum below dLim.
@@ -845,7 +859,7 @@ __global__ void __launch_bounds__(kLosWarps * 32) los_kernel(LosArgs a, int nb) 
             s0 += x * taps0[j];
             s1 += x * taps1[j];
         }
-        vals[i] = s0;   // ln of Smooth's vals: only compared below, exp is monotone
+        vals[i] = exp(s0);   // Smooth's vals, smooth.go:75
         ders[i] = s1;
     }
     __syncwarp();
@@ -1605,7 +1619,7 @@ cudaError_t launch_los(const LosArgs &a, const SgPoly *sg, int nb, cudaStream_t 
         cudaError_t e = cudaMemsetAsync(a.flatCount, 0, sizeof(unsigned long long), s);
         if (e != cudaSuccess) return e;
         LosArgs m = a;
-        m.flatLanes = (a.window / 2 - 6) / 8;
+        m.flatLanes = std::max(1, std::min(2, (a.window / 2 - 6) / 8));
         los_kernel_fast<8, true><<<grid, kLosWarps * 32, fsmem, s>>>(m, nb, *sg);
         // the lines with exact-tie hazards again, literally; warps beyond the list's length exit at once
         LosArgs b = a;

@@ -74,6 +74,7 @@ struct LosArgs {
     // redoes them (launch_los).  Sparse halos only: none in configs[1].
     long long *flatList;         // [nb * rings * spokes]
     unsigned long long *flatCount;   // [1]
+    unsigned long long *flatTotal;   // [1] lines handed over since sfk_begin_snapshot
     int listMode;                // tap-loop pass over flatList instead of [losBegin, losBegin + losCount)
     int flatLanes;               // run length, in whole lanes, that marks a line for the tap loop
 };

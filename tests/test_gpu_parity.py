@@ -480,7 +480,17 @@ def test_sparse_halos_with_flat_profile_windows():
 def test_randomized_small_configurations(case):
     """Seeded random shapes and sizes against the oracle: sparse and dense halos, ragged ring /
     spoke / bin counts (fast and generic los kernels, stored and RED-added bin tiles), windows,
-    KDE levels, orders, subsampling, several blocks with periodic wrap."""
+    KDE levels, orders, subsampling, several blocks with periodic wrap.
+
+    Sparse halos expose what float64 rounding decides in the reference: a profile made of a few
+    particles' plateaus repeats the same density levels and the same smoothed step patterns, and
+    SplashbackRadius orders them with strict comparisons.  Two roundings take part: (1) the
+    smoothing arithmetic -- the CUDA path hands every line of sight with long plateaus to a literal
+    instantiation (libm log, multiply-then-add taps, exp), so this part matches; (2) the bin sums --
+    the reference adds rho*(1-rem) + rho*rem, equal to rho only up to an ulp, where the CUDA path
+    adds exact integers (rho - q) + q.  The oracle's "exact bins" variant (orc_los.c) carries the
+    bin sums exactly and is otherwise the literal restatement: the CUDA path must agree with it on
+    EVERY line of sight, and the literal oracle may differ from both only on a handful of lines."""
     rng = np.random.default_rng(1000 + case)
     n_halos = int(rng.integers(1, 5))
     n_per = int(rng.choice([400, 1500, 6000, 20000]))
@@ -493,5 +503,19 @@ def test_randomized_small_configurations(case):
               smoothing_window=int(rng.choice([w for w in (31, 61, 121) if w < bins - 8])),
               levels=int(rng.integers(1, 4)), order=int(rng.integers(1, 5)),
               subsample_factor=int(rng.choice([1, 1, 2])), eta=float(rng.choice([10.0, 6.0, 14.0])))
-    ctx, c, s, ref = run_both(halos, blocks, mass, **kw)
-    assert_parity(ctx, c, s, ref, n_halos)
+    ctx, c, s, literal = run_both(halos, blocks, mass, **kw)
+    po.set_exact_bins(True)
+    try:
+        _, _, _, exact = run_both(halos, blocks, mass, **kw)
+    finally:
+        po.set_exact_bins(False)
+    assert_parity(ctx, c, s, exact, n_halos)
+    lines = differing = 0
+    for h in range(n_halos):
+        a, b = literal["rsp"][h], exact["rsp"][h]
+        bad = (np.isnan(a) != np.isnan(b)) | (~np.isnan(a) & ~np.isnan(b) & (np.abs(a - b) > RTOL * np.abs(a)))
+        lines += a.size
+        differing += int(bad.sum())
+    assert differing <= max(2, lines // 200), (differing, lines)   # rounding-decided lines of the reference
+    if differing == 0:
+        assert_parity(ctx, c, s, literal, n_halos)
