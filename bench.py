@@ -309,7 +309,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     ms, agg, nok, table, per_rank = timed(True, args.steps)
     clocks = sampler.stop() if sampler else None
-    work_keys = ("n_candidates", "n_intersections", "n_ring_hits", "launches", "bin_launches", "ms_bin")
+    work_keys = ("n_candidates", "n_intersections", "n_ring_hits", "launches", "bin_launches", "ms_bin", "n_los_literal")
     tot = sum_over_ranks(agg, work_keys)
     stage_keys = ("ms_cull", "ms_hits", "ms_bin", "ms_los", "ms_filter", "ms_fit")
     if world > 1:
@@ -369,6 +369,8 @@ def main():
             "intersections_per_s": tot["n_intersections"] / (ms * 1e-3),
             "stage_ms_per_step": dict(zip(stage_keys, stage_by_rank[int(np.argmax(per_rank))])),
             "gpu_launches": int(tot["launches"]),
+            # lines of sight with long plateaus, smoothed by the literal tap loop (exact ties), per step
+            "los_literal_per_step": tot["n_los_literal"] / args.steps,
             "roofline": {"bound": "hbm", "kernel": "bin_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_RATIO * alg_bytes / launches / 1e9,

@@ -476,7 +476,7 @@ def test_sparse_halos_with_flat_profile_windows():
     assert np.array_equal(c2, c) and np.array_equal(s2, s)
 
 
-@pytest.mark.parametrize("case", range(12))
+@pytest.mark.parametrize("case", range(20))
 def test_randomized_small_configurations(case):
     """Seeded random shapes and sizes against the oracle: sparse and dense halos, ragged ring /
     spoke / bin counts (fast and generic los kernels, stored and RED-added bin tiles), windows,
