@@ -230,13 +230,17 @@ def main():
     need = shard.blocks_needed(ctx, blocks, owned)
     my_blocks = [blocks[i] for i in need]
 
-    dev_blocks = [(torch.from_numpy(b["xs"]).cuda(), torch.from_numpy(b["ms"]).cuda()) for b in my_blocks]
+    # LGadget-2 snapshots carry one particle mass (io/lgadget2.go:228 fills ms with buf.MinMass()):
+    # such blocks are pushed without a mass array, as the CLI does for LGadget-2 and gotetra files
+    uniform = all(bool(np.all(b["ms"] == np.float32(mass))) for b in my_blocks)
+    dev_blocks = [(torch.from_numpy(b["xs"]).cuda(), None if uniform else torch.from_numpy(b["ms"]).cuda())
+                  for b in my_blocks]
     pin_blocks = []
     if not args.no_e2e:
         for b in my_blocks:
             pb = dict(b)
             pb["xs"] = torch.from_numpy(b["xs"]).pin_memory()
-            pb["ms"] = torch.from_numpy(b["ms"]).pin_memory()
+            pb["ms"] = None if uniform else torch.from_numpy(b["ms"]).pin_memory()
             pin_blocks.append(pb)
     torch.cuda.synchronize()
 
@@ -329,7 +333,7 @@ def main():
     if not args.no_e2e:
         step(False)
         ms_e, agg_e, _, _, _ = timed(False, args.steps)
-        h2d_own = sum(int(pb["xs"].numel() * 4 + pb["ms"].numel() * 4) for pb in pin_blocks)
+        h2d_own = sum(int(pb["xs"].numel() * 4 + (pb["ms"].numel() * 4 if pb["ms"] is not None else 0)) for pb in pin_blocks)
         d2h_own = int(nH * (P2 * 8 + 4 + 8 + 8 + 8 + R * 4) + (0 if world == 1 else world * n_max * cols * 8))
         if world > 1:
             t = torch.tensor([h2d_own, d2h_own], device="cuda", dtype=torch.float64)
@@ -364,7 +368,8 @@ def main():
             "config": config,
             "meta": dict(meta, parallelism="halo list partitioned over %d GPU(s) by estimated particle count "
                                           "(equal-weight runs along a Z-curve); no data-path collective; catalog rows gathered by "
-                                          "halo index" % world),
+                                          "halo index" % world,
+                         masses="uniform: blocks pushed without a mass array" if uniform else "per-particle mass arrays"),
             "halos_ok": nok // max(1, args.steps),
             "intersections_per_s": tot["n_intersections"] / (ms * 1e-3),
             "stage_ms_per_step": dict(zip(stage_keys, stage_by_rank[int(np.argmax(per_rank))])),

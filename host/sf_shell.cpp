@@ -339,6 +339,7 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
     if (!(err = ReadHeaders(static_cast<int>(firstSnap), *buf, cat, g.MemoDir, hds0, files)).empty()) return err;
     if (hds0.empty()) return "The snapshot has no blocks.";
     const float minMass = buf->MinMass();
+    const bool uniformMass = buf->UniformMass();   // LGadget-2, gotetra: ms[i] == minMass, not transferred
 
     sfk_params p;
     sfk_default_params(&p);
@@ -473,7 +474,8 @@ std::string RunShell(const GlobalConfig &g, const ShellConfig &c, const std::str
             const Header &h = hds[needed[k]];
             const sfk_cosmo hc{h.Cosmo.Z, h.Cosmo.OmegaM, h.Cosmo.OmegaL, h.Cosmo.H100};
             for (int d = 0; d < G; d++)
-                if (wantsOf[k][d] && sfk_push_block(ctxs[d], s.xs, s.ms, s.n, &hc, h.TotalWidth, h.Origin, h.Width) != 0)
+                if (wantsOf[k][d] && sfk_push_block(ctxs[d], s.xs, uniformMass ? nullptr : s.ms, s.n, &hc, h.TotalWidth, h.Origin,
+                                                    h.Width) != 0)
                     return sfk_last_error(ctxs[d]);
             std::lock_guard<std::mutex> lk(mu);
             consumed = k + 1;

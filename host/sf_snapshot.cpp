@@ -236,6 +236,7 @@ public:
         return "";
     }
     float MinMass() const override { return mass_; }
+    bool UniformMass() const override { return true; }
     std::string TotalParticles(const std::string &fname, int64_t &n) override {
         LGadget2Header hd{};
         std::string err = header(fname, hd);
@@ -497,6 +498,7 @@ public:
         return "";
     }
     float MinMass() const override { return mass_; }
+    bool UniformMass() const override { return true; }
     std::string TotalParticles(const std::string &, int64_t &n) override { n = -1; return ""; }
 private:
     // loadSheetHeader, io/gotetra.go:177-211

@@ -42,6 +42,9 @@ public:
     virtual std::string ReadIDs(const std::string &fname, const int64_t **ids, int64_t *n) = 0;
     virtual std::string ReadHeader(const std::string &fname, Header &out) = 0;
     virtual float MinMass() const = 0;
+    // true when Read fills ms with MinMass() for every particle (LGadget-2, gotetra): the caller may
+    // then push blocks without a mass array (sfk_push_block with mass == NULL)
+    virtual bool UniformMass() const { return false; }
     virtual std::string TotalParticles(const std::string &fname, int64_t &n) = 0;
 };
 

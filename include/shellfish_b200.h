@@ -132,7 +132,10 @@ int sfk_block_halo_mask(sfk_ctx *ctx, const float origin[3], const float width[3
  * touching the block, in halo order, Transform + Intersect
  * (los/halo.go:168-197,147-164) and queueing of the surviving particles with
  * the weight of chanLoadSphereVec (cmd/shell.go:479-500).  xyz is [n][3],
- * mass is [n]; both are host pointers, consumed when the call returns (the copy runs on
+ * mass is [n] -- or NULL when every particle of the block has the mass given to
+ * sfk_begin_snapshot (buf.MinMass(): what the LGadget-2 and gotetra readers fill ms with,
+ * io/lgadget2.go:228, io/gotetra.go:43), which saves a quarter of the transfer; both are
+ * host pointers, consumed when the call returns (the copy runs on
  * a second stream into one of two staging buffers and overlaps the cull of the previous
  * block, so page-locked host memory pays). */
 int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,

@@ -191,21 +191,24 @@ class ShellContext:
     def push_block(self, block):
         """block: dict with Z, OmegaM, OmegaL, H100, TotalWidth, Origin, Width,
         xs (N,3) float32 and ms (N,) float32 host arrays (numpy, or pinned
-        torch CPU tensors)."""
-        xs, ms = block["xs"], block["ms"]
+        torch CPU tensors).  ms may be None: every particle then has the min_mass
+        given to begin_snapshot (uniform-mass snapshots; a quarter less to transfer)."""
+        xs, ms = block["xs"], block.get("ms")
         c = Cosmo(block["Z"], block["OmegaM"], block["OmegaL"], block["H100"])
         if hasattr(xs, "data_ptr"):
-            n, px, pm = xs.shape[0], xs.data_ptr(), ms.data_ptr()
+            n, px, pm = xs.shape[0], xs.data_ptr(), (ms.data_ptr() if ms is not None else None)
         else:
-            assert xs.dtype == np.float32 and ms.dtype == np.float32 and xs.flags.c_contiguous
-            n, px, pm = len(xs), xs.ctypes.data, ms.ctypes.data
+            assert xs.dtype == np.float32 and xs.flags.c_contiguous and (ms is None or ms.dtype == np.float32)
+            n, px, pm = len(xs), xs.ctypes.data, (ms.ctypes.data if ms is not None else None)
         self._ck(lib().sfk_push_block(self._h, px, pm, n, C.byref(c), float(block["TotalWidth"]),
                                       _f3(block["Origin"]), _f3(block["Width"])), "sfk_push_block")
 
     def push_block_device(self, block, d_xs, d_ms):
-        """Same with positions/masses already on this context's GPU (torch CUDA tensors)."""
+        """Same with positions/masses already on this context's GPU (torch CUDA tensors; d_ms may
+        be None for uniform masses)."""
         c = Cosmo(block["Z"], block["OmegaM"], block["OmegaL"], block["H100"])
-        self._ck(lib().sfk_push_block_device(self._h, d_xs.data_ptr(), d_ms.data_ptr(), d_xs.shape[0],
+        self._ck(lib().sfk_push_block_device(self._h, d_xs.data_ptr(), d_ms.data_ptr() if d_ms is not None else None,
+                                             d_xs.shape[0],
                                              C.byref(c), float(block["TotalWidth"]),
                                              _f3(block["Origin"]), _f3(block["Width"])),
                  "sfk_push_block_device")

@@ -303,12 +303,12 @@ int push_block_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, int64_t
     // pageable source: the copy is staged before the call returns, `list` may die
     CU(ctx->dHaloList.upload(list, ctx->stream));
     CullArgs a{};
-    a.xyz = dxyz; a.mass = dmass; a.n = n; a.sf3 = sf3;
+    a.xyz = dxyz; a.mass = dmass; a.uniformMass = ctx->minMass; a.n = n; a.sf3 = sf3;
     a.haloList = ctx->dHaloList.p; a.nList = nList; a.halos = ctx->dHalos.p;
     a.tw = static_cast<float>(tw);
     // chanLoadSphereVec uses the block's own header, cmd/shell.go:487-488
     a.rhoM = rho_average(cosmo->h100 * 100, cosmo->omega_m, cosmo->omega_l, cosmo->z);
-    a.tma = sf3 == 1 && reinterpret_cast<uintptr_t>(dxyz) % 16 == 0 && reinterpret_cast<uintptr_t>(dmass) % 16 == 0;
+    a.tma = sf3 == 1 && reinterpret_cast<uintptr_t>(dxyz) % 16 == 0 && reinterpret_cast<uintptr_t>(dmass) % 16 == 0;   // null is aligned
     a.cands = ctx->dCandsRaw.p; a.cap = static_cast<int64_t>(ctx->dCandsRaw.cap);
     a.total = ctx->dCandTotal.p; a.haloCount = ctx->dHaloCandCount.p;
     if (!ctx->cullOpen) { ctx->timer.begin(ST_CULL, ctx->stream); ctx->cullOpen = true; }
@@ -866,7 +866,7 @@ int sfk_block_halo_mask(sfk_ctx *ctx, const float origin[3], const float width[3
 int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
                    const sfk_cosmo *cosmo, double total_width, const float origin[3],
                    const float width[3]) try {
-    if (!ctx || !ctx->inSnapshot || ctx->finished || !cosmo || n < 0 || (n > 0 && (!xyz || !mass)))
+    if (!ctx || !ctx->inSnapshot || ctx->finished || !cosmo || n < 0 || (n > 0 && !xyz))
         return fail(ctx, SFK_E_INVALID, "sfk_push_block: bad arguments or no snapshot open");
     CU(cudaSetDevice(ctx->p.device));
     int64_t hits = 0;
@@ -878,17 +878,17 @@ int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
     // has been culled.
     const int slot = static_cast<int>(ctx->pushIdx++ & 1);
     if (ctx->culledValid[slot]) CU(cudaStreamWaitEvent(ctx->copyStream, ctx->evCulled[slot], 0));
-    if (static_cast<size_t>(3 * n) > ctx->dXyz[slot].cap || static_cast<size_t>(n) > ctx->dMass[slot].cap) {
+    if (static_cast<size_t>(3 * n) > ctx->dXyz[slot].cap || (mass && static_cast<size_t>(n) > ctx->dMass[slot].cap)) {
         if (ctx->culledValid[slot]) CU(cudaEventSynchronize(ctx->evCulled[slot]));   // the old buffer is still being read
         CU(ctx->dXyz[slot].ensure(3 * n));
-        CU(ctx->dMass[slot].ensure(n));
+        if (mass) CU(ctx->dMass[slot].ensure(n));
     }
     CU(cudaMemcpyAsync(ctx->dXyz[slot].p, xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->copyStream));
-    CU(cudaMemcpyAsync(ctx->dMass[slot].p, mass, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copyStream));
+    if (mass) CU(cudaMemcpyAsync(ctx->dMass[slot].p, mass, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copyStream));
     CU(cudaEventRecord(ctx->evCopied[slot], ctx->copyStream));
     CU(cudaStreamSynchronize(ctx->copyStream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->evCopied[slot], 0));
-    int rc = push_block_impl(ctx, ctx->dXyz[slot].p, ctx->dMass[slot].p, n, cosmo, total_width, origin, width);
+    int rc = push_block_impl(ctx, ctx->dXyz[slot].p, mass ? ctx->dMass[slot].p : nullptr, n, cosmo, total_width, origin, width);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->evCulled[slot], ctx->stream));
     ctx->culledValid[slot] = true;
@@ -898,7 +898,7 @@ int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
 int sfk_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass, int64_t n,
                           const sfk_cosmo *cosmo, double total_width, const float origin[3],
                           const float width[3]) try {
-    if (!ctx || !ctx->inSnapshot || ctx->finished || !cosmo || n < 0 || (n > 0 && (!d_xyz || !d_mass)))
+    if (!ctx || !ctx->inSnapshot || ctx->finished || !cosmo || n < 0 || (n > 0 && !d_xyz))
         return fail(ctx, SFK_E_INVALID, "sfk_push_block_device: bad arguments or no snapshot open");
     CU(cudaSetDevice(ctx->p.device));
     // The caller's buffers were filled on other streams: everything queued on the device before

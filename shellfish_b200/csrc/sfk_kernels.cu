@@ -70,22 +70,22 @@ __global__ void __launch_bounds__(kCullThreads) cull_kernel(CullArgs a) {
         if (threadIdx.x == 0) {
             mbar_init(&bar, 1);
             fence_barrier_init();
-            mbar_expect_tx(&bar, 16 * kCullThreads);
+            mbar_expect_tx(&bar, (a.mass ? 16 : 12) * kCullThreads);
             tma_load_1d(sXyz, a.xyz + 3 * tile0, 12 * kCullThreads, &bar);
-            tma_load_1d(sMass, a.mass + tile0, 4 * kCullThreads, &bar);
+            if (a.mass) tma_load_1d(sMass, a.mass + tile0, 4 * kCullThreads, &bar);
         }
         __syncthreads();   // the barrier is initialised before anybody polls it
         mbar_wait(&bar, 0);
         x = sXyz[3 * threadIdx.x];       // stride 3 is coprime to the 32 banks: conflict-free
         y = sXyz[3 * threadIdx.x + 1];
         z = sXyz[3 * threadIdx.x + 2];
-        mScaled = static_cast<double>(sMass[threadIdx.x]);   // sf3 == 1
+        mScaled = static_cast<double>(a.mass ? sMass[threadIdx.x] : a.uniformMass);   // sf3 == 1
     } else if (live) {
         x = a.xyz[3 * i];
         y = a.xyz[3 * i + 1];
         z = a.xyz[3 * i + 2];
         // float64(ms[i]) * float64(sf^3), cmd/shell.go:494
-        mScaled = static_cast<double>(a.mass[i]) * static_cast<double>(a.sf3);
+        mScaled = static_cast<double>(a.mass ? a.mass[i] : a.uniformMass) * static_cast<double>(a.sf3);
     }
     const float tw = a.tw;
     const float tw2 = tw / 2;

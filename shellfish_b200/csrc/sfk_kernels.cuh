@@ -9,7 +9,8 @@ namespace sfk {
 
 struct CullArgs {
     const float *xyz;        // [n][3] block positions (device)
-    const float *mass;       // [n]
+    const float *mass;       // [n], or null: every particle has uniformMass
+    float uniformMass;       // buf.MinMass(), what the LGadget-2 / gotetra readers fill ms with
     int64_t n;
     int64_t sf3;             // SubsampleFactor^3, cmd/shell.go:490-493
     const int32_t *haloList; // halos touching the block, in halo order

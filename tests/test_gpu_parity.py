@@ -519,3 +519,27 @@ def test_randomized_small_configurations(case):
     assert differing <= max(2, lines // 200), (differing, lines)   # rounding-decided lines of the reference
     if differing == 0:
         assert_parity(ctx, c, s, literal, n_halos)
+
+
+def test_uniform_mass_push_equals_mass_array():
+    """sfk_push_block[_device] with mass == NULL: every particle has the min_mass of
+    sfk_begin_snapshot (what the LGadget-2 and gotetra readers fill ms with).  Bitwise the same
+    result as pushing the array, from host and from device memory."""
+    import torch
+    halos, blocks, mass = synth.make_box(17, 20.0, 3, 9000, 6000, 2, r200m_range=(0.6, 0.9))
+    params = api.default_params(seed=1337, rings=8)
+    _, c_ref, s_ref = api.run_shell(params, mass, halos, blocks)
+    assert all(np.all(b["ms"] == np.float32(mass)) for b in blocks)
+    for device in (False, True):
+        ctx = api.ShellContext(params)
+        ctx.begin_snapshot(blocks[0], mass)
+        ctx.add_halos(halos)
+        keep = []
+        for b in blocks:
+            if device:
+                keep.append(torch.from_numpy(b["xs"]).cuda())
+                ctx.push_block_device(b, keep[-1], None)
+            else:
+                ctx.push_block(dict(b, ms=None))
+        c, s = ctx.finish_snapshot()
+        assert np.array_equal(c, c_ref) and np.array_equal(s, s_ref)
