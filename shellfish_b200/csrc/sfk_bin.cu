@@ -46,10 +46,43 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+
+// ---- shared-memory accesses of the pair loop through 32-bit shared-window addresses.  The two
+// bases (this round's records, the CTA's tables) are made opaque once per round, so they stay in
+// two registers; as pointers the compiler re-derives them from the thread and CTA ids on every
+// pass of the loop (7 instructions of ~170) under the kernel's 64-register cap.
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void reds_add(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // Bin index and fractional position of radius r, rMin < r < rMax
 // (profile_ring.go:100-101: Modf((ln r - lowR)/dr)).
-__device__ __forceinline__ void bin_of(double r, double invRMin, float cK, double invDr,
-                                       const double *sInvG, int bins, int &idx, double &rem) {
+__device__ __forceinline__ void bin_of(double r, const BinArgs &a, double invRMin, float cK, double invDr,
+                                       uint32_t invGA, int &idx, double &rem) {
     const double u = r * invRMin;
     // float32 view of u (u in [1, rMax/rMin]): rebias the exponent, keep 20 mantissa bits.
     // The estimate is biased low by 1e-3 bins (its error is < 3e-4), so the true
@@ -60,10 +93,12 @@ __device__ __forceinline__ void bin_of(double r, double invRMin, float cK, doubl
     // callers guarantee rMin < r < rMax, and the estimate never exceeds the true position:
     // 0 <= k <= bins - 1 without clamping
     int k = static_cast<int>(fmaf(lg, cK, -1.0e-3f));
-    const double t = fma(u, sInvG[k], -1.0);   // r / (rMin g[k]) - 1
-    double L = fma(t, -1.0 / 6.0, 0.2);
+    const double t = fma(u, lds_f64(invGA + 8u * k), -1.0);   // r / (rMin g[k]) - 1
+    // -1/6, 1/5, 1/3 are read from the parameter bank (a constant-bank operand of the DFMA);
+    // as literals each costs two UMOVs per use under the kernel's 64-register cap
+    double L = fma(t, a.lnC[0], a.lnC[1]);
     L = fma(L, t, -0.25);
-    L = fma(L, t, 1.0 / 3.0);
+    L = fma(L, t, a.lnC[2]);
     L = fma(L, t, -0.5);
     L = fma(L, t, 1.0);
     double x = (L * t) * invDr;
@@ -74,16 +109,36 @@ __device__ __forceinline__ void bin_of(double r, double invRMin, float cK, doubl
     rem = x;
 }
 
-// 64-bit two's-complement add into split lo/hi words.
-__device__ __forceinline__ void acc_add(uint32_t *lo, uint32_t *hi, int idx, long long v) {
+// 64-bit two's-complement add into split lo/hi words; row = shared address of the low word of
+// (bin 0, this LoS), hiOff = byte distance from the low words to the high ones.
+__device__ __forceinline__ void acc_add(uint32_t row, uint32_t hiOff, int idx, long long v) {
     const uint32_t vlo = static_cast<uint32_t>(v);
     const uint32_t vhi = static_cast<uint32_t>(static_cast<unsigned long long>(v) >> 32);
-    const uint32_t old = atomicAdd(&lo[idx * kTileLos], vlo);
+    const uint32_t at = row + idx * (kTileLos * 4);
+    const uint32_t old = atoms_add(at, vlo);
     // hi += vhi + carry(old + vlo): add.cc / addc keep it at two integer instructions, and the
     // second atomic is issued unconditionally (vhi is almost never zero: values are ~2^45)
     uint32_t add;
     asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(add) : "r"(old), "r"(vlo), "r"(vhi));
-    atomicAdd(&hi[idx * kTileLos], add);
+    reds_add(at + hiOff, add);
+}
+
+// Two adds of one edge, (idx, v) and (idx + 1, w): both returning low-word atomics are issued
+// before either carry is formed, so their round trips overlap.  idx + 1 == bins (the reference
+// drops that half, profile_ring.go:104-118) goes to a scratch row that is never flushed.
+__device__ __forceinline__ void acc_add2(uint32_t row, uint32_t hiOff, int idx, int bins, long long v, long long w) {
+    const int idxW = idx < bins - 1 ? idx + 1 : bins + 1;
+    const uint32_t vlo = static_cast<uint32_t>(v), wlo = static_cast<uint32_t>(w);
+    const uint32_t vhi = static_cast<uint32_t>(static_cast<unsigned long long>(v) >> 32);
+    const uint32_t whi = static_cast<uint32_t>(static_cast<unsigned long long>(w) >> 32);
+    const uint32_t atV = row + idx * (kTileLos * 4), atW = row + idxW * (kTileLos * 4);
+    const uint32_t oldV = atoms_add(atV, vlo);
+    const uint32_t oldW = atoms_add(atW, wlo);
+    uint32_t addV, addW;
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(addV) : "r"(oldV), "r"(vlo), "r"(vhi));
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(addW) : "r"(oldW), "r"(wlo), "r"(whi));
+    reds_add(atV + hiOff, addV);
+    reds_add(atW + hiOff, addW);
 }
 
 constexpr int kChunkRecs = 128;   // raw records a warp draws at a time (4 x 32)
@@ -117,9 +172,19 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
     }
     const unsigned nPairs = __shfl_sync(0xffffffffu, incl, 31);
     const unsigned first = incl - nMine;   // index of my record's first pair
-    const unsigned meta = static_cast<unsigned>(st1 - t0) | static_cast<unsigned>(len1) << 8 |
-                          static_cast<unsigned>(st2 - t0) << 16;
+    // pair p of my record is LoS p + toLos1 of the tile while p < split, p + toLos2 from there on
+    // (both biased by kLosBias to stay unsigned)
+    constexpr unsigned kLosBias = 2048u;
+    const unsigned metaA = (first + static_cast<unsigned>(len1)) |
+                           (static_cast<unsigned>(st1 - t0) + kLosBias - first) << 16;
+    const unsigned metaB = static_cast<unsigned>(st2 - t0) + kLosBias - static_cast<unsigned>(len1) - first;
 
+    const uint32_t grpA = opaque_u32(smem_u32(grp));
+    const uint32_t tabA = opaque_u32(smem_u32(sTrig));
+    const uint32_t invGA = tabA + static_cast<uint32_t>(reinterpret_cast<const char *>(sInvG) - reinterpret_cast<const char *>(sTrig));
+    const uint32_t loA = tabA + static_cast<uint32_t>(reinterpret_cast<const char *>(lo) - reinterpret_cast<const char *>(sTrig));
+    const uint32_t hiOff = static_cast<uint32_t>(reinterpret_cast<const char *>(hi) - reinterpret_cast<const char *>(lo));
+    unsigned nBefore = 0;   // records whose first pair lies before this window
     for (unsigned p0 = 0; p0 < nPairs; p0 += 32) {
         // pair p -> record.  Every record of the round owns >= 1 pair, so the first-pair indices
         // are strictly increasing: one REDUX.OR marks the records that start inside this window
@@ -127,22 +192,21 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
         const unsigned p = p0 + lane;
         const unsigned rel = first - p0;   // wraps for records that started earlier
         const unsigned starts = __reduce_or_sync(0xffffffffu, (nMine && rel < 32u) ? 1u << rel : 0u);
-        const unsigned nBefore = __popc(__ballot_sync(0xffffffffu, nMine && first < p0));
         const unsigned r = (nBefore + __popc(starts & (0xffffffffu >> (31 - lane))) - 1u) & 31u;
-        const unsigned before = __shfl_sync(0xffffffffu, first, r);
-        const unsigned rmeta = __shfl_sync(0xffffffffu, meta, r);
+        nBefore += __popc(starts);
+        const unsigned rmA = __shfl_sync(0xffffffffu, metaA, r);
+        const unsigned rmB = __shfl_sync(0xffffffffu, metaB, r);
         if (p >= nPairs) continue;
-        const int off = static_cast<int>(p - before);
-        const int l1 = static_cast<int>((rmeta >> 8) & 0xffu);
-        const int ll = off < l1 ? static_cast<int>(rmeta & 0xffu) + off
-                                : static_cast<int>(rmeta >> 16) + (off - l1);   // LoS within the tile
-        const HitRec rec = grp[r];
-        const double2 cs = sTrig[ll];
-        const bool isA = (rec.r23 & kHitCaseA) != 0;
+        const int ll = static_cast<int>(p + (p < (rmA & 0xffffu) ? rmA >> 16 : rmB) - kLosBias);   // LoS within the tile
+        const uint4 recA = lds128(grpA + r * 32u), recB = lds128(grpA + r * 32u + 16u);   // one HitRec
+        const double2 cs = lds_f64x2(tabA + ll * 16u);
+        const bool isA = (recA.w & kHitCaseA) != 0;
+        const double rhoS = __hiloint2double(static_cast<int>(recB.y), static_cast<int>(recB.x));
         // literal geometry of insertToRing, los/halo.go:233-262
-        const double cx = rec.cx, cy = rec.cy;
+        const double cx = __uint_as_float(recA.x), cy = __uint_as_float(recA.y);
         const double projDist2 = cx * cx + cy * cy;
-        const double projRad2 = rec.projRad2;   // max(rad2 - cz*cz, 0), formed once per record by hits_kernel
+        // max(rad2 - cz*cz, 0), formed once per record by hits_kernel
+        const double projRad2 = __hiloint2double(static_cast<int>(recB.w), static_cast<int>(recB.z));
         const double b = cy * cs.x - cx * cs.y;
         const double b2 = b * b;
         const double m2 = projDist2 - b2;   // radicand of midDist / cMidDist
@@ -150,38 +214,39 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
         const bool bad = !(m2 >= 0) || !(d2 >= 0);   // a sqrt of the reference returns NaN
         // twoValIntrDist skips NaN (halo.go:262); oneValIntrDist's NaN goes into Insert
         if (bad && !isA) continue;
-        const double dir = cx * cs.x + cy * cs.y;
         const double mid = sqrt_pos(m2), diff = sqrt_pos(d2);
         const double rLo = mid - diff;
         // mid + diff, or diff - mid on the far side of a centre-containing circle
-        const double rHi = fma((isA && !(dir > 0)) ? -1.0 : 1.0, mid, diff);
+        // (diff - mid is diff + (-mid) exactly: the sign of mid is flipped as an integer)
+        const bool far = isA && !(cx * cs.x + cy * cs.y > 0);
+        const double rHi = diff + __hiloint2double(__double2hiint(mid) ^ (far ? 0x80000000 : 0), __double2loint(mid));
         const bool endNaN = bad;            // only reachable with isA
         // ProfileRing.Insert, profile_ring.go:92-120, with ln monotone:
         // end <= lowR <=> rHi <= rMin, start >= highR <=> rLo >= rMax, ...
         if (!endNaN && rHi <= rMin) continue;
         if (!isA && rLo >= rMax) continue;
         nIns++;
-        uint32_t *rowLo = lo + ll, *rowHi = hi + ll;
+        const uint32_t row = loA + ll * 4u;
         const size_t tapRow = tapRing + t0 + ll;
         if (TAPS) atomicAdd(&a.tapInsert[tapRow], 1u);
-        const long long Q = __double2ll_rn(rec.rhoS);
-        if (!isA && rLo > rMin) {
+        const long long Q = __double2ll_rn(rhoS);
+        const bool startIn = !isA && rLo > rMin;
+        const bool endIn = !endNaN && rHi < rMax;
+        if (startIn) {
             int idx; double rem;
-            bin_of(rLo, invRMin, cK, invDr, sInvG, bins, idx, rem);
-            const long long q1 = __double2ll_rn(rec.rhoS * rem);
-            acc_add(rowLo, rowHi, idx, Q - q1);
-            if (idx < bins - 1) acc_add(rowLo, rowHi, idx + 1, q1);
+            bin_of(rLo, a, invRMin, cK, invDr, invGA, idx, rem);
+            const long long q1 = __double2ll_rn(rhoS * rem);
+            acc_add2(row, hiOff, idx, bins, Q - q1, q1);
             if (TAPS && idx < bins) atomicAdd(&a.tapStart[tapRow * bins + idx], 1u);
         } else {
-            acc_add(rowLo, rowHi, 0, Q);
+            acc_add(row, hiOff, 0, Q);
             if (TAPS) atomicAdd(&a.tapStart[tapRow * bins], 1u);
         }
-        if (!endNaN && rHi < rMax) {
+        if (endIn) {
             int idx; double rem;
-            bin_of(rHi, invRMin, cK, invDr, sInvG, bins, idx, rem);
-            const long long q1 = __double2ll_rn(rec.rhoS * rem);
-            acc_add(rowLo, rowHi, idx, q1 - Q);
-            if (idx < bins - 1) acc_add(rowLo, rowHi, idx + 1, -q1);
+            bin_of(rHi, a, invRMin, cK, invDr, invGA, idx, rem);
+            const long long q1 = __double2ll_rn(rhoS * rem);
+            acc_add2(row, hiOff, idx, bins, q1 - Q, -q1);
             if (TAPS && idx < bins) atomicAdd(&a.tapEnd[tapRow * bins + idx], 1u);
         }
     }
@@ -194,7 +259,8 @@ template <bool TAPS, int BINS>
 __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const int bins = BINS ? BINS : a.bins;
-    const int stride = bins + 1;   // +1: slot for a start/end edge that lands exactly on rMax
+    // + 1: row for a start/end edge that lands exactly on rMax; + 1: acc_add2's scratch row
+    const int stride = bins + 2;
     // byte offsets from the one dynamic array: the compiler must keep seeing shared addresses
     HitRec *rings = reinterpret_cast<HitRec *>(smemRaw);                          // [warps][kRingSlots]
     double2 *sTrig = reinterpret_cast<double2 *>(rings + kBinConsumers * kRingSlots);   // [32] (cos, sin)
@@ -351,7 +417,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
         if (v == 0) continue;
         if (bin < bins) {
             atomicAdd(&g[static_cast<size_t>(gl) * bins + bin], v);
-        } else if (gl + 1 < a.spokes) {
+        } else if (bin == bins && gl + 1 < a.spokes) {
             // index == bins lands in the next LoS's first bin (derivs is one slice)
             atomicAdd(&g[static_cast<size_t>(gl + 1) * bins], v);
         }
@@ -376,7 +442,7 @@ bool bin_stores_whole_grid(const BinArgs &a) { return a.chunks == 1 && (a.bins &
 
 size_t bin_smem_bytes(int bins) {
     return sizeof(HitRec) * kBinConsumers * kRingSlots + sizeof(double2) * kTileLos + sizeof(double) * (bins + 1) +
-           2 * sizeof(unsigned int) + sizeof(uint32_t) * 2 * kTileLos * (bins + 1);
+           2 * sizeof(unsigned int) + sizeof(uint32_t) * 2 * kTileLos * (bins + 2);
 }
 
 cudaError_t launch_bin(const BinArgs &a, int nb, bool taps, cudaStream_t s) {

@@ -9,7 +9,7 @@ namespace sfk {
 // (~2^-44), one residual correction of the root (<= 1 ulp), branch free.
 // Callers test the sign first.
 __device__ __forceinline__ double sqrt_pos(double x) {
-    x += 1e-300;   // 0 -> 1e-150 (still far below every rMin); exact no-op for x > 1e-284
+    x += 0x1p-996;   // 0 -> 2^-498 (far below every rMin); exact no-op for x > 1e-284; a power of two is an immediate operand
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double hx = 0.5 * x;
