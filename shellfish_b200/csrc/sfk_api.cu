@@ -523,11 +523,8 @@ int stage_bin(sfk_ctx *ctx, const std::vector<int32_t> &batch) {
     ba.tapInsert = ctx->dTapInsert.p; ba.tapStart = ctx->dTapStart.p; ba.tapEnd = ctx->dTapEnd.p;
     ba.rings = R; ba.spokes = n; ba.bins = B;
     ba.binInvG = ctx->dBinInvG.p;
-    ba.invDr = 1.0 / ctx->tab.dr0;
+    ba.invDr60 = 1.0 / (60.0 * ctx->tab.dr0);
     ba.cK = static_cast<float>(0.6931471805599453 / ctx->tab.dr0);
-    ba.lnC[0] = -1.0 / 6.0;
-    ba.lnC[1] = 0.2;
-    ba.lnC[2] = 1.0 / 3.0;
     // split long hit lists when there are too few CTAs to fill 148 SMs x 2 for a few waves
     const int64_t ctas = static_cast<int64_t>((n + kTileLos - 1) / kTileLos) * R * nb;
     ba.chunks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(64, (148 * 2 * 4 + ctas - 1) / ctas)));

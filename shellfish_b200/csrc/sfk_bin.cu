@@ -55,6 +55,12 @@ __device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
     asm volatile("" : "+r"(v));
     return v;
 }
+// v << n for n < 32, 0 otherwise
+__device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned n) {
+    unsigned r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -81,7 +87,7 @@ __device__ __forceinline__ void reds_add(uint32_t addr, uint32_t v) {
 
 // Bin index and fractional position of radius r, rMin < r < rMax
 // (profile_ring.go:100-101: Modf((ln r - lowR)/dr)).
-__device__ __forceinline__ void bin_of(double r, const BinArgs &a, double invRMin, float cK, double invDr,
+__device__ __forceinline__ void bin_of(double r, double invRMin, float cK, double invDr60,
                                        uint32_t invGA, int &idx, double &rem) {
     const double u = r * invRMin;
     // float32 view of u (u in [1, rMax/rMin]): rebias the exponent, keep 20 mantissa bits.
@@ -94,14 +100,15 @@ __device__ __forceinline__ void bin_of(double r, const BinArgs &a, double invRMi
     // 0 <= k <= bins - 1 without clamping
     int k = static_cast<int>(fmaf(lg, cK, -1.0e-3f));
     const double t = fma(u, lds_f64(invGA + 8u * k), -1.0);   // r / (rMin g[k]) - 1
-    // -1/6, 1/5, 1/3 are read from the parameter bank (a constant-bank operand of the DFMA);
-    // as literals each costs two UMOVs per use under the kernel's 64-register cap
-    double L = fma(t, a.lnC[0], a.lnC[1]);
-    L = fma(L, t, -0.25);
-    L = fma(L, t, a.lnC[2]);
-    L = fma(L, t, -0.5);
-    L = fma(L, t, 1.0);
-    double x = (L * t) * invDr;
+    // 60 log1p(t)/t = 60 - 30 t + 20 t^2 - 15 t^3 + 12 t^4 - 10 t^5: every coefficient is an
+    // immediate operand of its DFMA (1/3, 1/5, 1/6 would each cost a constant load per use under
+    // the kernel's 64-register cap); invDr60 = 1/(60 dr)
+    double L = fma(t, -10.0, 12.0);
+    L = fma(L, t, -15.0);
+    L = fma(L, t, 20.0);
+    L = fma(L, t, -30.0);
+    L = fma(L, t, 60.0);
+    double x = (L * t) * invDr60;
     // if (x >= 1.0) { k += 1; x -= 1.0; } as two predicated instructions
     asm("{\n\t.reg .pred p;\n\tsetp.ge.f64 p, %0, 0d3FF0000000000000;\n\t@p add.f64 %0, %0, 0dBFF0000000000000;\n\t"
         "@p add.s32 %1, %1, 1;\n\t}" : "+d"(x), "+r"(k));
@@ -147,12 +154,12 @@ constexpr int kRingSlots = 64;    // per-warp ring of records that touch the til
 // One round: up to 32 records of the warp's ring (slots head .. head + cnt - 1): clip to the
 // tile, expand to (record, LoS) pairs, evaluate the chords and add them to the tile.
 template <bool TAPS>
-__device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring, int head, int cnt, int lane, int t0,
+__device__ __forceinline__ void bin_round(const BinArgs &a, HitRec *wring, int head, int cnt, int lane, int t0,
                                           int t1, int bins, double rMin, double rMax, double invRMin,
-                                          double invDr, float cK, const double2 *sTrig, const double *sInvG,
+                                          double invDr60, float cK, const double2 *sTrig, const double *sInvG,
                                           uint32_t *lo, uint32_t *hi, size_t tapRing, unsigned &nIns) {
     // rounds take 32 records at a time, so head is 0 or 32 and the round never wraps
-    const HitRec *grp = wring + head;
+    HitRec *grp = wring + head;
     // clip my record's two LoS ranges to the tile
     int len1 = 0, len2 = 0, st1 = 0, st2 = 0;
     if (lane < cnt) {
@@ -164,6 +171,14 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
         if (len1 == 0) st1 = t0;   // keep the packed start offsets within 0..31
         if (len2 == 0) st2 = t0;
     }
+    // cx^2 + cy^2 is formed once per record and takes the place of the LoS ranges (not needed
+    // after the clipping above); its sign bit carries the centre-containing flag of r23
+    if (lane < cnt) {
+        const double cx = grp[lane].cx, cy = grp[lane].cy;
+        const double pd2 = cx * cx + cy * cy;
+        *reinterpret_cast<double *>(&grp[lane].r01) = (grp[lane].r23 & kHitCaseA) ? -pd2 : pd2;
+    }
+    __syncwarp();
     const unsigned nMine = static_cast<unsigned>(len1 + len2);
     unsigned incl = nMine;
     for (int o = 1; o < 32; o <<= 1) {
@@ -184,14 +199,17 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
     const uint32_t invGA = tabA + static_cast<uint32_t>(reinterpret_cast<const char *>(sInvG) - reinterpret_cast<const char *>(sTrig));
     const uint32_t loA = tabA + static_cast<uint32_t>(reinterpret_cast<const char *>(lo) - reinterpret_cast<const char *>(sTrig));
     const uint32_t hiOff = static_cast<uint32_t>(reinterpret_cast<const char *>(hi) - reinterpret_cast<const char *>(lo));
+    constexpr unsigned kNoRecord = 0x80000000u;
+    const unsigned firstKey = nMine ? first : kNoRecord;
     unsigned nBefore = 0;   // records whose first pair lies before this window
     for (unsigned p0 = 0; p0 < nPairs; p0 += 32) {
         // pair p -> record.  Every record of the round owns >= 1 pair, so the first-pair indices
         // are strictly increasing: one REDUX.OR marks the records that start inside this window
         // of 32 pairs, and pair p belongs to the last record starting at or before it.
         const unsigned p = p0 + lane;
-        const unsigned rel = first - p0;   // wraps for records that started earlier
-        const unsigned starts = __reduce_or_sync(0xffffffffu, (nMine && rel < 32u) ? 1u << rel : 0u);
+        // 1 << (first - p0), or 0 where that is not in 0..31 (PTX shl clamps the amount to 32):
+        // records that started earlier wrap around, lanes without a record carry kNoRecord
+        const unsigned starts = __reduce_or_sync(0xffffffffu, shl_clamp(1u, firstKey - p0));
         const unsigned r = (nBefore + __popc(starts & (0xffffffffu >> (31 - lane))) - 1u) & 31u;
         nBefore += __popc(starts);
         const unsigned rmA = __shfl_sync(0xffffffffu, metaA, r);
@@ -204,7 +222,7 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
         const double rhoS = __hiloint2double(static_cast<int>(recB.y), static_cast<int>(recB.x));
         // literal geometry of insertToRing, los/halo.go:233-262
         const double cx = __uint_as_float(recA.x), cy = __uint_as_float(recA.y);
-        const double projDist2 = cx * cx + cy * cy;
+        const double projDist2 = fabs(__hiloint2double(static_cast<int>(recA.w), static_cast<int>(recA.z)));
         // max(rad2 - cz*cz, 0), formed once per record by hits_kernel
         const double projRad2 = __hiloint2double(static_cast<int>(recB.w), static_cast<int>(recB.z));
         const double b = cy * cs.x - cx * cs.y;
@@ -234,7 +252,7 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
         const bool endIn = !endNaN && rHi < rMax;
         if (startIn) {
             int idx; double rem;
-            bin_of(rLo, a, invRMin, cK, invDr, invGA, idx, rem);
+            bin_of(rLo, invRMin, cK, invDr60, invGA, idx, rem);
             const long long q1 = __double2ll_rn(rhoS * rem);
             acc_add2(row, hiOff, idx, bins, Q - q1, q1);
             if (TAPS && idx < bins) atomicAdd(&a.tapStart[tapRow * bins + idx], 1u);
@@ -244,7 +262,7 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, const HitRec *wring,
         }
         if (endIn) {
             int idx; double rem;
-            bin_of(rHi, a, invRMin, cK, invDr, invGA, idx, rem);
+            bin_of(rHi, invRMin, cK, invDr60, invGA, idx, rem);
             const long long q1 = __double2ll_rn(rhoS * rem);
             acc_add2(row, hiOff, idx, bins, q1 - Q, -q1);
             if (TAPS && idx < bins) atomicAdd(&a.tapEnd[tapRow * bins + idx], 1u);
@@ -303,7 +321,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
 
     {
         const double rMin = h.rMin, rMax = h.rMax, invRMin = h.invRMin;
-        const double invDr = a.invDr;
+        const double invDr60 = a.invDr60;
         const float cK = a.cK;
         const size_t tapRing = (static_cast<size_t>(haloIdx) * a.rings + ring) * a.spokes;
         HitRec *wring = rings + warp * kRingSlots;
@@ -350,7 +368,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
                     if (count >= 32) {
                         cp_async_wait_all();
                         __syncwarp();
-                        bin_round<TAPS>(a, wring, head, 32, lane, t0, t1, bins, rMin, rMax, invRMin, invDr, cK,
+                        bin_round<TAPS>(a, wring, head, 32, lane, t0, t1, bins, rMin, rMax, invRMin, invDr60, cK,
                                         sTrig, sInvG, lo, hi, tapRing, nIns);
                         __syncwarp();   // the slots may be overwritten from here on
                         head = (head + 32) & (kRingSlots - 1);
@@ -363,7 +381,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
             } else {
                 cp_async_wait_all();
                 __syncwarp();
-                bin_round<TAPS>(a, wring, head, count, lane, t0, t1, bins, rMin, rMax, invRMin, invDr, cK,
+                bin_round<TAPS>(a, wring, head, count, lane, t0, t1, bins, rMin, rMax, invRMin, invDr60, cK,
                                 sTrig, sInvG, lo, hi, tapRing, nIns);
                 count = 0;
             }

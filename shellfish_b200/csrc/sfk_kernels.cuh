@@ -42,9 +42,8 @@ struct BinArgs {
     unsigned long long *nIntersections; // [nHalo]
     uint32_t *tapInsert, *tapStart, *tapEnd; // TAPS only, indexed by halo
     const double *binInvG;      // [bins+1] 1/exp(k*dr): reciprocal bin edges in units of rMin
-    double invDr;               // 1/dr
+    double invDr60;             // 1/(60 dr), see bin_of
     float cK;                   // bins per octave: ln 2 / dr
-    double lnC[3];              // -1/6, 1/5, 1/3 of bin_of's log1p series
     int rings, spokes, bins, chunks;
     // chunks == 1: tiles are stored, not added; edges falling into the next LoS's bin 0 go here
     unsigned long long *ovfList;   // [ovfCap][2] (grid cell, value)
