@@ -232,7 +232,7 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, HitRec *wring, int h
         const bool bad = !(m2 >= 0) || !(d2 >= 0);   // a sqrt of the reference returns NaN
         // twoValIntrDist skips NaN (halo.go:262); oneValIntrDist's NaN goes into Insert
         if (bad && !isA) continue;
-        const double mid = sqrt_pos(m2), diff = sqrt_pos(d2);
+        const double mid = sqrt_pos0(m2), diff = sqrt_pos0(d2);
         const double rLo = mid - diff;
         // mid + diff, or diff - mid on the far side of a centre-containing circle
         // (diff - mid is diff + (-mid) exactly: the sign of mid is flipped as an integer)
