@@ -483,7 +483,7 @@ int stage_bin(sfk_ctx *ctx, const std::vector<int32_t> &batch) {
     const size_t rn = static_cast<size_t>(R) * n, rnb = rn * B;
     const int nb = static_cast<int>(batch.size());
     std::vector<int32_t> haloSlot(nHalo, -1);
-    std::vector<int64_t> hitOffset(static_cast<size_t>(nb) * R);
+    std::vector<int64_t> hitOffset(static_cast<size_t>(nb) * R + 1);   // + 1: end of the last list
     std::vector<Piece> pieces;
     int64_t run = 0;
     for (int s = 0; s < nb; s++) {
@@ -495,9 +495,10 @@ int stage_bin(sfk_ctx *ctx, const std::vector<int32_t> &batch) {
         }
         pieces.insert(pieces.end(), ctx->perHalo[hIdx].begin(), ctx->perHalo[hIdx].end());
     }
+    hitOffset[static_cast<size_t>(nb) * R] = run;
     CU(ctx->dRecs.ensure(std::max<int64_t>(run, 1)));
     CU(ctx->dGrid.ensure(static_cast<size_t>(nb) * rnb));
-    CU(ctx->dHitCursor.ensure(static_cast<size_t>(nb) * R));
+    CU(ctx->dHitCursor.ensure(static_cast<size_t>(nb) * R * 2));   // records written from the front / from the back
     CU(ctx->dFR.ensure(static_cast<size_t>(nb) * rn));
     CU(ctx->dFIdx.ensure(static_cast<size_t>(nb) * rn));
     CU(ctx->dFCount.ensure(static_cast<size_t>(nb) * R));
@@ -505,7 +506,7 @@ int stage_bin(sfk_ctx *ctx, const std::vector<int32_t> &batch) {
     CU(ctx->dBatchHalos.upload(batch, st));
     CU(ctx->dHaloSlot.upload(haloSlot, st));
     CU(ctx->dHitOffset.upload(hitOffset, st));
-    CU(cudaMemsetAsync(ctx->dHitCursor.p, 0, static_cast<size_t>(nb) * R * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(ctx->dHitCursor.p, 0, static_cast<size_t>(nb) * R * 2 * sizeof(uint32_t), st));
 
     ctx->timer.begin(ST_HITS, st);
     CU(launch_hits(ctx->dPieces.p, static_cast<int>(pieces.size()), ctx->dCands.p, ctx->dHalos.p,

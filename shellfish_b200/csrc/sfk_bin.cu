@@ -311,11 +311,17 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
 
     // this CTA's share of the ring's records
     const size_t hr = static_cast<size_t>(slot) * a.rings + ring;
-    const int64_t total = a.hitCount[hr];
+    // hits_kernel fills a list from both ends (circles whose chords all start in bin 0 at the
+    // front): records 0 .. nFront - 1 are contiguous, the others follow after a gap
+    const int64_t nFront = a.hitCount[2 * hr];
+    const int64_t total = nFront + a.hitCount[2 * hr + 1];
+    const int gap = static_cast<int>(a.hitOffset[hr + 1] - a.hitOffset[hr] - total);
     const int64_t rec0 = (total * chunk / a.chunks) & ~int64_t(31);
     const int64_t rec1 = chunk + 1 == a.chunks ? total : (total * (chunk + 1) / a.chunks) & ~int64_t(31);
     const HitRec *src = a.recs + a.hitOffset[hr] + rec0;
     const int nRecs = static_cast<int>(rec1 - rec0);
+    // first record of this CTA's share that sits behind the gap
+    const int backFrom = static_cast<int>(max(int64_t(0), min(int64_t(nRecs), nFront - rec0)));
     const unsigned nChunks = static_cast<unsigned>((nRecs + kChunkRecs - 1) / kChunkRecs);
     unsigned nIns = 0;
 
@@ -333,7 +339,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
             for (int sub = 0; sub < kChunkRecs / 32; sub++) {
                 const int idx = static_cast<int>(c) * kChunkRecs + sub * 32 + lane;
                 rr[sub] = make_uint2(0u, 0u);
-                if (c < nChunks && idx < nRecs) rr[sub] = *reinterpret_cast<const uint2 *>(&src[idx].r01);
+                if (c < nChunks && idx < nRecs) rr[sub] = *reinterpret_cast<const uint2 *>(&src[idx + (idx >= backFrom ? gap : 0)].r01);
             }
         };
         auto draw = [&]() {
@@ -360,7 +366,8 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_kernel(BinArgs a) {
                     const unsigned m = __ballot_sync(0xffffffffu, ov);
                     if (ov) {
                         const int at = (head + count + __popc(m & ((1u << lane) - 1u))) & (kRingSlots - 1);
-                        const HitRec *from = src + static_cast<int>(cur) * kChunkRecs + sub * 32 + lane;
+                        const int idx = static_cast<int>(cur) * kChunkRecs + sub * 32 + lane;
+                        const HitRec *from = src + idx + (idx >= backFrom ? gap : 0);
                         cp_async16(&wring[at], from);
                         cp_async16(reinterpret_cast<char *>(&wring[at]) + 16, reinterpret_cast<const char *>(from) + 16);
                     }

@@ -493,15 +493,24 @@ hits_kernel(const Piece *pieces, const Cand *cands, const HaloDev *halos, const 
             HitRec rec;
             const bool alive = e < nq && make_hit<PRUNE>(rots + 9 * ring, sCand[q & 0xffu], h, dPhi, invDPhi, spokes,
                                                   ringCos, ringSin, rec);
-            // one slot claim per (warp, ring): queue order keeps a ring's hits together
-            const unsigned peers = __match_any_sync(0xffffffffu, alive ? ring : -1 - static_cast<int>(lane_id()));
+            // A (halo, ring) list is filled from both ends: circles that contain the centre or whose
+            // tangent length stays below rMin (rLo <= sqrt(dist^2 - prad^2) <= rMin on every LoS: each
+            // chord starts in bin 0) from the front, the others from the back, so that a warp of
+            // bin_kernel mostly runs ONE branch of ProfileRing.Insert's start edge.  The class is a
+            // scheduling hint in float32: every record is evaluated literally wherever it lands.
+            const bool outer = alive && !(rec.r23 & kHitCaseA) &&
+                               (rec.cx * rec.cx + rec.cy * rec.cy) - static_cast<float>(rec.projRad2) >
+                                   static_cast<float>(h.rMin * h.rMin);
+            // one slot claim per (warp, ring, end): queue order keeps a ring's hits together
+            const unsigned peers = __match_any_sync(0xffffffffu, alive ? 2 * ring + (outer ? 1 : 0)
+                                                                       : -1 - static_cast<int>(lane_id()));
             if (alive) {
                 const size_t hr = static_cast<size_t>(slot) * rings + ring;
                 const int leader = __ffs(peers) - 1;
                 uint32_t base = 0;
-                if (static_cast<int>(lane_id()) == leader) base = atomicAdd(&hitCursor[hr], __popc(peers));
-                base = __shfl_sync(peers, base, leader);
-                recs[hitOffset[hr] + base + __popc(peers & ((1u << lane_id()) - 1u))] = rec;
+                if (static_cast<int>(lane_id()) == leader) base = atomicAdd(&hitCursor[2 * hr + (outer ? 1 : 0)], __popc(peers));
+                base = __shfl_sync(peers, base, leader) + __popc(peers & ((1u << lane_id()) - 1u));
+                recs[outer ? hitOffset[hr + 1] - 1 - base : hitOffset[hr] + base] = rec;
             }
         }
         }

@@ -33,8 +33,8 @@ cudaError_t launch_bucket(const Cand *cands, int64_t n, const int64_t *offset, u
 
 struct BinArgs {
     const HitRec *recs;
-    const int64_t *hitOffset;   // [nb][rings] first record of (halo, ring)
-    const uint32_t *hitCount;   // [nb][rings]
+    const int64_t *hitOffset;   // [nb * rings + 1] first slot of (halo, ring); the list owns the slots up to the next offset
+    const uint32_t *hitCount;   // [nb][rings][2] records written from the front / from the back of the list (hits_kernel)
     const HaloDev *halos;
     const int32_t *batchHalos;  // [nb] halo index of each batch slot
     const double *ringCos, *ringSin;
