@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--parity-halos", type=int, default=2, help="halos checked against the oracle when N>1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sync-push", action="store_true",
+                    help="e2e: sfk_push_block (returns once the block is copied) instead of sfk_push_block_async")
     ap.add_argument("--order", type=int, default=3, help="Penna order (BASELINE config 5 sweeps 2, 3, 4)")
     ap.add_argument("--subsample", type=int, default=1, help="SubsampleFactor (config 5: 1, 2)")
     ap.add_argument("--los-taploop", action="store_true",
@@ -257,7 +259,7 @@ def main():
                 ctx.push_block_device(b, dx, dm)
         else:
             for pb in pin_blocks:
-                ctx.push_block(pb)
+                ctx.push_block(pb, wait=args.sync_push)
         coeffs, status = ctx.finish_snapshot()
         rows = np.zeros((len(mine), cols))
         rows[:, :P2] = coeffs[mine]
@@ -369,7 +371,10 @@ def main():
             "meta": dict(meta, parallelism="halo list partitioned over %d GPU(s) by estimated particle count "
                                           "(equal-weight runs along a Z-curve); no data-path collective; catalog rows gathered by "
                                           "halo index" % world,
-                         masses="uniform: blocks pushed without a mass array" if uniform else "per-particle mass arrays"),
+                         masses="uniform: blocks pushed without a mass array" if uniform else "per-particle mass arrays",
+                         e2e_push=("sfk_push_block (returns once the block is copied)" if args.sync_push else
+                                   "sfk_push_block_async from page-locked buffers that hold the snapshot until "
+                                   "sfk_finish_snapshot (copies queued back to back)")),
             "halos_ok": nok // max(1, args.steps),
             "intersections_per_s": tot["n_intersections"] / (ms * 1e-3),
             "stage_ms_per_step": dict(zip(stage_keys, stage_by_rank[int(np.argmax(per_rank))])),

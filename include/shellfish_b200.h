@@ -142,6 +142,17 @@ int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
                    const sfk_cosmo *cosmo, double total_width,
                    const float origin[3], const float width[3]);
 
+/* sfk_push_block for a reader that owns several page-locked buffers (a ring of
+ * io.VectorBuffer slices allocated once, or a whole snapshot held in memory): the call only
+ * QUEUES the copy, so the copies of consecutive blocks run back to back on the bus instead of
+ * one per call round trip.  xyz / mass must stay unchanged until sfk_push_sync or
+ * sfk_finish_snapshot returns.  Same results as sfk_push_block. */
+int sfk_push_block_async(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
+                         const sfk_cosmo *cosmo, double total_width,
+                         const float origin[3], const float width[3]);
+/* Returns once every buffer handed to sfk_push_block_async has been copied (they may be reused). */
+int sfk_push_sync(sfk_ctx *ctx);
+
 /* Same with xyz/mass already in device memory of ctx's GPU (used to time the
  * kernels with inputs resident in HBM).  The buffers must be complete on the device when
  * they are handed over (work queued before the first device push of a snapshot is waited

@@ -51,7 +51,7 @@ class Stats(C.Structure):
 
 # every symbol include/shellfish_b200.h declares
 EXPORTS = ["sfk_device_count", "sfk_default_params", "sfk_create", "sfk_destroy", "sfk_last_error", "sfk_begin_snapshot",
-           "sfk_add_halos", "sfk_set_owned", "sfk_block_halo_mask", "sfk_push_block", "sfk_push_block_device",
+           "sfk_add_halos", "sfk_set_owned", "sfk_block_halo_mask", "sfk_push_block", "sfk_push_block_async", "sfk_push_sync", "sfk_push_block_device",
            "sfk_finish_snapshot", "sfk_row_length", "sfk_split_count", "sfk_split_bin", "sfk_split_buffer", "sfk_split_finish",
            "sfk_comm_unique_id", "sfk_comm_init", "sfk_split_finish_comm",
            "sfk_mass_begin", "sfk_mass_push_block", "sfk_mass_push_block_device", "sfk_mass_finish", "sfk_mass_set_band", "sfk_mass_take_band",
@@ -87,6 +87,8 @@ def lib():
         L.sfk_set_owned.argtypes = [vp, C.c_int64, C.POINTER(C.c_uint8)]
         L.sfk_block_halo_mask.argtypes = [vp, fp, fp, C.c_double, C.POINTER(C.c_uint8), C.POINTER(C.c_int64)]
         L.sfk_push_block.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Cosmo), C.c_double, fp, fp]
+        L.sfk_push_block_async.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Cosmo), C.c_double, fp, fp]
+        L.sfk_push_sync.argtypes = [vp]
         L.sfk_push_block_device.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Cosmo), C.c_double, fp, fp]
         L.sfk_finish_snapshot.argtypes = [vp, dp, C.POINTER(C.c_int32)]
         L.sfk_split_count.argtypes = [vp]
@@ -188,11 +190,13 @@ class ShellContext:
                  "sfk_block_halo_mask")
         return hit.astype(bool)
 
-    def push_block(self, block):
+    def push_block(self, block, wait=True):
         """block: dict with Z, OmegaM, OmegaL, H100, TotalWidth, Origin, Width,
         xs (N,3) float32 and ms (N,) float32 host arrays (numpy, or pinned
         torch CPU tensors).  ms may be None: every particle then has the min_mass
-        given to begin_snapshot (uniform-mass snapshots; a quarter less to transfer)."""
+        given to begin_snapshot (uniform-mass snapshots; a quarter less to transfer).
+        wait=False (sfk_push_block_async): the copy is only queued; xs / ms must stay
+        unchanged until push_sync() or finish_snapshot() returns."""
         xs, ms = block["xs"], block.get("ms")
         c = Cosmo(block["Z"], block["OmegaM"], block["OmegaL"], block["H100"])
         if hasattr(xs, "data_ptr"):
@@ -200,8 +204,12 @@ class ShellContext:
         else:
             assert xs.dtype == np.float32 and xs.flags.c_contiguous and (ms is None or ms.dtype == np.float32)
             n, px, pm = len(xs), xs.ctypes.data, (ms.ctypes.data if ms is not None else None)
-        self._ck(lib().sfk_push_block(self._h, px, pm, n, C.byref(c), float(block["TotalWidth"]),
-                                      _f3(block["Origin"]), _f3(block["Width"])), "sfk_push_block")
+        fn = lib().sfk_push_block if wait else lib().sfk_push_block_async
+        self._ck(fn(self._h, px, pm, n, C.byref(c), float(block["TotalWidth"]),
+                    _f3(block["Origin"]), _f3(block["Width"])), "sfk_push_block" if wait else "sfk_push_block_async")
+
+    def push_sync(self):
+        self._ck(lib().sfk_push_sync(self._h), "sfk_push_sync")
 
     def push_block_device(self, block, d_xs, d_ms):
         """Same with positions/masses already on this context's GPU (torch CUDA tensors; d_ms may

@@ -143,6 +143,7 @@ struct sfk_ctx {
     // batch scratch
     DevBuf<Piece> dPieces;
     DevBuf<HitRec> dRecs;
+    std::vector<int32_t> blockList;   // halos touching the block being pushed
     DevBuf<int64_t> dHitOffset;
     DevBuf<uint32_t> dHitCursor, dBatchHitCount;
     DevBuf<int32_t> dBatchHalos, dHaloSlot;
@@ -284,16 +285,20 @@ int reserve_cands(sfk_ctx *ctx, int64_t extra) {
     return SFK_OK;
 }
 
-int push_block_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, int64_t n,
-                    const sfk_cosmo *cosmo, double tw, const float origin[3], const float width[3]) {
-    // binIntersections for this header, cmd/shell.go:599-611 (halo order kept)
-    std::vector<int32_t> list;
-    int64_t nOwned = 0;
+// binIntersections for one header, cmd/shell.go:599-611 (halo order kept)
+void block_halo_list(const sfk_ctx *ctx, const float origin[3], const float width[3], double tw,
+                     std::vector<int32_t> &list, int64_t &nOwned) {
+    list.clear();
+    nOwned = 0;
     for (size_t i = 0; i < ctx->halos.size(); i++)
         if (ctx->halos[i].valid && sheet_intersect(ctx, i, origin, width, tw)) {
             list.push_back(static_cast<int32_t>(i));
             nOwned += ctx->halos[i].owned ? 1 : 0;
         }
+}
+
+int push_block_impl(sfk_ctx *ctx, const float *dxyz, const float *dmass, int64_t n,
+                    const sfk_cosmo *cosmo, double tw, const std::vector<int32_t> &list, int64_t nOwned) {
     if (list.empty() || n <= 0) return SFK_OK;
     const int nList = static_cast<int>(list.size());
     const int64_t sf = ctx->p.subsample_factor;
@@ -864,19 +869,20 @@ int sfk_block_halo_mask(sfk_ctx *ctx, const float origin[3], const float width[3
     return SFK_OK;
 } SFK_CATCH(ctx)
 
-int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
-                   const sfk_cosmo *cosmo, double total_width, const float origin[3],
-                   const float width[3]) try {
+// Host pushes: the copy runs on its own stream into one of two staging buffers, so it overlaps
+// the cull of the previous block.  wait: return once the caller's buffers have been consumed
+// (cgo may not retain Go pointers; io.VectorBuffer reuses its slices) -- not once the block has
+// been culled; otherwise the copy is only queued (sfk_push_block_async).
+static int push_block_host(sfk_ctx *ctx, const char *who, const float *xyz, const float *mass, int64_t n,
+                           const sfk_cosmo *cosmo, double total_width, const float origin[3],
+                           const float width[3], bool wait) {
     if (!ctx || !ctx->inSnapshot || ctx->finished || !cosmo || n < 0 || (n > 0 && !xyz))
-        return fail(ctx, SFK_E_INVALID, "sfk_push_block: bad arguments or no snapshot open");
+        return fail(ctx, SFK_E_INVALID, std::string(who) + ": bad arguments or no snapshot open");
     CU(cudaSetDevice(ctx->p.device));
-    int64_t hits = 0;
-    sfk_block_halo_mask(ctx, origin, width, total_width, nullptr, &hits);
-    if (hits == 0 || n == 0) return SFK_OK;   // sphereLoop skips the read, cmd/shell.go:389-391
-    // The copy runs on its own stream into one of two staging buffers, so it overlaps the cull
-    // of the previous block; the call returns once the caller's buffers have been consumed
-    // (cgo may not retain Go pointers; io.VectorBuffer reuses its slices), not once the block
-    // has been culled.
+    std::vector<int32_t> &list = ctx->blockList;
+    int64_t nOwned = 0;
+    block_halo_list(ctx, origin, width, total_width, list, nOwned);
+    if (list.empty() || n == 0) return SFK_OK;   // sphereLoop skips the read, cmd/shell.go:389-391
     const int slot = static_cast<int>(ctx->pushIdx++ & 1);
     if (ctx->culledValid[slot]) CU(cudaStreamWaitEvent(ctx->copyStream, ctx->evCulled[slot], 0));
     if (static_cast<size_t>(3 * n) > ctx->dXyz[slot].cap || (mass && static_cast<size_t>(n) > ctx->dMass[slot].cap)) {
@@ -887,12 +893,31 @@ int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
     CU(cudaMemcpyAsync(ctx->dXyz[slot].p, xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->copyStream));
     if (mass) CU(cudaMemcpyAsync(ctx->dMass[slot].p, mass, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copyStream));
     CU(cudaEventRecord(ctx->evCopied[slot], ctx->copyStream));
-    CU(cudaStreamSynchronize(ctx->copyStream));
+    if (wait) CU(cudaStreamSynchronize(ctx->copyStream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->evCopied[slot], 0));
-    int rc = push_block_impl(ctx, ctx->dXyz[slot].p, mass ? ctx->dMass[slot].p : nullptr, n, cosmo, total_width, origin, width);
+    int rc = push_block_impl(ctx, ctx->dXyz[slot].p, mass ? ctx->dMass[slot].p : nullptr, n, cosmo, total_width, list, nOwned);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->evCulled[slot], ctx->stream));
     ctx->culledValid[slot] = true;
+    return SFK_OK;
+}
+
+int sfk_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
+                   const sfk_cosmo *cosmo, double total_width, const float origin[3],
+                   const float width[3]) try {
+    return push_block_host(ctx, "sfk_push_block", xyz, mass, n, cosmo, total_width, origin, width, true);
+} SFK_CATCH(ctx)
+
+int sfk_push_block_async(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
+                         const sfk_cosmo *cosmo, double total_width, const float origin[3],
+                         const float width[3]) try {
+    return push_block_host(ctx, "sfk_push_block_async", xyz, mass, n, cosmo, total_width, origin, width, false);
+} SFK_CATCH(ctx)
+
+int sfk_push_sync(sfk_ctx *ctx) try {
+    if (!ctx) return SFK_E_INVALID;
+    CU(cudaSetDevice(ctx->p.device));
+    CU(cudaStreamSynchronize(ctx->copyStream));
     return SFK_OK;
 } SFK_CATCH(ctx)
 
@@ -906,7 +931,9 @@ int sfk_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass,
     // the FIRST device push of a snapshot is waited for once; later buffers must be complete when
     // they are handed over.  The cull of the block is queued, not finished, on return.
     if (!ctx->pushed) CU(cudaDeviceSynchronize());
-    return push_block_impl(ctx, d_xyz, d_mass, n, cosmo, total_width, origin, width);
+    int64_t nOwned = 0;
+    block_halo_list(ctx, origin, width, total_width, ctx->blockList, nOwned);
+    return push_block_impl(ctx, d_xyz, d_mass, n, cosmo, total_width, ctx->blockList, nOwned);
 } SFK_CATCH(ctx)
 
 int64_t sfk_row_length(const sfk_ctx *ctx) { return ctx ? ctx->P2 : 0; }

@@ -210,6 +210,32 @@ def test_device_and_host_push_agree():
     assert np.array_equal(c_host, c_dev) and np.array_equal(s_host, s_dev)
 
 
+def test_queued_host_push_agrees():
+    """sfk_push_block_async (copies only queued, buffers held by the caller until push_sync /
+    finish_snapshot) gives bitwise the result of sfk_push_block, from page-locked and from
+    pageable buffers, with and without a sync in the middle of the snapshot."""
+    import torch
+    halos, blocks, mass = synth.make_box(13, 20.0, 2, 12000, 8000, 2, r200m_range=(0.6, 0.9))
+    params = api.default_params(seed=1337, rings=8)
+    _, c_host, s_host = api.run_shell(params, mass, halos, blocks)
+    for pinned in (True, False):
+        ctx = api.ShellContext(params)
+        ctx.begin_snapshot(blocks[0], mass)
+        ctx.add_halos(halos)
+        keep = []
+        for k, b in enumerate(blocks):
+            pb = dict(b)
+            if pinned:
+                pb["xs"] = torch.from_numpy(b["xs"]).pin_memory()
+                pb["ms"] = torch.from_numpy(b["ms"]).pin_memory()
+            keep.append(pb)
+            ctx.push_block(pb, wait=False)
+            if k == len(blocks) // 2:
+                ctx.push_sync()
+        c, s = ctx.finish_snapshot()
+        assert np.array_equal(c_host, c) and np.array_equal(s_host, s)
+
+
 def test_ring_tables_match_oracle():
     params = api.default_params(seed=987654321, rings=100)
     ctx = api.ShellContext(params)
