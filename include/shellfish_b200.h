@@ -231,6 +231,8 @@ int sfk_mass_begin(sfk_ctx *ctx, int64_t n_halo, int32_t order, const float *cen
                    const double *coeffs, const double *r_low, const double *r_high);
 int sfk_mass_push_block(sfk_ctx *ctx, const float *xyz, const float *mass, int64_t n,
                         double total_width);
+/* Device buffers, as for sfk_push_block_device: complete on the device when handed over (work
+ * queued before the first device push of a pass is waited for once), valid until sfk_mass_finish. */
 int sfk_mass_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_mass,
                                int64_t n, double total_width);
 int sfk_mass_finish(sfk_ctx *ctx, double *masses);

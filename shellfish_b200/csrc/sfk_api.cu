@@ -125,6 +125,7 @@ struct sfk_ctx {
     int64_t massHalos = 0;
     int massOrder = 0;
     bool massOpen = false;
+    bool massDevSynced = false;   // work on other streams was waited for at the first device push of this pass
     // ShellParticleFile pass
     bool bandOn = false;
     int bandInside = 0;
@@ -1166,7 +1167,7 @@ int sfk_mass_begin(sfk_ctx *ctx, int64_t n_halo, int32_t order, const float *cen
     CU(ctx->dMassList.ensure(n_halo + 7));
     if (n_halo) CU(cudaMemsetAsync(ctx->dMassSums.p, 0, n_halo * sizeof(double), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));   // the host vectors die here
-    ctx->massHalos = n_halo; ctx->massOrder = order; ctx->massOpen = true;
+    ctx->massHalos = n_halo; ctx->massOrder = order; ctx->massOpen = true; ctx->massDevSynced = false;
     ctx->bandOn = false;
     return SFK_OK;
 } SFK_CATCH(ctx)
@@ -1212,7 +1213,9 @@ int sfk_mass_push_block_device(sfk_ctx *ctx, const float *d_xyz, const float *d_
     ctx->hBand.clear();
     if (n == 0 || ctx->massHalos == 0) return SFK_OK;
     CU(cudaSetDevice(ctx->p.device));
-    CU(cudaDeviceSynchronize());   // the caller's buffers live on other streams
+    // as sfk_push_block_device: work queued on other streams is waited for once per pass; later
+    // buffers must be complete on the device when they are handed over
+    if (!ctx->massDevSynced) { CU(cudaDeviceSynchronize()); ctx->massDevSynced = true; }
     int rc = mass_push_impl(ctx, d_xyz, d_mass, n, total_width);
     if (rc) return rc;
     if (ctx->bandOn) return band_pass(ctx, d_xyz, n, total_width);
