@@ -237,7 +237,7 @@ int validate(sfk_ctx *ctx, const sfk_params &p) {
         if (p.smoothing_window % 2 != 1) return fail(ctx, SFK_E_INVALID, "Kernel width must be odd.");
         if (p.smoothing_window <= 4) return fail(ctx, SFK_E_INVALID, "Kernel width cannot be smaller than pOrder.");
     }
-    if (bin_smem_bytes(static_cast<int>(p.radial_bins)) > 227 * 1024)
+    if (bin_smem_bytes(static_cast<int>(p.radial_bins), (p.flags & SFK_FLAG_TAPS) != 0) > 227 * 1024)
         return fail(ctx, SFK_E_UNSUPPORTED, "RadialBins too large for one shared-memory tile.");
     return SFK_OK;
 }
@@ -532,9 +532,12 @@ int stage_bin(sfk_ctx *ctx, const std::vector<int32_t> &batch) {
     ba.binInvG = ctx->dBinInvG.p;
     ba.invDr60 = 1.0 / (60.0 * ctx->tab.dr0);
     ba.cK = static_cast<float>(0.6931471805599453 / ctx->tab.dr0);
-    // split long hit lists when there are too few CTAs to fill 148 SMs x 2 for a few waves
-    const int64_t ctas = static_cast<int64_t>((n + kTileLos - 1) / kTileLos) * R * nb;
-    ba.chunks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(64, (148 * 2 * 4 + ctas - 1) / ctas)));
+    // split long hit lists when there are too few CTAs to fill 148 SMs (x 2 CTAs of a 32-LoS tile,
+    // x 1 of a 64-LoS tile) for a few waves
+    const int tile = bin_tile_los(B, ctx->taps);
+    const int64_t ctas = static_cast<int64_t>((n + tile - 1) / tile) * R * nb;
+    const int64_t want = 148 * (64 / tile) * 4;
+    ba.chunks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(64, (want + ctas - 1) / ctas)));
     constexpr unsigned kOvfCap = 1u << 16;
     if (!ctx->dOvfCount.p) {
         CU(ctx->dOvfList.ensure(2 * kOvfCap));

@@ -177,7 +177,8 @@ bool los_moments_supported(const LosArgs &a);
 cudaError_t launch_los(const LosArgs &a, const SgPoly *sg, int nb, cudaStream_t s);
 cudaError_t launch_filter(const FilterArgs &a, int nb, cudaStream_t s);
 cudaError_t launch_fit(const FitArgs &a, int nb, cudaStream_t s);
-size_t bin_smem_bytes(int bins);
+size_t bin_smem_bytes(int bins, bool taps);
+int bin_tile_los(int bins, bool taps);   // LoS per CTA of the instantiation launch_bin picks
 size_t fit_scratch_doubles(int nb, int rings, int spokes, int order, size_t *rows, size_t *gramPart, size_t *gramInv,
                            size_t *csPart);
 
