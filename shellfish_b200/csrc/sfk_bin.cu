@@ -40,9 +40,9 @@ namespace {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-// 16-byte asynchronous copy global -> shared (LDGSTS): the data never visits registers
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only: a CTA reads a record once): the data never visits registers
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
