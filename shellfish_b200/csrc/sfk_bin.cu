@@ -1,22 +1,26 @@
 // sfk_bin.cu -- the binning kernel: per-LoS chords of every (particle, ring)
 // hit and ProfileRing.Insert (los/halo.go:241-277, profile_ring.go:92-120).
 //
-// One CTA per (LoS tile of 32, ring, halo[, chunk of the hit list]).  The
-// tile's 32 x bins accumulators are 64-bit fixed point, split into lo/hi
+// One CTA per (LoS tile, ring, halo[, chunk of the hit list]); a tile is 64 lines of sight in
+// the product instantiation (32 warps, one CTA per SM) and 32 otherwise (16 warps, two CTAs).
+// The tile's TILE x bins accumulators are 64-bit fixed point, split into lo/hi
 // 32-bit words in shared memory so that native 32-bit shared atomics can be
 // used (64-bit shared atomics are CAS loops on sm_100).
 //
 // Every warp does the same job.  It draws 128-record chunks of the ring's hit
-// list from a shared counter, reads only the LoS ranges of those records
+// list from a shared counter (single groups of 32 near the end of the list, so that the warps
+// finish together), reads only the LoS ranges of those records
 // (prefetched one chunk ahead), and copies the records that touch this tile --
-// about one in four -- into its private 64-slot ring in shared memory with
+// one in three or four -- into its private 64-slot ring in shared memory with
 // cp.async.  Whenever 32 records are waiting, their ranges are clipped to the
 // tile, a warp scan turns the clipped lengths into a list of (record, LoS)
 // pairs, and the pairs are processed 32 at a time with one pair per lane (a
-// lane finds its record from one REDUX.OR over the records' first-pair indices
-// and two POPCs), so every lane does useful work whatever the range widths.
-// A CTA that owns its 32 rows alone stores the finished tile into the grid
+// lane finds its record from one REDUX.OR over the records' first-pair indices,
+// a POPC and a running count), so every lane does useful work whatever the range widths.
+// A CTA that owns its rows alone stores the finished tile into the grid
 // (no memset, no read-modify-write); otherwise it adds it with RED.64.
+// hits_kernel fills each list from both ends by the branch the records' chords take at the
+// start edge of ProfileRing.Insert, so a warp mostly runs one of the two.
 //
 // Arithmetic.  Everything that DECIDES something is evaluated literally, in
 // the reference's operation order with no FMA contraction (-fmad=false): the
@@ -331,7 +335,6 @@ __global__ void __launch_bounds__(TILE * 16, 64 / TILE) bin_kernel(BinArgs a) {
     const int nRecs = static_cast<int>(rec1 - rec0);
     // first record of this CTA's share that sits behind the gap
     const int backFrom = static_cast<int>(max(int64_t(0), min(int64_t(nRecs), nFront - rec0)));
-    const unsigned nChunks = static_cast<unsigned>((nRecs + kChunkRecs - 1) / kChunkRecs);
     unsigned nIns = 0;
 
     {
@@ -342,25 +345,37 @@ __global__ void __launch_bounds__(TILE * 16, 64 / TILE) bin_kernel(BinArgs a) {
         HitRec *wring = rings + warp * kRingSlots;
         int head = 0, count = 0;   // records waiting in the ring: slots head .. head + count - 1 (mod 64)
 
-        // (r01, r23) of record c * 128 + sub * 32 + lane of the drawn chunk; (0, 0) past the end
+        // A draw is the first record of a chunk; bit 31: a single group of 32 records instead of
+        // kChunkRecs.  Guided self-scheduling: whole chunks while plenty is left, single groups for
+        // the last kTailRecs records of the list, so that the warps of the CTA finish within one
+        // group of each other (with one CTA per SM nothing else fills the SM while the last warp
+        // works off a whole chunk).
+        constexpr unsigned kSmall = 0x80000000u;
+        constexpr unsigned kTailRecs = kBinThreads * 4;   // one whole chunk per warp
+        // (r01, r23) of record start + sub * 32 + lane of the drawn chunk; (0, 0) past its end
         auto load_ranges = [&](unsigned c, uint2 (&rr)[kChunkRecs / 32]) {
+            const int start = static_cast<int>(c & ~kSmall), len = (c & kSmall) ? 32 : kChunkRecs;
 #pragma unroll
             for (int sub = 0; sub < kChunkRecs / 32; sub++) {
-                const int idx = static_cast<int>(c) * kChunkRecs + sub * 32 + lane;
+                const int idx = start + sub * 32 + lane;
                 rr[sub] = make_uint2(0u, 0u);
-                if (c < nChunks && idx < nRecs) rr[sub] = *reinterpret_cast<const uint2 *>(&src[idx + (idx >= backFrom ? gap : 0)].r01);
+                if (sub * 32 < len && idx < nRecs) rr[sub] = *reinterpret_cast<const uint2 *>(&src[idx + (idx >= backFrom ? gap : 0)].r01);
             }
         };
         auto draw = [&]() {
             unsigned c = 0;
-            if (lane == 0) c = atomicAdd(nextChunk, 1u);
+            if (lane == 0) {
+                const unsigned seen = *reinterpret_cast<volatile unsigned *>(nextChunk);
+                const bool small = seen + kTailRecs >= static_cast<unsigned>(nRecs);
+                c = atomicAdd(nextChunk, small ? 32u : static_cast<unsigned>(kChunkRecs)) | (small ? kSmall : 0u);
+            }
             return __shfl_sync(0xffffffffu, c, 0);
         };
         unsigned cur = draw();
         uint2 rr[kChunkRecs / 32];
         load_ranges(cur, rr);
         for (;;) {
-            const bool flush = cur >= nChunks;   // nothing left to draw: work off what is waiting
+            const bool flush = (cur & ~kSmall) >= static_cast<unsigned>(nRecs);   // nothing left to draw: work off what is waiting
             if (flush && count == 0) break;
             if (!flush) {
                 // draw the next chunk and start its range loads before working on this one
@@ -375,7 +390,7 @@ __global__ void __launch_bounds__(TILE * 16, 64 / TILE) bin_kernel(BinArgs a) {
                     const unsigned m = __ballot_sync(0xffffffffu, ov);
                     if (ov) {
                         const int at = (head + count + __popc(m & ((1u << lane) - 1u))) & (kRingSlots - 1);
-                        const int idx = static_cast<int>(cur) * kChunkRecs + sub * 32 + lane;
+                        const int idx = static_cast<int>(cur & ~kSmall) + sub * 32 + lane;
                         const HitRec *from = src + idx + (idx >= backFrom ? gap : 0);
                         cp_async16(&wring[at], from);
                         cp_async16(reinterpret_cast<char *>(&wring[at]) + 16, reinterpret_cast<const char *>(from) + 16);
