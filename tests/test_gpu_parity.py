@@ -488,6 +488,24 @@ def test_product_bin_kernel_writes_the_grid_whose_taps_are_checked(rings, n):
     assert np.max(np.abs(rho - rp) / np.maximum(np.abs(rp), bg)) <= RTOL
 
 
+@pytest.mark.parametrize("spokes", [100, 96, 40, 300])
+def test_wide_and_narrow_bin_tiles_leave_the_same_grid(spokes):
+    """RadialBins = 256 without taps runs bin_kernel<false, 256, 64> (64 lines of sight per CTA), the
+    tap instantiation 32 per CTA.  With line-of-sight counts that are not a multiple of either tile
+    (a ragged last tile, a ring narrower than one tile) both must leave the same int64 grid and
+    the same rows."""
+    halos, blocks, mass = synth.single_halo(seed=47, n=20000, n_background=5000)
+    K = api.SFK_FLAG_KEEP_GRID
+    prod, cp, sp_ = _taps_of(K, halos, blocks, mass, rings=5, spokes=spokes)
+    taps, ct, st = _taps_of(K | api.SFK_FLAG_TAPS, halos, blocks, mass, rings=5, spokes=spokes)
+    gp, qp = prod.grid(0)
+    gt, qt = taps.grid(0)
+    assert qp == qt and np.array_equal(gp, gt)
+    assert np.array_equal(cp, ct) and np.array_equal(sp_, st)
+    assert np.array_equal(prod.rsp(0), taps.rsp(0), equal_nan=True)
+    assert prod.stats()["n_intersections"] == taps.stats()["n_intersections"]
+
+
 def test_sparse_halos_with_flat_profile_windows():
     """Halos of 1500 particles: many lines of sight are clamped to the background, or see no kernel
     edge, over more than a smoothing window.  There the reference's smoothed values at consecutive
