@@ -31,6 +31,15 @@ def test_kernel_equals_its_host_compiled_source():
             np.testing.assert_allclose(props[h], hc.shell_props(cs, *api.SHELL_RULE), rtol=1e-9, atol=1e-12)
 
 
+def test_reference_quickstart_known_answer_through_the_c_abi():
+    """doc/quickstart.md:99-106,150-155: the reference's printed `shell | stats` rows of one halo.
+    sfk_shell_props must give the R_sp, Volume, Surface Area and axes the reference printed, within
+    the noise of its 50 000-sample Monte-Carlo estimate (tests/test_shellprops.py has the details)."""
+    ctx = api.ShellContext(api.default_params(rings=3))
+    p = ctx.shell_props(np.array([shells.QUICKSTART_COEFFS]))[0]
+    shells.assert_matches_quickstart(p)
+
+
 def test_sphere_and_edge_cases():
     ctx = api.ShellContext(api.default_params(rings=3))
     R = 2.5

@@ -114,6 +114,29 @@ def test_axes_agree_with_monte_carlo_statistically():
         assert abs(np.linalg.norm(p[6:9]) - 1) < 1e-14 and p[6:9][np.abs(p[6:9]).argmax()] > 0
 
 
+def test_reference_quickstart_known_answer():
+    """doc/quickstart.md: the coefficients `shellfish shell` printed for halo 80431577 and the row
+    `shellfish stats` made of them.  The one vector the reference holds for Shell.Volume /
+    SurfaceArea / Axes and the R_sp formula: the product's quadrature must reproduce it within
+    the sampling noise of the reference's own 50 000-sample estimate, and so must the oracle's
+    Monte-Carlo restatement (which pins it beyond the cross-checks above)."""
+    cs = shells.QUICKSTART_COEFFS
+    p = hc.shell_props(cs)
+    shells.assert_matches_quickstart(p)
+    # measured: R_sp -2.2e-4, volume -6.5e-4, area -9.2e-4, axes +2.8e-3 / -8e-4 / -2.8e-3 relative
+    tables = shells.axis_tables()
+    for seed in (1, 2, 3):
+        ax = po.shell_axes(cs, 50000, seed, tables)
+        vol = po.shell_volume(cs, 50000, 10 + seed)
+        row = np.concatenate([[(vol / (4 * np.pi / 3)) ** 0.33333, vol, po.shell_surface_area(cs, 50000, 20 + seed)],
+                              ax[:3], ax[3]])
+        # two independent estimates: sqrt(2) x the one-run scatter
+        shells.assert_matches_quickstart(row, n_sigma=4.5)
+    # the estimators' scatter quoted in shell_cases.QUICKSTART_SIGMA
+    vols = np.array([po.shell_volume(cs, 50000, s) for s in range(30, 38)])
+    assert 0.3 * shells.QUICKSTART_SIGMA["volume"] < vols.std(ddof=1) / vols.mean() < 2.5 * shells.QUICKSTART_SIGMA["volume"]
+
+
 def test_axes_closing_arithmetic_against_numpy():
     """sfk_axes_from_moments (libsfk.so host code) vs shell.go:140-198 written out with
     numpy.linalg.eigh and the oracle's BiCubic."""
