@@ -139,6 +139,26 @@ def test_format_cols():   # catalog.go:52-141: right-aligned to the widest entry
     assert H.format_cols([], [], []) == []
 
 
+def test_format_cols_reference_documents():
+    """Rows the reference's documentation prints (its only catalog text besides the unit tests):
+    doc/quickstart.md:105 (one `shell` row: no padding, "%.6g") and doc/walkthrough.md:86-89 (three
+    `stats` rows: every column right-aligned to its widest entry -- "0.3129  0.429")."""
+    import shell_cases as shells
+    row = [13.6225, 86.3578, 53.1017, 0.815028] + list(shells.QUICKSTART_COEFFS)
+    lines = H.format_cols([[80431577], [100]], [[v] for v in row], list(range(2 + len(row))))
+    assert lines == ["80431577 100 13.6225 86.3578 53.1017 0.815028 0.979897 -0.0616729 0.35461 0.122959 0.281588 "
+                     "-0.0869048 -0.0560629 0.0831245 0.244373 -0.0405277 -0.0488017 -0.302187 -0.61362 0.357011 "
+                     "2.46993 0.0243595 0.525989 2.74402"]
+    ints, flts = H.parse_catalog(lines[0] + "\n", [0, 1], list(range(2, 24)))
+    assert ints[:, 0].tolist() == [80431577, 100] and flts[:, 0].tolist() == row
+    lines = H.format_cols([[169665239, 168208646, 168863226], [100, 100, 100]],
+                          [[1.373e12, 1.244e12, 1.284e12], [0.4084, 0.3683, 0.3576], [0.3121, 0.3129, 0.2613],
+                           [0.5297, 0.429, 0.4081]], [0, 1, 2, 3, 4, 5])
+    assert lines == ["169665239 100 1.373e+12 0.4084 0.3121 0.5297",
+                     "168208646 100 1.244e+12 0.3683 0.3129  0.429",
+                     "168863226 100 1.284e+12 0.3576 0.2613 0.4081"]
+
+
 def test_parse_catalog():   # catalog.go:143-231
     text = "# comment\n1 100 1.5 2.5 3.5 0.5\n\n  2 100 4 5 6 0.25 # trailing\n"
     ic, fc = H.parse_catalog(text, [0, 1], [2, 3, 4, 5])
