@@ -285,7 +285,7 @@ __device__ __forceinline__ void bin_round(const BinArgs &a, HitRec *wring, int h
 // ranges per record (-2.5 %); the 132 KB of accumulators then leave room for one CTA only.
 template <bool TAPS, int BINS, int TILE>
 __global__ void __launch_bounds__(TILE * 16, 64 / TILE) bin_kernel(BinArgs a) {
-    constexpr int kTileLos = TILE;              // shadows the narrow default of sfk_internal.h
+    constexpr int kTileLos = TILE;              // shadows the narrow width of sfk_internal.h
     constexpr int kBinConsumers = TILE / 2;     // warps
     constexpr int kBinThreads = kBinConsumers * 32;
     extern __shared__ __align__(128) unsigned char smemRaw[];

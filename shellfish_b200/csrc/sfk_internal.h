@@ -9,11 +9,9 @@
 
 namespace sfk {
 
-// LoS per binning tile: one lane per LoS, one warp pass per (particle, ring).
+// LoS per binning tile of the narrow instantiations (sfk_bin.cu; the product instantiation takes 64):
+// TILE / 2 warps per CTA, every warp filters the ring's hit records into a private ring and bins them.
 constexpr int kTileLos = 32;
-// Binning CTA: every warp filters the ring's hit records into a private ring and bins them.
-constexpr int kBinConsumers = 16;
-constexpr int kBinThreads = kBinConsumers * 32;
 constexpr int kKdeKnots = 100;   // rn and the KDE knot count, kde.go:70,99
 constexpr int kMaxLevels = 6;    // KDE tree depth supported on the device
 constexpr int kMaxOrder = 4;     // Penna order (2*order^2 <= 32 coefficients)
