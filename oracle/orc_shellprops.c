@@ -10,9 +10,13 @@
  * (un-vendored, gonum/matrix@c518dec07be9).  The sample stream is therefore an
  * input here (a callback returning rand.Float64()-like uniforms; the repo's
  * xorshift restatement serves as a stand-in), the eigen-decomposition is a
- * cyclic Jacobi iteration, and results can only be compared statistically.  The
- * correction tables are inputs too (the product generates its own, see
- * scripts/make_axis_tables.py). */
+ * cyclic Jacobi iteration, and results can only be compared statistically.  ONE
+ * reference-held row exists for that comparison: doc/quickstart.md:99-106,150-155
+ * prints the coefficients of a halo and the `stats` row made of them; this
+ * restatement reproduces its R_sp, Volume, Surface Area and axes within the scatter
+ * of the 50 000-sample estimate (tests/test_shellprops.py).  The correction tables
+ * are inputs too (the product interpolates the reference's own ellipse_grid values,
+ * scripts/import_axis_tables.py; scripts/make_axis_tables.py recomputes them). */
 #define _GNU_SOURCE
 #include "shellfish_oracle.h"
 

@@ -19,7 +19,9 @@
  *     twoValIntrDist / oneValIntrDist / idxRange / sphereIntersectRing
  *     (los/geom_test.go), Savitzky-Golay taps
  *     (math/interpolate/filter_test.go:40-51), Euler rotations
- *     (los/geom/rotation_test.go:25-79), LU solve/invert (math/mat/mat_test.go).
+ *     (los/geom/rotation_test.go:25-79), LU solve/invert (math/mat/mat_test.go);
+ *     statistically, by the one documented `shell | stats` row (doc/quickstart.md):
+ *     Shell.Volume / SurfaceArea / Axes and the R_sp formula (orc_shellprops.c).
  *   PARITY UNPINNED (no reference test holds a known answer and the Go
  *   toolchain is absent, so the reference cannot be run here): Smooth output,
  *   SplashbackRadius, the KDE filter, the Penna fit (gonum mat64 is an

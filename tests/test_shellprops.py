@@ -2,7 +2,7 @@
 
 Three implementations meet here:
   * the oracle's literal Monte-Carlo restatement of los/analyze/shell.go
-    (oracle/orc_shellprops.c; PARITY UNPINNED: the reference's sample stream is Go's
+    (oracle/orc_shellprops.c; no sample-exact parity: the reference's sample stream is Go's
     unseeded global math/rand),
   * the product's per-node arithmetic, i.e. the source of shell_props_kernel compiled
     for the host (tests/hostcheck), on the product's quadrature rule,
