@@ -19,7 +19,8 @@
  *     twoValIntrDist / oneValIntrDist / idxRange / sphereIntersectRing
  *     (los/geom_test.go), Savitzky-Golay taps
  *     (math/interpolate/filter_test.go:40-51), Euler rotations
- *     (los/geom/rotation_test.go:25-79), LU solve/invert (math/mat/mat_test.go);
+ *     (los/geom/rotation_test.go:25-79) -- math/mat's tests are benchmarks only, the LU
+ *     restatement is cross-checked against numpy instead;
  *     statistically, by the one documented `shell | stats` row (doc/quickstart.md):
  *     Shell.Volume / SurfaceArea / Axes and the R_sp formula (orc_shellprops.c).
  *   PARITY UNPINNED (no reference test holds a known answer and the Go
